@@ -1,0 +1,21 @@
+# Builds libmstts_b200.so (sm_100a only) in-tree.  `python __graft_entry__.py build` calls this.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CSRC := multi_speaker_tts_b200/csrc
+OUT  := multi_speaker_tts_b200/libmstts_b200.so
+SRCS := $(wildcard $(CSRC)/*.cu)
+OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v \
+           --expt-relaxed-constexpr -Iinclude
+
+all: $(OUT)
+
+build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/mstts_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(OUT): $(OBJS)
+	$(NVCC) -shared -o $@ $(OBJS) -L/usr/local/cuda/lib64 -lcublas -lcufft \
+	  -Xlinker -rpath=/usr/local/cuda/lib64
+
+clean:
+	rm -rf build $(OUT)

@@ -1,0 +1,147 @@
+/*
+ * mstts_b200.h -- C ABI of libmstts_b200.so, the sm_100a hot path of CODEJIN/multi_speaker_tts.
+ *
+ * The reference is pure Python/TF1 and has no FFI: the seam it offers is its Python module surface
+ * (SURVEY.md 8b).  Each entry point below replaces the TF graph section named beside it; the Python
+ * mirror of that surface (multi_speaker_tts_b200/Modules.py, Audio.py, WaveGlow/Modules.py) binds
+ * these symbols through ctypes.
+ *
+ * Conventions
+ *   - extern "C"; every function returns int: 0 = ok, <0 = MSTTS_E_* (mstts_last_error() gives a
+ *     thread-local message).
+ *   - all data pointers are DEVICE pointers owned by the caller, contiguous, fp32 unless noted;
+ *     the library never allocates or frees caller memory.  Scratch ("workspace") is passed in with
+ *     its size; query it with the matching *_workspace_bytes().
+ *   - every call takes a cudaStream_t (as void*) and is asynchronous on it.
+ *   - no torch types, no C++ types in signatures.
+ */
+#ifndef MSTTS_B200_H_
+#define MSTTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSTTS_VERSION 100 /* 0.1.0 */
+
+enum {
+  MSTTS_OK = 0,
+  MSTTS_E_INVALID = -1,     /* bad argument (null pointer, size out of range) */
+  MSTTS_E_WORKSPACE = -2,   /* workspace too small */
+  MSTTS_E_CUDA = -3,        /* a CUDA runtime / cuBLAS / cuFFT call failed */
+  MSTTS_E_UNSUPPORTED = -4, /* configuration not implemented (e.g. conv stride != 1) */
+  MSTTS_E_DEVICE = -5       /* device is not sm_100 or cannot co-schedule the persistent grid */
+};
+
+/* precision modes of the recurrent GEMVs */
+enum {
+  MSTTS_MODE_FP32 = 0,  /* fp32 weights, fp32 FMA: the parity mode (L_inf vs oracle ~1e-5) */
+  MSTTS_MODE_BF16X3 = 1,/* tcgen05, weights and activations split hi+lo bf16, 3 MMAs, fp32 accum */
+  MSTTS_MODE_BF16 = 2   /* tcgen05, bf16 in / fp32 accum (fast mode; does not meet the 1e-3 gate) */
+};
+
+int mstts_version(void);
+const char* mstts_last_error(void);
+/* number of SMs / whether the device can run the persistent cluster grid; <0 on error */
+int mstts_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tacotron2 decoder loop.
+ * Replaces: Modules.Decoder_LSTM (Modules.py:76-119) = Decoder_Helper (:148-255) + ZoneoutLSTMCell x2
+ * (ZoneoutLSTMCell.py:188-271) + Location_Sensitive_Attention (Location_Sensitive_Attention.py:43-85,
+ * incl. the BahdanauAttention memory_layer built at :36-41) + Decoder_Decoder.projection
+ * (Modules.py:309-321) + Decoder_Dynamic_Decode (:323-472).
+ * Weights are in the TF variable layouts ([in, out] row-major; conv kernel [k, in, out]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MsttsDecoderWeights {
+  const float* prenet0_kernel; /* [80,256]   decoder/decoder/prenet_0/dense/kernel */
+  const float* prenet0_bias;   /* [256] */
+  const float* prenet1_kernel; /* [256,256] */
+  const float* prenet1_bias;   /* [256] */
+  const float* cell0_kernel;   /* [256+2*D+1024, 4096]  rows: prenet | ctx | ctx | h ; cols: i j f o */
+  const float* cell0_bias;     /* [4096] */
+  const float* cell1_kernel;   /* [2048, 4096] */
+  const float* cell1_bias;     /* [4096] */
+  const float* memory_kernel;  /* [D,128]    attention/memory_layer/kernel (no bias) */
+  const float* query_kernel;   /* [1024,128] query_layer/kernel (no bias) */
+  const float* loc_conv_kernel;/* [31,1,32] */
+  const float* loc_conv_bias;  /* [32] */
+  const float* loc_dense_kernel;/* [32,128] (no bias) */
+  const float* score_w;        /* [128] weight_w */
+  const float* score_b;        /* [128] bias_b */
+  const float* proj_kernel;    /* [1024+D, 81] */
+  const float* proj_bias;      /* [81] */
+} MsttsDecoderWeights;
+
+/* Same fields, gradient outputs (fp32, caller-allocated, OVERWRITTEN not accumulated). */
+typedef struct MsttsDecoderWeightGrads {
+  float* prenet0_kernel; float* prenet0_bias; float* prenet1_kernel; float* prenet1_bias;
+  float* cell0_kernel; float* cell0_bias; float* cell1_kernel; float* cell1_bias;
+  float* memory_kernel; float* query_kernel;
+  float* loc_conv_kernel; float* loc_conv_bias; float* loc_dense_kernel;
+  float* score_w; float* score_b; float* proj_kernel; float* proj_bias;
+} MsttsDecoderWeightGrads;
+
+typedef struct MsttsDecoderIO {
+  int B;            /* batch */
+  int Te;           /* padded text length (memory time axis) */
+  int L;            /* padded mel length (teacher-forcing frames) */
+  int D;            /* memory depth (768 = 2*256 encoder + 256 speaker) */
+  int n_steps;      /* training: max(mel_len)+1 (Modules.py:215,395).  inference: step cap (1000)+1 */
+  int is_training;  /* 1: teacher forcing + zoneout masks; 0: free running (prenet dropout stays on) */
+  int mode;         /* MSTTS_MODE_* */
+  const float* memory;        /* [B,Te,D] encoder output ++ speaker embedding, un-masked */
+  const int32_t* text_len;    /* [B] */
+  const float* mel;           /* [B,L,80] */
+  const int32_t* mel_len;     /* [B] */
+  const uint8_t* prenet_mask; /* [n_steps,2,B,256] 0/1, step t consumes [t] (always applied) */
+  const uint8_t* zone_mask;   /* [n_steps,2,2,B,1024] 0/1 ([t][cell][c|h]); NULL at inference */
+  float* linear;              /* out [B,n_steps,80] */
+  float* stop;                /* out [B,n_steps]    (logits) */
+  float* align;               /* out [B,n_steps,Te] */
+  int32_t* steps_done;        /* out [1] device: number of executed steps (== n_steps in training) */
+} MsttsDecoderIO;
+
+/* upstream gradients / data gradients of the decoder op (SURVEY A-11) */
+typedef struct MsttsDecoderGrads {
+  const float* d_linear;  /* in  [B,n_steps,80] */
+  const float* d_stop;    /* in  [B,n_steps] */
+  float* d_memory;        /* out [B,Te,D]  (through values and keys; zero beyond text_len) */
+} MsttsDecoderGrads;
+
+size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int n_steps, int mode);
+int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws, size_t ws_bytes,
+                      void* stream);
+/* must be called with the SAME io / ws that mstts_decoder_fwd filled (saved activations live in ws) */
+int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const MsttsDecoderGrads* g,
+                      const MsttsDecoderWeightGrads* dw, void* ws, size_t ws_bytes, void* stream);
+
+/* decoder part of the loss, MSTTS_SV.py:127-144: linear MSE(+L1) on linear[:, :-1] vs mel (un-masked
+ * mean) and stop BCE-with-logits vs 1-sequence_mask(mel_len, n_steps).  Writes loss[0]=linear,
+ * loss[1]=stop and the gradients of (linear_loss + stop_loss) w.r.t. linear / stop. */
+int mstts_decoder_loss(const float* linear, const float* stop, const float* mel, const int32_t* mel_len,
+                       int B, int L, int n_steps, int use_l1, float* loss2, float* d_linear, float* d_stop,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Random masks: counter-based generator so dropout / zoneout bits never cross PCIe.
+ * Replaces tf.layers.dropout's / ZoneoutLSTMCell.dropout_no_scale's floor(U + keep) (Modules.py:248-253,
+ * ZoneoutLSTMCell.py:266-271).  out[i] = (hash(seed, i) < keep) ? 1 : 0.
+ * ---------------------------------------------------------------------------------------------- */
+int mstts_fill_mask(uint8_t* out, size_t n, float keep_prob, uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tf.train.AdamOptimizer update, epsilon-hat form (MSTTS_SV.py:171-176): flat fp32 buffers.
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  grad_scale multiplies g first
+ * (1/world_size after the allreduce; clip factor for WaveGlow).
+ * ---------------------------------------------------------------------------------------------- */
+int mstts_adam_tf(float* p, float* m, float* v, const float* g, size_t n, float lr_t, float b1, float b2,
+                  float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSTTS_B200_H_ */

@@ -1,0 +1,103 @@
+"""ctypes binding of libmstts_b200.so (the C ABI in include/mstts_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmstts_b200.so")
+
+MODE_FP32, MODE_BF16X3, MODE_BF16 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+
+_fp = C.c_void_p
+
+DECODER_WEIGHT_FIELDS = [
+    # (struct field, key in the python weight dict)
+    ("prenet0_kernel", "prenet_0/kernel"), ("prenet0_bias", "prenet_0/bias"),
+    ("prenet1_kernel", "prenet_1/kernel"), ("prenet1_bias", "prenet_1/bias"),
+    ("cell0_kernel", "cell_0/kernel"), ("cell0_bias", "cell_0/bias"),
+    ("cell1_kernel", "cell_1/kernel"), ("cell1_bias", "cell_1/bias"),
+    ("memory_kernel", "memory_layer/kernel"), ("query_kernel", "query_layer/kernel"),
+    ("loc_conv_kernel", "location/conv1d/kernel"), ("loc_conv_bias", "location/conv1d/bias"),
+    ("loc_dense_kernel", "location/dense/kernel"),
+    ("score_w", "score/weight_w"), ("score_b", "score/bias_b"),
+    ("proj_kernel", "projection/kernel"), ("proj_bias", "projection/bias"),
+]
+
+
+class MsttsDecoderWeights(C.Structure):
+    _fields_ = [(f, _fp) for f, _ in DECODER_WEIGHT_FIELDS]
+
+
+class MsttsDecoderWeightGrads(C.Structure):
+    _fields_ = [(f, _fp) for f, _ in DECODER_WEIGHT_FIELDS]
+
+
+class MsttsDecoderIO(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("Te", C.c_int), ("L", C.c_int), ("D", C.c_int), ("n_steps", C.c_int),
+        ("is_training", C.c_int), ("mode", C.c_int),
+        ("memory", _fp), ("text_len", _fp), ("mel", _fp), ("mel_len", _fp),
+        ("prenet_mask", _fp), ("zone_mask", _fp),
+        ("linear", _fp), ("stop", _fp), ("align", _fp), ("steps_done", _fp),
+    ]
+
+
+class MsttsDecoderGrads(C.Structure):
+    _fields_ = [("d_linear", _fp), ("d_stop", _fp), ("d_memory", _fp)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "mstts_version": (C.c_int, []),
+    "mstts_last_error": (C.c_char_p, []),
+    "mstts_device_check": (C.c_int, [C.c_int]),
+    "mstts_decoder_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "mstts_decoder_fwd": (C.c_int, [C.POINTER(MsttsDecoderWeights), C.POINTER(MsttsDecoderIO), _fp, C.c_size_t, _fp]),
+    "mstts_decoder_bwd": (C.c_int, [C.POINTER(MsttsDecoderWeights), C.POINTER(MsttsDecoderIO),
+                                    C.POINTER(MsttsDecoderGrads), C.POINTER(MsttsDecoderWeightGrads),
+                                    _fp, C.c_size_t, _fp]),
+    "mstts_decoder_loss": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
+    "mstts_fill_mask": (C.c_int, [_fp, C.c_size_t, C.c_float, C.c_uint64, _fp]),
+    "mstts_adam_tf": (C.c_int, [_fp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, _fp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libmstts_b200.so not found at %s -- build it with `python __graft_entry__.py build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(l, name)  # raises AttributeError if a declared symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+class MsttsError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().mstts_last_error()
+        raise MsttsError("%s failed (%d): %s" % (what or "libmstts_b200 call", rc, msg.decode() if msg else ""))
+
+
+def ptr(t):
+    """device pointer of a contiguous tensor (None -> NULL)"""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "libmstts_b200 needs contiguous tensors"
+    return C.c_void_p(t.data_ptr())

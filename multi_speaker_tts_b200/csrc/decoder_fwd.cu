@@ -1,0 +1,376 @@
+// Tacotron2 decoder loop, forward, as ONE persistent kernel (training / teacher-forced mode).
+//
+// Replaces the tf.while_loop body of Modules.py:397-443 (Decoder_Dynamic_Decode) and everything it calls
+// per step: ZoneoutLSTMCell.call x2 (ZoneoutLSTMCell.py:228-264), Location_Sensitive_Attention.__call__
+// (Location_Sensitive_Attention.py:43-85) and the AttentionWrapper context.  Input-only work (prenet,
+// the prenet rows of cell0's kernel, memory_layer keys, the mel/stop projection in teacher-forced mode)
+// is hoisted out of the loop into batched GEMMs.
+//
+// Grid: 128 CTAs = 32 clusters x 4 (B200: 148 SMs, cluster-4 can place 33 clusters).
+//   phase A  cell 0 : CTA j owns LSTM units 8j..8j+7 (32 gate columns), K split over its 8 warps
+//   phase B  cell 1 : same split; epilogue also emits this CTA's partial query projection
+//   phase C  attention: cluster c owns batch row c; CTA r of the cluster owns attention units 32r..32r+31
+//            (keys slice resident in smem) and context dims r*D/4.. (values slice resident in smem);
+//            partial energies are exchanged through distributed shared memory.
+//   one device-wide barrier after each phase.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "decoder_layout.h"
+
+namespace cg = cooperative_groups;
+
+struct DecFwdParams {
+  int B, Te, T, D, training, resident;
+  const float *W0r, *W1, *b0, *b1, *Wq, *F, *fb, *sw;
+  const float *g0pre, *keys, *values;
+  const int* text_len;
+  const uint8_t* zone_mask;
+  float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart;
+  unsigned* barrier;
+};
+
+constexpr int kRedStride = 40;  // floats per (warp, batch) row of the K-split reduction buffer
+
+// ---- K-split GEMV of one LSTM cell for NB batch rows: this CTA's 32 gate columns ------------------
+// x = [xa (Ka) | xb (Kb)] per batch row; W is [K][4096] row-major in TF column order (i|j|f|o).
+template <int NB>
+__device__ __forceinline__ void lstm_gemv(const float* __restrict__ W, int K, const float* xa, int Ka,
+                                          const float* xb, int Kb, int nb, float* red, int unit0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = (lane >> 3) * kCell + unit0 + (lane & 7);
+  const int kslice = K >> 3;
+  const int k0 = warp * kslice, k1 = k0 + kslice;
+  float acc[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+#pragma unroll 2
+  for (int k = k0; k < k1; k += 4) {
+    const float* xp;
+    int xs;
+    if (k < Ka) {
+      xp = xa + k;
+      xs = Ka;
+    } else {
+      xp = xb + (k - Ka);
+      xs = Kb;
+    }
+    const float* wp = W + (size_t)k * kGates + col;
+    const float w0 = ld_nc_na(wp), w1 = ld_nc_na(wp + kGates), w2 = ld_nc_na(wp + 2 * kGates),
+                w3 = ld_nc_na(wp + 3 * kGates);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (b < nb) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + (size_t)b * xs);
+        acc[b] = fmaf(xv.x, w0, acc[b]);
+        acc[b] = fmaf(xv.y, w1, acc[b]);
+        acc[b] = fmaf(xv.z, w2, acc[b]);
+        acc[b] = fmaf(xv.w, w3, acc[b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) red[(warp * NB + b) * kRedStride + lane] = acc[b];
+}
+
+// ---- gate math + zoneout for this CTA's 8 units (ZoneoutLSTMCell.py:230-264) ----------------------
+template <int NB>
+__device__ __forceinline__ void lstm_epilogue(const float* red, int nb, int unit0, const float* addend,
+                                              const float* __restrict__ bias, const float* c_prev,
+                                              const float* h_prev, const uint8_t* __restrict__ mask_c,
+                                              const uint8_t* __restrict__ mask_h, float* act, float* cn,
+                                              float* cz, float* hz, float* m, float* m_s) {
+  for (int p = threadIdx.x; p < nb * kUnitsPerCta; p += blockDim.x) {
+    const int b = p >> 3, u = p & 7, unit = unit0 + u;
+    float g[4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[(w * NB + b) * kRedStride + gi * 8 + u];
+      if (addend) s += addend[(size_t)b * kGates + gi * kCell + unit];
+      s += bias[gi * kCell + unit];
+      g[gi] = s;
+    }
+    const float ig = sigmoidf_precise(g[0]);
+    const float jg = tanhf(g[1]);
+    const float fg = sigmoidf_precise(g[2] + kForgetBias);
+    const float og = sigmoidf_precise(g[3]);
+    const size_t si = (size_t)b * kCell + unit;
+    const float cp = c_prev[si], hp = h_prev[si];
+    const float c = fg * cp + ig * jg;
+    const float mm = og * tanhf(c);
+    float dc = c - cp, dm = mm - hp;
+    if (mask_c) {
+      dc *= (float)mask_c[si];
+      dm *= (float)mask_h[si];
+    }
+    const size_t ai = (size_t)b * kGates + unit;
+    act[ai] = ig;
+    act[ai + kCell] = jg;
+    act[ai + 2 * kCell] = fg;
+    act[ai + 3 * kCell] = og;
+    cn[si] = c;
+    cz[si] = kZoneKeep * dc + cp;
+    hz[si] = kZoneKeep * dm + hp;
+    m[si] = mm;
+    if (m_s) m_s[b * kUnitsPerCta + u] = mm;
+  }
+}
+
+template <int NB>
+__global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThreads, 1)
+    decoder_fwd_kernel(const DecFwdParams P) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int B = P.B, Te = P.Te, D = P.D, Dq = D / kDecCluster;
+  const int unit0 = blockIdx.x * kUnitsPerCta;
+  const int crank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / kDecCluster;
+  const int nclusters = gridDim.x / kDecCluster;
+  const int TeP = (Te + 15) & ~15;
+
+  // ---- shared memory carve-up ----
+  float* red = smem;                                  // [8][NB][40]
+  float* wq_s = red + 8 * NB * kRedStride;            // [8][128]  query_layer rows of this CTA's units
+  float* m_s = wq_s + kUnitsPerCta * kAtt;            // [NB][8]
+  float* qred = m_s + NB * kUnitsPerCta;              // [8][32]
+  float* qf_s = qred + 8 * 32;                        // [32]   q + composed bias, this CTA's unit slice
+  float* cum_s = qf_s + 32;                           // [TeP+32] cum shifted by 15, zero padded
+  float* e_loc = cum_s + TeP + 32;                    // [TeP]
+  float* e_parts = e_loc + TeP;                       // [4][TeP]  written by the 4 CTAs of the cluster
+  float* a_s = e_parts + kDecCluster * TeP;           // [TeP]
+  float* bred = a_s + TeP;                            // [16]
+  float* keys_s = bred + 16;                          // [Te][32]   (resident)
+  float* vals_s = keys_s + (P.resident ? Te * 32 : 0);// [Te][Dq]   (resident)
+
+  // ---- one-time staging ----
+  for (int i = tid; i < kUnitsPerCta * kAtt; i += kDecThreads)
+    wq_s[i] = P.Wq[(size_t)(unit0 + i / kAtt) * kAtt + (i % kAtt)];
+  float F_reg[kConvK];
+#pragma unroll
+  for (int k = 0; k < kConvK; ++k) F_reg[k] = P.F[k * kAtt + crank * 32 + lane];
+  const float sw_l = P.sw[crank * 32 + lane];
+  const float fb_l = P.fb[crank * 32 + lane];
+  if (P.resident && cid < B) {
+    const float* kg = P.keys + (size_t)cid * Te * kAtt;
+    for (int i = tid; i < Te * 32; i += kDecThreads) keys_s[i] = kg[(size_t)(i >> 5) * kAtt + crank * 32 + (i & 31)];
+    const float* vg = P.values + (size_t)cid * Te * D;
+    for (int i = tid; i < Te * Dq; i += kDecThreads) vals_s[i] = vg[(size_t)(i / Dq) * D + crank * Dq + (i % Dq)];
+  }
+  for (int i = tid; i < TeP + 32; i += kDecThreads) cum_s[i] = 0.f;
+  __syncthreads();
+
+  unsigned bar_target = 0;
+  const size_t BC = (size_t)B * kCell, BG = (size_t)B * kGates;
+
+  for (int t = 0; t < P.T; ++t) {
+    const uint8_t* zm = P.training ? P.zone_mask + (size_t)t * 4 * BC : nullptr;
+    // ================= phase A: LSTM cell 0 =================
+    for (int b0 = 0; b0 < B; b0 += NB) {
+      const int nb = min(NB, B - b0);
+      lstm_gemv<NB>(P.W0r, D + kCell, P.ctx + ((size_t)t * B + b0) * D, D, P.hz0 + (size_t)t * BC + (size_t)b0 * kCell,
+                    kCell, nb, red, unit0);
+      __syncthreads();
+      lstm_epilogue<NB>(red, nb, unit0, P.g0pre + (size_t)t * BG + (size_t)b0 * kGates, P.b0,
+                        P.cz0 + (size_t)t * BC + (size_t)b0 * kCell, P.hz0 + (size_t)t * BC + (size_t)b0 * kCell,
+                        zm ? zm + (size_t)b0 * kCell : nullptr, zm ? zm + BC + (size_t)b0 * kCell : nullptr,
+                        P.act0 + (size_t)t * BG + (size_t)b0 * kGates, P.c0n + (size_t)t * BC + (size_t)b0 * kCell,
+                        P.cz0 + (size_t)(t + 1) * BC + (size_t)b0 * kCell,
+                        P.hz0 + (size_t)(t + 1) * BC + (size_t)b0 * kCell, P.m0 + (size_t)t * BC + (size_t)b0 * kCell,
+                        nullptr);
+      __syncthreads();
+    }
+    grid_barrier(P.barrier, bar_target, gridDim.x);
+
+    // ================= phase B: LSTM cell 1 (+ partial query projection) =================
+    for (int b0 = 0; b0 < B; b0 += NB) {
+      const int nb = min(NB, B - b0);
+      lstm_gemv<NB>(P.W1, 2 * kCell, P.m0 + (size_t)t * BC + (size_t)b0 * kCell, kCell,
+                    P.hz1 + (size_t)t * BC + (size_t)b0 * kCell, kCell, nb, red, unit0);
+      __syncthreads();
+      lstm_epilogue<NB>(red, nb, unit0, nullptr, P.b1, P.cz1 + (size_t)t * BC + (size_t)b0 * kCell,
+                        P.hz1 + (size_t)t * BC + (size_t)b0 * kCell, zm ? zm + 2 * BC + (size_t)b0 * kCell : nullptr,
+                        zm ? zm + 3 * BC + (size_t)b0 * kCell : nullptr, P.act1 + (size_t)t * BG + (size_t)b0 * kGates,
+                        P.c1n + (size_t)t * BC + (size_t)b0 * kCell, P.cz1 + (size_t)(t + 1) * BC + (size_t)b0 * kCell,
+                        P.hz1 + (size_t)(t + 1) * BC + (size_t)b0 * kCell, P.m1 + (size_t)t * BC + (size_t)b0 * kCell,
+                        m_s);
+      __syncthreads();
+      // partial q[b][a] = sum over this CTA's 8 units of m1[b][unit] * Wq[unit][a]
+      for (int i = tid; i < nb * kAtt; i += kDecThreads) {
+        const int b = i >> 7, a = i & 127;
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < kUnitsPerCta; ++u) s = fmaf(m_s[b * kUnitsPerCta + u], wq_s[u * kAtt + a], s);
+        P.qpart[((size_t)blockIdx.x * B + b0 + b) * kAtt + a] = s;
+      }
+      __syncthreads();
+    }
+    grid_barrier(P.barrier, bar_target, gridDim.x);
+
+    // ================= phase C: location-sensitive attention, one batch row per cluster ==========
+    for (int b = cid; b < B; b += nclusters) {
+      const int tl = min(P.text_len[b], Te);
+      const float* keys_b = P.resident ? keys_s : P.keys + (size_t)b * Te * kAtt + crank * 32;
+      const int kstride = P.resident ? 32 : kAtt;
+      const float* vals_b = P.resident ? vals_s : P.values + (size_t)b * Te * D + crank * Dq;
+      const int vstride = P.resident ? Dq : D;
+      // previous cumulative alignment (slot t), shifted by 15 so cum_s[x] = cum[x-15]
+      const float* cum_prev = P.cum + ((size_t)t * B + b) * Te;
+      for (int x = tid; x < Te; x += kDecThreads) cum_s[15 + x] = cum_prev[x];
+      // q slice = sum of the 128 per-CTA partials (fixed order -> identical in every run)
+      {
+        float s = 0.f;
+        for (int j = warp; j < kDecGrid; j += 8) s += __ldcg(P.qpart + ((size_t)j * B + b) * kAtt + crank * 32 + lane);
+        qred[warp * 32 + lane] = s;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
+        qf_s[tid] = s + fb_l;
+      }
+      __syncthreads();
+      // partial energies over this CTA's 32 attention units, 16 positions per warp pass
+      const float qf = qf_s[lane];
+      for (int blk = warp; blk * 16 < tl; blk += 8) {
+        const int t0 = blk * 16;
+        float acc[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16 + kConvK - 1; ++c) {
+          const float cv = cum_s[t0 + c];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int k = c - p;
+            if (k >= 0 && k < kConvK) acc[p] = fmaf(cv, F_reg[k], acc[p]);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int x = t0 + p;
+          float v = 0.f;
+          if (x < tl) v = sw_l * tanhf(keys_b[(size_t)x * kstride + lane] + qf + acc[p]);
+          v = warp_sum(v);
+          if (lane == 0) e_loc[x] = v;
+        }
+      }
+      __syncthreads();
+      // all-gather the partial energies across the cluster through DSMEM
+#pragma unroll
+      for (int dst = 0; dst < kDecCluster; ++dst) {
+        float* remote = cluster.map_shared_rank(e_parts, dst) + crank * TeP;
+        for (int x = tid; x < tl; x += kDecThreads) remote[x] = e_loc[x];
+      }
+      cluster.sync();
+      // masked softmax over positions < tl (score_mask_value = -inf => exactly 0 beyond tl)
+      float lmax = -INFINITY;
+      for (int x = tid; x < tl; x += kDecThreads) {
+        const float e = ((e_parts[x] + e_parts[TeP + x]) + e_parts[2 * TeP + x]) + e_parts[3 * TeP + x];
+        a_s[x] = e;
+        lmax = fmaxf(lmax, e);
+      }
+      lmax = warp_max(lmax);
+      if (lane == 0) bred[warp] = lmax;
+      __syncthreads();
+      float gmax = bred[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) gmax = fmaxf(gmax, bred[w]);
+      float lsum = 0.f;
+      for (int x = tid; x < tl; x += kDecThreads) {
+        const float ex = expf(a_s[x] - gmax);
+        a_s[x] = ex;
+        lsum += ex;
+      }
+      lsum = warp_sum(lsum);
+      if (lane == 0) bred[8 + warp] = lsum;
+      __syncthreads();
+      float gsum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) gsum += bred[8 + w];
+      for (int x = tid; x < Te; x += kDecThreads) {
+        const float a = (x < tl) ? a_s[x] / gsum : 0.f;
+        a_s[x] = a;
+        if (crank == 0) {
+          P.align_tm[((size_t)t * B + b) * Te + x] = a;
+          P.cum[((size_t)(t + 1) * B + b) * Te + x] = cum_s[15 + x] + a;
+        }
+      }
+      __syncthreads();
+      // context slice: ctx[d] = sum_x a[x] * values[x][d]
+      if (tid < Dq) {
+        float s = 0.f;
+        for (int x = 0; x < tl; ++x) s = fmaf(a_s[x], vals_b[(size_t)x * vstride + tid], s);
+        P.ctx[((size_t)(t + 1) * B + b) * D + crank * Dq + tid] = s;
+      }
+      if (b + nclusters < B) cluster.sync();  // e_parts is reused by the next row
+    }
+    grid_barrier(P.barrier, bar_target, gridDim.x);
+  }
+}
+
+// ======================================== host side ================================================
+size_t dec_fwd_smem_bytes(int NB, int Te, int D, int resident) {
+  const int TeP = (Te + 15) & ~15;
+  size_t f = (size_t)8 * NB * kRedStride + kUnitsPerCta * kAtt + NB * kUnitsPerCta + 8 * 32 + 32 + (TeP + 32) + TeP +
+             kDecCluster * TeP + TeP + 16;
+  if (resident) f += (size_t)Te * 32 + (size_t)Te * (D / kDecCluster);
+  return f * sizeof(float);
+}
+
+template <int NB>
+static int launch_fwd(const DecFwdParams& P, cudaStream_t stream) {
+  int dev = 0;
+  MSTTS_CUDA(cudaGetDevice(&dev));
+  int max_optin = 0;
+  MSTTS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  DecFwdParams Q = P;
+  Q.resident = (P.B <= kDecGrid / kDecCluster) && dec_fwd_smem_bytes(NB, P.Te, P.D, 1) <= (size_t)max_optin;
+  const size_t smem = dec_fwd_smem_bytes(NB, P.Te, P.D, Q.resident);
+  MSTTS_REQUIRE(smem <= (size_t)max_optin, MSTTS_E_UNSUPPORTED, "decoder_fwd: Te=%d needs %zu B smem > %d", P.Te, smem,
+                max_optin);
+  MSTTS_CUDA(cudaFuncSetAttribute(decoder_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(kDecGrid);
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  int nclusters = 0;
+  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_kernel<NB>, &cfg));
+  MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
+                "decoder_fwd: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
+                kDecGrid / kDecCluster);
+  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_kernel<NB>, Q));
+  return MSTTS_OK;
+}
+
+int dec_fwd_persistent(const DecFwdParams& P, cudaStream_t stream) {
+  const int B = P.B;
+  if (B <= 1) return launch_fwd<1>(P, stream);
+  if (B <= 2) return launch_fwd<2>(P, stream);
+  if (B <= 4) return launch_fwd<4>(P, stream);
+  if (B <= 8) return launch_fwd<8>(P, stream);
+  if (B <= 16) return launch_fwd<16>(P, stream);
+  return launch_fwd<32>(P, stream);
+}
+
+int dec_fwd_persistent_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws,
+                             cudaStream_t s) {
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  DecFwdParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = io->B; P.Te = io->Te; P.T = io->n_steps; P.D = io->D; P.training = io->is_training;
+  P.W0r = F(l.W0r); P.W1 = w->cell1_kernel; P.b0 = w->cell0_bias; P.b1 = w->cell1_bias; P.Wq = w->query_kernel;
+  P.F = F(l.locF); P.fb = F(l.locFb); P.sw = w->score_w;
+  P.g0pre = F(l.g0pre); P.keys = F(l.keys); P.values = F(l.values);
+  P.text_len = io->text_len; P.zone_mask = io->zone_mask;
+  P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n);
+  P.cz0 = F(l.cz0); P.hz0 = F(l.hz0); P.cz1 = F(l.cz1); P.hz1 = F(l.hz1);
+  P.m0 = F(l.m0); P.m1 = F(l.m1); P.ctx = F(l.ctx); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.qpart = F(l.qpart);
+  P.barrier = (unsigned*)(ws + l.barrier);
+  return dec_fwd_persistent(P, s);
+}

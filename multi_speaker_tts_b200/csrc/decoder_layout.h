@@ -1,0 +1,73 @@
+// Workspace layout of the decoder op: prepared weights, hoisted pre-GEMM results and every activation
+// the reverse pass needs.  One function computes the offsets so fwd, bwd and workspace_bytes agree.
+#pragma once
+#include "common.cuh"
+
+struct DecLayout {
+  // ---- prepared operands (rebuilt every fwd call: weights change each optimiser step) ----
+  size_t values;   // [B,Te,D]   memory * sequence_mask(text_len)
+  size_t keys;     // [B,Te,128] values @ memory_layer
+  size_t W0r;      // [D+1024,4096] recurrent rows of cell0: (ctx block a + ctx block b) ; h rows
+  size_t locF;     // [31,128]  location conv (x) dense composed
+  size_t locFb;    // [128]     conv bias @ dense + score bias_b
+  // ---- hoisted, input-only work (training: teacher-forced frames are known up front) ----
+  size_t frames;   // [T,B,80]   frame fed at step t (zeros at t=0, mel[:,t-1] after)
+  size_t pre_h;    // [T,B,256]  prenet layer 0 after relu*mask*2
+  size_t pre;      // [T,B,256]  prenet output
+  size_t g0pre;    // [T,B,4096] pre @ cell0_kernel[0:256]   (bias added in the cell epilogue)
+  // ---- recurrent state / saved activations, time-major; "slot" arrays have T+1 entries, slot 0 = 0 ----
+  size_t act0, act1;          // [T,B,4096] gate activations sigma(i) tanh(j) sigma(f+1) sigma(o)
+  size_t c0n, c1n;            // [T,B,1024] new cell value before zoneout
+  size_t cz0, hz0, cz1, hz1;  // [T+1,B,1024] zoned state after step t at slot t+1
+  size_t m0, m1;              // [T,B,1024] cell outputs (un-zoned)
+  size_t ctx;                 // [T+1,B,D]
+  size_t cum;                 // [T+1,B,Te]
+  size_t align_tm;            // [T,B,Te]
+  size_t qpart;               // [128,B,128] per-CTA partial query projections of the current step
+  size_t proj_tm;             // [T,B,81]
+  size_t barrier;             // 64 B of counters
+  // ---- reverse pass scratch ----
+  size_t bwd_begin;
+  size_t total;
+};
+
+static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode) {
+  (void)L;
+  (void)mode;
+  DecLayout l;
+  size_t off = 0;
+  auto take = [&](size_t nfloats) {
+    size_t o = off;
+    off += align_up(nfloats * sizeof(float), 256);
+    return o;
+  };
+  const size_t TB = (size_t)T * B, SB = (size_t)(T + 1) * B;
+  l.values = take((size_t)B * Te * D);
+  l.keys = take((size_t)B * Te * kAtt);
+  l.W0r = take((size_t)(D + kCell) * kGates);
+  l.locF = take(kConvK * kAtt);
+  l.locFb = take(kAtt);
+  l.frames = take(TB * kMel);
+  l.pre_h = take(TB * kPrenet);
+  l.pre = take(TB * kPrenet);
+  l.g0pre = take(TB * kGates);
+  l.act0 = take(TB * kGates);
+  l.act1 = take(TB * kGates);
+  l.c0n = take(TB * kCell);
+  l.c1n = take(TB * kCell);
+  l.cz0 = take(SB * kCell);
+  l.hz0 = take(SB * kCell);
+  l.cz1 = take(SB * kCell);
+  l.hz1 = take(SB * kCell);
+  l.m0 = take(TB * kCell);
+  l.m1 = take(TB * kCell);
+  l.ctx = take(SB * D);
+  l.cum = take(SB * Te);
+  l.align_tm = take(TB * Te);
+  l.qpart = take((size_t)kDecGrid * B * kAtt);
+  l.proj_tm = take(TB * (kMel + 1));
+  l.barrier = take(16);
+  l.bwd_begin = off;
+  l.total = off;
+  return l;
+}

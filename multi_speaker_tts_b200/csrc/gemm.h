@@ -1,0 +1,16 @@
+// Plain dense GEMMs that sit outside the recurrent loop (hoisted prenet / projection / weight-gradient
+// products).  Row-major in, row-major out, fp32.
+#pragma once
+#include "common.cuh"
+
+// C[M,N] = op(A) * op(B) + beta * C, all row-major with leading dimensions lda/ldb/ldc.
+// op(A) is M x K (A stored K x M when transA), op(B) is K x N (B stored N x K when transB).
+int gemm_rowmajor_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
+                     const float* B, int ldb, float* C, int ldc, float beta);
+
+static inline int gemm_rowmajor(cudaStream_t s, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                                float* C, int ldc, float beta) {
+  return gemm_rowmajor_ex(s, false, false, M, N, K, A, lda, B, ldb, C, ldc, beta);
+}
+
+size_t dec_bwd_extra_bytes(int B, int Te, int D, int T);

@@ -1,0 +1,64 @@
+"""GPU parity: CUDA decoder (through the C ABI) vs the CPU oracle on identical inputs and masks.
+
+Gates (BASELINE.json north_star): linear/stop L_inf < 1e-3 (fp32), alignment argmax and the stop decision
+(stop_logit >= 0) bit-exact."""
+import pytest
+import torch
+
+from multi_speaker_tts_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # north_star: mel L_inf < 1e-3 in fp32
+
+
+def _run_both(B, Te, L, ragged, dev, seed=1234, bias_scale=0.05):
+    from oracle import decoder_oracle as O
+    from multi_speaker_tts_b200.decoder import decoder_forward
+    w = S.init_decoder_weights(0, bias_scale=bias_scale)
+    b = S.synthetic_decoder_batch(B, Te, L, seed=seed, ragged=ragged)
+    T = int(b['mel_len'].max()) + 1
+    ref = O.decoder_forward(w, b['memory'], b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'], b['zone_mask'])
+    wd = {k: v.to(dev) for k, v in w.items()}
+    bd = {k: v.to(dev) for k, v in b.items()}
+    lin, stop, align, _ = decoder_forward(wd, bd['memory'], bd['text_len'], bd['mel'], bd['mel_len'],
+                                          bd['prenet_mask'][:T].contiguous(), bd['zone_mask'][:T].contiguous(),
+                                          is_training=True, n_steps=T, mode="fp32")
+    torch.cuda.synchronize()
+    return ref, (lin.cpu(), stop.cpu(), align.cpu()), b
+
+
+def _check(ref, got, b):
+    rl, rs, ra = ref
+    gl, gs, ga = got
+    assert gl.shape == rl.shape and gs.shape == rs.shape and ga.shape == ra.shape
+    assert torch.isfinite(gl).all() and torch.isfinite(gs).all() and torch.isfinite(ga).all()
+    e_lin = (gl - rl).abs().max().item()
+    e_stop = (gs - rs).abs().max().item()
+    e_al = (ga - ra).abs().max().item()
+    print("Linf linear %.3e stop %.3e align %.3e" % (e_lin, e_stop, e_al))
+    assert e_lin < TOL and e_stop < TOL and e_al < TOL
+    assert torch.equal(ga.argmax(-1), ra.argmax(-1)), "alignment argmax differs"
+    assert torch.equal(gs >= 0, rs >= 0), "stop decision differs"
+    # attention rows: sum to 1 and are exactly 0 beyond text_len
+    assert (ga.sum(-1) - 1).abs().max() < 1e-5
+    Te = ga.shape[-1]
+    beyond = torch.arange(Te)[None, None, :] >= b['text_len'][:, None, None]
+    assert (ga[beyond.expand_as(ga)] == 0).all()
+
+
+def test_config1_parity(cuda_dev):
+    """BASELINE config 1: B=2, Te=32, L=200."""
+    ref, got, b = _run_both(2, 32, 200, False, cuda_dev)
+    _check(ref, got, b)
+
+
+def test_ragged_parity(cuda_dev):
+    ref, got, b = _run_both(3, 40, 60, True, cuda_dev, seed=7)
+    _check(ref, got, b)
+
+
+@pytest.mark.parametrize("B,Te,L", [(1, 16, 8), (5, 33, 12), (8, 128, 10), (16, 100, 6), (32, 128, 6), (40, 48, 5)])
+def test_shapes_parity(cuda_dev, B, Te, L):
+    ref, got, b = _run_both(B, Te, L, True, cuda_dev, seed=B * 100 + Te)
+    _check(ref, got, b)
