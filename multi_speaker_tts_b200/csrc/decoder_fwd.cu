@@ -26,52 +26,12 @@ struct DecFwdParams {
   const float *g0pre, *keys, *values;
   const int* text_len;
   const uint8_t* zone_mask;
-  float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart;
+  float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart, *qf;
   unsigned* barrier;
 };
 
-constexpr int kRedStride = 40;  // floats per (warp, batch) row of the K-split reduction buffer
 
-// ---- K-split GEMV of one LSTM cell for NB batch rows: this CTA's 32 gate columns ------------------
-// x = [xa (Ka) | xb (Kb)] per batch row; W is [K][4096] row-major in TF column order (i|j|f|o).
-template <int NB>
-__device__ __forceinline__ void lstm_gemv(const float* __restrict__ W, int K, const float* xa, int Ka,
-                                          const float* xb, int Kb, int nb, float* red, int unit0) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = (lane >> 3) * kCell + unit0 + (lane & 7);
-  const int kslice = K >> 3;
-  const int k0 = warp * kslice, k1 = k0 + kslice;
-  float acc[NB];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) acc[b] = 0.f;
-#pragma unroll 2
-  for (int k = k0; k < k1; k += 4) {
-    const float* xp;
-    int xs;
-    if (k < Ka) {
-      xp = xa + k;
-      xs = Ka;
-    } else {
-      xp = xb + (k - Ka);
-      xs = Kb;
-    }
-    const float* wp = W + (size_t)k * kGates + col;
-    const float w0 = ld_nc_na(wp), w1 = ld_nc_na(wp + kGates), w2 = ld_nc_na(wp + 2 * kGates),
-                w3 = ld_nc_na(wp + 3 * kGates);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      if (b < nb) {
-        const float4 xv = *reinterpret_cast<const float4*>(xp + (size_t)b * xs);
-        acc[b] = fmaf(xv.x, w0, acc[b]);
-        acc[b] = fmaf(xv.y, w1, acc[b]);
-        acc[b] = fmaf(xv.z, w2, acc[b]);
-        acc[b] = fmaf(xv.w, w3, acc[b]);
-      }
-    }
-  }
-#pragma unroll
-  for (int b = 0; b < NB; ++b) red[(warp * NB + b) * kRedStride + lane] = acc[b];
-}
+#include "decoder_gemv.cuh"
 
 // ---- gate math + zoneout for this CTA's 8 units (ZoneoutLSTMCell.py:230-264) ----------------------
 template <int NB>
@@ -231,6 +191,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
 #pragma unroll
         for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
         qf_s[tid] = s + fb_l;
+        P.qf[((size_t)t * B + b) * kAtt + crank * 32 + tid] = s + fb_l;  // saved for the reverse pass
       }
       __syncthreads();
       // partial energies over this CTA's 32 attention units, 16 positions per warp pass
@@ -370,7 +331,7 @@ int dec_fwd_persistent_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO*
   P.text_len = io->text_len; P.zone_mask = io->zone_mask;
   P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n);
   P.cz0 = F(l.cz0); P.hz0 = F(l.hz0); P.cz1 = F(l.cz1); P.hz1 = F(l.hz1);
-  P.m0 = F(l.m0); P.m1 = F(l.m1); P.ctx = F(l.ctx); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.qpart = F(l.qpart);
+  P.m0 = F(l.m0); P.m1 = F(l.m1); P.ctx = F(l.ctx); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.qpart = F(l.qpart); P.qf = F(l.qf);
   P.barrier = (unsigned*)(ws + l.barrier);
   return dec_fwd_persistent(P, s);
 }

@@ -115,7 +115,7 @@ static inline int ew_grid(size_t n) {
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int n_steps, int mode) {
   if (B <= 0 || Te <= 0 || D <= 0 || n_steps <= 0) return 0;
-  return dec_layout(B, Te, L, D, n_steps, mode).total + dec_bwd_extra_bytes(B, Te, D, n_steps);
+  return dec_layout(B, Te, L, D, n_steps, mode).total;
 }
 
 static int check_io(const MsttsDecoderWeights* w, const MsttsDecoderIO* io) {

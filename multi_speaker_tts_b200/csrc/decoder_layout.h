@@ -24,10 +24,25 @@ struct DecLayout {
   size_t cum;                 // [T+1,B,Te]
   size_t align_tm;            // [T,B,Te]
   size_t qpart;               // [128,B,128] per-CTA partial query projections of the current step
+  size_t qf;                  // [T,B,128]  query projection + composed bias, saved for the reverse pass
   size_t proj_tm;             // [T,B,81]
   size_t barrier;             // 64 B of counters
   // ---- reverse pass scratch ----
   size_t bwd_begin;
+  size_t W0rT;      // [4096, D+1024]  transpose of W0r
+  size_t W1T;       // [4096, 2048]    transpose of cell1_kernel
+  size_t dproj_tm;  // [T,B,81]   upstream gradient, time-major
+  size_t dm1_proj;  // [T,B,1024] dproj @ Wp[0:1024]^T
+  size_t dctx;      // [T,B,D]    in: dproj @ Wp[1024:]^T ; out: total gradient w.r.t. ctx_t
+  size_t dG0, dG1;  // [T,B,4096] gradients w.r.t. the gate pre-activations
+  size_t dq;        // [T,B,128]
+  size_t dkeys;     // [B,Te,128]
+  size_t dvalues;   // [B,Te,D]
+  size_t dF;        // [31,128] (+ dfb [128] + dsw [128] right behind, one zeroed block)
+  size_t dfb, dsw;
+  size_t dcum;      // [B,Te]
+  size_t dpre;      // [T,B,256]
+  size_t dpre_h;    // [T,B,256]
   size_t total;
 };
 
@@ -65,9 +80,26 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.cum = take(SB * Te);
   l.align_tm = take(TB * Te);
   l.qpart = take((size_t)kDecGrid * B * kAtt);
+  l.qf = take(TB * kAtt);
   l.proj_tm = take(TB * (kMel + 1));
   l.barrier = take(16);
   l.bwd_begin = off;
+  l.W0rT = take((size_t)kGates * (D + kCell));
+  l.W1T = take((size_t)kGates * 2 * kCell);
+  l.dproj_tm = take(TB * (kMel + 1));
+  l.dm1_proj = take(TB * kCell);
+  l.dctx = take(TB * D);
+  l.dG0 = take(TB * kGates);
+  l.dG1 = take(TB * kGates);
+  l.dq = take(TB * kAtt);
+  l.dkeys = take((size_t)B * Te * kAtt);
+  l.dvalues = take((size_t)B * Te * D);
+  l.dF = take(kConvK * kAtt + 2 * kAtt);
+  l.dfb = l.dF + (size_t)kConvK * kAtt * sizeof(float);
+  l.dsw = l.dfb + (size_t)kAtt * sizeof(float);
+  l.dcum = take((size_t)B * Te);
+  l.dpre = take(TB * kPrenet);
+  l.dpre_h = take(TB * kPrenet);
   l.total = off;
   return l;
 }

@@ -46,3 +46,24 @@ int gemm_rowmajor_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int
   }
   return MSTTS_OK;
 }
+
+int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
+                          long long sA, const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta,
+                          int batch) {
+  int rc;
+  cublasHandle_t h = get_handle(&rc);
+  if (!h) return rc;
+  cublasStatus_t st = cublasSetStream(h, s);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
+    return MSTTS_E_CUDA;
+  }
+  const float alpha = 1.f;
+  st = cublasSgemmStridedBatched(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha,
+                                 B, ldb, sB, A, lda, sA, &beta, C, ldc, sC, batch);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasSgemmStridedBatched(M=%d,N=%d,K=%d,batch=%d) failed (%d)", M, N, K, batch, (int)st);
+    return MSTTS_E_CUDA;
+  }
+  return MSTTS_OK;
+}

@@ -13,4 +13,8 @@ static inline int gemm_rowmajor(cudaStream_t s, int M, int N, int K, const float
   return gemm_rowmajor_ex(s, false, false, M, N, K, A, lda, B, ldb, C, ldc, beta);
 }
 
-size_t dec_bwd_extra_bytes(int B, int Te, int D, int T);
+
+// batched: for i in [0,batch): C_i = op(A_i) op(B_i) + beta C_i with element strides sA/sB/sC between batches
+int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
+                          long long sA, const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta,
+                          int batch);

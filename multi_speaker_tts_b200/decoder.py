@@ -82,3 +82,71 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
     st.keep = keep + [memory, text_len, mel, mel_len, prenet_mask, zone_mask, steps_done]
     st.shape = (B, Te, L, D, T)
     return linear, stop, align, st
+
+
+def decoder_backward(state, weights, d_linear, d_stop, stream=None, want_d_memory=True):
+    """Reverse pass for a ``decoder_forward`` call.  Returns (grads dict keyed like ``weights``, d_memory)."""
+    lib = _lib.lib()
+    B, Te, L, D, T = state.shape
+    dev = d_linear.device
+    d_linear = d_linear.contiguous().float()
+    d_stop = d_stop.contiguous().float()
+    assert tuple(d_linear.shape) == (B, T, MEL) and tuple(d_stop.shape) == (B, T)
+    grads = {key: torch.empty_like(weights[key], dtype=torch.float32).contiguous() for _, key in _lib.DECODER_WEIGHT_FIELDS}
+    gstruct = _lib.MsttsDecoderWeightGrads()
+    for field, key in _lib.DECODER_WEIGHT_FIELDS:
+        setattr(gstruct, field, grads[key].data_ptr())
+    d_memory = torch.empty(B, Te, D, device=dev, dtype=torch.float32) if want_d_memory else None
+    g = _lib.MsttsDecoderGrads(d_linear=d_linear.data_ptr(), d_stop=d_stop.data_ptr(),
+                               d_memory=d_memory.data_ptr() if d_memory is not None else None)
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = lib.mstts_decoder_bwd(C.byref(state.wstruct), C.byref(state.io), C.byref(g), C.byref(gstruct),
+                                   C.c_void_p(state.ws.data_ptr()), state.ws.numel(), C.c_void_p(s.cuda_stream))
+    _lib.check(rc, "mstts_decoder_bwd")
+    return grads, d_memory
+
+
+def decoder_loss(linear, stop, mel, mel_len, use_l1=True, stream=None):
+    """Decoder terms of MSTTS_SV.py:127-144 and their gradients, on device.
+    Returns (loss2 [linear_loss, stop_loss], d_linear, d_stop)."""
+    lib = _lib.lib()
+    B, T, _ = linear.shape
+    L = mel.shape[1]
+    dev = linear.device
+    loss2 = torch.empty(2, device=dev, dtype=torch.float32)
+    d_linear = torch.empty_like(linear)
+    d_stop = torch.empty_like(stop)
+    mel = mel.contiguous().float()
+    mel_len = mel_len.contiguous().to(torch.int32)
+    s = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        rc = lib.mstts_decoder_loss(_lib.ptr(linear), _lib.ptr(stop), _lib.ptr(mel), _lib.ptr(mel_len), B, L, T,
+                                    int(bool(use_l1)), _lib.ptr(loss2), _lib.ptr(d_linear), _lib.ptr(d_stop),
+                                    C.c_void_p(s.cuda_stream))
+    _lib.check(rc, "mstts_decoder_loss")
+    return loss2, d_linear, d_stop
+
+
+def fill_mask(out, keep_prob, seed, stream=None):
+    """out (uint8 CUDA tensor) <- Bernoulli(keep_prob) bits from the counter-based generator."""
+    lib = _lib.lib()
+    assert out.dtype == torch.uint8 and out.is_cuda and out.is_contiguous()
+    s = stream if stream is not None else torch.cuda.current_stream(out.device)
+    with torch.cuda.device(out.device):
+        rc = lib.mstts_fill_mask(_lib.ptr(out), out.numel(), float(keep_prob), int(seed) & (2 ** 64 - 1),
+                                 C.c_void_p(s.cuda_stream))
+    _lib.check(rc, "mstts_fill_mask")
+    return out
+
+
+def adam_tf(p, m, v, g, lr_t, b1=0.9, b2=0.999, eps=1e-6, grad_scale=1.0, stream=None):
+    """In-place tf.train.AdamOptimizer update on flat fp32 CUDA buffers."""
+    lib = _lib.lib()
+    for t in (p, m, v, g):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    s = stream if stream is not None else torch.cuda.current_stream(p.device)
+    with torch.cuda.device(p.device):
+        rc = lib.mstts_adam_tf(_lib.ptr(p), _lib.ptr(m), _lib.ptr(v), _lib.ptr(g), p.numel(), float(lr_t), float(b1),
+                               float(b2), float(eps), float(grad_scale), C.c_void_p(s.cuda_stream))
+    _lib.check(rc, "mstts_adam_tf")
