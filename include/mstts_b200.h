@@ -47,6 +47,11 @@ int mstts_version(void);
 const char* mstts_last_error(void);
 /* number of SMs / whether the device can run the persistent cluster grid; <0 on error */
 int mstts_device_check(int device);
+/* measurement hooks: with profiling on, CUDA events bracket every launch of the persistent kernels on the
+ * caller's stream (no synchronisation); mstts_kernel_ms(which) waits for them and returns the summed
+ * device time and the launch count (0 = decoder forward loop, 1 = decoder reverse loop) for this thread. */
+int mstts_set_profiling(int on);                       /* also resets the recorded launches */
+int mstts_kernel_ms(int which, float* sum_ms, int* count);
 
 /* ------------------------------------------------------------------------------------------------
  * Tacotron2 decoder loop.
@@ -135,11 +140,12 @@ int mstts_fill_mask(uint8_t* out, size_t n, float keep_prob, uint64_t seed, void
 
 /* ------------------------------------------------------------------------------------------------
  * tf.train.AdamOptimizer update, epsilon-hat form (MSTTS_SV.py:171-176): flat fp32 buffers.
- * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  grad_scale multiplies g first
- * (1/world_size after the allreduce; clip factor for WaveGlow).
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller.  The effective gradient is
+ * g*grad_scale + l2*p: grad_scale = 1/world_size after the allreduce (or the clip factor for WaveGlow),
+ * l2 = Weight_Regularization_Rate for the tensors in the reference's regularised set (MSTTS_SV.py:145-159).
  * ---------------------------------------------------------------------------------------------- */
 int mstts_adam_tf(float* p, float* m, float* v, const float* g, size_t n, float lr_t, float b1, float b2,
-                  float eps, float grad_scale, void* stream);
+                  float eps, float grad_scale, float l2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ EXPORTS = {
     "mstts_version": (C.c_int, []),
     "mstts_last_error": (C.c_char_p, []),
     "mstts_device_check": (C.c_int, [C.c_int]),
+    "mstts_set_profiling": (C.c_int, [C.c_int]),
+    "mstts_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mstts_decoder_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "mstts_decoder_fwd": (C.c_int, [C.POINTER(MsttsDecoderWeights), C.POINTER(MsttsDecoderIO), _fp, C.c_size_t, _fp]),
     "mstts_decoder_bwd": (C.c_int, [C.POINTER(MsttsDecoderWeights), C.POINTER(MsttsDecoderIO),
@@ -62,7 +64,7 @@ EXPORTS = {
     "mstts_decoder_loss": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "mstts_fill_mask": (C.c_int, [_fp, C.c_size_t, C.c_float, C.c_uint64, _fp]),
     "mstts_adam_tf": (C.c_int, [_fp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
-                                C.c_float, _fp]),
+                                C.c_float, C.c_float, _fp]),
 }
 
 _lib = None

@@ -13,6 +13,57 @@ void mstts_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- optional kernel timing (bench / roofline): events around the persistent kernels ----
+// With profiling on, every launch of a persistent kernel is bracketed by a fresh event pair on the caller's
+// stream (no synchronisation); mstts_kernel_ms(which) later waits for them and returns sum / count.
+#include <vector>
+static int g_profiling = 0;
+struct KernelTimer {
+  std::vector<cudaEvent_t> ev;  // start0, stop0, start1, stop1, ...
+  size_t used = 0;
+};
+static thread_local KernelTimer g_timers[2];  // 0 = decoder forward loop, 1 = decoder reverse loop
+
+void mstts_timer_start(int which, cudaStream_t s) {
+  if (!g_profiling) return;
+  KernelTimer& t = g_timers[which];
+  if (t.used + 2 > t.ev.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    t.ev.push_back(a);
+    t.ev.push_back(b);
+  }
+  cudaEventRecord(t.ev[t.used], s);
+}
+void mstts_timer_stop(int which, cudaStream_t s) {
+  if (!g_profiling) return;
+  KernelTimer& t = g_timers[which];
+  cudaEventRecord(t.ev[t.used + 1], s);
+  t.used += 2;
+}
+
+extern "C" int mstts_set_profiling(int on) {
+  g_profiling = on;
+  g_timers[0].used = 0;
+  g_timers[1].used = 0;
+  return MSTTS_OK;
+}
+extern "C" int mstts_kernel_ms(int which, float* sum_ms, int* count) {
+  MSTTS_REQUIRE(which >= 0 && which < 2 && sum_ms && count, MSTTS_E_INVALID, "kernel_ms: bad argument");
+  KernelTimer& t = g_timers[which];
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < t.used; i += 2) {
+    float ms = 0.f;
+    MSTTS_CUDA(cudaEventSynchronize(t.ev[i + 1]));
+    MSTTS_CUDA(cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]));
+    total += ms;
+  }
+  *sum_ms = total;
+  *count = (int)(t.used / 2);
+  return MSTTS_OK;
+}
+
 extern "C" int mstts_version(void) { return MSTTS_VERSION; }
 extern "C" const char* mstts_last_error(void) { return g_err; }
 
@@ -67,7 +118,7 @@ extern "C" int mstts_fill_mask(uint8_t* out, size_t n, float keep_prob, uint64_t
 // ---- TF-style Adam (epsilon outside the bias-corrected step) -----------------------------------
 __global__ void adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                const float* __restrict__ g, size_t n, float lr_t, float b1, float b2, float eps,
-                               float gs) {
+                               float gs, float l2) {
   const size_t n4 = n / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -80,7 +131,7 @@ __global__ void adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, flo
     const float* ga = &gg.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float gj = ga[j] * gs;
+      const float gj = ga[j] * gs + l2 * pa[j];
       ma[j] = b1 * ma[j] + (1.f - b1) * gj;
       va[j] = b2 * va[j] + (1.f - b2) * gj * gj;
       pa[j] -= lr_t * ma[j] / (sqrtf(va[j]) + eps);
@@ -90,7 +141,7 @@ __global__ void adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, flo
     reinterpret_cast<float4*>(v)[i] = vv;
   }
   for (size_t i = n4 * 4 + tid0; i < n; i += stride) {
-    const float gj = g[i] * gs;
+    const float gj = g[i] * gs + l2 * p[i];
     const float mj = b1 * m[i] + (1.f - b1) * gj;
     const float vj = b2 * v[i] + (1.f - b2) * gj * gj;
     m[i] = mj;
@@ -100,7 +151,7 @@ __global__ void adam_tf_kernel(float* __restrict__ p, float* __restrict__ m, flo
 }
 
 extern "C" int mstts_adam_tf(float* p, float* m, float* v, const float* g, size_t n, float lr_t, float b1, float b2,
-                             float eps, float grad_scale, void* stream) {
+                             float eps, float grad_scale, float l2, void* stream) {
   MSTTS_REQUIRE(p && m && v && g, MSTTS_E_INVALID, "adam: null pointer");
   MSTTS_REQUIRE((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) == 0, MSTTS_E_INVALID,
                 "adam: buffers must be 16-byte aligned");
@@ -108,7 +159,7 @@ extern "C" int mstts_adam_tf(float* p, float* m, float* v, const float* g, size_
   size_t gsz = (n / 4 + 255) / 256;
   if (gsz > 148 * 8) gsz = 148 * 8;
   if (gsz == 0) gsz = 1;
-  adam_tf_kernel<<<(int)gsz, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, lr_t, b1, b2, eps, grad_scale);
+  adam_tf_kernel<<<(int)gsz, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, lr_t, b1, b2, eps, grad_scale, l2);
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }

@@ -10,6 +10,8 @@
 
 // ---- error plumbing -------------------------------------------------------------------------
 void mstts_set_error(const char* fmt, ...);
+void mstts_timer_start(int which, cudaStream_t s);  // no-ops unless mstts_set_profiling(1)
+void mstts_timer_stop(int which, cudaStream_t s);
 
 #define MSTTS_CUDA(call)                                                                         \
   do {                                                                                           \

@@ -414,7 +414,9 @@ static int launch_bwd(const DecBwdParams& P, cudaStream_t stream) {
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
                 "decoder_bwd: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
                 kDecGrid / kDecCluster);
+  mstts_timer_start(1, stream);
   MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_bwd_kernel<NB>, Q));
+  mstts_timer_stop(1, stream);
   return MSTTS_OK;
 }
 

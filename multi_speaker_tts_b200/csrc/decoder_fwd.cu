@@ -305,7 +305,9 @@ static int launch_fwd(const DecFwdParams& P, cudaStream_t stream) {
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
                 "decoder_fwd: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
                 kDecGrid / kDecCluster);
+  mstts_timer_start(0, stream);
   MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_kernel<NB>, Q));
+  mstts_timer_stop(0, stream);
   return MSTTS_OK;
 }
 

@@ -84,15 +84,17 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
     return linear, stop, align, st
 
 
-def decoder_backward(state, weights, d_linear, d_stop, stream=None, want_d_memory=True):
-    """Reverse pass for a ``decoder_forward`` call.  Returns (grads dict keyed like ``weights``, d_memory)."""
+def decoder_backward(state, weights, d_linear, d_stop, stream=None, want_d_memory=True, grad_out=None):
+    """Reverse pass for a ``decoder_forward`` call.  Returns (grads dict keyed like ``weights``, d_memory).
+    ``grad_out``: optional dict of preallocated fp32 tensors (e.g. views of one flat buffer) to write into."""
     lib = _lib.lib()
     B, Te, L, D, T = state.shape
     dev = d_linear.device
     d_linear = d_linear.contiguous().float()
     d_stop = d_stop.contiguous().float()
     assert tuple(d_linear.shape) == (B, T, MEL) and tuple(d_stop.shape) == (B, T)
-    grads = {key: torch.empty_like(weights[key], dtype=torch.float32).contiguous() for _, key in _lib.DECODER_WEIGHT_FIELDS}
+    grads = grad_out if grad_out is not None else {
+        key: torch.empty_like(weights[key], dtype=torch.float32).contiguous() for _, key in _lib.DECODER_WEIGHT_FIELDS}
     gstruct = _lib.MsttsDecoderWeightGrads()
     for field, key in _lib.DECODER_WEIGHT_FIELDS:
         setattr(gstruct, field, grads[key].data_ptr())
@@ -140,7 +142,7 @@ def fill_mask(out, keep_prob, seed, stream=None):
     return out
 
 
-def adam_tf(p, m, v, g, lr_t, b1=0.9, b2=0.999, eps=1e-6, grad_scale=1.0, stream=None):
+def adam_tf(p, m, v, g, lr_t, b1=0.9, b2=0.999, eps=1e-6, grad_scale=1.0, l2=0.0, stream=None):
     """In-place tf.train.AdamOptimizer update on flat fp32 CUDA buffers."""
     lib = _lib.lib()
     for t in (p, m, v, g):
@@ -148,5 +150,16 @@ def adam_tf(p, m, v, g, lr_t, b1=0.9, b2=0.999, eps=1e-6, grad_scale=1.0, stream
     s = stream if stream is not None else torch.cuda.current_stream(p.device)
     with torch.cuda.device(p.device):
         rc = lib.mstts_adam_tf(_lib.ptr(p), _lib.ptr(m), _lib.ptr(v), _lib.ptr(g), p.numel(), float(lr_t), float(b1),
-                               float(b2), float(eps), float(grad_scale), C.c_void_p(s.cuda_stream))
+                               float(b2), float(eps), float(grad_scale), float(l2), C.c_void_p(s.cuda_stream))
     _lib.check(rc, "mstts_adam_tf")
+
+
+def set_profiling(on):
+    _lib.check(_lib.lib().mstts_set_profiling(int(bool(on))), "mstts_set_profiling")
+
+
+def kernel_ms(which):
+    """(sum of device ms, launch count) of the persistent kernel `which` (0 fwd loop, 1 reverse loop)."""
+    ms, n = C.c_float(0), C.c_int(0)
+    _lib.check(_lib.lib().mstts_kernel_ms(int(which), C.byref(ms), C.byref(n)), "mstts_kernel_ms")
+    return ms.value, n.value

@@ -49,7 +49,7 @@ def test_workspace_query_and_argument_errors_without_gpu():
     # null arguments are rejected before any CUDA call
     assert lib.mstts_decoder_fwd(None, None, None, 0, None) == -1
     assert b"null" in lib.mstts_last_error()
-    assert lib.mstts_adam_tf(None, None, None, None, 16, 0.1, 0.9, 0.999, 1e-6, 1.0, None) == -1
+    assert lib.mstts_adam_tf(None, None, None, None, 16, 0.1, 0.9, 0.999, 1e-6, 1.0, 0.0, None) == -1
 
 
 def test_product_does_not_import_oracle():
