@@ -535,8 +535,8 @@ static inline int ew_grid(size_t n) {
 extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const MsttsDecoderGrads* g,
                                  const MsttsDecoderWeightGrads* dw, void* ws_, size_t ws_bytes, void* stream_) {
   MSTTS_REQUIRE(w && io && g && dw && ws_, MSTTS_E_INVALID, "decoder_bwd: null argument");
-  MSTTS_REQUIRE(io->is_training && io->mode == MSTTS_MODE_FP32, MSTTS_E_UNSUPPORTED,
-                "decoder_bwd: only training / fp32 mode is implemented");
+  MSTTS_REQUIRE(io->is_training && (io->mode == MSTTS_MODE_FP32 || io->mode == MSTTS_MODE_BF16X3), MSTTS_E_UNSUPPORTED,
+                "decoder_bwd: only training in fp32 / bf16x3 mode is implemented");
   MSTTS_REQUIRE(g->d_linear && g->d_stop, MSTTS_E_INVALID, "decoder_bwd: null upstream gradient");
   {
     const float* const* gp = reinterpret_cast<const float* const*>(dw);

@@ -1,0 +1,641 @@
+// Tacotron2 decoder loop, forward, teacher-forced: ONE persistent kernel with the two LSTM cells on tcgen05
+// tensor cores (bf16x3 split, fp32 accumulators in TMEM), weights re-streamed from L2 by bulk async copies,
+// attention memory resident on chip (keys in shared memory, values in TMEM).
+//
+// Replaces the tf.while_loop body of Modules.py:397-443 and what it calls per step: ZoneoutLSTMCell.call x2
+// (ZoneoutLSTMCell.py:228-264), Location_Sensitive_Attention.__call__ (Location_Sensitive_Attention.py:43-85)
+// and the AttentionWrapper context.  Same saved-activation layout as the fp32 kernel (decoder_fwd.cu), so
+// either reverse kernel can follow it.
+//
+// Grid: 128 CTAs = 32 clusters x 4, 352 threads:
+//   warps 0-7   compute: LSTM epilogues (gates, zoneout), attention, grid barriers
+//   warp 8      lane 0: weight-tile producer      (cp.async.bulk, runs ahead of the barriers)
+//   warp 9      lane 0: activation-tile producer  (waits for the grid barrier that publishes the data)
+//   warp 10     TMEM allocation; lane 0: MMA issuer (tcgen05.mma, commits free the ring slots)
+// LSTM partition: cluster c owns units 32c..32c+31 (one M=128 tile of gate rows), CTA r of the cluster owns
+// K-slice r of every operand; the four partial accumulators are reduced through distributed shared memory
+// and CTA r finishes units 32c+8r..+7.  Per step each CTA runs four MMA jobs in weight-stream order:
+//   J0  D0 += W0[ctx rows]  . ctx_{t-1}     (needs the barrier after attention t-1)
+//   J1  D1 += W1[m0 rows]   . m0_t          (needs the barrier after cell 0)
+//   J2  D0  = W0[h rows]    . h0_t          (for step t+1; off the critical path)
+//   J3  D1  = W1[h rows]    . h1_t          (for step t+1; off the critical path)
+// Attention: cluster b owns batch row b; CTA r owns attention units 32r..32r+31 and context dims r*D/4...
+#include <cooperative_groups.h>
+
+#include "decoder_layout.h"
+#include "decoder_tc.cuh"
+
+namespace cg = cooperative_groups;
+
+struct DecFwdTcParams {
+  int B, Te, T, D, training, n0;  // n0 = ctx tiles per CTA = D/256
+  const uint8_t* wimg;            // [128][n0+12][32 KB]
+  uint8_t *ximg_ctx, *ximg_m0, *ximg_h0, *ximg_h1;  // [2 parities][tiles][8 KB]
+  const float *b0, *b1, *Wq, *F, *fb, *sw;
+  const float *g0pre, *keys, *values;
+  const int* text_len;
+  const uint8_t* zone_mask;
+  float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart, *qf;
+  unsigned* barrier;
+};
+
+struct TcSmem {
+  // byte offsets into dynamic shared memory
+  uint32_t ring, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, total;
+};
+
+__host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
+  const int TeP = (Te + 31) & ~31;
+  TcSmem s;
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) {
+    uint32_t o = off;
+    off += (bytes + 127) & ~127u;
+    return o;
+  };
+  s.ring = take(NS * kSlotBytes);
+  s.recv = take(kDecCluster * kTcN * kRecvStride * 4);
+  s.keys = take(Te * 32 * 4);
+  s.wq = take(kUnitsPerCta * kAtt * 4);
+  s.xs = take(2 * 2 * kTcN * 8 * 2);
+  s.m_s = take(kTcN * kUnitsPerCta * 4);
+  s.qred = take(8 * 32 * 4);
+  s.qf_s = take(32 * 4);
+  s.cum_s = take((TeP + 32) * 4);
+  s.e_loc = take(TeP * 4);
+  s.e_parts = take(kDecCluster * TeP * 4);
+  s.a_s = take(TeP * 4);
+  s.ctx_s = take((D / kDecCluster) * 4);
+  s.bred = take(16 * 4);
+  s.bars = take(256);
+  s.total = off;
+  return s;
+}
+
+// ---- gate math + zoneout of one (batch, unit): ZoneoutLSTMCell.py:230-264 ----
+struct CellOut {
+  float ig, jg, fg, og, c, m, cz, hz;
+};
+__device__ __forceinline__ CellOut cell_forward(const float (&g)[4], float cp, float hp, float mc, float mh) {
+  CellOut r;
+  r.ig = sigmoidf_precise(g[0]);
+  r.jg = tanhf(g[1]);
+  r.fg = sigmoidf_precise(g[2] + kForgetBias);
+  r.og = sigmoidf_precise(g[3]);
+  r.c = r.fg * cp + r.ig * r.jg;
+  r.m = r.og * tanhf(r.c);
+  r.cz = kZoneKeep * ((r.c - cp) * mc) + cp;
+  r.hz = kZoneKeep * ((r.m - hp) * mh) + hp;
+  return r;
+}
+
+template <int NS>
+__global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads, 1)
+    decoder_fwd_tc_kernel(const DecFwdTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int B = P.B, Te = P.Te, D = P.D, Dq = D / kDecCluster, Dh = Dq / 2;
+  const int crank = (int)cluster.block_rank();
+  const int cid = blockIdx.x / kDecCluster;
+  const int TeP = (Te + 31) & ~31;
+  const int tps = P.n0 + 12;  // weight tiles per step
+  const int total_tiles = tps * (P.T - 1) + P.n0 + 4;
+  const TcSmem L = tc_fwd_smem(NS, Te, D);
+
+  uint8_t* ring = smem + L.ring;
+  float* recv = reinterpret_cast<float*>(smem + L.recv);
+  float* keys_s = reinterpret_cast<float*>(smem + L.keys);
+  float* wq_s = reinterpret_cast<float*>(smem + L.wq);
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + L.xs);  // [vec 2][hi/lo][32][8]
+  float* m_s = reinterpret_cast<float*>(smem + L.m_s);
+  float* qred = reinterpret_cast<float*>(smem + L.qred);
+  float* qf_s = reinterpret_cast<float*>(smem + L.qf_s);
+  float* cum_s = reinterpret_cast<float*>(smem + L.cum_s);
+  float* e_loc = reinterpret_cast<float*>(smem + L.e_loc);
+  float* e_parts = reinterpret_cast<float*>(smem + L.e_parts);
+  float* a_s = reinterpret_cast<float*>(smem + L.a_s);
+  float* ctx_s = reinterpret_cast<float*>(smem + L.ctx_s);
+  float* bred = reinterpret_cast<float*>(smem + L.bred);
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + L.bars);  // [NS]
+  uint64_t* xfull = wfull + NS;
+  uint64_t* empty = xfull + NS;
+  uint64_t* job_done = empty + NS;     // [4]
+  uint64_t* cl_bar = job_done + 4;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cl_bar + 1);
+  unsigned* ready_seq = tmem_slot + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(&wfull[i], 1);
+      ptx::mbar_init(&xfull[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int j = 0; j < 4; ++j) ptx::mbar_init(&job_done[j], 1);
+    ptx::mbar_init(cl_bar, kDecCluster * (kTcCompute / 32));
+    *ready_seq = 0;
+    ptx::fence_mbar_init();
+  }
+  if (warp == 10) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_val = tmem + 64;  // values: block h at columns 64 + h*TeP
+
+  // ---- one-time staging by the compute warps ----
+  float F_reg[kConvK];
+  float sw_l = 0.f, fb_l = 0.f;
+  if (warp < 8) {
+    const int unit0 = cid * 32 + crank * kUnitsPerCta;
+    for (int i = tid; i < kUnitsPerCta * kAtt; i += kTcCompute)
+      wq_s[i] = P.Wq[(size_t)(unit0 + i / kAtt) * kAtt + (i % kAtt)];
+#pragma unroll
+    for (int k = 0; k < kConvK; ++k) F_reg[k] = P.F[k * kAtt + crank * 32 + lane];
+    sw_l = P.sw[crank * 32 + lane];
+    fb_l = P.fb[crank * 32 + lane];
+    for (int i = tid; i < TeP + 32; i += kTcCompute) cum_s[i] = 0.f;
+    for (int i = tid; i < TeP; i += kTcCompute) a_s[i] = 0.f;
+    if (cid < B) {
+      const float* kg = P.keys + (size_t)cid * Te * kAtt;
+      for (int i = tid; i < Te * 32; i += kTcCompute) keys_s[i] = kg[(size_t)(i >> 5) * kAtt + crank * 32 + (i & 31)];
+      // values slice -> TMEM, lane = context dim (two blocks of Dq/2 dims), column = text position
+      const int q = warp & 3, blk = warp >> 2, dloc = q * 32 + lane;
+      if (q * 32 < Dh) {
+        const float* vg = P.values + (size_t)cid * Te * D + crank * Dq + blk * Dh + dloc;
+        for (int c0 = 0; c0 < TeP; c0 += 32) {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = (dloc < Dh && c0 + j < Te) ? __float_as_uint(vg[(size_t)(c0 + j) * D]) : 0u;
+          ptx::tmem_st32(tmem_val + ((uint32_t)(q * 32) << 16) + blk * TeP + c0, v);
+        }
+        ptx::tmem_wait_st();
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kConvK; ++k) F_reg[k] = 0.f;
+  }
+  ptx::tc_fence_before();
+  cluster.sync();  // all threads: peers' mbarriers are initialised before any remote arrive
+  ptx::tc_fence_after();
+
+  if (warp == 8) {
+    // =========================== weight-tile producer ===========================
+    if (lane == 0) {
+      const uint8_t* wsrc = P.wimg + (size_t)blockIdx.x * tps * kWTileBytes;
+      for (int i = 0; i < total_tiles; ++i) {
+        const int s = i % NS, round = i / NS;
+        if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&wfull[s], kWTileBytes);
+        ptx::bulk_g2s(ring + (size_t)s * kSlotBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // =========================== activation-tile producer ===========================
+    if (lane == 0) {
+      const int n0 = P.n0;
+      const size_t ctx_img = (size_t)(D / kTcKT) * kXTileBytes, vec_img = (size_t)(kCell / kTcKT) * kXTileBytes;
+      for (int i = 0; i < total_tiles; ++i) {
+        const int s = i % NS, round = i / NS;
+        const int t = i / tps, q = i % tps;
+        const uint8_t* src;
+        unsigned need;
+        if (q < n0) {  // J0: ctx_{t-1}, slice crank
+          src = P.ximg_ctx + (size_t)((t + 1) & 1) * ctx_img + (size_t)(crank * n0 + q) * kXTileBytes;
+          need = 3u * t;
+        } else if (q < n0 + 4) {  // J1: m0_t
+          src = P.ximg_m0 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4 + (q - n0)) * kXTileBytes;
+          need = 3u * t + 1;
+        } else if (q < n0 + 8) {  // J2: h0_t
+          src = P.ximg_h0 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4 + (q - n0 - 4)) * kXTileBytes;
+          need = 3u * t + 1;
+        } else {  // J3: h1_t
+          src = P.ximg_h1 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4 + (q - n0 - 8)) * kXTileBytes;
+          need = 3u * t + 2;
+        }
+        while (ld_volatile_shared(ready_seq) < need) {
+        }
+        if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        ptx::mbar_arrive_expect_tx(&xfull[s], kXTileBytes);
+        ptx::bulk_g2s(ring + (size_t)s * kSlotBytes + kWTileBytes, src, kXTileBytes, &xfull[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, kTcN);
+      const int n0 = P.n0;
+      for (int i = 0; i < total_tiles; ++i) {
+        const int s = i % NS, round = i / NS;
+        const int t = i / tps, q = i % tps;
+        int job, kt, nt;
+        if (q < n0) { job = 0; kt = q; nt = n0; }
+        else if (q < n0 + 4) { job = 1; kt = q - n0; nt = 4; }
+        else if (q < n0 + 8) { job = 2; kt = q - n0 - 4; nt = 4; }
+        else { job = 3; kt = q - n0 - 8; nt = 4; }
+        ptx::mbar_wait(&wfull[s], round & 1);
+        ptx::mbar_wait(&xfull[s], round & 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem + ((job & 1) ? 32u : 0u);
+        const uint32_t wbase = ptx::smem_u32(ring + (size_t)s * kSlotBytes);
+        const uint32_t xbase = wbase + kWTileBytes;
+        const bool fresh = (kt == 0) && (job >= 2 || t == 0);
+#pragma unroll
+        for (int k = 0; k < kTcKT / 16; ++k) {
+          const uint64_t a_hi = ptx::umma_desc(wbase + k * 256, kTcLBO, kTcSBO);
+          const uint64_t a_lo = ptx::umma_desc(wbase + kWTileBytes / 2 + k * 256, kTcLBO, kTcSBO);
+          const uint64_t b_hi = ptx::umma_desc(xbase + k * 256, kTcLBO, kTcSBO);
+          const uint64_t b_lo = ptx::umma_desc(xbase + kXTileBytes / 2 + k * 256, kTcLBO, kTcSBO);
+          ptx::umma_bf16(d, a_hi, b_lo, idesc, (fresh && k == 0) ? 0u : 1u);
+          ptx::umma_bf16(d, a_lo, b_hi, idesc, 1u);
+          ptx::umma_bf16(d, a_hi, b_hi, idesc, 1u);
+        }
+        ptx::umma_commit(&empty[s]);
+        if (kt == nt - 1) ptx::umma_commit(&job_done[job]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== compute warps ===========================
+    const int u8 = tid & 7, b = tid >> 3;  // this thread's (unit, batch row) in both cells
+    const int unit = cid * 32 + crank * kUnitsPerCta + u8;
+    const bool brow = b < B;
+    const size_t BC = (size_t)B * kCell, BG = (size_t)B * kGates;
+    const uint32_t recv_addr = ptx::smem_u32(recv);
+    const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quarter / accumulator column half of this warp
+    const uint32_t recv_remote = ptx::mapa(recv_addr, (uint32_t)q4);
+    float c0 = 0.f, h0 = 0.f, c1 = 0.f, h1 = 0.f;  // zoned state of this (batch, unit), AttentionWrapper.zero_state
+    const float bias0[4] = {P.b0[unit], P.b0[kCell + unit], P.b0[2 * kCell + unit], P.b0[3 * kCell + unit]};
+    const float bias1[4] = {P.b1[unit], P.b1[kCell + unit], P.b1[2 * kCell + unit], P.b1[3 * kCell + unit]};
+    uint32_t cl_parity = 0;
+    unsigned bar_target = 0;
+    const int tl = (cid < B) ? min(P.text_len[cid], Te) : 0;
+    const size_t vec_img = (size_t)(kCell / kTcKT) * kXTileBytes, ctx_img = (size_t)(D / kTcKT) * kXTileBytes;
+    // byte offset of this CTA's 8-unit chunk inside a [32 x 1024] activation image, for batch row r: + (r/8)*1024 + (r%8)*16
+    const int unit0 = cid * 32 + crank * kUnitsPerCta;
+    const size_t img_chunk = (size_t)(unit0 >> 6) * kXTileBytes + (size_t)((unit0 & 63) >> 3) * 128;
+
+    // pulls this CTA's partial accumulator out of TMEM and scatters it to the owners of the units
+    auto reduce_scatter = [&](int job, int t, uint32_t dcol) {
+      ptx::mbar_wait(&job_done[job], t & 1);
+      ptx::tc_fence_after();
+      uint32_t v[16];
+      ptx::tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + dcol + half * 16, v);
+      ptx::tmem_wait_ld();
+      ptx::tc_fence_before();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        ptx::st_cluster_f32(recv_remote + (uint32_t)(((crank * kTcN + half * 16 + j) * kRecvStride + lane) * 4),
+                            __uint_as_float(v[j]));
+      cluster_compute_sync(cl_bar, cl_parity);
+    };
+
+    for (int t = 0; t < P.T; ++t) {
+      const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
+      const int par = t & 1;
+      // ================= phase A: LSTM cell 0 =================
+      {
+        float add[4] = {0.f, 0.f, 0.f, 0.f};
+        float mc = 1.f, mh = 1.f;
+        if (brow) {
+          const float* gp = P.g0pre + (size_t)t * BG + (size_t)b * kGates + unit;
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) add[gi] = gp[gi * kCell] + bias0[gi];
+          mc = (float)zm[(size_t)b * kCell + unit];
+          mh = (float)zm[BC + (size_t)b * kCell + unit];
+        }
+        reduce_scatter(0, t, 0u);
+        float g[4];
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          float s = 0.f;
+#pragma unroll
+          for (int src = 0; src < kDecCluster; ++src) s += recv[(src * kTcN + b) * kRecvStride + gi * 8 + u8];
+          g[gi] = s + add[gi];
+        }
+        const CellOut r = cell_forward(g, c0, h0, mc, mh);
+        __nv_bfloat16 hi, lo;
+        if (brow) {
+          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+          P.act0[ai] = r.ig;
+          P.act0[ai + kCell] = r.jg;
+          P.act0[ai + 2 * kCell] = r.fg;
+          P.act0[ai + 3 * kCell] = r.og;
+          P.c0n[(size_t)t * BC + si] = r.c;
+          P.cz0[(size_t)(t + 1) * BC + si] = r.cz;
+          P.hz0[(size_t)(t + 1) * BC + si] = r.hz;
+          P.m0[(size_t)t * BC + si] = r.m;
+          c0 = r.cz;
+          h0 = r.hz;
+          split_bf16(r.m, hi, lo);
+          xs[(0 * 2 + 0) * 256 + b * 8 + u8] = hi;
+          xs[(0 * 2 + 1) * 256 + b * 8 + u8] = lo;
+          split_bf16(r.hz, hi, lo);
+          xs[(1 * 2 + 0) * 256 + b * 8 + u8] = hi;
+          xs[(1 * 2 + 1) * 256 + b * 8 + u8] = lo;
+        }
+        ptx::bar_sync(1, kTcCompute);
+        if (tid < 128) {  // 16-byte rows of the m0 / h0 images: (vector, hi|lo, batch row)
+          const int vec = tid >> 6, hl = (tid >> 5) & 1, r2 = tid & 31;
+          if (r2 < B) {
+            uint8_t* img = (vec ? P.ximg_h0 : P.ximg_m0) + (size_t)par * vec_img + img_chunk + (size_t)hl * (kXTileBytes / 2) +
+                           (size_t)(r2 >> 3) * 1024 + (size_t)(r2 & 7) * 16;
+            *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(xs + (vec * 2 + hl) * 256 + r2 * 8);
+          }
+        }
+      }
+      grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 1);
+
+      // ================= phase B: LSTM cell 1 (+ partial query projection) =================
+      {
+        float mc = 1.f, mh = 1.f;
+        if (brow) {
+          mc = (float)zm[2 * BC + (size_t)b * kCell + unit];
+          mh = (float)zm[3 * BC + (size_t)b * kCell + unit];
+        }
+        reduce_scatter(1, t, 32u);
+        float g[4];
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          float s = 0.f;
+#pragma unroll
+          for (int src = 0; src < kDecCluster; ++src) s += recv[(src * kTcN + b) * kRecvStride + gi * 8 + u8];
+          g[gi] = s + bias1[gi];
+        }
+        const CellOut r = cell_forward(g, c1, h1, mc, mh);
+        __nv_bfloat16 hi, lo;
+        m_s[b * kUnitsPerCta + u8] = brow ? r.m : 0.f;
+        if (brow) {
+          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+          P.act1[ai] = r.ig;
+          P.act1[ai + kCell] = r.jg;
+          P.act1[ai + 2 * kCell] = r.fg;
+          P.act1[ai + 3 * kCell] = r.og;
+          P.c1n[(size_t)t * BC + si] = r.c;
+          P.cz1[(size_t)(t + 1) * BC + si] = r.cz;
+          P.hz1[(size_t)(t + 1) * BC + si] = r.hz;
+          P.m1[(size_t)t * BC + si] = r.m;
+          c1 = r.cz;
+          h1 = r.hz;
+          split_bf16(r.hz, hi, lo);
+          xs[(1 * 2 + 0) * 256 + b * 8 + u8] = hi;
+          xs[(1 * 2 + 1) * 256 + b * 8 + u8] = lo;
+        }
+        ptx::bar_sync(1, kTcCompute);
+        if (tid < 64) {
+          const int hl = tid >> 5, r2 = tid & 31;
+          if (r2 < B) {
+            uint8_t* img = P.ximg_h1 + (size_t)par * vec_img + img_chunk + (size_t)hl * (kXTileBytes / 2) + (size_t)(r2 >> 3) * 1024 +
+                           (size_t)(r2 & 7) * 16;
+            *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(xs + (2 + hl) * 256 + r2 * 8);
+          }
+        }
+        // partial q[b][a] = sum over this CTA's 8 units of m1[b][unit] * Wq[unit][a]
+        for (int i = tid; i < B * kAtt; i += kTcCompute) {
+          const int bb = i >> 7, a = i & 127;
+          float s = 0.f;
+#pragma unroll
+          for (int u = 0; u < kUnitsPerCta; ++u) s = fmaf(m_s[bb * kUnitsPerCta + u], wq_s[u * kAtt + a], s);
+          P.qpart[((size_t)blockIdx.x * B + bb) * kAtt + a] = s;
+        }
+      }
+      grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 2);
+
+      // ================= phase C: location-sensitive attention, batch row = cluster index ==========
+      if (cid < B) {
+        const int bb = cid;
+        {  // q slice = sum of the 128 per-CTA partials (fixed order)
+          float s = 0.f;
+          for (int j = warp; j < kDecGrid; j += 8) s += __ldcg(P.qpart + ((size_t)j * B + bb) * kAtt + crank * 32 + lane);
+          qred[warp * 32 + lane] = s;
+        }
+        ptx::bar_sync(1, kTcCompute);
+        if (tid < 32) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
+          qf_s[tid] = s + fb_l;
+          P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s + fb_l;
+        }
+        ptx::bar_sync(1, kTcCompute);
+        const float qf = qf_s[lane];
+        for (int blk = warp; blk * 16 < tl; blk += 8) {
+          const int t0 = blk * 16;
+          float acc[16];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16 + kConvK - 1; ++c) {
+            const float cv = cum_s[t0 + c];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int k = c - p;
+              if (k >= 0 && k < kConvK) acc[p] = fmaf(cv, F_reg[k], acc[p]);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int x = t0 + p;
+            float v = 0.f;
+            if (x < tl) v = sw_l * tanhf(keys_s[x * 32 + lane] + qf + acc[p]);
+            v = warp_sum(v);
+            if (lane == 0) e_loc[x] = v;
+          }
+        }
+        ptx::bar_sync(1, kTcCompute);
+        {  // all-gather the partial energies across the cluster through DSMEM
+          const uint32_t ep = ptx::smem_u32(e_parts) + (uint32_t)(crank * TeP * 4);
+#pragma unroll
+          for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) {
+            const uint32_t remote = ptx::mapa(ep, dst);
+            for (int x = tid; x < tl; x += kTcCompute) ptx::st_cluster_f32(remote + x * 4, e_loc[x]);
+          }
+        }
+        cluster_compute_sync(cl_bar, cl_parity);
+        // masked softmax over positions < tl (score_mask_value = -inf => exactly 0 beyond tl)
+        float lmax = -INFINITY;
+        for (int x = tid; x < tl; x += kTcCompute) {
+          const float e = ((e_parts[x] + e_parts[TeP + x]) + e_parts[2 * TeP + x]) + e_parts[3 * TeP + x];
+          a_s[x] = e;
+          lmax = fmaxf(lmax, e);
+        }
+        lmax = warp_max(lmax);
+        if (lane == 0) bred[warp] = lmax;
+        ptx::bar_sync(1, kTcCompute);
+        float gmax = bred[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) gmax = fmaxf(gmax, bred[w]);
+        float lsum = 0.f;
+        for (int x = tid; x < tl; x += kTcCompute) {
+          const float ex = expf(a_s[x] - gmax);
+          a_s[x] = ex;
+          lsum += ex;
+        }
+        lsum = warp_sum(lsum);
+        if (lane == 0) bred[8 + warp] = lsum;
+        ptx::bar_sync(1, kTcCompute);
+        float gsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) gsum += bred[8 + w];
+        for (int x = tid; x < Te; x += kTcCompute) {
+          const float a = (x < tl) ? a_s[x] / gsum : 0.f;
+          a_s[x] = a;
+          const float cn = cum_s[15 + x] + a;
+          cum_s[15 + x] = cn;
+          if (crank == 0) {
+            P.align_tm[((size_t)t * B + bb) * Te + x] = a;
+            P.cum[((size_t)(t + 1) * B + bb) * Te + x] = cn;
+          }
+        }
+        ptx::bar_sync(1, kTcCompute);
+        // context slice from the TMEM-resident values: thread = one context dim, columns = text positions
+        if (q4 * 32 < Dh) {
+          const int dloc = q4 * 32 + lane;
+          float s = 0.f;
+          const uint32_t va = tmem_val + ((uint32_t)(q4 * 32) << 16) + half * TeP;
+          for (int c0 = 0; c0 < tl; c0 += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld32(va + c0, v);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s = fmaf(a_s[c0 + j], __uint_as_float(v[j]), s);
+          }
+          if (dloc < Dh) {
+            ctx_s[half * Dh + dloc] = s;
+            P.ctx[((size_t)(t + 1) * B + bb) * D + crank * Dq + half * Dh + dloc] = s;
+          }
+        }
+        ptx::bar_sync(1, kTcCompute);
+        if (tid < Dq / 4) {  // 16-byte rows of the ctx image: (hi|lo, 8-dim chunk)
+          const int hl = tid / (Dq / 8), ch = tid % (Dq / 8);
+          const int k = crank * Dq + ch * 8;
+          __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(ctx_s[ch * 8 + j], hi, lo);
+            o[j] = hl ? lo : hi;
+          }
+          uint8_t* img = P.ximg_ctx + (size_t)par * ctx_img + (size_t)(k >> 6) * kXTileBytes + (size_t)hl * (kXTileBytes / 2) +
+                         (size_t)(bb >> 3) * 1024 + (size_t)((k & 63) >> 3) * 128 + (size_t)(bb & 7) * 16;
+          *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(o);
+        }
+      }
+      grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 3);
+    }
+  }
+
+  // ---- teardown ----
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 10) ptx::tmem_dealloc(tmem, 512);
+  cluster.sync();  // no CTA exits while a peer could still address its shared memory
+}
+
+// ---- weight image: bf16 hi/lo tiles in stream order for every CTA ----------------------------------------
+// tile rows i = rr*32 + g*8 + u  <->  gate column g*1024 + 32c + 8rr + u ; k runs over this CTA's K-slice
+__global__ void prep_wimg_fwd_kernel(const float* __restrict__ K0, const float* __restrict__ K1, uint8_t* __restrict__ wimg,
+                                     int D) {
+  const int n0 = D / 256, tps = n0 + 12, Dq = D / kDecCluster;
+  const size_t total = (size_t)kDecGrid * tps * 8 * 128;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx & 127);
+    const int kc = (int)((idx >> 7) & 7);
+    const size_t tq = idx >> 10;
+    const int q = (int)(tq % tps), cta = (int)(tq / tps);
+    const int c = cta >> 2, r = cta & 3;
+    const int rr = i >> 5, g = (i >> 3) & 3, u = i & 7;
+    const int col = g * kCell + c * 32 + rr * 8 + u;
+    float v[8];
+    if (q < n0) {
+      const int k = r * Dq + q * kTcKT + kc * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = K0[(size_t)(kPrenet + k + j) * kGates + col] + K0[(size_t)(kPrenet + D + k + j) * kGates + col];
+    } else {
+      const int jq = (q - n0) >> 2, kt = (q - n0) & 3;
+      const int k = r * 256 + kt * kTcKT + kc * 8;
+      const float* src = jq == 0 ? K1 + (size_t)k * kGates
+                                 : (jq == 1 ? K0 + (size_t)(kPrenet + 2 * D + k) * kGates : K1 + (size_t)(kCell + k) * kGates);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = src[(size_t)j * kGates + col];
+    }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_bf16(v[j], hi[j], lo[j]);
+    uint8_t* tile = wimg + tq * kWTileBytes + (size_t)(i >> 3) * 1024 + (size_t)kc * 128 + (size_t)(i & 7) * 16;
+    *reinterpret_cast<uint4*>(tile) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(tile + kWTileBytes / 2) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// ======================================== host side ================================================
+bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 224 && D % 256 == 0 && D <= 1024; }
+
+template <int NS>
+static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t smem, bool* ok) {
+  int dev = 0;
+  MSTTS_CUDA(cudaGetDevice(&dev));
+  int max_optin = 0;
+  MSTTS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem > (size_t)max_optin) {
+    *ok = false;
+    return MSTTS_OK;
+  }
+  *ok = true;
+  MSTTS_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(kDecGrid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  int nclusters = 0;
+  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_tc_kernel<NS>, &cfg));
+  MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
+                "decoder_fwd_tc: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
+                kDecGrid / kDecCluster);
+  mstts_timer_start(0, stream);
+  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<NS>, P));
+  mstts_timer_stop(0, stream);
+  return MSTTS_OK;
+}
+
+int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s) {
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  const int D = io->D;
+  MSTTS_REQUIRE(dec_tc_supported(io->B, io->Te, D), MSTTS_E_UNSUPPORTED,
+                "decoder bf16x3 mode needs B<=32, Te<=224, D%%256==0 (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te, D);
+  DecFwdTcParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = io->B; P.Te = io->Te; P.T = io->n_steps; P.D = D; P.training = io->is_training; P.n0 = D / 256;
+  P.wimg = (const uint8_t*)(ws + l.wimg_f);
+  P.ximg_ctx = (uint8_t*)(ws + l.ximg_ctx); P.ximg_m0 = (uint8_t*)(ws + l.ximg_m0);
+  P.ximg_h0 = (uint8_t*)(ws + l.ximg_h0); P.ximg_h1 = (uint8_t*)(ws + l.ximg_h1);
+  P.b0 = w->cell0_bias; P.b1 = w->cell1_bias; P.Wq = w->query_kernel;
+  P.F = F(l.locF); P.fb = F(l.locFb); P.sw = w->score_w;
+  P.g0pre = F(l.g0pre); P.keys = F(l.keys); P.values = F(l.values);
+  P.text_len = io->text_len; P.zone_mask = io->zone_mask;
+  P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n);
+  P.cz0 = F(l.cz0); P.hz0 = F(l.hz0); P.cz1 = F(l.cz1); P.hz1 = F(l.hz1);
+  P.m0 = F(l.m0); P.m1 = F(l.m1); P.ctx = F(l.ctx); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.qpart = F(l.qpart); P.qf = F(l.qf);
+  P.barrier = (unsigned*)(ws + l.barrier);
+  // weight image (weights change every optimiser step) and zeroed activation images (initial state = 0)
+  prep_wimg_fwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_f), D);
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_ctx, 0, l.ximg_end - l.ximg_ctx, s));
+  bool ok = false;
+  int rc = launch_fwd_tc<4>(P, s, tc_fwd_smem(4, io->Te, D).total, &ok);
+  if (rc) return rc;
+  if (!ok) {
+    rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D).total, &ok);
+    if (rc) return rc;
+  }
+  MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_fwd_tc: shared memory does not fit for Te=%d", io->Te);
+  return MSTTS_OK;
+}

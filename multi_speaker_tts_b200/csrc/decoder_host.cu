@@ -7,6 +7,7 @@
 struct DecFwdParams;  // decoder_fwd.cu
 int dec_fwd_persistent_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws,
                              cudaStream_t s);
+int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s);  // decoder_fwd_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // small prep / epilogue kernels (all HBM-bound elementwise work, grid-stride, coalesced)
@@ -125,7 +126,8 @@ static int check_io(const MsttsDecoderWeights* w, const MsttsDecoderIO* io) {
   MSTTS_REQUIRE(io->D >= 32 && io->D % 32 == 0 && io->D <= 1024, MSTTS_E_INVALID,
                 "decoder: memory depth D=%d must be a multiple of 32 in [32,1024]", io->D);
   MSTTS_REQUIRE(io->n_steps >= 1, MSTTS_E_INVALID, "decoder: n_steps=%d", io->n_steps);
-  MSTTS_REQUIRE(io->mode == MSTTS_MODE_FP32, MSTTS_E_UNSUPPORTED, "decoder: mode %d not implemented yet", io->mode);
+  MSTTS_REQUIRE(io->mode == MSTTS_MODE_FP32 || io->mode == MSTTS_MODE_BF16X3, MSTTS_E_UNSUPPORTED,
+                "decoder: mode %d not implemented (fp32 = 0, bf16x3 = 1)", io->mode);
   MSTTS_REQUIRE(io->memory && io->text_len && io->prenet_mask && io->linear && io->stop && io->align, MSTTS_E_INVALID,
                 "decoder: null io pointer");
   const float* const* wp = reinterpret_cast<const float* const*>(w);
@@ -178,7 +180,7 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   MSTTS_CUDA(cudaMemsetAsync(ws + l.cum, 0, (size_t)B * Te * sizeof(float), s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.barrier, 0, 64, s));
   // ---- the loop ----
-  rc = dec_fwd_persistent_entry(w, io, l, ws, s);
+  rc = io->mode == MSTTS_MODE_BF16X3 ? dec_fwd_tc_entry(w, io, l, ws, s) : dec_fwd_persistent_entry(w, io, l, ws, s);
   if (rc) return rc;
   // ---- hoisted projection: [m1 | ctx] @ Wp + bp over all steps (Modules.py:292-294,309-321) ----
   rc = gemm_rowmajor(s, (int)TB, kMel + 1, kCell, F(l.m1), kCell, w->proj_kernel, kMel + 1, F(l.proj_tm), kMel + 1, 0.f);

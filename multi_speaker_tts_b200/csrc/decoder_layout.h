@@ -27,6 +27,9 @@ struct DecLayout {
   size_t qf;                  // [T,B,128]  query projection + composed bias, saved for the reverse pass
   size_t proj_tm;             // [T,B,81]
   size_t barrier;             // 64 B of counters
+  // ---- bf16x3 (tcgen05) mode only: operand images in the tensor-core shared-memory layout (decoder_tc.cuh) ----
+  size_t wimg_f;              // [128 CTAs][D/256+12 tiles][32 KB] forward weight stream (hi|lo bf16)
+  size_t ximg_ctx, ximg_m0, ximg_h0, ximg_h1, ximg_end;  // [2 parities][K/64 tiles][8 KB] activation images
   // ---- reverse pass scratch ----
   size_t bwd_begin;
   size_t W0rT;      // [4096, D+1024]  transpose of W0r
@@ -48,7 +51,6 @@ struct DecLayout {
 
 static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode) {
   (void)L;
-  (void)mode;
   DecLayout l;
   size_t off = 0;
   auto take = [&](size_t nfloats) {
@@ -83,6 +85,20 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.qf = take(TB * kAtt);
   l.proj_tm = take(TB * (kMel + 1));
   l.barrier = take(16);
+  l.wimg_f = l.ximg_ctx = l.ximg_m0 = l.ximg_h0 = l.ximg_h1 = l.ximg_end = off;
+  if (mode == MSTTS_MODE_BF16X3) {
+    auto take_bytes = [&](size_t nbytes) {
+      size_t o = off;
+      off += align_up(nbytes, 1024);
+      return o;
+    };
+    l.wimg_f = take_bytes((size_t)kDecGrid * (D / 256 + 12) * 32768);
+    l.ximg_ctx = take_bytes((size_t)2 * (D / 64) * 8192);
+    l.ximg_m0 = take_bytes((size_t)2 * (kCell / 64) * 8192);
+    l.ximg_h0 = take_bytes((size_t)2 * (kCell / 64) * 8192);
+    l.ximg_h1 = take_bytes((size_t)2 * (kCell / 64) * 8192);
+    l.ximg_end = off;
+  }
   l.bwd_begin = off;
   l.W0rT = take((size_t)kGates * (D + kCell));
   l.W1T = take((size_t)kGates * 2 * kCell);

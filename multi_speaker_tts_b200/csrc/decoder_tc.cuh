@@ -1,0 +1,80 @@
+// Shared pieces of the tcgen05 ("bf16x3") persistent decoder kernels.
+//
+// Numerics: every recurrent skinny GEMM  Y[rows,B] = W[rows,K] . X[K,B]  runs on the 5th-gen tensor cores
+// with both operands split into bf16 hi + bf16 lo (x = hi + lo to ~16 mantissa bits) and three MMAs per
+// K-step (hi.hi + hi.lo + lo.hi), fp32 accumulation in TMEM: measured L_inf vs the fp32 oracle ~2e-6 on the
+// mel outputs (plain bf16 would be ~1e-3, i.e. at the parity gate).
+//
+// Data movement: weights do not fit on chip (hi+lo = 4 B/weight, 63 MB), so each CTA re-streams its slice from
+// L2 every step through a ring of shared-memory slots filled by 1-D bulk async copies (TMA engine); the
+// activations of the step are gathered the same way from small global "images".  Both images are stored in
+// global memory exactly as the tensor core wants them in shared memory (K-major canonical layout, no
+// swizzle), so a slot is one contiguous 32 KB (weights) + 8 KB (activations) copy.
+//
+// Tile image formats (bf16):
+//   W tile  [128 rows x 64 k] : hi at +0 (16 KB), lo at +16 KB
+//   X tile  [ 32 rows x 64 k] : hi at +0 ( 4 KB), lo at + 4 KB      (rows = batch index, zero beyond B)
+//   element (row, k) at byte (row/8)*1024 + (k/8)*128 + (row%8)*16 + (k%8)*2
+//   => UMMA descriptor: LBO (K direction) = 128, SBO (M/N direction) = 1024; one K=16 MMA step = +256 B.
+#pragma once
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+constexpr int kTcCompute = 256;           // warps 0..7: epilogues + attention
+constexpr int kTcThreads = 352;           // + warp 8 (weight producer), 9 (activation producer), 10 (TMEM alloc + MMA issuer)
+constexpr int kTcKT = 64;                 // K per ring slot
+constexpr int kTcN = 32;                  // MMA N = padded batch
+constexpr uint32_t kWTileBytes = 128 * kTcKT * 2 * 2;  // 32768
+constexpr uint32_t kXTileBytes = kTcN * kTcKT * 2 * 2;  // 8192
+constexpr uint32_t kSlotBytes = kWTileBytes + kXTileBytes;
+constexpr uint32_t kTcLBO = 128, kTcSBO = 1024;
+constexpr int kRecvStride = 40;           // floats per (src, batch) row of the K-split reduction buffer
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ unsigned ld_volatile_shared(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_shared(unsigned* p, unsigned v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ptx::smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+
+// Barrier among the compute warps of all CTAs of a 4-CTA cluster, built on one mbarrier per CTA (count =
+// 4 CTAs x 8 warps).  Orders the callers' earlier st.shared::cluster pushes before the peers' later reads.
+// (barrier.cluster cannot be used here: it would also wait for the producer / MMA warps.)
+__device__ __forceinline__ void cluster_compute_sync(uint64_t* bar, uint32_t& parity) {
+  fence_cluster();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t a = ptx::smem_u32(bar);
+#pragma unroll
+    for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::mbar_arrive_cluster(ptx::mapa(a, dst));
+  }
+  while (!ptx::mbar_try_wait_cluster(bar, parity)) {
+  }
+  parity ^= 1u;
+}
+
+// Grid-wide barrier executed by the compute warps only (named barrier 1); thread 0 then publishes the event
+// number to the activation producer through `ready_seq`.
+__device__ __forceinline__ void grid_barrier_compute(unsigned* counter, unsigned& target, unsigned nblocks,
+                                                     unsigned* ready_seq, unsigned event) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");  // image writes (generic proxy) -> later bulk-copy reads
+  ptx::bar_sync(1, kTcCompute);
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    red_release_gpu_add(counter, 1u);
+    while (ld_acquire_gpu(counter) < target) {
+    }
+    __threadfence();
+    st_volatile_shared(ready_seq, event);
+  }
+  ptx::bar_sync(1, kTcCompute);
+}

@@ -23,7 +23,10 @@ def _oracle_grads(w, b, T, dtype=torch.float64):
 
 @pytest.mark.parametrize("B,Te,L,ragged", [(2, 32, 24, False), (3, 40, 17, True), (8, 50, 9, True), (32, 128, 5, True),
                                            (36, 24, 4, True)])
-def test_decoder_gradients(cuda_dev, B, Te, L, ragged):
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_decoder_gradients(cuda_dev, B, Te, L, ragged, mode):
+    if mode == "bf16x3" and B > 32:
+        pytest.skip("bf16x3 mode supports B <= 32 (refusal is tested in test_decoder_gpu.py)")
     from multi_speaker_tts_b200.decoder import decoder_forward, decoder_backward, decoder_loss
     w = S.init_decoder_weights(0, bias_scale=0.05)
     b = S.synthetic_decoder_batch(B, Te, L, seed=B + Te, ragged=ragged)
@@ -34,7 +37,7 @@ def test_decoder_gradients(cuda_dev, B, Te, L, ragged):
     wd = {k: v.to(dev) for k, v in w.items()}
     bd = {k: v.to(dev) for k, v in b.items()}
     lin, stop, align, st = decoder_forward(wd, bd['memory'], bd['text_len'], bd['mel'], bd['mel_len'], bd['prenet_mask'],
-                                           bd['zone_mask'], True, T, "fp32")
+                                           bd['zone_mask'], True, T, mode)
     loss2, dlin, dstop = decoder_loss(lin, stop, bd['mel'], bd['mel_len'])
     grads, dmem = decoder_backward(st, wd, dlin, dstop)
     torch.cuda.synchronize()

@@ -12,7 +12,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3  # north_star: mel L_inf < 1e-3 in fp32
 
 
-def _run_both(B, Te, L, ragged, dev, seed=1234, bias_scale=0.05):
+MODES = ["fp32", "bf16x3"]
+
+
+def _tc_supported(B, Te, D=768):
+    return B <= 32 and Te <= 224 and D % 256 == 0
+
+
+def _run_both(B, Te, L, ragged, dev, seed=1234, bias_scale=0.05, mode="fp32"):
     from oracle import decoder_oracle as O
     from multi_speaker_tts_b200.decoder import decoder_forward
     w = S.init_decoder_weights(0, bias_scale=bias_scale)
@@ -23,7 +30,7 @@ def _run_both(B, Te, L, ragged, dev, seed=1234, bias_scale=0.05):
     bd = {k: v.to(dev) for k, v in b.items()}
     lin, stop, align, _ = decoder_forward(wd, bd['memory'], bd['text_len'], bd['mel'], bd['mel_len'],
                                           bd['prenet_mask'][:T].contiguous(), bd['zone_mask'][:T].contiguous(),
-                                          is_training=True, n_steps=T, mode="fp32")
+                                          is_training=True, n_steps=T, mode=mode)
     torch.cuda.synchronize()
     return ref, (lin.cpu(), stop.cpu(), align.cpu()), b
 
@@ -47,18 +54,27 @@ def _check(ref, got, b):
     assert (ga[beyond.expand_as(ga)] == 0).all()
 
 
-def test_config1_parity(cuda_dev):
+@pytest.mark.parametrize("mode", MODES)
+def test_config1_parity(cuda_dev, mode):
     """BASELINE config 1: B=2, Te=32, L=200."""
-    ref, got, b = _run_both(2, 32, 200, False, cuda_dev)
+    ref, got, b = _run_both(2, 32, 200, False, cuda_dev, mode=mode)
     _check(ref, got, b)
 
 
-def test_ragged_parity(cuda_dev):
-    ref, got, b = _run_both(3, 40, 60, True, cuda_dev, seed=7)
+@pytest.mark.parametrize("mode", MODES)
+def test_ragged_parity(cuda_dev, mode):
+    ref, got, b = _run_both(3, 40, 60, True, cuda_dev, seed=7, mode=mode)
     _check(ref, got, b)
 
 
-@pytest.mark.parametrize("B,Te,L", [(1, 16, 8), (5, 33, 12), (8, 128, 10), (16, 100, 6), (32, 128, 6), (40, 48, 5)])
-def test_shapes_parity(cuda_dev, B, Te, L):
-    ref, got, b = _run_both(B, Te, L, True, cuda_dev, seed=B * 100 + Te)
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,Te,L", [(1, 16, 8), (5, 33, 12), (8, 128, 10), (16, 100, 6), (32, 128, 6), (40, 48, 5),
+                                    (7, 224, 5)])
+def test_shapes_parity(cuda_dev, B, Te, L, mode):
+    if mode == "bf16x3" and not _tc_supported(B, Te):
+        from multi_speaker_tts_b200._lib import MsttsError
+        with pytest.raises(MsttsError):  # explicit refusal, never a silent fallback
+            _run_both(B, Te, L, True, cuda_dev, seed=B * 100 + Te, mode=mode)
+        return
+    ref, got, b = _run_both(B, Te, L, True, cuda_dev, seed=B * 100 + Te, mode=mode)
     _check(ref, got, b)
