@@ -21,7 +21,7 @@ clean:
 	rm -rf build $(OUT)
 
 # standalone hardware probes (run on the GPU box): make probes && build/umma_probe && build/stream_probe
-probes: build/umma_probe build/stream_probe
+probes: build/umma_probe build/stream_probe build/mma_probe
 build/%_probe: tools/%_probe.cu multi_speaker_tts_b200/csrc/sm100_ptx.cuh
 	@mkdir -p build
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o $@ $<

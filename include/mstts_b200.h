@@ -118,6 +118,9 @@ typedef struct MsttsDecoderGrads {
 } MsttsDecoderGrads;
 
 size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int n_steps, int mode);
+/* byte offset of a named workspace region ("m1", "ctx", "dbg", ...; see decoder_layout.h) or (size_t)-1:
+ * lets tests and profiling tools read saved activations / phase time stamps */
+size_t mstts_decoder_ws_offset(const char* name, int B, int Te, int L, int D, int n_steps, int mode);
 int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws, size_t ws_bytes,
                       void* stream);
 /* must be called with the SAME io / ws that mstts_decoder_fwd filled (saved activations live in ws) */

@@ -57,6 +57,7 @@ EXPORTS = {
     "mstts_set_profiling": (C.c_int, [C.c_int]),
     "mstts_kernel_ms": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mstts_decoder_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "mstts_decoder_ws_offset": (C.c_size_t, [C.c_char_p] + [C.c_int] * 6),
     "mstts_decoder_fwd": (C.c_int, [C.POINTER(MsttsDecoderWeights), C.POINTER(MsttsDecoderIO), _fp, C.c_size_t, _fp]),
     "mstts_decoder_bwd": (C.c_int, [C.POINTER(MsttsDecoderWeights), C.POINTER(MsttsDecoderIO),
                                     C.POINTER(MsttsDecoderGrads), C.POINTER(MsttsDecoderWeightGrads),

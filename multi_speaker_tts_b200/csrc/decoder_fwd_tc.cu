@@ -37,11 +37,12 @@ struct DecFwdTcParams {
   const uint8_t* zone_mask;
   float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart, *qf;
   unsigned* barrier;
+  long long* dbg;  // [T][32] phase time stamps of CTA 0 (may be null)
 };
 
 struct TcSmem {
   // byte offsets into dynamic shared memory
-  uint32_t ring, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, total;
+  uint32_t ring, recv, comb, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, total;
 };
 
 __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
@@ -55,6 +56,7 @@ __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
   };
   s.ring = take(NS * kSlotBytes);
   s.recv = take(kDecCluster * kTcN * kRecvStride * 4);
+  s.comb = take(128 * kTcN * 4);
   s.keys = take(Te * 32 * 4);
   s.wq = take(kUnitsPerCta * kAtt * 4);
   s.xs = take(2 * 2 * kTcN * 8 * 2);
@@ -105,6 +107,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 
   uint8_t* ring = smem + L.ring;
   float* recv = reinterpret_cast<float*>(smem + L.recv);
+  float* comb = reinterpret_cast<float*>(smem + L.comb);  // [128 gate rows][32 batch]: x_lo-row partials
   float* keys_s = reinterpret_cast<float*>(smem + L.keys);
   float* wq_s = reinterpret_cast<float*>(smem + L.wq);
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + L.xs);  // [vec 2][hi/lo][32][8]
@@ -121,8 +124,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   uint64_t* xfull = wfull + NS;
   uint64_t* empty = xfull + NS;
   uint64_t* job_done = empty + NS;     // [4]
-  uint64_t* cl_bar = job_done + 4;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cl_bar + 1);
+  uint64_t* rs_bar = job_done + 4;     // K-split reduction pushes (st.async complete_tx)
+  uint64_t* e_bar = rs_bar + 1;        // partial-energy all-gather
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_bar + 1);
   unsigned* ready_seq = tmem_slot + 1;
 
   if (tid == 0) {
@@ -132,7 +136,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       ptx::mbar_init(&empty[i], 1);
     }
     for (int j = 0; j < 4; ++j) ptx::mbar_init(&job_done[j], 1);
-    ptx::mbar_init(cl_bar, kDecCluster * (kTcCompute / 32));
+    ptx::mbar_init(rs_bar, 1);
+    ptx::mbar_init(e_bar, 1);
     *ready_seq = 0;
     ptx::fence_mbar_init();
   }
@@ -141,7 +146,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_val = tmem + 64;  // values: block h at columns 64 + h*TeP
+  // accumulators (M=64 uses lanes 0-15 of every 32-lane quarter): cell 0 at lane offset 0, cell 1 at lane offset 16,
+  // both columns 0..255 (0..127: W_hi rows, 128..255: W_lo rows); values: block h at columns 256 + h*TeP
+  const uint32_t tmem_val = tmem + 256;
 
   // ---- one-time staging by the compute warps ----
   float F_reg[kConvK];
@@ -218,17 +225,20 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         }
         while (ld_volatile_shared(ready_seq) < need) {
         }
+        if (P.dbg && blockIdx.x == 0 && q == 0) P.dbg[(size_t)t * 32 + 16] = clock64();
+        if (P.dbg && blockIdx.x == 0 && q == n0) P.dbg[(size_t)t * 32 + 21] = clock64();
         if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
-        asm volatile("fence.proxy.async;" ::: "memory");
         ptx::mbar_arrive_expect_tx(&xfull[s], kXTileBytes);
         ptx::bulk_g2s(ring + (size_t)s * kSlotBytes + kWTileBytes, src, kXTileBytes, &xfull[s]);
+        if (P.dbg && blockIdx.x == 0 && q == n0 - 1) P.dbg[(size_t)t * 32 + 17] = clock64();
+        if (P.dbg && blockIdx.x == 0 && q == n0 + 3) P.dbg[(size_t)t * 32 + 22] = clock64();
       }
     }
     __syncwarp();
   } else if (warp == 10) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, kTcN);
+      const uint32_t idesc = ptx::umma_idesc_bf16(64, 256);
       const int n0 = P.n0;
       for (int i = 0; i < total_tiles; ++i) {
         const int s = i % NS, round = i / NS;
@@ -239,24 +249,32 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         else if (q < n0 + 8) { job = 2; kt = q - n0 - 4; nt = 4; }
         else { job = 3; kt = q - n0 - 8; nt = 4; }
         ptx::mbar_wait(&wfull[s], round & 1);
+        if (P.dbg && blockIdx.x == 0) {
+          if (q == 0) P.dbg[(size_t)t * 32 + 18] = clock64();
+          if (q == n0) P.dbg[(size_t)t * 32 + 23] = clock64();
+          if (q == n0 + 3) P.dbg[(size_t)t * 32 + 26] = clock64();
+        }
         ptx::mbar_wait(&xfull[s], round & 1);
+        if (P.dbg && blockIdx.x == 0) {
+          if (q == 0) P.dbg[(size_t)t * 32 + 19] = clock64();
+          if (q == n0) P.dbg[(size_t)t * 32 + 24] = clock64();
+          if (q == n0 + 3) P.dbg[(size_t)t * 32 + 27] = clock64();
+        }
         ptx::tc_fence_after();
-        const uint32_t d = tmem + ((job & 1) ? 32u : 0u);
+        const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
         const uint32_t wbase = ptx::smem_u32(ring + (size_t)s * kSlotBytes);
         const uint32_t xbase = wbase + kWTileBytes;
         const bool fresh = (kt == 0) && (job >= 2 || t == 0);
 #pragma unroll
         for (int k = 0; k < kTcKT / 16; ++k) {
-          const uint64_t a_hi = ptx::umma_desc(wbase + k * 256, kTcLBO, kTcSBO);
-          const uint64_t a_lo = ptx::umma_desc(wbase + kWTileBytes / 2 + k * 256, kTcLBO, kTcSBO);
-          const uint64_t b_hi = ptx::umma_desc(xbase + k * 256, kTcLBO, kTcSBO);
-          const uint64_t b_lo = ptx::umma_desc(xbase + kXTileBytes / 2 + k * 256, kTcLBO, kTcSBO);
-          ptx::umma_bf16(d, a_hi, b_lo, idesc, (fresh && k == 0) ? 0u : 1u);
-          ptx::umma_bf16(d, a_lo, b_hi, idesc, 1u);
-          ptx::umma_bf16(d, a_hi, b_hi, idesc, 1u);
+          // A = [X_hi ; X_lo] (64 rows), B = [W_hi ; W_lo] (256 rows): hh, hl, lh, ll in one instruction
+          const uint64_t a = ptx::umma_desc(xbase + k * 256, kTcLBO, kTcSBO);
+          const uint64_t bd = ptx::umma_desc(wbase + k * 256, kTcLBO, kTcSBO);
+          ptx::umma_bf16(d, a, bd, idesc, (fresh && k == 0) ? 0u : 1u);
         }
         ptx::umma_commit(&empty[s]);
         if (kt == nt - 1) ptx::umma_commit(&job_done[job]);
+        if (P.dbg && blockIdx.x == 0 && kt == nt - 1 && job < 2) P.dbg[(size_t)t * 32 + 20 + 5 * job] = clock64();
       }
     }
     __syncwarp();
@@ -268,12 +286,11 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     const size_t BC = (size_t)B * kCell, BG = (size_t)B * kGates;
     const uint32_t recv_addr = ptx::smem_u32(recv);
     const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quarter / accumulator column half of this warp
-    const uint32_t recv_remote = ptx::mapa(recv_addr, (uint32_t)q4);
+    uint32_t rs_parity = 0, e_parity = 0;
     float c0 = 0.f, h0 = 0.f, c1 = 0.f, h1 = 0.f;  // zoned state of this (batch, unit), AttentionWrapper.zero_state
     const float bias0[4] = {P.b0[unit], P.b0[kCell + unit], P.b0[2 * kCell + unit], P.b0[3 * kCell + unit]};
     const float bias1[4] = {P.b1[unit], P.b1[kCell + unit], P.b1[2 * kCell + unit], P.b1[3 * kCell + unit]};
-    uint32_t cl_parity = 0;
-    unsigned bar_target = 0;
+        unsigned bar_target = 0;
     const int tl = (cid < B) ? min(P.text_len[cid], Te) : 0;
     const size_t vec_img = (size_t)(kCell / kTcKT) * kXTileBytes, ctx_img = (size_t)(D / kTcKT) * kXTileBytes;
     // byte offset of this CTA's 8-unit chunk inside a [32 x 1024] activation image, for batch row r: + (r/8)*1024 + (r%8)*16
@@ -281,23 +298,87 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     const size_t img_chunk = (size_t)(unit0 >> 6) * kXTileBytes + (size_t)((unit0 & 63) >> 3) * 128;
 
     // pulls this CTA's partial accumulator out of TMEM and scatters it to the owners of the units
-    auto reduce_scatter = [&](int job, int t, uint32_t dcol) {
-      ptx::mbar_wait(&job_done[job], t & 1);
+    // Pulls this CTA's partial accumulator (cell = job & 1) out of TMEM, adds its four hi/lo quadrants and scatters
+    // the 128 gate rows to the CTAs that own the units.  Warp w reads lane quarter q4 = w & 3 (quarters 0,1: x_hi rows
+    // of batch 0-15 / 16-31, quarters 2,3: x_lo rows) and gate-row columns 64*half .. +63.
+    auto reduce_scatter = [&](int job, int t) {
+      if (tid == 0) ptx::mbar_arrive_expect_tx(rs_bar, kDecCluster * 32 * kTcN * 4);
+      mbar_wait_warp(&job_done[job], t & 1);
+      if (P.dbg && blockIdx.x == 0 && tid == 0) P.dbg[(size_t)t * 32 + 1 + 4 * job] = clock64();
       ptx::tc_fence_after();
-      uint32_t v[16];
-      ptx::tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + dcol + half * 16, v);
-      ptx::tmem_wait_ld();
-      ptx::tc_fence_before();
+      const int l16 = lane - ((job & 1) ? 16 : 0);
+      const bool mine = l16 >= 0 && l16 < 16;          // lanes of the quarter that hold this cell's accumulator
+      const int bq = 16 * (q4 & 1) + l16;              // batch row of this lane
+      const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16) + half * 64;
+      if (q4 >= 2) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        ptx::st_cluster_f32(recv_remote + (uint32_t)(((crank * kTcN + half * 16 + j) * kRecvStride + lane) * 4),
-                            __uint_as_float(v[j]));
-      cluster_compute_sync(cl_bar, cl_parity);
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t vh[32], vl[32];
+          ptx::tmem_ld32(ta + ch * 32, vh);
+          ptx::tmem_ld32(ta + 128 + ch * 32, vl);
+          ptx::tmem_wait_ld();
+          if (mine) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) comb[(half * 64 + ch * 32 + j) * kTcN + bq] = __uint_as_float(vh[j]) + __uint_as_float(vl[j]);
+          }
+        }
+      }
+      ptx::bar_sync(1, kTcCompute);
+      if (q4 < 2) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t vh[32], vl[32];
+          ptx::tmem_ld32(ta + ch * 32, vh);
+          ptx::tmem_ld32(ta + 128 + ch * 32, vl);
+          ptx::tmem_wait_ld();
+          if (mine) {
+            const int rr = half * 2 + ch;  // 32 gate rows = the units of cluster CTA rr
+            const uint32_t dst = ptx::mapa(recv_addr, (uint32_t)rr) + (uint32_t)(((crank * kTcN + bq) * kRecvStride) * 4);
+            const uint32_t rbar = ptx::mapa(ptx::smem_u32(rs_bar), (uint32_t)rr);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = (__uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e])) + comb[(half * 64 + ch * 32 + j + e) * kTcN + bq];
+              ptx::st_async_v4(dst + j * 4, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]), rbar);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      mbar_wait_warp(rs_bar, rs_parity);
+      rs_parity ^= 1u;
     };
-
+    long long* dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
+#define STAMP(k) do { if (dbg) dbg[(size_t)t * 32 + (k)] = clock64(); } while (0)
     for (int t = 0; t < P.T; ++t) {
       const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
       const int par = t & 1;
+      STAMP(0);
+      // location features of THIS step's attention depend only on cum_{t-1}: compute them now, while the tensor
+      // core works on J0 (keys + conv, Location_Sensitive_Attention.py:48-61,82); the query part is added in phase C
+      float pre_e[16];
+      {
+        const int t0 = warp * 16;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) pre_e[p] = 0.f;
+        if (t0 < tl) {
+#pragma unroll
+          for (int c = 0; c < 16 + kConvK - 1; ++c) {
+            const float cv = cum_s[t0 + c];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int k = c - p;
+              if (k >= 0 && k < kConvK) pre_e[p] = fmaf(cv, F_reg[k], pre_e[p]);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < 16; ++p)
+            if (t0 + p < tl) pre_e[p] += keys_s[(t0 + p) * 32 + lane];
+        }
+      }
+      STAMP(28);
       // ================= phase A: LSTM cell 0 =================
       {
         float add[4] = {0.f, 0.f, 0.f, 0.f};
@@ -309,7 +390,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           mc = (float)zm[(size_t)b * kCell + unit];
           mh = (float)zm[BC + (size_t)b * kCell + unit];
         }
-        reduce_scatter(0, t, 0u);
+        reduce_scatter(0, t);
+        STAMP(2);
         float g[4];
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
@@ -349,7 +431,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           }
         }
       }
+      STAMP(3);
       grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 1);
+      STAMP(4);
 
       // ================= phase B: LSTM cell 1 (+ partial query projection) =================
       {
@@ -358,7 +442,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           mc = (float)zm[2 * BC + (size_t)b * kCell + unit];
           mh = (float)zm[3 * BC + (size_t)b * kCell + unit];
         }
-        reduce_scatter(1, t, 32u);
+        reduce_scatter(1, t);
+        STAMP(6);
         float g[4];
 #pragma unroll
         for (int gi = 0; gi < 4; ++gi) {
@@ -404,14 +489,21 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           P.qpart[((size_t)blockIdx.x * B + bb) * kAtt + a] = s;
         }
       }
+      STAMP(7);
       grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 2);
+      STAMP(8);
 
       // ================= phase C: location-sensitive attention, batch row = cluster index ==========
       if (cid < B) {
         const int bb = cid;
         {  // q slice = sum of the 128 per-CTA partials (fixed order)
+          float pq[kDecGrid / 8];
+#pragma unroll
+          for (int j = 0; j < kDecGrid / 8; ++j)
+            pq[j] = __ldcg(P.qpart + ((size_t)(warp + 8 * j) * B + bb) * kAtt + crank * 32 + lane);
           float s = 0.f;
-          for (int j = warp; j < kDecGrid; j += 8) s += __ldcg(P.qpart + ((size_t)j * B + bb) * kAtt + crank * 32 + lane);
+#pragma unroll
+          for (int j = 0; j < kDecGrid / 8; ++j) s += pq[j];
           qred[warp * 32 + lane] = s;
         }
         ptx::bar_sync(1, kTcCompute);
@@ -423,40 +515,63 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s + fb_l;
         }
         ptx::bar_sync(1, kTcCompute);
+        STAMP(14);
         const float qf = qf_s[lane];
-        for (int blk = warp; blk * 16 < tl; blk += 8) {
-          const int t0 = blk * 16;
-          float acc[16];
+        {
+          const int t0 = warp * 16;  // Te <= 128: one 16-position block per warp
+          if (t0 < tl) {
+            float v[16];
 #pragma unroll
-          for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+            for (int p = 0; p < 16; ++p) v[p] = (t0 + p < tl) ? sw_l * tanhf(pre_e[p] + qf) : 0.f;
+            // sum over the 32 lanes (attention units) of 16 independent values: halve the value count at every
+            // butterfly step (31 shuffles instead of 80, all independent within a level)
 #pragma unroll
-          for (int c = 0; c < 16 + kConvK - 1; ++c) {
-            const float cv = cum_s[t0 + c];
+            for (int p = 0; p < 8; ++p) {
+              const float send = (lane & 16) ? v[p] : v[p + 8];
+              const float keep = (lane & 16) ? v[p + 8] : v[p];
+              v[p] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
 #pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              const int k = c - p;
-              if (k >= 0 && k < kConvK) acc[p] = fmaf(cv, F_reg[k], acc[p]);
+            for (int p = 0; p < 4; ++p) {
+              const float send = (lane & 8) ? v[p] : v[p + 4];
+              const float keep = (lane & 8) ? v[p + 4] : v[p];
+              v[p] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              const float send = (lane & 4) ? v[p] : v[p + 2];
+              const float keep = (lane & 4) ? v[p + 2] : v[p];
+              v[p] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+              const float send = (lane & 2) ? v[0] : v[1];
+              const float keep = (lane & 2) ? v[1] : v[0];
+              v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+            // lane L now holds position index ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)
+            if ((lane & 1) == 0) {
+              const int p = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              e_loc[t0 + p] = v[0];
             }
           }
-#pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const int x = t0 + p;
-            float v = 0.f;
-            if (x < tl) v = sw_l * tanhf(keys_s[x * 32 + lane] + qf + acc[p]);
-            v = warp_sum(v);
-            if (lane == 0) e_loc[x] = v;
-          }
         }
+        STAMP(15);
         ptx::bar_sync(1, kTcCompute);
-        {  // all-gather the partial energies across the cluster through DSMEM
+        {  // all-gather the partial energies across the cluster through DSMEM (st.async counts bytes on e_bar)
+          if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
           const uint32_t ep = ptx::smem_u32(e_parts) + (uint32_t)(crank * TeP * 4);
+          const uint32_t eb = ptx::smem_u32(e_bar);
 #pragma unroll
           for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) {
-            const uint32_t remote = ptx::mapa(ep, dst);
-            for (int x = tid; x < tl; x += kTcCompute) ptx::st_cluster_f32(remote + x * 4, e_loc[x]);
+            const uint32_t remote = ptx::mapa(ep, dst), rbar = ptx::mapa(eb, dst);
+            for (int x = tid; x < tl; x += kTcCompute) ptx::st_async_f32(remote + x * 4, e_loc[x], rbar);
           }
         }
-        cluster_compute_sync(cl_bar, cl_parity);
+        STAMP(11);
+        mbar_wait_warp(e_bar, e_parity);
+        e_parity ^= 1u;
+        STAMP(12);
         // masked softmax over positions < tl (score_mask_value = -inf => exactly 0 beyond tl)
         float lmax = -INFINITY;
         for (int x = tid; x < tl; x += kTcCompute) {
@@ -493,6 +608,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           }
         }
         ptx::bar_sync(1, kTcCompute);
+        STAMP(13);
         // context slice from the TMEM-resident values: thread = one context dim, columns = text positions
         if (q4 * 32 < Dh) {
           const int dloc = q4 * 32 + lane;
@@ -526,8 +642,11 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(o);
         }
       }
+      STAMP(9);
       grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 3);
+      STAMP(10);
     }
+#undef STAMP
   }
 
   // ---- teardown ----
@@ -576,7 +695,7 @@ __global__ void prep_wimg_fwd_kernel(const float* __restrict__ K0, const float* 
 }
 
 // ======================================== host side ================================================
-bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 224 && D % 256 == 0 && D <= 1024; }
+bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 128 && D % 256 == 0 && D <= 1024; }
 
 template <int NS>
 static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t smem, bool* ok) {
@@ -611,7 +730,7 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   auto F = [&](size_t off) { return (float*)(ws + off); };
   const int D = io->D;
   MSTTS_REQUIRE(dec_tc_supported(io->B, io->Te, D), MSTTS_E_UNSUPPORTED,
-                "decoder bf16x3 mode needs B<=32, Te<=224, D%%256==0 (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te, D);
+                "decoder bf16x3 mode needs B<=32, Te<=128, D%%256==0 (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te, D);
   DecFwdTcParams P;
   memset(&P, 0, sizeof(P));
   P.B = io->B; P.Te = io->Te; P.T = io->n_steps; P.D = D; P.training = io->is_training; P.n0 = D / 256;
@@ -626,6 +745,7 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   P.cz0 = F(l.cz0); P.hz0 = F(l.hz0); P.cz1 = F(l.cz1); P.hz1 = F(l.hz1);
   P.m0 = F(l.m0); P.m1 = F(l.m1); P.ctx = F(l.ctx); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.qpart = F(l.qpart); P.qf = F(l.qf);
   P.barrier = (unsigned*)(ws + l.barrier);
+  P.dbg = (long long*)(ws + l.dbg);
   // weight image (weights change every optimiser step) and zeroed activation images (initial state = 0)
   prep_wimg_fwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_f), D);
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_ctx, 0, l.ximg_end - l.ximg_ctx, s));

@@ -119,6 +119,19 @@ extern "C" size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int
   return dec_layout(B, Te, L, D, n_steps, mode).total;
 }
 
+// offset (bytes) of a named workspace region, or (size_t)-1: lets tests / profiling tools look at saved
+// activations and the phase time stamps without knowing the layout
+extern "C" size_t mstts_decoder_ws_offset(const char* name, int B, int Te, int L, int D, int n_steps, int mode) {
+  if (!name || B <= 0 || Te <= 0 || D <= 0 || n_steps <= 0) return (size_t)-1;
+  const DecLayout l = dec_layout(B, Te, L, D, n_steps, mode);
+#define REGION(x) if (!strcmp(name, #x)) return l.x;
+  REGION(values) REGION(keys) REGION(g0pre) REGION(act0) REGION(act1) REGION(c0n) REGION(c1n) REGION(cz0) REGION(hz0)
+  REGION(cz1) REGION(hz1) REGION(m0) REGION(m1) REGION(ctx) REGION(cum) REGION(align_tm) REGION(qf) REGION(dG0) REGION(dG1)
+  REGION(dctx) REGION(dq) REGION(dbg) REGION(wimg_f) REGION(total)
+#undef REGION
+  return (size_t)-1;
+}
+
 static int check_io(const MsttsDecoderWeights* w, const MsttsDecoderIO* io) {
   MSTTS_REQUIRE(w && io, MSTTS_E_INVALID, "decoder: null weights/io");
   MSTTS_REQUIRE(io->B >= 1 && io->B <= 256, MSTTS_E_INVALID, "decoder: B=%d out of range [1,256]", io->B);

@@ -1,9 +1,11 @@
 // Shared pieces of the tcgen05 ("bf16x3") persistent decoder kernels.
 //
-// Numerics: every recurrent skinny GEMM  Y[rows,B] = W[rows,K] . X[K,B]  runs on the 5th-gen tensor cores
-// with both operands split into bf16 hi + bf16 lo (x = hi + lo to ~16 mantissa bits) and three MMAs per
-// K-step (hi.hi + hi.lo + lo.hi), fp32 accumulation in TMEM: measured L_inf vs the fp32 oracle ~2e-6 on the
-// mel outputs (plain bf16 would be ~1e-3, i.e. at the parity gate).
+// Numerics: every recurrent skinny GEMM  Y[B,rows] = X[B,K] . W[rows,K]^T  runs on the 5th-gen tensor cores
+// with both operands split into bf16 hi + bf16 lo (x = hi + lo to ~16 mantissa bits), fp32 accumulation in
+// TMEM: measured L_inf vs the fp32 oracle ~2e-6 on the mel outputs (plain bf16 would be ~1e-3, i.e. at the
+// parity gate).  One tcgen05.mma costs ~150 cycles to issue whatever its shape (tools/mma_probe.cu), so the
+// hi/lo halves are STACKED into one instruction per K-step: A = [X_hi ; X_lo] (M = 64 rows), B = [W_hi ; W_lo]
+// (N = 256 rows) gives all four partial products in one 64 x 256 accumulator; the epilogue adds the quadrants.
 //
 // Data movement: weights do not fit on chip (hi+lo = 4 B/weight, 63 MB), so each CTA re-streams its slice from
 // L2 every step through a ring of shared-memory slots filled by 1-D bulk async copies (TMA engine); the
@@ -15,7 +17,8 @@
 //   W tile  [128 rows x 64 k] : hi at +0 (16 KB), lo at +16 KB
 //   X tile  [ 32 rows x 64 k] : hi at +0 ( 4 KB), lo at + 4 KB      (rows = batch index, zero beyond B)
 //   element (row, k) at byte (row/8)*1024 + (k/8)*128 + (row%8)*16 + (k%8)*2
-//   => UMMA descriptor: LBO (K direction) = 128, SBO (M/N direction) = 1024; one K=16 MMA step = +256 B.
+//   => UMMA descriptor: LBO (K direction) = 128, SBO (M/N direction) = 1024; one K=16 MMA step = +256 B;
+//      hi and lo are adjacent, so a W tile doubles as a 256-row B operand and an X tile as a 64-row A operand.
 #pragma once
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -28,7 +31,7 @@ constexpr uint32_t kWTileBytes = 128 * kTcKT * 2 * 2;  // 32768
 constexpr uint32_t kXTileBytes = kTcN * kTcKT * 2 * 2;  // 8192
 constexpr uint32_t kSlotBytes = kWTileBytes + kXTileBytes;
 constexpr uint32_t kTcLBO = 128, kTcSBO = 1024;
-constexpr int kRecvStride = 40;           // floats per (src, batch) row of the K-split reduction buffer
+constexpr int kRecvStride = 40;           // floats per (src, batch) row of the K-split reduction buffer [src][batch][gate*8+unit]
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -59,6 +62,13 @@ __device__ __forceinline__ void cluster_compute_sync(uint64_t* bar, uint32_t& pa
   while (!ptx::mbar_try_wait_cluster(bar, parity)) {
   }
   parity ^= 1u;
+}
+
+// One lane per warp polls the mbarrier, the rest of the warp parks in __syncwarp: 256 threads spinning on
+// try_wait would compete with the producer / MMA threads for the shared-memory pipeline.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) ptx::mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // Grid-wide barrier executed by the compute warps only (named barrier 1); thread 0 then publishes the event

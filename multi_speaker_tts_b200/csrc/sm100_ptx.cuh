@@ -71,6 +71,18 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, f
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float a) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
 }
+// remote store that counts its bytes on an mbarrier of the destination CTA (both addresses from mapa):
+// the receiver posts expect_tx and waits -- no fences or arrives on the sender side
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float a, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr),
+               "r"(__float_as_uint(a)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
 // remote arrive on an mbarrier living in another CTA of the cluster (address from mapa)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
@@ -84,6 +96,14 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
+}
+
+// one lane of a CONVERGED warp; ptxas recognises regions guarded by elect.sync as single-thread and issues the
+// uniform-datapath instructions (UTCHMMA, UBLKCP, ...) directly instead of through a per-thread election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- named barriers (sub-CTA groups)

@@ -1,0 +1,48 @@
+"""Per-phase cycle breakdown of the bf16x3 persistent decoder kernels (CTA 0's clock64 stamps):
+python tools/phase_times.py B Te L [fwd|bwd]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multi_speaker_tts_b200 import synthetic as S, _lib
+from multi_speaker_tts_b200.decoder import decoder_forward, decoder_backward, decoder_loss
+
+B, Te, L = (int(x) for x in sys.argv[1:4])
+which = sys.argv[4] if len(sys.argv) > 4 else "fwd"
+dev = torch.device("cuda:0")
+w = {k: v.to(dev) for k, v in S.init_decoder_weights(0).items()}
+b = {k: v.to(dev) for k, v in S.synthetic_decoder_batch(B, Te, L).items()}
+T = L + 1
+ws = None
+for it in range(3):
+    lin, stop, al, st = decoder_forward(w, b['memory'], b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'],
+                                        b['zone_mask'], True, T, "bf16x3", workspace=ws)
+    ws = st.ws
+    if which == "bwd":
+        loss2, dlin, dstop = decoder_loss(lin, stop, b['mel'], b['mel_len'])
+        decoder_backward(st, w, dlin, dstop)
+torch.cuda.synchronize()
+off = _lib.lib().mstts_decoder_ws_offset(b"dbg" if which == "fwd" else b"dbg_b", B, Te, L, 768, T, 1)
+stamps = ws[off:off + T * 32 * 8].view(torch.int64).view(T, 32).cpu().double()
+mhz = 1.0
+names_f = ["start", "J0 done", "reduceA done", "epiA done", "barA done", "J1 done", "reduceB done", "epiB done", "barB done",
+           "attn done", "barC done", "e pushed", "e gathered", "softmax done", "q ready", "energies done"]
+order_f = [0, 1, 2, 3, 4, 5, 6, 7, 8, 14, 15, 11, 12, 13, 9, 10]
+sel = stamps[T // 4: 3 * T // 4]
+prev = sel[:, 0]
+print("cycles per step (mean over the middle half of the steps), CTA 0:")
+for k in order_f:
+    d = (sel[:, k] - prev).mean().item()
+    print("  %-14s +%8.0f" % (names_f[k], d))
+    prev = sel[:, k]
+print("  total/step   %8.0f cycles" % (sel[:, 10] - sel[:, 0]).mean().item())
+if which == "fwd":
+    rn = {16: "Xprod sees barC(t-1)", 17: "Xprod J0 issued", 18: "MMA J0 tile0 W ok", 19: "MMA J0 tile0 X ok", 20: "MMA J0 committed",
+          1: "compute J0 done"}
+    print("role threads, relative to step start:")
+    for k in [16, 17, 18, 19, 20, 1]:
+        print("  %-22s %8.0f" % (rn[k], (sel[:, k] - sel[:, 0]).mean().item()))
+    rn = {21: "Xprod sees barA", 22: "Xprod J1 issued", 23: "MMA J1 tile0 W ok", 24: "MMA J1 tile0 X ok", 26: "MMA J1 tile3 W ok",
+          27: "MMA J1 tile3 X ok", 25: "MMA J1 committed", 5: "compute J1 done"}
+    print("relative to barA done:")
+    for k in [21, 22, 23, 24, 26, 27, 25, 5]:
+        print("  %-22s %8.0f" % (rn[k], (sel[:, k] - sel[:, 4]).mean().item()))
