@@ -42,7 +42,7 @@ struct DecFwdTcParams {
 
 struct TcSmem {
   // byte offsets into dynamic shared memory
-  uint32_t ring, recv, comb, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, total;
+  uint32_t ring, xbuf, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, total;
 };
 
 __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
@@ -54,9 +54,9 @@ __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
     off += (bytes + 127) & ~127u;
     return o;
   };
-  s.ring = take(NS * kSlotBytes);
+  s.ring = take(NS * kWTileBytes);
+  s.xbuf = take(2 * 4 * kXTileBytes);
   s.recv = take(kDecCluster * kTcN * kRecvStride * 4);
-  s.comb = take(128 * kTcN * 4);
   s.keys = take(Te * 32 * 4);
   s.wq = take(kUnitsPerCta * kAtt * 4);
   s.xs = take(2 * 2 * kTcN * 8 * 2);
@@ -101,13 +101,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   const int crank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kDecCluster;
   const int TeP = (Te + 31) & ~31;
-  const int tps = P.n0 + 12;  // weight tiles per step
-  const int total_tiles = tps * (P.T - 1) + P.n0 + 4;
+  const int n0 = P.n0;
+  const int tps = n0 + 12;  // weight tiles per step
+  const int total_tiles = tps * (P.T - 1) + n0 + 4;
   const TcSmem L = tc_fwd_smem(NS, Te, D);
 
-  uint8_t* ring = smem + L.ring;
+  uint8_t* ring = smem + L.ring;   // [NS][32 KB] weight tiles
+  uint8_t* xbuf = smem + L.xbuf;   // [2][32 KB]  activation operand of the running jobs (A: J0/J2, B: J1/J3)
   float* recv = reinterpret_cast<float*>(smem + L.recv);
-  float* comb = reinterpret_cast<float*>(smem + L.comb);  // [128 gate rows][32 batch]: x_lo-row partials
   float* keys_s = reinterpret_cast<float*>(smem + L.keys);
   float* wq_s = reinterpret_cast<float*>(smem + L.wq);
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + L.xs);  // [vec 2][hi/lo][32][8]
@@ -121,9 +122,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   float* ctx_s = reinterpret_cast<float*>(smem + L.ctx_s);
   float* bred = reinterpret_cast<float*>(smem + L.bred);
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + L.bars);  // [NS]
-  uint64_t* xfull = wfull + NS;
-  uint64_t* empty = xfull + NS;
-  uint64_t* job_done = empty + NS;     // [4]
+  uint64_t* empty = wfull + NS;        // [NS]
+  uint64_t* xfull = empty + NS;        // [2]
+  uint64_t* job_done = xfull + 2;      // [4]
   uint64_t* rs_bar = job_done + 4;     // K-split reduction pushes (st.async complete_tx)
   uint64_t* e_bar = rs_bar + 1;        // partial-energy all-gather
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_bar + 1);
@@ -132,16 +133,17 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
       ptx::mbar_init(&wfull[i], 1);
-      ptx::mbar_init(&xfull[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
+    ptx::mbar_init(&xfull[0], 1);
+    ptx::mbar_init(&xfull[1], 1);
     for (int j = 0; j < 4; ++j) ptx::mbar_init(&job_done[j], 1);
     ptx::mbar_init(rs_bar, 1);
     ptx::mbar_init(e_bar, 1);
     *ready_seq = 0;
     ptx::fence_mbar_init();
   }
-  if (warp == 10) ptx::tmem_alloc(tmem_slot, 512);
+  if (warp == kTcMmaWarp) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -185,96 +187,87 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     for (int k = 0; k < kConvK; ++k) F_reg[k] = 0.f;
   }
   ptx::tc_fence_before();
-  cluster.sync();  // all threads: peers' mbarriers are initialised before any remote arrive
+  cluster.sync();  // all threads: peers' mbarriers are initialised before any remote store / arrive
   ptx::tc_fence_after();
 
-  if (warp == 8) {
-    // =========================== weight-tile producer ===========================
+  if (warp == 8 || warp == 9) {
+    // =========================== weight-tile producers (even / odd tiles) ===========================
+    // one thread sustains ~80 GB/s of 32 KB bulk copies, two reach the ~150 GB/s an SM can pull from L2
     if (lane == 0) {
       const uint8_t* wsrc = P.wimg + (size_t)blockIdx.x * tps * kWTileBytes;
-      for (int i = 0; i < total_tiles; ++i) {
+      for (int i = warp - 8; i < total_tiles; i += 2) {
         const int s = i % NS, round = i / NS;
         if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
         ptx::mbar_arrive_expect_tx(&wfull[s], kWTileBytes);
-        ptx::bulk_g2s(ring + (size_t)s * kSlotBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // =========================== activation-tile producer ===========================
-    if (lane == 0) {
-      const int n0 = P.n0;
-      const size_t ctx_img = (size_t)(D / kTcKT) * kXTileBytes, vec_img = (size_t)(kCell / kTcKT) * kXTileBytes;
-      for (int i = 0; i < total_tiles; ++i) {
-        const int s = i % NS, round = i / NS;
-        const int t = i / tps, q = i % tps;
-        const uint8_t* src;
-        unsigned need;
-        if (q < n0) {  // J0: ctx_{t-1}, slice crank
-          src = P.ximg_ctx + (size_t)((t + 1) & 1) * ctx_img + (size_t)(crank * n0 + q) * kXTileBytes;
-          need = 3u * t;
-        } else if (q < n0 + 4) {  // J1: m0_t
-          src = P.ximg_m0 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4 + (q - n0)) * kXTileBytes;
-          need = 3u * t + 1;
-        } else if (q < n0 + 8) {  // J2: h0_t
-          src = P.ximg_h0 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4 + (q - n0 - 4)) * kXTileBytes;
-          need = 3u * t + 1;
-        } else {  // J3: h1_t
-          src = P.ximg_h1 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4 + (q - n0 - 8)) * kXTileBytes;
-          need = 3u * t + 2;
-        }
-        while (ld_volatile_shared(ready_seq) < need) {
-        }
-        if (P.dbg && blockIdx.x == 0 && q == 0) P.dbg[(size_t)t * 32 + 16] = clock64();
-        if (P.dbg && blockIdx.x == 0 && q == n0) P.dbg[(size_t)t * 32 + 21] = clock64();
-        if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
-        ptx::mbar_arrive_expect_tx(&xfull[s], kXTileBytes);
-        ptx::bulk_g2s(ring + (size_t)s * kSlotBytes + kWTileBytes, src, kXTileBytes, &xfull[s]);
-        if (P.dbg && blockIdx.x == 0 && q == n0 - 1) P.dbg[(size_t)t * 32 + 17] = clock64();
-        if (P.dbg && blockIdx.x == 0 && q == n0 + 3) P.dbg[(size_t)t * 32 + 22] = clock64();
+        ptx::bulk_g2s(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s]);
       }
     }
     __syncwarp();
   } else if (warp == 10) {
+    // =========================== activation producer: one bulk copy per job ===========================
+    if (lane == 0) {
+      const size_t ctx_img = (size_t)(D / kTcKT) * kXTileBytes, vec_img = (size_t)(kCell / kTcKT) * kXTileBytes;
+      for (int t = 0; t < P.T; ++t) {
+        const int njobs = (t == P.T - 1) ? 2 : 4;
+        for (int job = 0; job < njobs; ++job) {
+          const uint8_t* src;
+          uint32_t bytes = 4 * kXTileBytes;
+          unsigned need;
+          if (job == 0) {  // ctx_{t-1}, K-slice crank
+            src = P.ximg_ctx + (size_t)((t + 1) & 1) * ctx_img + (size_t)(crank * n0) * kXTileBytes;
+            bytes = (uint32_t)n0 * kXTileBytes;
+            need = 3u * t;
+          } else if (job == 1) {  // m0_t
+            src = P.ximg_m0 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4) * kXTileBytes;
+            need = 3u * t + 1;
+          } else if (job == 2) {  // h0_t
+            src = P.ximg_h0 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4) * kXTileBytes;
+            need = 3u * t + 1;
+          } else {  // h1_t
+            src = P.ximg_h1 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4) * kXTileBytes;
+            need = 3u * t + 2;
+          }
+          // the buffer is free once the previous job that read it has completed
+          if (job >= 2) ptx::mbar_wait(&job_done[job - 2], t & 1);
+          else if (t > 0) ptx::mbar_wait(&job_done[job + 2], (t - 1) & 1);
+          while (ld_volatile_shared(ready_seq) < need) {
+          }
+          ptx::mbar_arrive_expect_tx(&xfull[job & 1], bytes);
+          ptx::bulk_g2s(xbuf + (size_t)(job & 1) * 4 * kXTileBytes, src, bytes, &xfull[job & 1]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kTcMmaWarp) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(64, 256);
-      const int n0 = P.n0;
-      for (int i = 0; i < total_tiles; ++i) {
-        const int s = i % NS, round = i / NS;
-        const int t = i / tps, q = i % tps;
-        int job, kt, nt;
-        if (q < n0) { job = 0; kt = q; nt = n0; }
-        else if (q < n0 + 4) { job = 1; kt = q - n0; nt = 4; }
-        else if (q < n0 + 8) { job = 2; kt = q - n0 - 4; nt = 4; }
-        else { job = 3; kt = q - n0 - 8; nt = 4; }
-        ptx::mbar_wait(&wfull[s], round & 1);
-        if (P.dbg && blockIdx.x == 0) {
-          if (q == 0) P.dbg[(size_t)t * 32 + 18] = clock64();
-          if (q == n0) P.dbg[(size_t)t * 32 + 23] = clock64();
-          if (q == n0 + 3) P.dbg[(size_t)t * 32 + 26] = clock64();
-        }
-        ptx::mbar_wait(&xfull[s], round & 1);
-        if (P.dbg && blockIdx.x == 0) {
-          if (q == 0) P.dbg[(size_t)t * 32 + 19] = clock64();
-          if (q == n0) P.dbg[(size_t)t * 32 + 24] = clock64();
-          if (q == n0 + 3) P.dbg[(size_t)t * 32 + 27] = clock64();
-        }
-        ptx::tc_fence_after();
-        const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
-        const uint32_t wbase = ptx::smem_u32(ring + (size_t)s * kSlotBytes);
-        const uint32_t xbase = wbase + kWTileBytes;
-        const bool fresh = (kt == 0) && (job >= 2 || t == 0);
+      int i = 0;
+      for (int t = 0; t < P.T; ++t) {
+        const int njobs = (t == P.T - 1) ? 2 : 4;
+        for (int job = 0; job < njobs; ++job) {
+          const int nt = job == 0 ? n0 : 4;
+          ptx::mbar_wait(&xfull[job & 1], (uint32_t)(job >> 1));  // buffer A: J0, J2, J0, ... ; buffer B: J1, J3, ...
+          const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
+          const uint32_t xbase = ptx::smem_u32(xbuf + (size_t)(job & 1) * 4 * kXTileBytes);
+          for (int kt = 0; kt < nt; ++kt, ++i) {
+            const int s = i % NS, round = i / NS;
+            ptx::mbar_wait(&wfull[s], round & 1);
+            ptx::tc_fence_after();
+            const uint32_t wbase = ptx::smem_u32(ring + (size_t)s * kWTileBytes);
+            const bool fresh = (kt == 0) && (job >= 2 || t == 0);
 #pragma unroll
-        for (int k = 0; k < kTcKT / 16; ++k) {
-          // A = [X_hi ; X_lo] (64 rows), B = [W_hi ; W_lo] (256 rows): hh, hl, lh, ll in one instruction
-          const uint64_t a = ptx::umma_desc(xbase + k * 256, kTcLBO, kTcSBO);
-          const uint64_t bd = ptx::umma_desc(wbase + k * 256, kTcLBO, kTcSBO);
-          ptx::umma_bf16(d, a, bd, idesc, (fresh && k == 0) ? 0u : 1u);
+            for (int k = 0; k < kTcKT / 16; ++k) {
+              // A = [X_hi ; X_lo] (64 rows), B = [W_hi ; W_lo] (256 rows): hh, hl, lh, ll in one instruction
+              const uint64_t a = ptx::umma_desc(xbase + kt * kXTileBytes + k * 256, kTcLBO, kTcSBO);
+              const uint64_t bd = ptx::umma_desc(wbase + k * 256, kTcLBO, kTcSBO);
+              ptx::umma_bf16(d, a, bd, idesc, (fresh && k == 0) ? 0u : 1u);
+            }
+            ptx::umma_commit(&empty[s]);
+          }
+          ptx::umma_commit(&job_done[job]);
+          if (P.dbg && blockIdx.x == 0 && job < 2) P.dbg[(size_t)t * 32 + 20 + 5 * job] = clock64();
         }
-        ptx::umma_commit(&empty[s]);
-        if (kt == nt - 1) ptx::umma_commit(&job_done[job]);
-        if (P.dbg && blockIdx.x == 0 && kt == nt - 1 && job < 2) P.dbg[(size_t)t * 32 + 20 + 5 * job] = clock64();
       }
     }
     __syncwarp();
@@ -290,95 +283,86 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     float c0 = 0.f, h0 = 0.f, c1 = 0.f, h1 = 0.f;  // zoned state of this (batch, unit), AttentionWrapper.zero_state
     const float bias0[4] = {P.b0[unit], P.b0[kCell + unit], P.b0[2 * kCell + unit], P.b0[3 * kCell + unit]};
     const float bias1[4] = {P.b1[unit], P.b1[kCell + unit], P.b1[2 * kCell + unit], P.b1[3 * kCell + unit]};
-        unsigned bar_target = 0;
+    float wq_r[kUnitsPerCta];  // query_layer rows of this CTA's units, column tid & 127
+#pragma unroll
+    for (int u = 0; u < kUnitsPerCta; ++u) wq_r[u] = wq_s[u * kAtt + (tid & 127)];
+    unsigned bar_target = 0;
     const int tl = (cid < B) ? min(P.text_len[cid], Te) : 0;
     const size_t vec_img = (size_t)(kCell / kTcKT) * kXTileBytes, ctx_img = (size_t)(D / kTcKT) * kXTileBytes;
     // byte offset of this CTA's 8-unit chunk inside a [32 x 1024] activation image, for batch row r: + (r/8)*1024 + (r%8)*16
     const int unit0 = cid * 32 + crank * kUnitsPerCta;
     const size_t img_chunk = (size_t)(unit0 >> 6) * kXTileBytes + (size_t)((unit0 & 63) >> 3) * 128;
+    long long* dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
+#define STAMP(k) do { if (dbg) dbg[(size_t)t * 32 + (k)] = clock64(); } while (0)
 
-    // pulls this CTA's partial accumulator out of TMEM and scatters it to the owners of the units
     // Pulls this CTA's partial accumulator (cell = job & 1) out of TMEM, adds its four hi/lo quadrants and scatters
-    // the 128 gate rows to the CTAs that own the units.  Warp w reads lane quarter q4 = w & 3 (quarters 0,1: x_hi rows
-    // of batch 0-15 / 16-31, quarters 2,3: x_lo rows) and gate-row columns 64*half .. +63.
+    // the 128 gate rows to the CTAs that own the units.  X-image rows are ordered so that TMEM lane quarter q holds
+    // batch rows 8q..8q+7: x_hi rows on lanes 0-7, x_lo rows on lanes 8-15 (cell 1: +16).  Warp w reads quarter
+    // q4 = w & 3 and gate-row columns 64*half .. +63 (W_hi) and 128+64*half .. (W_lo).
     auto reduce_scatter = [&](int job, int t) {
       if (tid == 0) ptx::mbar_arrive_expect_tx(rs_bar, kDecCluster * 32 * kTcN * 4);
       mbar_wait_warp(&job_done[job], t & 1);
-      if (P.dbg && blockIdx.x == 0 && tid == 0) P.dbg[(size_t)t * 32 + 1 + 4 * job] = clock64();
+      STAMP(1 + 4 * job);
       ptx::tc_fence_after();
       const int l16 = lane - ((job & 1) ? 16 : 0);
-      const bool mine = l16 >= 0 && l16 < 16;          // lanes of the quarter that hold this cell's accumulator
-      const int bq = 16 * (q4 & 1) + l16;              // batch row of this lane
+      const bool pusher = l16 >= 0 && l16 < 8;          // lanes holding the x_hi rows of this cell's accumulator
+      const int bq = 8 * q4 + (l16 & 7);                // batch row of this lane
       const uint32_t ta = tmem + ((uint32_t)(q4 * 32) << 16) + half * 64;
-      if (q4 >= 2) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t vh[32], vl[32];
-          ptx::tmem_ld32(ta + ch * 32, vh);
-          ptx::tmem_ld32(ta + 128 + ch * 32, vl);
-          ptx::tmem_wait_ld();
-          if (mine) {
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t vh[32], vl[32];
+        ptx::tmem_ld32(ta + ch * 32, vh);
+        ptx::tmem_ld32(ta + 128 + ch * 32, vl);
+        ptx::tmem_wait_ld();
+        const int rr = half * 2 + ch;  // 32 gate rows = the units of cluster CTA rr
+        const uint32_t dst = ptx::mapa(recv_addr, (uint32_t)rr) + (uint32_t)(((crank * kTcN + bq) * kRecvStride) * 4);
+        const uint32_t rbar = ptx::mapa(ptx::smem_u32(rs_bar), (uint32_t)rr);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) comb[(half * 64 + ch * 32 + j) * kTcN + bq] = __uint_as_float(vh[j]) + __uint_as_float(vl[j]);
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v = __uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e]);
+            o[e] = v + __shfl_down_sync(0xffffffffu, v, 8);  // + the x_lo row of the same batch
           }
-        }
-      }
-      ptx::bar_sync(1, kTcCompute);
-      if (q4 < 2) {
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t vh[32], vl[32];
-          ptx::tmem_ld32(ta + ch * 32, vh);
-          ptx::tmem_ld32(ta + 128 + ch * 32, vl);
-          ptx::tmem_wait_ld();
-          if (mine) {
-            const int rr = half * 2 + ch;  // 32 gate rows = the units of cluster CTA rr
-            const uint32_t dst = ptx::mapa(recv_addr, (uint32_t)rr) + (uint32_t)(((crank * kTcN + bq) * kRecvStride) * 4);
-            const uint32_t rbar = ptx::mapa(ptx::smem_u32(rs_bar), (uint32_t)rr);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o[e] = (__uint_as_float(vh[j + e]) + __uint_as_float(vl[j + e])) + comb[(half * 64 + ch * 32 + j + e) * kTcN + bq];
-              ptx::st_async_v4(dst + j * 4, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]), rbar);
-            }
-          }
+          if (pusher)
+            ptx::st_async_v4(dst + j * 4, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]), rbar);
         }
       }
       ptx::tc_fence_before();
       mbar_wait_warp(rs_bar, rs_parity);
       rs_parity ^= 1u;
     };
-    long long* dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
-#define STAMP(k) do { if (dbg) dbg[(size_t)t * 32 + (k)] = clock64(); } while (0)
+
+    // keys + location features of the NEXT attention step: depends only on the cumulative alignment, so it runs
+    // inside the barrier wait that follows the softmax (Location_Sensitive_Attention.py:48-61,82)
+    float pre_e[16];
+    auto location_features = [&]() {
+      const int t0 = warp * 16;  // Te <= 128: one 16-position block per warp
+#pragma unroll
+      for (int p = 0; p < 16; ++p) pre_e[p] = 0.f;
+      if (t0 < tl) {
+#pragma unroll
+        for (int c = 0; c < 16 + kConvK - 1; ++c) {
+          const float cv = cum_s[t0 + c];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int k = c - p;
+            if (k >= 0 && k < kConvK) pre_e[p] = fmaf(cv, F_reg[k], pre_e[p]);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p)
+          if (t0 + p < tl) pre_e[p] += keys_s[(t0 + p) * 32 + lane];
+      }
+    };
+    ptx::bar_sync(1, kTcCompute);
+    location_features();
+
     for (int t = 0; t < P.T; ++t) {
       const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
       const int par = t & 1;
       STAMP(0);
-      // location features of THIS step's attention depend only on cum_{t-1}: compute them now, while the tensor
-      // core works on J0 (keys + conv, Location_Sensitive_Attention.py:48-61,82); the query part is added in phase C
-      float pre_e[16];
-      {
-        const int t0 = warp * 16;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) pre_e[p] = 0.f;
-        if (t0 < tl) {
-#pragma unroll
-          for (int c = 0; c < 16 + kConvK - 1; ++c) {
-            const float cv = cum_s[t0 + c];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              const int k = c - p;
-              if (k >= 0 && k < kConvK) pre_e[p] = fmaf(cv, F_reg[k], pre_e[p]);
-            }
-          }
-#pragma unroll
-          for (int p = 0; p < 16; ++p)
-            if (t0 + p < tl) pre_e[p] += keys_s[(t0 + p) * 32 + lane];
-        }
-      }
-      STAMP(28);
       // ================= phase A: LSTM cell 0 =================
       {
         float add[4] = {0.f, 0.f, 0.f, 0.f};
@@ -401,17 +385,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           g[gi] = s + add[gi];
         }
         const CellOut r = cell_forward(g, c0, h0, mc, mh);
-        __nv_bfloat16 hi, lo;
         if (brow) {
-          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          P.act0[ai] = r.ig;
-          P.act0[ai + kCell] = r.jg;
-          P.act0[ai + 2 * kCell] = r.fg;
-          P.act0[ai + 3 * kCell] = r.og;
-          P.c0n[(size_t)t * BC + si] = r.c;
-          P.cz0[(size_t)(t + 1) * BC + si] = r.cz;
-          P.hz0[(size_t)(t + 1) * BC + si] = r.hz;
-          P.m0[(size_t)t * BC + si] = r.m;
+          __nv_bfloat16 hi, lo;
           c0 = r.cz;
           h0 = r.hz;
           split_bf16(r.m, hi, lo);
@@ -425,14 +400,25 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         if (tid < 128) {  // 16-byte rows of the m0 / h0 images: (vector, hi|lo, batch row)
           const int vec = tid >> 6, hl = (tid >> 5) & 1, r2 = tid & 31;
           if (r2 < B) {
-            uint8_t* img = (vec ? P.ximg_h0 : P.ximg_m0) + (size_t)par * vec_img + img_chunk + (size_t)hl * (kXTileBytes / 2) +
-                           (size_t)(r2 >> 3) * 1024 + (size_t)(r2 & 7) * 16;
+            uint8_t* img = (vec ? P.ximg_h0 : P.ximg_m0) + (size_t)par * vec_img + img_chunk + ximg_row_offset(r2, hl);
             *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(xs + (vec * 2 + hl) * 256 + r2 * 8);
           }
         }
+        STAMP(3);
+        grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+        if (brow) {  // activations saved for the reverse pass: nobody waits for these inside the loop
+          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+          P.act0[ai] = r.ig;
+          P.act0[ai + kCell] = r.jg;
+          P.act0[ai + 2 * kCell] = r.fg;
+          P.act0[ai + 3 * kCell] = r.og;
+          P.c0n[(size_t)t * BC + si] = r.c;
+          P.cz0[(size_t)(t + 1) * BC + si] = r.cz;
+          P.hz0[(size_t)(t + 1) * BC + si] = r.hz;
+          P.m0[(size_t)t * BC + si] = r.m;
+        }
+        grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 1);
       }
-      STAMP(3);
-      grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 1);
       STAMP(4);
 
       // ================= phase B: LSTM cell 1 (+ partial query projection) =================
@@ -453,18 +439,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           g[gi] = s + bias1[gi];
         }
         const CellOut r = cell_forward(g, c1, h1, mc, mh);
-        __nv_bfloat16 hi, lo;
         m_s[b * kUnitsPerCta + u8] = brow ? r.m : 0.f;
         if (brow) {
-          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          P.act1[ai] = r.ig;
-          P.act1[ai + kCell] = r.jg;
-          P.act1[ai + 2 * kCell] = r.fg;
-          P.act1[ai + 3 * kCell] = r.og;
-          P.c1n[(size_t)t * BC + si] = r.c;
-          P.cz1[(size_t)(t + 1) * BC + si] = r.cz;
-          P.hz1[(size_t)(t + 1) * BC + si] = r.hz;
-          P.m1[(size_t)t * BC + si] = r.m;
+          __nv_bfloat16 hi, lo;
           c1 = r.cz;
           h1 = r.hz;
           split_bf16(r.hz, hi, lo);
@@ -475,25 +452,49 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         if (tid < 64) {
           const int hl = tid >> 5, r2 = tid & 31;
           if (r2 < B) {
-            uint8_t* img = P.ximg_h1 + (size_t)par * vec_img + img_chunk + (size_t)hl * (kXTileBytes / 2) + (size_t)(r2 >> 3) * 1024 +
-                           (size_t)(r2 & 7) * 16;
+            uint8_t* img = P.ximg_h1 + (size_t)par * vec_img + img_chunk + ximg_row_offset(r2, hl);
             *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(xs + (2 + hl) * 256 + r2 * 8);
           }
         }
-        // partial q[b][a] = sum over this CTA's 8 units of m1[b][unit] * Wq[unit][a]
-        for (int i = tid; i < B * kAtt; i += kTcCompute) {
-          const int bb = i >> 7, a = i & 127;
-          float s = 0.f;
-#pragma unroll
-          for (int u = 0; u < kUnitsPerCta; ++u) s = fmaf(m_s[bb * kUnitsPerCta + u], wq_s[u * kAtt + a], s);
-          P.qpart[((size_t)blockIdx.x * B + bb) * kAtt + a] = s;
+        // partial q[b][a] = sum over this CTA's 8 units of m1[b][unit] * Wq[unit][a]; thread = (a, half of the batch)
+        {
+          const int a = tid & 127;
+#pragma unroll 4
+          for (int bb = (tid >> 7) * 16; bb < (tid >> 7) * 16 + 16; ++bb) {
+            if (bb < B) {
+              const float4 ma = *reinterpret_cast<const float4*>(m_s + bb * kUnitsPerCta);
+              const float4 mb = *reinterpret_cast<const float4*>(m_s + bb * kUnitsPerCta + 4);
+              float s = ma.x * wq_r[0];
+              s = fmaf(ma.y, wq_r[1], s);
+              s = fmaf(ma.z, wq_r[2], s);
+              s = fmaf(ma.w, wq_r[3], s);
+              s = fmaf(mb.x, wq_r[4], s);
+              s = fmaf(mb.y, wq_r[5], s);
+              s = fmaf(mb.z, wq_r[6], s);
+              s = fmaf(mb.w, wq_r[7], s);
+              P.qpart[((size_t)blockIdx.x * B + bb) * kAtt + a] = s;
+            }
+          }
         }
+        STAMP(7);
+        grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+        if (brow) {
+          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+          P.act1[ai] = r.ig;
+          P.act1[ai + kCell] = r.jg;
+          P.act1[ai + 2 * kCell] = r.fg;
+          P.act1[ai + 3 * kCell] = r.og;
+          P.c1n[(size_t)t * BC + si] = r.c;
+          P.cz1[(size_t)(t + 1) * BC + si] = r.cz;
+          P.hz1[(size_t)(t + 1) * BC + si] = r.hz;
+          P.m1[(size_t)t * BC + si] = r.m;
+        }
+        grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 2);
       }
-      STAMP(7);
-      grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 2);
       STAMP(8);
 
       // ================= phase C: location-sensitive attention, batch row = cluster index ==========
+      float ctx_keep = 0.f;
       if (cid < B) {
         const int bb = cid;
         {  // q slice = sum of the 128 per-CTA partials (fixed order)
@@ -507,18 +508,13 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           qred[warp * 32 + lane] = s;
         }
         ptx::bar_sync(1, kTcCompute);
-        if (tid < 32) {
-          float s = 0.f;
+        float qf = fb_l;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
-          qf_s[tid] = s + fb_l;
-          P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s + fb_l;
-        }
-        ptx::bar_sync(1, kTcCompute);
+        for (int w = 0; w < 8; ++w) qf += qred[w * 32 + lane];
+        if (warp == 0) P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane] = qf;
         STAMP(14);
-        const float qf = qf_s[lane];
         {
-          const int t0 = warp * 16;  // Te <= 128: one 16-position block per warp
+          const int t0 = warp * 16;
           if (t0 < tl) {
             float v[16];
 #pragma unroll
@@ -549,62 +545,53 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
               v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
             }
             v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-            // lane L now holds position index ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)
+            // lane L now holds position ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1) of the block:
+            // push it straight to the four CTAs of the cluster (st.async counts the bytes on their e_bar)
             if ((lane & 1) == 0) {
-              const int p = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-              e_loc[t0 + p] = v[0];
+              const int x = t0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+              if (x < tl) {
+                const uint32_t ep = ptx::smem_u32(e_parts) + (uint32_t)((crank * TeP + x) * 4);
+                const uint32_t eb = ptx::smem_u32(e_bar);
+#pragma unroll
+                for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), v[0], ptx::mapa(eb, dst));
+              }
             }
           }
         }
-        STAMP(15);
-        ptx::bar_sync(1, kTcCompute);
-        {  // all-gather the partial energies across the cluster through DSMEM (st.async counts bytes on e_bar)
-          if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
-          const uint32_t ep = ptx::smem_u32(e_parts) + (uint32_t)(crank * TeP * 4);
-          const uint32_t eb = ptx::smem_u32(e_bar);
-#pragma unroll
-          for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) {
-            const uint32_t remote = ptx::mapa(ep, dst), rbar = ptx::mapa(eb, dst);
-            for (int x = tid; x < tl; x += kTcCompute) ptx::st_async_f32(remote + x * 4, e_loc[x], rbar);
-          }
-        }
+        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
         STAMP(11);
         mbar_wait_warp(e_bar, e_parity);
         e_parity ^= 1u;
         STAMP(12);
-        // masked softmax over positions < tl (score_mask_value = -inf => exactly 0 beyond tl)
+        // masked softmax over positions < tl (score_mask_value = -inf => exactly 0 beyond tl); Te <= 128: every
+        // warp redundantly reduces all positions (4 per lane), no block-level exchange
+        float ev[4];
         float lmax = -INFINITY;
-        for (int x = tid; x < tl; x += kTcCompute) {
-          const float e = ((e_parts[x] + e_parts[TeP + x]) + e_parts[2 * TeP + x]) + e_parts[3 * TeP + x];
-          a_s[x] = e;
-          lmax = fmaxf(lmax, e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = lane + 32 * j;
+          ev[j] = -INFINITY;
+          if (x < tl) ev[j] = ((e_parts[x] + e_parts[TeP + x]) + e_parts[2 * TeP + x]) + e_parts[3 * TeP + x];
+          lmax = fmaxf(lmax, ev[j]);
         }
         lmax = warp_max(lmax);
-        if (lane == 0) bred[warp] = lmax;
-        ptx::bar_sync(1, kTcCompute);
-        float gmax = bred[0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) gmax = fmaxf(gmax, bred[w]);
         float lsum = 0.f;
-        for (int x = tid; x < tl; x += kTcCompute) {
-          const float ex = expf(a_s[x] - gmax);
-          a_s[x] = ex;
-          lsum += ex;
-        }
-        lsum = warp_sum(lsum);
-        if (lane == 0) bred[8 + warp] = lsum;
-        ptx::bar_sync(1, kTcCompute);
-        float gsum = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) gsum += bred[8 + w];
-        for (int x = tid; x < Te; x += kTcCompute) {
-          const float a = (x < tl) ? a_s[x] / gsum : 0.f;
-          a_s[x] = a;
-          const float cn = cum_s[15 + x] + a;
-          cum_s[15 + x] = cn;
-          if (crank == 0) {
-            P.align_tm[((size_t)t * B + bb) * Te + x] = a;
-            P.cum[((size_t)(t + 1) * B + bb) * Te + x] = cn;
+        for (int j = 0; j < 4; ++j) {
+          ev[j] = (lane + 32 * j < tl) ? expf(ev[j] - lmax) : 0.f;
+          lsum += ev[j];
+        }
+        // fixed-order sum (same in every warp and every CTA of the cluster)
+        lsum = warp_sum(lsum);
+        if (warp == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int x = lane + 32 * j;
+            if (x < Te) {
+              const float a = ev[j] / lsum;
+              a_s[x] = a;
+              cum_s[15 + x] += a;
+            }
           }
         }
         ptx::bar_sync(1, kTcCompute);
@@ -621,10 +608,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 #pragma unroll
             for (int j = 0; j < 32; ++j) s = fmaf(a_s[c0 + j], __uint_as_float(v[j]), s);
           }
-          if (dloc < Dh) {
-            ctx_s[half * Dh + dloc] = s;
-            P.ctx[((size_t)(t + 1) * B + bb) * D + crank * Dq + half * Dh + dloc] = s;
-          }
+          if (dloc < Dh) ctx_s[half * Dh + dloc] = s;
+          ctx_keep = s;
         }
         ptx::bar_sync(1, kTcCompute);
         if (tid < Dq / 4) {  // 16-byte rows of the ctx image: (hi|lo, 8-dim chunk)
@@ -637,13 +622,26 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             split_bf16(ctx_s[ch * 8 + j], hi, lo);
             o[j] = hl ? lo : hi;
           }
-          uint8_t* img = P.ximg_ctx + (size_t)par * ctx_img + (size_t)(k >> 6) * kXTileBytes + (size_t)hl * (kXTileBytes / 2) +
-                         (size_t)(bb >> 3) * 1024 + (size_t)((k & 63) >> 3) * 128 + (size_t)(bb & 7) * 16;
+          uint8_t* img = P.ximg_ctx + (size_t)par * ctx_img + (size_t)(k >> 6) * kXTileBytes + (size_t)((k & 63) >> 3) * 128 +
+                         ximg_row_offset(bb, hl);
           *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(o);
         }
       }
       STAMP(9);
-      grid_barrier_compute(P.barrier, bar_target, gridDim.x, ready_seq, 3u * t + 3);
+      grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+      if (cid < B) {  // saved outputs + next step's location features ride in the barrier wait
+        const int bb = cid;
+        if (q4 * 32 < Dh && q4 * 32 + lane < Dh)
+          P.ctx[((size_t)(t + 1) * B + bb) * D + crank * Dq + half * Dh + q4 * 32 + lane] = ctx_keep;
+        if (crank == 0) {
+          for (int x = tid; x < Te; x += kTcCompute) {
+            P.align_tm[((size_t)t * B + bb) * Te + x] = a_s[x];
+            P.cum[((size_t)(t + 1) * B + bb) * Te + x] = cum_s[15 + x];
+          }
+        }
+        location_features();
+      }
+      grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 3);
       STAMP(10);
     }
 #undef STAMP
@@ -653,7 +651,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (warp == 10) ptx::tmem_dealloc(tmem, 512);
+  if (warp == kTcMmaWarp) ptx::tmem_dealloc(tmem, 512);
   cluster.sync();  // no CTA exits while a peer could still address its shared memory
 }
 
@@ -750,10 +748,10 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   prep_wimg_fwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_f), D);
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_ctx, 0, l.ximg_end - l.ximg_ctx, s));
   bool ok = false;
-  int rc = launch_fwd_tc<4>(P, s, tc_fwd_smem(4, io->Te, D).total, &ok);
+  int rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D).total, &ok);
   if (rc) return rc;
   if (!ok) {
-    rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D).total, &ok);
+    rc = launch_fwd_tc<2>(P, s, tc_fwd_smem(2, io->Te, D).total, &ok);
     if (rc) return rc;
   }
   MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_fwd_tc: shared memory does not fit for Te=%d", io->Te);

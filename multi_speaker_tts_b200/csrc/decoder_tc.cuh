@@ -15,7 +15,10 @@
 //
 // Tile image formats (bf16):
 //   W tile  [128 rows x 64 k] : hi at +0 (16 KB), lo at +16 KB
-//   X tile  [ 32 rows x 64 k] : hi at +0 ( 4 KB), lo at + 4 KB      (rows = batch index, zero beyond B)
+//   X tile  [ 64 rows x 64 k] : 8-row groups alternate hi / lo: rows 16g..16g+7 = x_hi of batch 8g..8g+7, rows
+//                               16g+8..16g+15 = x_lo of the same batches (zero beyond B).  With M = 64 the tensor core
+//                               puts accumulator rows 16g..16g+15 on TMEM lanes 32g..32g+15, so the hi and lo partial
+//                               sums of a batch row sit in the same warp's lanes (l, l+8) and combine with one shuffle.
 //   element (row, k) at byte (row/8)*1024 + (k/8)*128 + (row%8)*16 + (k%8)*2
 //   => UMMA descriptor: LBO (K direction) = 128, SBO (M/N direction) = 1024; one K=16 MMA step = +256 B;
 //      hi and lo are adjacent, so a W tile doubles as a 256-row B operand and an X tile as a 64-row A operand.
@@ -24,7 +27,8 @@
 #include "sm100_ptx.cuh"
 
 constexpr int kTcCompute = 256;           // warps 0..7: epilogues + attention
-constexpr int kTcThreads = 352;           // + warp 8 (weight producer), 9 (activation producer), 10 (TMEM alloc + MMA issuer)
+constexpr int kTcThreads = 384;           // + warps 8,9 (weight producers), 10 (activation producer), 11 (TMEM alloc + MMA issuer)
+constexpr int kTcMmaWarp = 11;
 constexpr int kTcKT = 64;                 // K per ring slot
 constexpr int kTcN = 32;                  // MMA N = padded batch
 constexpr uint32_t kWTileBytes = 128 * kTcKT * 2 * 2;  // 32768
@@ -37,6 +41,9 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+
+// byte offset of batch row b's hi (hl = 0) / lo (hl = 1) 16-byte row inside an X tile (add (k/8)*128 for the k chunk)
+__device__ __forceinline__ size_t ximg_row_offset(int b, int hl) { return (size_t)(2 * (b >> 3) + hl) * 1024 + (size_t)(b & 7) * 16; }
 
 __device__ __forceinline__ unsigned ld_volatile_shared(const unsigned* p) {
   unsigned v;
@@ -71,19 +78,21 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
   __syncwarp();
 }
 
-// Grid-wide barrier executed by the compute warps only (named barrier 1); thread 0 then publishes the event
-// number to the activation producer through `ready_seq`.
-__device__ __forceinline__ void grid_barrier_compute(unsigned* counter, unsigned& target, unsigned nblocks,
-                                                     unsigned* ready_seq, unsigned event) {
+// Grid-wide barrier executed by the compute warps only (named barrier 1), split into arrive and wait so that work
+// nobody else depends on (stores of saved activations, the next step's location features) fills the ~1.3 us
+// round trip.  After the wait thread 0 publishes the event number to the activation producer (`ready_seq`).
+__device__ __forceinline__ void grid_arrive_compute(unsigned* counter, unsigned& target, unsigned nblocks) {
   asm volatile("fence.proxy.async.global;" ::: "memory");  // image writes (generic proxy) -> later bulk-copy reads
   ptx::bar_sync(1, kTcCompute);
   if (threadIdx.x == 0) {
     target += nblocks;
-    __threadfence();
-    red_release_gpu_add(counter, 1u);
+    red_release_gpu_add(counter, 1u);  // release is cumulative over the writes ordered by the bar.sync above
+  }
+}
+__device__ __forceinline__ void grid_wait_compute(unsigned* counter, unsigned target, unsigned* ready_seq, unsigned event) {
+  if (threadIdx.x == 0) {
     while (ld_acquire_gpu(counter) < target) {
     }
-    __threadfence();
     st_volatile_shared(ready_seq, event);
   }
   ptx::bar_sync(1, kTcCompute);
