@@ -420,6 +420,8 @@ static int launch_bwd(const DecBwdParams& P, cudaStream_t stream) {
   return MSTTS_OK;
 }
 
+int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s);  // decoder_bwd_tc.cu
+
 static int dec_bwd_persistent(const DecBwdParams& P, cudaStream_t stream) {
   const int B = P.B;
   if (B <= 1) return launch_bwd<1>(P, stream);
@@ -564,9 +566,12 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kCell, NP, F(l.dproj_tm), NP, w->proj_kernel, NP, F(l.dm1_proj), kCell, 0.f))) return rc;
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, D, NP, F(l.dproj_tm), NP, w->proj_kernel + (size_t)kCell * NP, NP,
                              F(l.dctx), D, 0.f))) return rc;
-  // ---- transposed recurrent weights ----
-  transpose_kernel<<<dim3(kGates / 32, (K0r + 31) / 32), dim3(32, 8), 0, s>>>(F(l.W0r), F(l.W0rT), K0r, kGates);
-  transpose_kernel<<<dim3(kGates / 32, 2 * kCell / 32), dim3(32, 8), 0, s>>>(w->cell1_kernel, F(l.W1T), 2 * kCell, kGates);
+  const bool tc = io->mode == MSTTS_MODE_BF16X3;
+  // ---- transposed recurrent weights (the tcgen05 kernel reads the reference layout directly) ----
+  if (!tc) {
+    transpose_kernel<<<dim3(kGates / 32, (K0r + 31) / 32), dim3(32, 8), 0, s>>>(F(l.W0r), F(l.W0rT), K0r, kGates);
+    transpose_kernel<<<dim3(kGates / 32, 2 * kCell / 32), dim3(32, 8), 0, s>>>(w->cell1_kernel, F(l.W1T), 2 * kCell, kGates);
+  }
   MSTTS_CUDA(cudaMemsetAsync(ws + l.dF, 0, (kConvK * kAtt + 2 * kAtt) * sizeof(float), s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.dkeys, 0, (size_t)B * Te * kAtt * sizeof(float), s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.barrier, 0, 64, s));
@@ -582,7 +587,7 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   P.dctx = F(l.dctx); P.dG0 = F(l.dG0); P.dG1 = F(l.dG1); P.dq = F(l.dq); P.dkeys = F(l.dkeys);
   P.dF = F(l.dF); P.dsw = F(l.dsw); P.dcum = F(l.dcum);
   P.barrier = (unsigned*)(ws + l.barrier);
-  if ((rc = dec_bwd_persistent(P, s))) return rc;
+  if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
 
   // ---- weight gradients: batched GEMMs over all steps ----
   // cell 1: rows [m0 | h1_prev]

@@ -693,7 +693,7 @@ __global__ void prep_wimg_fwd_kernel(const float* __restrict__ K0, const float* 
 }
 
 // ======================================== host side ================================================
-bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 128 && D % 256 == 0 && D <= 1024; }
+bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 128 && D % 256 == 0 && D <= 768; }
 
 template <int NS>
 static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t smem, bool* ok) {
@@ -728,7 +728,7 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   auto F = [&](size_t off) { return (float*)(ws + off); };
   const int D = io->D;
   MSTTS_REQUIRE(dec_tc_supported(io->B, io->Te, D), MSTTS_E_UNSUPPORTED,
-                "decoder bf16x3 mode needs B<=32, Te<=128, D%%256==0 (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te, D);
+                "decoder bf16x3 mode needs B<=32, Te<=128, D in {256,512,768} (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te, D);
   DecFwdTcParams P;
   memset(&P, 0, sizeof(P));
   P.B = io->B; P.Te = io->Te; P.T = io->n_steps; P.D = D; P.training = io->is_training; P.n0 = D / 256;

@@ -47,6 +47,11 @@ struct DecLayout {
   size_t dcum;      // [B,Te]
   size_t dpre;      // [T,B,256]
   size_t dpre_h;    // [T,B,256]
+  // ---- bf16x3 reverse kernel only ----
+  size_t wimg_b;                         // [128 CTAs][16 tiles][32 KB] reverse weight stream
+  size_t ximg_g1, ximg_g0, ximg_g_end;   // [64 k-tiles][8 KB] operand images of dG1_t / dG0_t
+  size_t pm0, ph1, ph0, pctx;            // K-quarter partials [4][B][1024] / [4][B][D]
+  size_t dbg_b;                          // [T][32] int64 phase stamps of the reverse kernel
   size_t total;
 };
 
@@ -118,6 +123,23 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dcum = take((size_t)B * Te);
   l.dpre = take(TB * kPrenet);
   l.dpre_h = take(TB * kPrenet);
+  l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = off;
+  if (mode == MSTTS_MODE_BF16X3) {
+    auto take_bytes = [&](size_t nbytes) {
+      size_t o = off;
+      off += align_up(nbytes, 1024);
+      return o;
+    };
+    l.wimg_b = take_bytes((size_t)kDecGrid * 16 * 32768);
+    l.ximg_g1 = take_bytes((size_t)(kGates / 64) * 8192);
+    l.ximg_g0 = take_bytes((size_t)(kGates / 64) * 8192);
+    l.ximg_g_end = off;
+    l.pm0 = take((size_t)4 * B * kCell);
+    l.ph1 = take((size_t)4 * B * kCell);
+    l.ph0 = take((size_t)4 * B * kCell);
+    l.pctx = take((size_t)4 * B * D);
+    l.dbg_b = take_bytes((size_t)T * 32 * 8);
+  }
   l.total = off;
   return l;
 }

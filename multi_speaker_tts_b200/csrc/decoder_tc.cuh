@@ -71,6 +71,62 @@ __device__ __forceinline__ void cluster_compute_sync(uint64_t* bar, uint32_t& pa
   parity ^= 1u;
 }
 
+// gate backward of one (batch, unit): ZoneoutLSTMCell.py:237-260 differentiated (same math as decoder_bwd.cu)
+struct CellGradTc {
+  float di, dj, df, dop, dc_prev, dh_prev;
+};
+__device__ __forceinline__ CellGradTc cell_backward_tc(float dm_direct, float dhz, float dcz, float ig, float jg, float fg,
+                                                       float og, float cn, float cp, float mc, float mh) {
+  CellGradTc r;
+  const float dm = dm_direct + kZoneKeep * mh * dhz;
+  r.dh_prev = dhz * (1.f - kZoneKeep * mh);
+  float dc = kZoneKeep * mc * dcz;
+  r.dc_prev = dcz * (1.f - kZoneKeep * mc);
+  const float tc = tanhf(cn);
+  const float d_o = dm * tc;
+  dc += dm * og * (1.f - tc * tc);
+  const float d_f = dc * cp;
+  r.dc_prev += dc * fg;
+  const float d_i = dc * jg, d_j = dc * ig;
+  r.di = d_i * ig * (1.f - ig);
+  r.dj = d_j * (1.f - jg * jg);
+  r.df = d_f * fg * (1.f - fg);
+  r.dop = d_o * og * (1.f - og);
+  return r;
+}
+
+// sum over the 32 lanes of 16 independent per-lane values with a transposing butterfly (31 shuffles instead of 80);
+// on return lane L (even lanes only) holds the total of value index ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const float send = (lane & 16) ? v[p] : v[p + 8];
+    const float keep = (lane & 16) ? v[p + 8] : v[p];
+    v[p] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float send = (lane & 8) ? v[p] : v[p + 4];
+    const float keep = (lane & 8) ? v[p + 4] : v[p];
+    v[p] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float send = (lane & 4) ? v[p] : v[p + 2];
+    const float keep = (lane & 4) ? v[p + 2] : v[p];
+    v[p] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = (lane & 2) ? v[0] : v[1];
+    const float keep = (lane & 2) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int warp_sum16_index(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 // One lane per warp polls the mbarrier, the rest of the warp parks in __syncwarp: 256 threads spinning on
 // try_wait would compete with the producer / MMA threads for the shared-memory pipeline.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
