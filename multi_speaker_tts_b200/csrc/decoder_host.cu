@@ -181,7 +181,15 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   rc = gemm_rowmajor(s, (int)TB, kPrenet, kPrenet, F(l.pre_h), kPrenet, w->prenet1_kernel, kPrenet, F(l.pre), kPrenet, 0.f);
   if (rc) return rc;
   prenet_act_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.pre), w->prenet1_bias, io->prenet_mask, 1, B, TB * kPrenet);
-  rc = gemm_rowmajor(s, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
+  if (io->mode == MSTTS_MODE_BF16X3) {  // 54 GFLOP at config 2: tensor cores, bf16x3
+    const Bf16Pair a = {(__nv_bfloat16*)(ws + l.sp_left_hi), (__nv_bfloat16*)(ws + l.sp_left_lo)};
+    const Bf16Pair b = {(__nv_bfloat16*)(ws + l.sp_w_hi), (__nv_bfloat16*)(ws + l.sp_w_lo)};
+    if ((rc = split_bf16_matrix(s, F(l.pre), TB, kPrenet, kPrenet, a))) return rc;
+    if ((rc = split_bf16_matrix(s, w->cell0_kernel, kPrenet, kGates, kGates, b))) return rc;
+    rc = gemm_rowmajor_x3(s, false, false, (int)TB, kGates, kPrenet, a, kPrenet, b, kGates, F(l.g0pre), kGates, 0.f);
+  } else {
+    rc = gemm_rowmajor(s, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
+  }
   if (rc) return rc;
   // ---- zero initial state (AttentionWrapper.zero_state, Modules.py:112) and the barrier counter ----
   const size_t BC = (size_t)B * kCell * sizeof(float);

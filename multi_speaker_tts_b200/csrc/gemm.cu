@@ -67,3 +67,56 @@ int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N
   }
   return MSTTS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ src, size_t rows, size_t cols, size_t ld, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo) {
+  const size_t n = rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols, c = i - r * cols;
+    const float x = src[r * ld + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+int split_bf16_matrix(cudaStream_t s, const float* src, size_t rows, size_t cols, size_t ld, Bf16Pair dst) {
+  const size_t n = rows * cols;
+  if (n == 0) return MSTTS_OK;
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  split_bf16_kernel<<<(int)g, 256, 0, s>>>(src, rows, cols, ld, dst.hi, dst.lo);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+int gemm_rowmajor_x3(cudaStream_t s, bool transA, bool transB, int M, int N, int K, Bf16Pair A, int lda, Bf16Pair B, int ldb,
+                     float* C, int ldc, float beta) {
+  int rc;
+  cublasHandle_t h = get_handle(&rc);
+  if (!h) return rc;
+  cublasStatus_t st = cublasSetStream(h, s);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
+    return MSTTS_E_CUDA;
+  }
+  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);  // the handle is pedantic for the fp32 path
+  const float one = 1.f;
+  const cublasOperation_t opB = transB ? CUBLAS_OP_T : CUBLAS_OP_N, opA = transA ? CUBLAS_OP_T : CUBLAS_OP_N;
+  // small terms first, the dominant hi.hi product last
+  const __nv_bfloat16* a_ops[3] = {A.lo, A.hi, A.hi};
+  const __nv_bfloat16* b_ops[3] = {B.hi, B.lo, B.hi};
+  for (int i = 0; i < 3; ++i) {
+    const float bt = i == 0 ? beta : 1.f;
+    st = cublasGemmEx(h, opB, opA, N, M, K, &one, b_ops[i], CUDA_R_16BF, ldb, a_ops[i], CUDA_R_16BF, lda, &bt, C, CUDA_R_32F, ldc,
+                      CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    if (st != CUBLAS_STATUS_SUCCESS) {
+      cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+      mstts_set_error("gemm: cublasGemmEx bf16 (M=%d,N=%d,K=%d) failed (%d)", M, N, K, (int)st);
+      return MSTTS_E_CUDA;
+    }
+  }
+  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+  return MSTTS_OK;
+}

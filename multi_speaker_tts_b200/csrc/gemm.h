@@ -18,3 +18,15 @@ static inline int gemm_rowmajor(cudaStream_t s, int M, int N, int K, const float
 int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
                           long long sA, const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta,
                           int batch);
+
+// ---- bf16x3 library GEMMs (same numerics contract as the recurrent tcgen05 kernels) -------------------------
+// An fp32 matrix is split once into bf16 hi + bf16 lo; C = A_hi.B_hi + A_hi.B_lo + A_lo.B_hi on the tensor cores
+// (three cublasGemmEx calls, fp32 accumulation), ~16 mantissa bits per operand.
+struct Bf16Pair {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+};
+// dst.{hi,lo}[r*cols + c] = split(src[r*ld + c])
+int split_bf16_matrix(cudaStream_t s, const float* src, size_t rows, size_t cols, size_t ld, Bf16Pair dst);
+int gemm_rowmajor_x3(cudaStream_t s, bool transA, bool transB, int M, int N, int K, Bf16Pair A, int lda, Bf16Pair B, int ldb,
+                     float* C, int ldc, float beta);

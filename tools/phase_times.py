@@ -24,10 +24,19 @@ torch.cuda.synchronize()
 off = _lib.lib().mstts_decoder_ws_offset(b"dbg" if which == "fwd" else b"dbg_b", B, Te, L, 768, T, 1)
 stamps = ws[off:off + T * 32 * 8].view(torch.int64).view(T, 32).cpu().double()
 mhz = 1.0
+names_b = ["start", "attn bwd done", "bar1", "B'e done", "bar2", "drain B'g done", "bar3", "A'e done", "bar4", "drain A'g done", "bar5"]
 names_f = ["start", "J0 done", "reduceA done", "epiA done", "barA done", "J1 done", "reduceB done", "epiB done", "barB done",
            "attn done", "barC done", "e pushed", "e gathered", "softmax done", "q ready", "energies done"]
 order_f = [0, 1, 2, 3, 4, 5, 6, 7, 8, 14, 15, 11, 12, 13, 9, 10]
 sel = stamps[T // 4: 3 * T // 4]
+if which == "bwd":
+    prev = sel[:, 0]
+    print("reverse kernel, cycles per step (mean over the middle half of the steps), CTA 0:")
+    for k in range(11):
+        print("  %-16s +%8.0f" % (names_b[k], (sel[:, k] - prev).mean().item()))
+        prev = sel[:, k]
+    print("  total/step     %8.0f cycles" % (sel[:, 10] - sel[:, 0]).mean().item())
+    sys.exit(0)
 prev = sel[:, 0]
 print("cycles per step (mean over the middle half of the steps), CTA 0:")
 for k in order_f:
