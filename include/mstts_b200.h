@@ -150,6 +150,35 @@ int mstts_fill_mask(uint8_t* out, size_t n, float keep_prob, uint64_t seed, void
 int mstts_adam_tf(float* p, float* m, float* v, const float* g, size_t n, float lr_t, float b1, float b2,
                   float eps, float grad_scale, float l2, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * WaveGlow affine-coupling flows.
+ * Replaces: WaveGlow.Modules.Glow_Train / Glow_Inference (WaveGlow/Modules.py:329-371) = 12 x Affine_Coupling_Layer
+ * (:210-250) = Invertible 1x1 (WaveGlow/Inv1x1.py:9-32) + WaveNet (:252-327) with weight-normalised convs (:9-33).
+ * Raw variables in TF layouts: weight-normed conv = (g [out], v [k,in,out], b [out]); end conv plain [1,512,c]; c = 8,6,4.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct MsttsWaveGlowWeights {
+  const float* inv_w[12];     /* [c,c]; direction 1 expects the INVERSE kernel here */
+  const float* start_g[12];   const float* start_v[12];   const float* start_b[12];     /* audio_initial_conv [1,c/2,512] */
+  const float* in_g[12][8];   const float* in_v[12][8];   const float* in_b[12][8];     /* audio_in_i  [3,512,1024] */
+  const float* cond_g[12][8]; const float* cond_v[12][8]; const float* cond_b[12][8];   /* mel_cond_i  [1,640,1024] */
+  const float* res_g[12][8];  const float* res_v[12][8];  const float* res_b[12][8];    /* res_i [1,512,1024] (last: 512) */
+  const float* end_w[12];     const float* end_b[12];                                   /* conv1d [1,512,c] (not weight-normed) */
+} MsttsWaveGlowWeights;
+
+size_t mstts_waveglow_workspace_bytes(int N, int T);
+/* direction 0 (Glow_Train): audio_in [N,T,8] -> out z [N,T,8] (early outputs first, Modules.py:348-350),
+ *   sums[0] = sum over flows of sum(log_s), sums[1] = sum(z^2)  (device doubles; log-det of the 1x1 kernels is host math).
+ * direction 1 (Glow_Inference): audio_in = z [N,T,4], early_noise[0] / [1] = the [N,T,2] tensors concatenated after
+ *   undoing flows 8 / 4 (already scaled by sigma) -> out [N,T,8].
+ * mel_nt640: up-sampled, cropped and folded conditioning [N,T,640] (Restructure_*_Data, Modules.py:135-195). */
+int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
+                         int direction, const float* const* early_noise, float* out, double* sums, void* ws,
+                         size_t ws_bytes, void* stream);
+/* Upsample_Mel (Modules.py:198-208): ConvTranspose1d 80->80, k=1024, stride 256, VALID; kernel [1024, out, in];
+ * writes the first `keep` of the (Tm-1)*256+1024 output frames: out [N, keep, 80]. */
+int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias, int N, int Tm, int keep, float* out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

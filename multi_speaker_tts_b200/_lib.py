@@ -49,6 +49,12 @@ class MsttsDecoderGrads(C.Structure):
     _fields_ = [("d_linear", _fp), ("d_stop", _fp), ("d_memory", _fp)]
 
 
+class MsttsWaveGlowWeights(C.Structure):
+    _fields_ = ([("inv_w", _fp * 12), ("start_g", _fp * 12), ("start_v", _fp * 12), ("start_b", _fp * 12)] +
+                [(n + "_" + k, (_fp * 8) * 12) for n in ("in", "cond", "res") for k in ("g", "v", "b")] +
+                [("end_w", _fp * 12), ("end_b", _fp * 12)])
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mstts_version": (C.c_int, []),
@@ -63,6 +69,10 @@ EXPORTS = {
                                     C.POINTER(MsttsDecoderGrads), C.POINTER(MsttsDecoderWeightGrads),
                                     _fp, C.c_size_t, _fp]),
     "mstts_decoder_loss": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
+    "mstts_waveglow_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mstts_waveglow_flows": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp,
+                                       C.c_size_t, _fp]),
+    "mstts_upsample_mel": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     "mstts_fill_mask": (C.c_int, [_fp, C.c_size_t, C.c_float, C.c_uint64, _fp]),
     "mstts_adam_tf": (C.c_int, [_fp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _fp]),

@@ -1,0 +1,466 @@
+// WaveGlow affine-coupling flows (WaveGlow/Modules.py:210-371, WaveGlow/Inv1x1.py:9-32), forward (training direction,
+// with the log-likelihood sums) and reverse (synthesis direction).
+//
+// Round-1 structure: the dense contractions of the WN stack (dilated k=3 conv 512->1024, mel conditioning 640->1024,
+// res/skip 512->1024) run as bf16x3 tensor-core GEMMs through cuBLAS (gemm.h: hi/lo split operands, fp32 accumulation,
+// same numerics contract as the decoder kernels); everything around them is hand-written and fused:
+//   wn_prepare_kernel   weight norm g*v/sqrt(max(sum v^2,1e-5)) -> bf16 hi/lo weight operands
+//   flow_pre_kernel     invertible 1x1 (or plain split in reverse) + the K<=4 start conv -> bf16 hi/lo activations
+//   gate_kernel         bias + tanh * sigmoid -> fp32 + bf16 hi/lo
+//   resskip_kernel      residual onto the GATED activation (reference quirk) + skip accumulation
+//   flow_post_kernel    512->c end conv + affine transform (clamp log_s at 8 in forward only) + sum(log_s), or the
+//                       inverse transform followed by the inverse 1x1
+// Activations live in a time-padded layout [N][T+2P][C], P = 128 zero rows on both sides of every utterance, so the
+// dilated conv is three GEMMs over row-shifted views of one buffer (no im2col, no per-utterance launches).
+// A single fused tcgen05 kernel per flow is the planned replacement ("what comes next").
+#include "common.cuh"
+#include "gemm.h"
+
+constexpr int kWnCh = 512, kWnLayers = 8, kWnMel = 640, kWgPad = 128, kWgFlows = 12;
+
+static inline int ew_grid(size_t n, int per = 256) {
+  size_t g = (n + per - 1) / per;
+  const size_t cap = 148 * 8;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+// ---- weight norm + split: v [k*in, out] (out fastest), g [out] (NULL: plain kernel) -> hi/lo [k*in, out] ----
+__global__ void wn_prepare_kernel(const float* __restrict__ v, const float* __restrict__ g, int kin, int out,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ eff) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out) return;
+  float scale = 1.f;
+  if (g) {
+    float ss = 0.f;
+    for (int r = 0; r < kin; ++r) {
+      const float x = v[(size_t)r * out + o];
+      ss = fmaf(x, x, ss);
+    }
+    scale = g[o] * rsqrtf(fmaxf(ss, 1e-5f));
+  }
+  for (int r = 0; r < kin; ++r) {
+    const float w = v[(size_t)r * out + o] * scale;
+    if (eff) eff[(size_t)r * out + o] = w;
+    if (hi) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(w);
+      hi[(size_t)r * out + o] = h;
+      lo[(size_t)r * out + o] = __float2bfloat16_rn(w - __bfloat162float(h));
+    }
+  }
+}
+
+// ---- ConvTranspose1d 80->80, k=1024, stride 256, VALID (WaveGlow/Modules.py:198-208) ----
+// out[n, p, co] = bias[co] + sum_{t: 0 <= p-256t < 1024} sum_ci mel[n,t,ci] * K[p-256t, co, ci]
+__global__ void upsample_mel_kernel(const float* __restrict__ mel, const float* __restrict__ K, const float* __restrict__ bias,
+                                    float* __restrict__ out, int N, int Tm, int Lout, int Lkeep) {
+  const size_t n_out = (size_t)N * Lkeep * 80;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % 80);
+    const size_t np = i / 80;
+    const int p = (int)(np % Lkeep), n = (int)(np / Lkeep);
+    float s = bias[co];
+    const int t_hi = min(Tm - 1, p / 256), t_lo = max(0, (p - 1023 + 255) / 256);
+    for (int t = t_lo; t <= t_hi; ++t) {
+      const int k = p - 256 * t;
+      const float* kr = K + ((size_t)k * 80 + co) * 80;
+      const float* mr = mel + ((size_t)n * Tm + t) * 80;
+#pragma unroll 8
+      for (int ci = 0; ci < 80; ++ci) s = fmaf(mr[ci], kr[ci], s);
+    }
+    out[i] = s;
+  }
+  (void)Lout;
+}
+
+// mel [N,T,640] fp32 -> padded hi/lo [N][Tp][640]
+__global__ void pad_split_kernel(const float* __restrict__ src, int N, int T, int C, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo) {
+  const int Tp = T + 2 * kWgPad;
+  const size_t n = (size_t)N * T * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t nt = i / C;
+    const int t = (int)(nt % T), b = (int)(nt / T);
+    const float x = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const size_t o = ((size_t)b * Tp + kWgPad + t) * C + c;
+    hi[o] = h;
+    lo[o] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+// ---- flow prologue: y = x W (forward) or y = x (reverse); start conv h = y[:half] Ws + bs -> hi/lo padded ----
+// x [N,T,c] -> y [N,T,c] fp32 (coupling input kept for the epilogue); Wm [c,c] row-major (y_j = sum_i x_i Wm[i][j])
+__global__ void flow_pre_kernel(const float* __restrict__ x, const float* __restrict__ Wm, const float* __restrict__ Ws,
+                                const float* __restrict__ bs, float* __restrict__ y, __nv_bfloat16* __restrict__ h_hi,
+                                __nv_bfloat16* __restrict__ h_lo, int N, int T, int c, int apply_w) {
+  __shared__ float w_s[64], ws_s[4 * kWnCh], bs_s[kWnCh];
+  const int half = c / 2, Tp = T + 2 * kWgPad;
+  for (int i = threadIdx.x; i < c * c; i += blockDim.x) w_s[i] = Wm[i];
+  for (int i = threadIdx.x; i < half * kWnCh; i += blockDim.x) ws_s[i] = Ws[i];
+  for (int i = threadIdx.x; i < kWnCh; i += blockDim.x) bs_s[i] = bs[i];
+  __syncthreads();
+  const size_t rows = (size_t)N * T;
+  // one warp per row: lanes 0..c-1 compute y, then all lanes sweep the 512 channels
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (size_t r = (size_t)blockIdx.x * wpb + warp; r < rows; r += (size_t)gridDim.x * wpb) {
+    float yv = 0.f;
+    if (lane < c) {
+      if (apply_w) {
+        for (int i = 0; i < c; ++i) yv = fmaf(x[r * c + i], w_s[i * c + lane], yv);
+      } else {
+        yv = x[r * c + lane];
+      }
+      y[r * c + lane] = yv;
+    }
+    float x0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x0[j] = __shfl_sync(0xffffffffu, yv, j);
+    const int b = (int)(r / T), t = (int)(r % T);
+    const size_t o = ((size_t)b * Tp + kWgPad + t) * kWnCh;
+    for (int ch = lane; ch < kWnCh; ch += 32) {
+      float s = bs_s[ch];
+      for (int j = 0; j < half; ++j) s = fmaf(x0[j], ws_s[j * kWnCh + ch], s);
+      const __nv_bfloat16 h = __float2bfloat16_rn(s);
+      h_hi[o + ch] = h;
+      h_lo[o + ch] = __float2bfloat16_rn(s - __bfloat162float(h));
+    }
+  }
+}
+
+// ---- gate: g = tanh(a[:, :512] + b1[:512] + b2[:512]) * sigmoid(a[:, 512:] + ...) over the valid rows ----
+__global__ void gate_kernel(const float* __restrict__ a, const float* __restrict__ b_in, const float* __restrict__ b_cond,
+                            float* __restrict__ g, __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int N, int T) {
+  const int Tp = T + 2 * kWgPad;
+  const size_t n = (size_t)N * T * kWnCh;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % kWnCh);
+    const size_t nt = i / kWnCh;
+    const size_t row = (nt / T) * Tp + kWgPad + (nt % T);
+    const float at = a[row * 2 * kWnCh + ch] + b_in[ch] + b_cond[ch];
+    const float as = a[row * 2 * kWnCh + kWnCh + ch] + b_in[kWnCh + ch] + b_cond[kWnCh + ch];
+    const float v = tanhf(at) * (1.f / (1.f + expf(-as)));
+    g[row * kWnCh + ch] = v;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    g_hi[row * kWnCh + ch] = h;
+    g_lo[row * kWnCh + ch] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ---- residual + skip: h = g + rs[:, :512] + b[:512] (-> hi/lo), skip (+)= rs[:, 512:] + b[512:]; last layer: skip += rs + b ----
+__global__ void resskip_kernel(const float* __restrict__ rs, const float* __restrict__ b_res, const float* __restrict__ g,
+                               __nv_bfloat16* __restrict__ h_hi, __nv_bfloat16* __restrict__ h_lo, float* __restrict__ skip, int N,
+                               int T, int first, int lastl) {
+  const int Tp = T + 2 * kWgPad;
+  const int ldr = lastl ? kWnCh : 2 * kWnCh;
+  const size_t n = (size_t)N * T * kWnCh;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % kWnCh);
+    const size_t nt = i / kWnCh;
+    const size_t row = (nt / T) * Tp + kWgPad + (nt % T);
+    float sk;
+    if (!lastl) {
+      const float hv = g[row * kWnCh + ch] + (rs[row * ldr + ch] + b_res[ch]);
+      const __nv_bfloat16 h = __float2bfloat16_rn(hv);
+      h_hi[row * kWnCh + ch] = h;
+      h_lo[row * kWnCh + ch] = __float2bfloat16_rn(hv - __bfloat162float(h));
+      sk = rs[row * ldr + kWnCh + ch] + b_res[kWnCh + ch];
+    } else {
+      sk = rs[row * ldr + ch] + b_res[ch];
+    }
+    skip[row * kWnCh + ch] = first ? sk : skip[row * kWnCh + ch] + sk;
+  }
+}
+
+// ---- flow epilogue: o = skip We + be (512 -> c); forward: x1' = exp(min(log_s, 8)) x1 + b, sums += log_s;
+//      reverse: x1 = (x1' - b) / exp(log_s), then x = [x0, x1] Winv.   One warp per row. ----
+__global__ void flow_post_kernel(const float* __restrict__ skip, const float* __restrict__ We, const float* __restrict__ be,
+                                 const float* __restrict__ y, const float* __restrict__ Winv, float* __restrict__ xout,
+                                 double* __restrict__ partial, int N, int T, int c, int reverse) {
+  __shared__ float we_s[kWnCh * 8], w_s[64];
+  __shared__ double red[8];
+  const int half = c / 2, Tp = T + 2 * kWgPad;
+  for (int i = threadIdx.x; i < kWnCh * c; i += blockDim.x) we_s[i] = We[i];
+  if (reverse)
+    for (int i = threadIdx.x; i < c * c; i += blockDim.x) w_s[i] = Winv[i];
+  __syncthreads();
+  const size_t rows = (size_t)N * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  double local = 0.0;
+  for (size_t r = (size_t)blockIdx.x * wpb + warp; r < rows; r += (size_t)gridDim.x * wpb) {
+    const size_t prow = (r / T) * Tp + kWgPad + (r % T);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < kWnCh; k += 32) {
+      const float sv = skip[prow * kWnCh + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < c) acc[j] = fmaf(sv, we_s[k * c + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+    // lane j < half owns coupling channel j: log_s = o[j], b = o[half + j]
+    float ls = 0.f, bb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j == lane) ls = acc[j] + be[j];
+      if (j == lane + half && j < c) bb = acc[j] + be[j];
+    }
+    float outv = 0.f;
+    if (lane < half) {
+      const float x1 = y[r * c + half + lane];
+      if (!reverse) {
+        ls = fminf(ls, 8.0f);
+        outv = expf(ls) * x1 + bb;
+        local += (double)ls;
+      } else {
+        outv = (x1 - bb) / expf(ls);
+      }
+    }
+    if (!reverse) {
+      if (lane < half) {
+        xout[r * c + lane] = y[r * c + lane];
+        xout[r * c + half + lane] = outv;
+      }
+    } else {
+      // z = [x0, x1]; x = z Winv
+      float z = 0.f;
+      if (lane < half) z = y[r * c + lane];
+      const float x1v = __shfl_sync(0xffffffffu, outv, (lane >= half && lane < c) ? lane - half : 0);
+      if (lane >= half && lane < c) z = x1v;
+      float s = 0.f;
+      for (int i = 0; i < c; ++i) {
+        const float zi = __shfl_sync(0xffffffffu, z, i);
+        if (lane < c) s = fmaf(zi, w_s[i * c + lane], s);
+      }
+      if (lane < c) xout[r * c + lane] = s;
+    }
+  }
+  if (!reverse) {
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0) red[warp] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w2 = 0; w2 < wpb; ++w2) s += red[w2];
+      partial[blockIdx.x] = s;
+    }
+  }
+}
+
+// fixed-order final sums: out[0] += sum(partial[0..n)) ; optionally out[1] = sum z^2 handled by sumsq_kernel
+__global__ void finish_sum_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    out[0] += s;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ z, size_t n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double local = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) local += (double)z[i] * (double)z[i];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) s += red[w2];
+    partial[blockIdx.x] = s;
+  }
+}
+
+// early-output bookkeeping: dst[n,t, dc0 .. dc0+nc) = src[n,t, sc0 .. sc0+nc)
+__global__ void copy_channels_kernel(const float* __restrict__ src, int sc, int sc0, float* __restrict__ dst, int dc, int dc0, int nc,
+                                     size_t rows) {
+  const size_t n = rows * nc;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / nc;
+    const int j = (int)(i % nc);
+    dst[r * dc + dc0 + j] = src[r * sc + sc0 + j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct WgLayout {
+  size_t w_hi, w_lo;        // per flow: in[8] (3*512*1024) | cond[8] (640*1024) | res[7] (512*1024) + res[7] (512*512)
+  size_t start_eff;         // [12][4*512] effective start kernels (fp32)
+  size_t mel_up;            // [N, S, 80] = [N, T, 640]
+  size_t mel_hi, mel_lo;    // padded [N][Tp][640]
+  size_t h_hi, h_lo, g_hi, g_lo;  // padded [N][Tp][512]
+  size_t g, skip;           // padded fp32 [N][Tp][512]
+  size_t a;                 // padded fp32 [N][Tp][1024]
+  size_t y, xa, xb;         // [N,T,8]
+  size_t partial;           // doubles
+  size_t total;
+};
+constexpr size_t kWgFlowW = (size_t)kWnLayers * (3 * kWnCh * 2 * kWnCh + kWnMel * 2 * kWnCh) + (size_t)(kWnLayers - 1) * kWnCh * 2 * kWnCh +
+                            (size_t)kWnCh * kWnCh;
+
+static WgLayout wg_layout(int N, int T) {
+  WgLayout l;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  const size_t rows_p = (size_t)N * (T + 2 * kWgPad);
+  l.w_hi = take(kWgFlowW * kWgFlows * 2);
+  l.w_lo = take(kWgFlowW * kWgFlows * 2);
+  l.start_eff = take((size_t)kWgFlows * 4 * kWnCh * 4);
+  l.mel_up = take((size_t)N * T * kWnMel * 4);
+  l.mel_hi = take(rows_p * kWnMel * 2);
+  l.mel_lo = take(rows_p * kWnMel * 2);
+  l.h_hi = take(rows_p * kWnCh * 2);
+  l.h_lo = take(rows_p * kWnCh * 2);
+  l.g_hi = take(rows_p * kWnCh * 2);
+  l.g_lo = take(rows_p * kWnCh * 2);
+  l.g = take(rows_p * kWnCh * 4);
+  l.skip = take(rows_p * kWnCh * 4);
+  l.a = take(rows_p * 2 * kWnCh * 4);
+  l.y = take((size_t)N * T * 8 * 4);
+  l.xa = take((size_t)N * T * 8 * 4);
+  l.xb = take((size_t)N * T * 8 * 4);
+  l.partial = take(4096 * 8);
+  l.total = off;
+  return l;
+}
+
+extern "C" size_t mstts_waveglow_workspace_bytes(int N, int T) {
+  if (N <= 0 || T <= 0) return 0;
+  return wg_layout(N, T).total;
+}
+
+static inline int flow_c(int f) { return 8 - 2 * (f / 4); }
+
+// Runs all 12 flows.  direction 0: training direction x -> z with sums[0] = sum(log_s), sums[1] = sum(z^2);
+// direction 1: synthesis z -> x (early_noise[2]: the two [N,T,2] noise tensors injected before flows 7 and 3 are run,
+// i.e. after undoing flows 8 and 4; inv_w then holds the INVERSE 1x1 kernels).
+extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
+                                    int direction, const float* const* early_noise, float* out, double* sums, void* ws_, size_t ws_bytes,
+                                    void* stream_) {
+  MSTTS_REQUIRE(w && audio_in && mel_nt640 && out && ws_, MSTTS_E_INVALID, "waveglow: null argument");
+  MSTTS_REQUIRE(N >= 1 && T >= 1, MSTTS_E_INVALID, "waveglow: N=%d T=%d", N, T);
+  MSTTS_REQUIRE(direction == 0 || (early_noise && early_noise[0] && early_noise[1]), MSTTS_E_INVALID, "waveglow: reverse needs early noise");
+  MSTTS_REQUIRE(direction == 1 || sums, MSTTS_E_INVALID, "waveglow: forward needs the sums output");
+  const WgLayout l = wg_layout(N, T);
+  MSTTS_REQUIRE(ws_bytes >= l.total, MSTTS_E_WORKSPACE, "waveglow: workspace %zu < %zu", ws_bytes, l.total);
+  cudaStream_t s = (cudaStream_t)stream_;
+  char* ws = (char*)ws_;
+  const int Tp = T + 2 * kWgPad;
+  const size_t rows = (size_t)N * T, rows_p = (size_t)N * Tp;
+  auto BF = [&](size_t off) { return (__nv_bfloat16*)(ws + off); };
+  auto FP = [&](size_t off) { return (float*)(ws + off); };
+  int rc;
+
+  // ---- effective weights (weight norm is part of the per-step graph in the reference, Modules.py:31-33) ----
+  for (int f = 0; f < kWgFlows; ++f) {
+    size_t wo = (size_t)f * kWgFlowW;
+    const int half = flow_c(f) / 2;
+    wn_prepare_kernel<<<(kWnCh + 127) / 128, 128, 0, s>>>(w->start_v[f], w->start_g[f], half, kWnCh, nullptr, nullptr,
+                                                          FP(l.start_eff) + (size_t)f * 4 * kWnCh);
+    for (int i = 0; i < kWnLayers; ++i) {
+      wn_prepare_kernel<<<2 * kWnCh / 128, 128, 0, s>>>(w->in_v[f][i], w->in_g[f][i], 3 * kWnCh, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo,
+                                                        nullptr);
+      wo += (size_t)3 * kWnCh * 2 * kWnCh;
+      wn_prepare_kernel<<<2 * kWnCh / 128, 128, 0, s>>>(w->cond_v[f][i], w->cond_g[f][i], kWnMel, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo,
+                                                        nullptr);
+      wo += (size_t)kWnMel * 2 * kWnCh;
+      const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
+      wn_prepare_kernel<<<(rout + 127) / 128, 128, 0, s>>>(w->res_v[f][i], w->res_g[f][i], kWnCh, rout, BF(l.w_hi) + wo, BF(l.w_lo) + wo,
+                                                           nullptr);
+      wo += (size_t)kWnCh * rout;
+    }
+  }
+  // ---- conditioning operand + zeroed pads ----
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.mel_hi, 0, rows_p * kWnMel * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.mel_lo, 0, rows_p * kWnMel * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.h_hi, 0, rows_p * kWnCh * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.h_lo, 0, rows_p * kWnCh * 2, s));
+  pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel_hi), BF(l.mel_lo));
+  if (direction == 0) MSTTS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
+
+  const int M = (int)(rows_p - 2 * kWgPad);  // GEMM rows: everything except the outermost pads
+  const float* xcur = audio_in;              // [N,T,c] of the current flow
+  float* xbuf[2] = {FP(l.xa), FP(l.xb)};
+  int xsel = 0;
+  int zc0 = 0;  // forward: next output channel of z
+  const int nblk_post = 148 * 2;
+  for (int step = 0; step < kWgFlows; ++step) {
+    const int f = direction == 0 ? step : kWgFlows - 1 - step;
+    const int c = flow_c(f), half = c / 2;
+    if (direction == 0 && f % 4 == 0 && f > 0) {
+      // early output: first 2 channels leave the chain (Modules.py:334-336)
+      copy_channels_kernel<<<ew_grid(rows * 2), 256, 0, s>>>(xcur, c + 2, 0, out, 8, zc0, 2, rows);
+      zc0 += 2;
+      float* nx = xbuf[xsel ^ 1];
+      copy_channels_kernel<<<ew_grid(rows * c), 256, 0, s>>>(xcur, c + 2, 2, nx, c, 0, c, rows);
+      xcur = nx;
+      xsel ^= 1;
+    }
+    flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], FP(l.y), BF(l.h_hi),
+                                            BF(l.h_lo), N, T, c, direction == 0 ? 1 : 0);
+    size_t wo = (size_t)f * kWgFlowW;
+    for (int i = 0; i < kWnLayers; ++i) {
+      const int d = 1 << i;
+      const Bf16Pair Wc = {BF(l.w_hi) + wo + (size_t)3 * kWnCh * 2 * kWnCh, BF(l.w_lo) + wo + (size_t)3 * kWnCh * 2 * kWnCh};
+      float* a_out = FP(l.a) + (size_t)kWgPad * 2 * kWnCh;
+      // conditioning first (beta = 0), then the three taps accumulate
+      const Bf16Pair melp = {BF(l.mel_hi) + (size_t)kWgPad * kWnMel, BF(l.mel_lo) + (size_t)kWgPad * kWnMel};
+      if ((rc = gemm_rowmajor_x3(s, false, false, M, 2 * kWnCh, kWnMel, melp, kWnMel, Wc, 2 * kWnCh, a_out, 2 * kWnCh, 0.f))) return rc;
+      for (int k = 0; k < 3; ++k) {
+        const long long shift = (long long)(kWgPad + (k - 1) * d) * kWnCh;
+        const Bf16Pair hp = {BF(l.h_hi) + shift, BF(l.h_lo) + shift};
+        const Bf16Pair Wk = {BF(l.w_hi) + wo + (size_t)k * kWnCh * 2 * kWnCh, BF(l.w_lo) + wo + (size_t)k * kWnCh * 2 * kWnCh};
+        if ((rc = gemm_rowmajor_x3(s, false, false, M, 2 * kWnCh, kWnCh, hp, kWnCh, Wk, 2 * kWnCh, a_out, 2 * kWnCh, 1.f))) return rc;
+      }
+      wo += (size_t)3 * kWnCh * 2 * kWnCh + (size_t)kWnMel * 2 * kWnCh;
+      gate_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->in_b[f][i], w->cond_b[f][i], FP(l.g), BF(l.g_hi), BF(l.g_lo), N, T);
+      const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
+      const Bf16Pair gp = {BF(l.g_hi) + (size_t)kWgPad * kWnCh, BF(l.g_lo) + (size_t)kWgPad * kWnCh};
+      const Bf16Pair Wr = {BF(l.w_hi) + wo, BF(l.w_lo) + wo};
+      // res/skip output reuses the pre-activation buffer (row stride = rout)
+      if ((rc = gemm_rowmajor_x3(s, false, false, M, rout, kWnCh, gp, kWnCh, Wr, rout, FP(l.a) + (size_t)kWgPad * rout, rout, 0.f))) return rc;
+      wo += (size_t)kWnCh * rout;
+      resskip_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->res_b[f][i], FP(l.g), BF(l.h_hi), BF(l.h_lo), FP(l.skip), N, T,
+                                                           i == 0, i == kWnLayers - 1);
+    }
+    float* xnext = xbuf[xsel ^ 1];
+    flow_post_kernel<<<nblk_post, 256, 0, s>>>(FP(l.skip), w->end_w[f], w->end_b[f], FP(l.y), w->inv_w[f], xnext, (double*)(ws + l.partial),
+                                               N, T, c, direction);
+    if (direction == 0) finish_sum_kernel<<<1, 32, 0, s>>>((double*)(ws + l.partial), nblk_post, sums);
+    xcur = xnext;
+    xsel ^= 1;
+    if (direction == 1 && f % 4 == 0 && f > 0) {
+      // prepend 2 fresh noise channels (Modules.py:363-369): early_noise[0] after flow 8, [1] after flow 4
+      float* nx = xbuf[xsel ^ 1];
+      copy_channels_kernel<<<ew_grid(rows * 2), 256, 0, s>>>(early_noise[f == 8 ? 0 : 1], 2, 0, nx, c + 2, 0, 2, rows);
+      copy_channels_kernel<<<ew_grid(rows * c), 256, 0, s>>>(xcur, c, 0, nx, c + 2, 2, c, rows);
+      xcur = nx;
+      xsel ^= 1;
+    }
+  }
+  if (direction == 0) {
+    copy_channels_kernel<<<ew_grid(rows * 4), 256, 0, s>>>(xcur, 4, 0, out, 8, zc0, 4, rows);
+    sumsq_kernel<<<256, 256, 0, s>>>(out, rows * 8, (double*)(ws + l.partial));
+    finish_sum_kernel<<<1, 32, 0, s>>>((double*)(ws + l.partial), 256, sums + 1);
+  } else {
+    MSTTS_CUDA(cudaMemcpyAsync(out, xcur, rows * 8 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+extern "C" int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias, int N, int Tm, int keep, float* out,
+                                  void* stream) {
+  MSTTS_REQUIRE(mel && kernel && bias && out, MSTTS_E_INVALID, "upsample_mel: null pointer");
+  const int Lout = (Tm - 1) * 256 + 1024;
+  MSTTS_REQUIRE(keep >= 1 && keep <= Lout, MSTTS_E_INVALID, "upsample_mel: keep=%d outside [1,%d] (the reference's tf.slice would fail)", keep,
+                Lout);
+  upsample_mel_kernel<<<ew_grid((size_t)N * keep * 80), 256, 0, (cudaStream_t)stream>>>(mel, kernel, bias, out, N, Tm, Lout, keep);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
