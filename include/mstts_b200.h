@@ -179,6 +179,17 @@ int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, c
 int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias, int N, int Tm, int keep, float* out,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Audio features.  Replaces Audio.melspectrogram / spectrogram / spectrogram_and_mel (Audio.py:19-48,62-96):
+ * pre-emphasis 0.97, librosa.stft (centre, reflect padding, periodic Hann(win) centred in n_fft), magnitude, optional
+ * spectral subtraction, slaney mel filter bank (librosa.filters.mel defaults), 20 log10(max(1e-5,.)), clip to
+ * [-max_abs, max_abs] (max_abs > 0) or [0,1].  wav [B,S] -> mel_out [B, 1+S/hop, n_mels] and/or spec_out
+ * [B, 1+S/hop, n_fft/2+1] (either may be NULL).  One fused kernel, the complex spectrogram stays on chip.
+ * ---------------------------------------------------------------------------------------------- */
+size_t mstts_stft_mel_workspace_bytes(int B, int S, int n_fft, int hop, int n_mels, int spectral_subtract);
+int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop, int win, int n_mels, int sample_rate, float max_abs,
+                   int spectral_subtract, float* mel_out, float* spec_out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
