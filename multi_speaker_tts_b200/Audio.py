@@ -18,6 +18,9 @@ def _stft_parameters(num_freq, frame_shift_ms, frame_length_ms, sample_rate):
     return n_fft, hop_length, win_length
 
 
+_WS_CACHE = {}  # (device, n_fft, win, n_mels, sr) -> workspace tensor whose tables are already built
+
+
 def stft_features(wav, n_fft, hop, win, sample_rate, num_mels=None, max_abs_value=None, spectral_subtract=False,
                   want_mel=True, want_spec=False, device=None):
     """wav [B,S] or [S] -> (mel [B,frames,num_mels] | None, spec [B,frames,n_fft/2+1] | None) on the GPU"""
@@ -40,7 +43,11 @@ def stft_features(wav, n_fft, hop, win, sample_rate, num_mels=None, max_abs_valu
     mel = torch.empty(B, frames, n_mels, device=dev) if want_mel else None
     spec = torch.empty(B, frames, n_fft // 2 + 1, device=dev) if want_spec else None
     nbytes = lib.mstts_stft_mel_workspace_bytes(B, S, n_fft, hop, max(n_mels, 1), int(bool(spectral_subtract)))
-    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    key = (dev, n_fft, win, n_mels, int(sample_rate))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, device=dev, dtype=torch.uint8)  # zero tag: tables get built on first use
+        _WS_CACHE[key] = ws
     with torch.cuda.device(dev):
         rc = lib.mstts_stft_mel(_lib.ptr(wav), B, S, n_fft, hop, win, n_mels, int(sample_rate),
                                 float(max_abs_value) if max_abs_value is not None else 0.0, int(bool(spectral_subtract)),

@@ -141,7 +141,15 @@ __global__ void mag_mean_kernel(const float* __restrict__ mag, int B, int frames
 }
 
 // tables: periodic Hann(win) centred in n_fft, twiddles, slaney mel filter bank (librosa.filters.mel defaults)
-__global__ void stft_tables_kernel(int n_fft, int win, int n_mels, int sr, float* window, float2* tw, float* fb, int* fb_range) {
+// The tables depend only on (n_fft, win, n_mels, sr): a tag in the workspace lets repeated calls with the same
+// workspace skip the rebuild (the reference rebuilds the mel basis on every call, Audio.py:78).
+__global__ void stft_tag_kernel(int4* tag, int n_fft, int win, int n_mels, int sr) { *tag = make_int4(n_fft, win, n_mels, sr); }
+
+__global__ void stft_tables_kernel(const int4* tag, int n_fft, int win, int n_mels, int sr, float* window, float2* tw, float* fb, int* fb_range) {
+  {
+    const int4 t = *tag;
+    if (t.x == n_fft && t.y == win && t.z == n_mels && t.w == sr) return;
+  }
   const int nb = n_fft / 2 + 1;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const int off = (n_fft - win) / 2;
@@ -181,7 +189,7 @@ __global__ void stft_tables_kernel(int n_fft, int win, int n_mels, int sr, float
   }
 }
 
-static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtract, size_t* o_win, size_t* o_tw, size_t* o_fb,
+static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtract, size_t* o_tag, size_t* o_win, size_t* o_tw, size_t* o_fb,
                              size_t* o_rng, size_t* o_mag, size_t* o_mean) {
   const size_t nb = n_fft / 2 + 1;
   size_t off = 0;
@@ -190,6 +198,7 @@ static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtr
     off += align_up(bytes, 256);
     return o;
   };
+  *o_tag = take(16);
   *o_win = take((size_t)n_fft * 4);
   *o_tw = take((size_t)n_fft / 2 * 8);
   *o_fb = take((size_t)n_mels * nb * 4);
@@ -201,8 +210,8 @@ static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtr
 
 extern "C" size_t mstts_stft_mel_workspace_bytes(int B, int S, int n_fft, int hop, int n_mels, int spectral_subtract) {
   if (B <= 0 || S <= 0 || n_fft <= 0 || hop <= 0) return 0;
-  size_t a, b2, c, d, e, f;
-  return stft_ws_layout(B, 1 + S / hop, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &a, &b2, &c, &d, &e, &f);
+  size_t t, a, b2, c, d, e, f;
+  return stft_ws_layout(B, 1 + S / hop, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &t, &a, &b2, &c, &d, &e, &f);
 }
 
 extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop, int win, int n_mels, int sample_rate,
@@ -217,8 +226,8 @@ extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop
                 sample_rate);
   cudaStream_t s = (cudaStream_t)stream;
   const int frames = 1 + S / hop;
-  size_t o_win, o_tw, o_fb, o_rng, o_mag, o_mean;
-  const size_t need = stft_ws_layout(B, frames, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &o_win, &o_tw, &o_fb, &o_rng, &o_mag, &o_mean);
+  size_t o_tag, o_win, o_tw, o_fb, o_rng, o_mag, o_mean;
+  const size_t need = stft_ws_layout(B, frames, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &o_tag, &o_win, &o_tw, &o_fb, &o_rng, &o_mag, &o_mean);
   MSTTS_REQUIRE(ws_bytes >= need, MSTTS_E_WORKSPACE, "stft_mel: workspace %zu < %zu", ws_bytes, need);
   char* ws = (char*)ws_;
   StftParams P;
@@ -229,8 +238,12 @@ extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop
   P.log2h = lg;
   P.window = (float*)(ws + o_win); P.tw = (float2*)(ws + o_tw); P.fb = (float*)(ws + o_fb); P.fb_range = (int*)(ws + o_rng);
   P.max_abs = max_abs; P.mel_out = mel_out; P.spec_out = spec_out;
-  stft_tables_kernel<<<8, 128, 0, s>>>(n_fft, win, n_mels > 0 ? n_mels : 1, sample_rate > 0 ? sample_rate : 1, (float*)(ws + o_win),
-                                       (float2*)(ws + o_tw), (float*)(ws + o_fb), (int*)(ws + o_rng));
+  {
+    const int nm = n_mels > 0 ? n_mels : 1, sr = sample_rate > 0 ? sample_rate : 1;
+    stft_tables_kernel<<<16, 128, 0, s>>>((const int4*)(ws + o_tag), n_fft, win, nm, sr, (float*)(ws + o_win), (float2*)(ws + o_tw),
+                                          (float*)(ws + o_fb), (int*)(ws + o_rng));
+    stft_tag_kernel<<<1, 1, 0, s>>>((int4*)(ws + o_tag), n_fft, win, nm, sr);
+  }
   const size_t smem = (size_t)(3 * (n_fft / 2)) * sizeof(float2) + (size_t)(n_fft / 2 + 1) * sizeof(float);
   MSTTS_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t nframes = (size_t)B * frames;

@@ -4,7 +4,7 @@
 // Round-1 structure: the dense contractions of the WN stack (dilated k=3 conv 512->1024, mel conditioning 640->1024,
 // res/skip 512->1024) run as bf16x3 tensor-core GEMMs through cuBLAS (gemm.h: hi/lo split operands, fp32 accumulation,
 // same numerics contract as the decoder kernels); everything around them is hand-written and fused:
-//   wn_prepare_kernel   weight norm g*v/sqrt(max(sum v^2,1e-5)) -> bf16 hi/lo weight operands
+//   wn_scale / wn_apply weight norm g*v/sqrt(max(sum v^2,1e-5)) -> bf16 hi/lo weight operands
 //   flow_pre_kernel     invertible 1x1 (or plain split in reverse) + the K<=4 start conv -> bf16 hi/lo activations
 //   gate_kernel         bias + tanh * sigmoid -> fp32 + bf16 hi/lo
 //   resskip_kernel      residual onto the GATED activation (reference quirk) + skip accumulation
@@ -25,26 +25,35 @@ static inline int ew_grid(size_t n, int per = 256) {
 }
 
 // ---- weight norm + split: v [k*in, out] (out fastest), g [out] (NULL: plain kernel) -> hi/lo [k*in, out] ----
-__global__ void wn_prepare_kernel(const float* __restrict__ v, const float* __restrict__ g, int kin, int out,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ eff) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= out) return;
-  float scale = 1.f;
-  if (g) {
-    float ss = 0.f;
-    for (int r = 0; r < kin; ++r) {
+// pass 1: scale[o] = g[o] / sqrt(max(sum_r v[r][o]^2, 1e-5)); one block per 32 output channels, 8 row lanes, fixed order
+__global__ void wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, int kin, int out, float* __restrict__ scale) {
+  __shared__ float part[8][33];
+  const int o = blockIdx.x * 32 + threadIdx.x;
+  float ss = 0.f;
+  if (o < out)
+    for (int r = threadIdx.y; r < kin; r += 8) {
       const float x = v[(size_t)r * out + o];
       ss = fmaf(x, x, ss);
     }
-    scale = g[o] * rsqrtf(fmaxf(ss, 1e-5f));
+  part[threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y == 0 && o < out) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += part[j][threadIdx.x];
+    scale[o] = g[o] * rsqrtf(fmaxf(tot, 1e-5f));
   }
-  for (int r = 0; r < kin; ++r) {
-    const float w = v[(size_t)r * out + o] * scale;
-    if (eff) eff[(size_t)r * out + o] = w;
+}
+// pass 2: w = v * scale -> fp32 (eff) and/or bf16 hi/lo
+__global__ void wn_apply_kernel(const float* __restrict__ v, const float* __restrict__ scale, size_t n, int out,
+                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ eff) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float w = v[i] * scale[i % out];
+    if (eff) eff[i] = w;
     if (hi) {
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
-      hi[(size_t)r * out + o] = h;
-      lo[(size_t)r * out + o] = __float2bfloat16_rn(w - __bfloat162float(h));
+      hi[i] = h;
+      lo[i] = __float2bfloat16_rn(w - __bfloat162float(h));
     }
   }
 }
@@ -287,6 +296,7 @@ __global__ void copy_channels_kernel(const float* __restrict__ src, int sc, int 
 struct WgLayout {
   size_t w_hi, w_lo;        // per flow: in[8] (3*512*1024) | cond[8] (640*1024) | res[7] (512*1024) + res[7] (512*512)
   size_t start_eff;         // [12][4*512] effective start kernels (fp32)
+  size_t wscale;            // [12][25][1024] weight-norm scales
   size_t mel_up;            // [N, S, 80] = [N, T, 640]
   size_t mel_hi, mel_lo;    // padded [N][Tp][640]
   size_t h_hi, h_lo, g_hi, g_lo;  // padded [N][Tp][512]
@@ -311,6 +321,7 @@ static WgLayout wg_layout(int N, int T) {
   l.w_hi = take(kWgFlowW * kWgFlows * 2);
   l.w_lo = take(kWgFlowW * kWgFlows * 2);
   l.start_eff = take((size_t)kWgFlows * 4 * kWnCh * 4);
+  l.wscale = take((size_t)kWgFlows * 25 * 2 * kWnCh * 4);
   l.mel_up = take((size_t)N * T * kWnMel * 4);
   l.mel_hi = take(rows_p * kWnMel * 2);
   l.mel_lo = take(rows_p * kWnMel * 2);
@@ -357,22 +368,26 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
   int rc;
 
   // ---- effective weights (weight norm is part of the per-step graph in the reference, Modules.py:31-33) ----
-  for (int f = 0; f < kWgFlows; ++f) {
-    size_t wo = (size_t)f * kWgFlowW;
-    const int half = flow_c(f) / 2;
-    wn_prepare_kernel<<<(kWnCh + 127) / 128, 128, 0, s>>>(w->start_v[f], w->start_g[f], half, kWnCh, nullptr, nullptr,
-                                                          FP(l.start_eff) + (size_t)f * 4 * kWnCh);
-    for (int i = 0; i < kWnLayers; ++i) {
-      wn_prepare_kernel<<<2 * kWnCh / 128, 128, 0, s>>>(w->in_v[f][i], w->in_g[f][i], 3 * kWnCh, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo,
-                                                        nullptr);
-      wo += (size_t)3 * kWnCh * 2 * kWnCh;
-      wn_prepare_kernel<<<2 * kWnCh / 128, 128, 0, s>>>(w->cond_v[f][i], w->cond_g[f][i], kWnMel, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo,
-                                                        nullptr);
-      wo += (size_t)kWnMel * 2 * kWnCh;
-      const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
-      wn_prepare_kernel<<<(rout + 127) / 128, 128, 0, s>>>(w->res_v[f][i], w->res_g[f][i], kWnCh, rout, BF(l.w_hi) + wo, BF(l.w_lo) + wo,
-                                                           nullptr);
-      wo += (size_t)kWnCh * rout;
+  {
+    int slot = 0;
+    auto prep = [&](const float* v, const float* g, int kin, int outc, __nv_bfloat16* hi, __nv_bfloat16* lo, float* eff) {
+      float* sc = FP(l.wscale) + (size_t)(slot++) * 2 * kWnCh;
+      wn_scale_kernel<<<(outc + 31) / 32, dim3(32, 8), 0, s>>>(v, g, kin, outc, sc);
+      wn_apply_kernel<<<ew_grid((size_t)kin * outc), 256, 0, s>>>(v, sc, (size_t)kin * outc, outc, hi, lo, eff);
+    };
+    for (int f = 0; f < kWgFlows; ++f) {
+      size_t wo = (size_t)f * kWgFlowW;
+      const int half = flow_c(f) / 2;
+      prep(w->start_v[f], w->start_g[f], half, kWnCh, nullptr, nullptr, FP(l.start_eff) + (size_t)f * 4 * kWnCh);
+      for (int i = 0; i < kWnLayers; ++i) {
+        prep(w->in_v[f][i], w->in_g[f][i], 3 * kWnCh, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo, nullptr);
+        wo += (size_t)3 * kWnCh * 2 * kWnCh;
+        prep(w->cond_v[f][i], w->cond_g[f][i], kWnMel, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo, nullptr);
+        wo += (size_t)kWnMel * 2 * kWnCh;
+        const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
+        prep(w->res_v[f][i], w->res_g[f][i], kWnCh, rout, BF(l.w_hi) + wo, BF(l.w_lo) + wo, nullptr);
+        wo += (size_t)kWnCh * rout;
+      }
     }
   }
   // ---- conditioning operand + zeroed pads ----

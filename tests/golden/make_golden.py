@@ -41,8 +41,33 @@ def decoder_case(B, Te, L, ragged, seed):
     return out
 
 
+def waveglow_case():
+    """tiny WaveGlow forward: N=1, 192 samples, orthogonal 1x1 kernels, small random end conv (seed 3)"""
+    from oracle import waveglow_oracle as W
+    raws, upk, upb = W.init_waveglow(3, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
+    flows = [W.effective_params(r) for r in raws]
+    audio, mel = W.synthetic_batch(1, 8 * 24, 2, seed=77)
+    a, m = W.restructure_train_data(audio, mel, upk, upb)
+    z, ls, ld = W.glow_train(a, m, flows)
+    l = W.glow_loss(z, ls, ld)
+    return {"z": z.numpy(), "mel640_checksum": np.float64(m.double().sum().item()), "log_s_sum": np.float64(torch.stack(ls).sum().item()),
+            "losses": np.array([float(x) for x in l])}
+
+
+def audio_case():
+    """Audio.melspectrogram of 0.4 s of seeded noise at the reference defaults and at the config-4 parameters"""
+    from oracle import audio_oracle as A
+    x = np.random.default_rng(5).uniform(-0.9, 0.9, 6400).astype(np.float32)
+    return {"mel_ref_defaults": A.melspectrogram(x, 1025, 12.5, 50, 80, 16000, max_abs_value=4).astype(np.float32),
+            "mel_config4": A.melspectrogram(x, 513, 256 / 22050 * 1000, 1024 / 22050 * 1000, 80, 22050, max_abs_value=4).astype(np.float32),
+            "spec_ref_defaults_checksum": np.float64(A.spectrogram(x, 1025, 12.5, 50, 16000).sum())}
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     for name, cfg in DECODER_CASES.items():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **decoder_case(*cfg))
         print("wrote", name)
+    np.savez_compressed(os.path.join(HERE, "waveglow_n1_t24.npz"), **waveglow_case())
+    np.savez_compressed(os.path.join(HERE, "audio_mel.npz"), **audio_case())
+    print("wrote waveglow / audio fixtures")

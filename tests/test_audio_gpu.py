@@ -51,3 +51,13 @@ def test_bad_arguments_are_refused(cuda_dev):
         G.stft_features(_wav(4000, 1), 1000, 250, 1000, 16000, 80)      # n_fft not a power of two
     with pytest.raises(MsttsError):
         G.stft_features(_wav(100, 1), 1024, 256, 1024, 16000, 80)       # too short to reflect-pad
+
+
+def test_against_committed_golden(cuda_dev):
+    import os
+    from multi_speaker_tts_b200 import Audio as G
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "audio_mel.npz"))
+    x = np.random.default_rng(5).uniform(-0.9, 0.9, 6400).astype(np.float32)
+    assert np.abs(G.melspectrogram(x, 1025, 12.5, 50, 80, 16000, max_abs_value=4) - g["mel_ref_defaults"]).max() < TOL
+    assert np.abs(G.melspectrogram(x, 513, 256 / 22050 * 1000, 1024 / 22050 * 1000, 80, 22050, max_abs_value=4) - g["mel_config4"]).max() < TOL
+    assert abs(float(G.spectrogram(x, 1025, 12.5, 50, 16000).sum()) - float(g["spec_ref_defaults_checksum"])) < 1e-2

@@ -40,3 +40,11 @@ def test_melspectrogram_ranges_and_shapes():
     assert s.shape == (1025, 81) and 0 <= s.min() and s.max() <= 1 and np.allclose(m, m2)
     m3 = A.melspectrogram(x, 1025, 12.5, 50, 80, 16000, max_abs_value=4, spectral_subtract=True)
     assert (m3 <= m + 1e-9).all()
+
+
+def test_golden_fixture_reproduces():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "audio_mel.npz"))
+    x = np.random.default_rng(5).uniform(-0.9, 0.9, 6400).astype(np.float32)
+    assert np.abs(A.melspectrogram(x, 1025, 12.5, 50, 80, 16000, max_abs_value=4) - g["mel_ref_defaults"]).max() < 1e-5
+    assert np.abs(A.melspectrogram(x, 513, 256 / 22050 * 1000, 1024 / 22050 * 1000, 80, 22050, max_abs_value=4) - g["mel_config4"]).max() < 1e-5

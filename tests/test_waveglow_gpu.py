@@ -64,3 +64,19 @@ def test_upsample_keep_out_of_range_is_refused(cuda_dev):
     from multi_speaker_tts_b200._lib import MsttsError
     with pytest.raises(MsttsError):
         M.Upsample_Mel(mel.to(cuda_dev), params, keep=10 ** 6)
+
+
+def test_against_committed_golden(cuda_dev):
+    import os
+    import numpy as np
+    from oracle import waveglow_oracle as W
+    from multi_speaker_tts_b200.WaveGlow import Modules as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "waveglow_n1_t24.npz"))
+    raws, upk, upb = W.init_waveglow(3, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
+    params = M.WaveGlowParams(raws, upk, upb, cuda_dev)
+    audio, mel = W.synthetic_batch(1, 8 * 24, 2, seed=77)
+    a, m = M.Restructure_Train_Data(audio.to(cuda_dev), mel.to(cuda_dev), params)
+    z, ls_sum, ld_list, ss = M.Glow_Train(a, m, params)
+    assert np.abs(z.cpu().numpy() - g["z"]).max() < 1e-3
+    got = [float(x) for x in M.Glow_Loss(z, ls_sum, ld_list, ss)]
+    assert np.allclose(got, g["losses"], rtol=1e-5, atol=1e-6)

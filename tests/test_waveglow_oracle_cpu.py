@@ -92,3 +92,17 @@ def test_zero_end_conv_gives_identity_coupling():
     y, ls, ld = W.affine_coupling(x, mel, flows[0])
     assert float(ls) == 0.0
     assert torch.allclose(y, x @ flows[0]['inv_w'], atol=1e-6)
+
+
+def test_golden_fixture_reproduces():
+    """oracle drift guard: tests/golden/waveglow_n1_t24.npz (made by tests/golden/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "waveglow_n1_t24.npz"))
+    raws, upk, upb = W.init_waveglow(3, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
+    flows = [W.effective_params(r) for r in raws]
+    audio, mel = W.synthetic_batch(1, 8 * 24, 2, seed=77)
+    a, m = W.restructure_train_data(audio, mel, upk, upb)
+    z, ls, ld = W.glow_train(a, m, flows)
+    assert np.abs(z.numpy() - g["z"]).max() < 1e-5
+    assert abs(float(torch.stack(ls).sum()) - float(g["log_s_sum"])) < 1e-4
+    assert np.allclose([float(x) for x in W.glow_loss(z, ls, ld)], g["losses"], rtol=1e-5, atol=1e-6)
