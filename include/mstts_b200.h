@@ -176,8 +176,9 @@ int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, c
                          size_t ws_bytes, void* stream);
 /* Upsample_Mel (Modules.py:198-208): ConvTranspose1d 80->80, k=1024, stride 256, VALID; kernel [1024, out, in];
  * writes the first `keep` of the (Tm-1)*256+1024 output frames: out [N, keep, 80]. */
+size_t mstts_upsample_mel_workspace_bytes(int N, int Tm);
 int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias, int N, int Tm, int keep, float* out,
-                       void* stream);
+                       void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Audio features.  Replaces Audio.melspectrogram / spectrogram / spectrogram_and_mel (Audio.py:19-48,62-96):

@@ -76,9 +76,10 @@ def Upsample_Mel(inputs, params, keep=None):
     keep = L if keep is None else keep
     x = inputs.contiguous().float()
     out = torch.empty(N, keep, hp.Sound.Mel_Dim, device=x.device)
+    ws = torch.empty(_lib.lib().mstts_upsample_mel_workspace_bytes(N, Tm), device=x.device, dtype=torch.uint8)
     with torch.cuda.device(x.device):
         rc = _lib.lib().mstts_upsample_mel(_lib.ptr(x), _lib.ptr(params.up_kernel), _lib.ptr(params.up_bias), N, Tm, keep,
-                                           _lib.ptr(out), _stream(x))
+                                           _lib.ptr(out), C.c_void_p(ws.data_ptr()), ws.numel(), _stream(x))
     _lib.check(rc, "mstts_upsample_mel")
     return out
 

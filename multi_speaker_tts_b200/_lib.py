@@ -72,7 +72,8 @@ EXPORTS = {
     "mstts_waveglow_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mstts_waveglow_flows": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp,
                                        C.c_size_t, _fp]),
-    "mstts_upsample_mel": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "mstts_upsample_mel_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mstts_upsample_mel": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "mstts_stft_mel_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "mstts_stft_mel": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp,
                                  _fp, C.c_size_t, _fp]),

@@ -3,7 +3,7 @@
 // the waveform once + write [frames, 80]).  Replaces Audio.melspectrogram / spectrogram / spectrogram_and_mel
 // (Audio.py:19-48,62-96).
 //
-// One CTA per frame: gather the reflect-padded, pre-emphasised, Hann-windowed frame into shared memory, real FFT of size
+// Persistent CTAs (8 per SM) loop over frames with the window / twiddle / filter tables staged once in shared memory: gather the reflect-padded, pre-emphasised, Hann-windowed frame into shared memory, real FFT of size
 // n_fft as a complex Stockham radix-2 FFT of size n_fft/2 plus the split post-pass, |.|, sparse triangular filters
 // (a warp per filter over its non-zero bin range), 20 log10(max(1e-5, .)), clip.
 #include "common.cuh"
@@ -17,6 +17,8 @@ struct StftParams {
   const float2* tw;     // [n_fft/2] exp(-2 pi i j / n_fft)
   const float* fb;      // [n_mels, n_fft/2+1] dense filter bank
   const int* fb_range;  // [n_mels, 2] first / one-past-last non-zero bin
+  const float* fbc;     // compact filter weights: filter m occupies fbc[fb_off[m] .. fb_off[m] + hi - lo)
+  const int* fb_off;    // [n_mels + 1]
   float max_abs;        // > 0: symmetric normalisation to [-max_abs, max_abs]; <= 0: [0, 1]
   float* mel_out;       // [B, frames, n_mels] or NULL
   float* spec_out;      // [B, frames, n_fft/2+1] or NULL (Audio.spectrogram: ref level 20 dB, [0,1])
@@ -27,15 +29,27 @@ struct StftParams {
 
 __device__ __forceinline__ float amp_to_db(float x) { return 20.f * log10f(fmaxf(1e-5f, x)); }
 
-// mel filter bank + dB + normalisation of one frame whose magnitudes sit in shared memory
-__device__ __forceinline__ void finish_frame(const StftParams& P, const float* mag_s, size_t frame_index) {
+// mel filter bank + dB + normalisation of one frame whose magnitudes sit in shared memory; the sparse (triangular)
+// filter weights and their bin ranges are staged in shared memory once per CTA (fbc_s / rng_s, null: read global)
+__device__ __forceinline__ void finish_frame(const StftParams& P, const float* mag_s, size_t frame_index, const float* fbc_s,
+                                             const int* rng_s) {
   const int nb = P.n_fft / 2 + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   if (P.mel_out) {
     for (int m = warp; m < P.n_mels; m += nw) {
-      const int lo = P.fb_range[2 * m], hi = P.fb_range[2 * m + 1];
+      int lo, hi, off;
+      if (rng_s) {
+        lo = rng_s[3 * m];
+        hi = rng_s[3 * m + 1];
+        off = rng_s[3 * m + 2];
+      } else {
+        lo = P.fb_range[2 * m];
+        hi = P.fb_range[2 * m + 1];
+        off = P.fb_off[m];
+      }
+      const float* wts = (fbc_s ? fbc_s : P.fbc) + off - lo;
       float s = 0.f;
-      for (int k = lo + lane; k < hi; k += 32) s = fmaf(P.fb[(size_t)m * nb + k], mag_s[k], s);
+      for (int k = lo + lane; k < hi; k += 32) s = fmaf(wts[k], mag_s[k], s);
       s = warp_sum(s);
       if (lane == 0) {
         const float db = amp_to_db(s);
@@ -54,67 +68,85 @@ __device__ __forceinline__ void finish_frame(const StftParams& P, const float* m
   }
 }
 
-__global__ void __launch_bounds__(256) stft_mel_kernel(const StftParams P) {
+__global__ void __launch_bounds__(256) stft_mel_kernel(const StftParams P, size_t nframes) {
   extern __shared__ __align__(16) float smem_f[];
   const int N = P.n_fft, H = N / 2;
   float2* za = reinterpret_cast<float2*>(smem_f);  // [H]
   float2* zb = za + H;                             // [H]
   float2* tw_s = zb + H;                           // [H]
-  float* mag_s = reinterpret_cast<float*>(tw_s + H);  // [H+1]
+  float* win_s = reinterpret_cast<float*>(tw_s + H);  // [N]
+  float* mag_s = win_s + N;                           // [H+1] (+pad)
+  float* fbc_s = mag_s + H + 4;                       // [3*(H+1)] compact filter weights
+  int* rng_s = reinterpret_cast<int*>(fbc_s + 3 * (H + 1));  // [n_mels][3]
   const int tid = threadIdx.x;
-  const size_t fi = blockIdx.x;  // frame index over all utterances
-  const int b = (int)(fi / P.frames), fr = (int)(fi % P.frames);
-  const float* x = P.wav + (size_t)b * P.S;
-  // ---- frame gather: reflect padding of the PRE-EMPHASISED signal (librosa pads after Audio.preemphasis ran) ----
-  for (int i = tid; i < N; i += blockDim.x) {
-    int j = fr * P.hop + i - H;
-    if (j < 0) j = -j;
-    if (j >= P.S) j = 2 * (P.S - 1) - j;
-    j = min(max(j, 0), P.S - 1);
-    const float y = (j > 0) ? x[j] - 0.97f * x[j - 1] : x[0];
-    reinterpret_cast<float*>(za)[i] = y * P.window[i];  // z[k] = (x[2k], x[2k+1])
-  }
+  // ---- per-CTA tables (a CTA then loops over many frames) ----
   for (int i = tid; i < H; i += blockDim.x) tw_s[i] = P.tw[i];
+  for (int i = tid; i < N; i += blockDim.x) win_s[i] = P.window[i];
+  if (P.mel_out) {
+    const int nnz = P.fb_off[P.n_mels];
+    for (int i = tid; i < nnz; i += blockDim.x) fbc_s[i] = P.fbc[i];
+    for (int m = tid; m < P.n_mels; m += blockDim.x) {
+      rng_s[3 * m] = P.fb_range[2 * m];
+      rng_s[3 * m + 1] = P.fb_range[2 * m + 1];
+      rng_s[3 * m + 2] = P.fb_off[m];
+    }
+  }
   __syncthreads();
-  // ---- complex FFT of size H (Stockham autosort, radix 2, decimation in frequency) ----
-  float2* src = za;
-  float2* dst = zb;
-  for (int s = 0; s < P.log2h; ++s) {
-    const int l = H >> (s + 1);  // butterflies per group pattern: n/2 >> s
-    const int m = 1 << s;        // stride
-    for (int i = tid; i < H / 2; i += blockDim.x) {
-      const int j = i / m, k = i % m;  // i = j*m + k, j < l
-      const float2 c0 = src[k + j * m];
-      const float2 c1 = src[k + j * m + l * m];
-      const float2 w = tw_s[j * 2 * m];  // exp(-2 pi i j / (H >> s)) = tw[j * N / (H >> s)]
-      const float2 sum = make_float2(c0.x + c1.x, c0.y + c1.y);
-      const float2 dif = make_float2(c0.x - c1.x, c0.y - c1.y);
-      dst[k + 2 * j * m] = sum;
-      dst[k + (2 * j + 1) * m] = make_float2(dif.x * w.x - dif.y * w.y, dif.x * w.y + dif.y * w.x);
+  for (size_t fi = blockIdx.x; fi < nframes; fi += gridDim.x) {
+    const int b = (int)(fi / P.frames), fr = (int)(fi % P.frames);
+    const float* x = P.wav + (size_t)b * P.S;
+    // ---- frame gather: reflect padding of the PRE-EMPHASISED signal (librosa pads after Audio.preemphasis ran) ----
+#pragma unroll 4
+    for (int i = tid; i < N; i += blockDim.x) {
+      int j = fr * P.hop + i - H;
+      if (j < 0) j = -j;
+      if (j >= P.S) j = 2 * (P.S - 1) - j;
+      j = min(max(j, 0), P.S - 1);
+      const float x0 = x[j], x1 = x[max(j - 1, 0)];
+      const float y = (j > 0) ? x0 - 0.97f * x1 : x0;
+      reinterpret_cast<float*>(za)[i] = y * win_s[i];  // z[k] = (x[2k], x[2k+1])
     }
     __syncthreads();
-    float2* t = src;
-    src = dst;
-    dst = t;
+    // ---- complex FFT of size H (Stockham autosort, radix 2): stage s has stride 1<<s ----
+    float2* src = za;
+    float2* dst = zb;
+    for (int s = 0; s < P.log2h; ++s) {
+      const int l = H >> (s + 1);
+      const int m = 1 << s;
+      for (int i = tid; i < H / 2; i += blockDim.x) {
+        const int j = i >> s, k = i & (m - 1);  // i = j*m + k, j < l
+        const float2 c0 = src[k + j * m];
+        const float2 c1 = src[k + j * m + l * m];
+        const float2 w = tw_s[j * 2 * m];  // exp(-2 pi i j / (H >> s)) = tw[j * N / (H >> s)]
+        const float2 sum = make_float2(c0.x + c1.x, c0.y + c1.y);
+        const float2 dif = make_float2(c0.x - c1.x, c0.y - c1.y);
+        dst[k + 2 * j * m] = sum;
+        dst[k + (2 * j + 1) * m] = make_float2(dif.x * w.x - dif.y * w.y, dif.x * w.y + dif.y * w.x);
+      }
+      __syncthreads();
+      float2* t = src;
+      src = dst;
+      dst = t;
+    }
+    // ---- split post-pass: X[k] = (Z[k] + conj(Z[H-k]))/2 - i e^{-2 pi i k/N} (Z[k] - conj(Z[H-k]))/2 ----
+    for (int k = tid; k <= H; k += blockDim.x) {
+      const float2 zk = src[k % H];
+      const float2 zc = src[(H - k) % H];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 o = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
+      const float2 w = (k < H) ? tw_s[k] : make_float2(-1.f, 0.f);
+      const float2 wo = make_float2(w.x * o.x - w.y * o.y, w.x * o.y + w.y * o.x);
+      const float re = e.x + wo.y, im = e.y - wo.x;
+      mag_s[k] = sqrtf(re * re + im * im);
+    }
+    __syncthreads();
+    if (P.mag_out) {
+      for (int k = tid; k <= H; k += blockDim.x) P.mag_out[fi * (H + 1) + k] = mag_s[k];
+    } else {
+      finish_frame(P, mag_s, fi, fbc_s, rng_s);
+    }
+    __syncthreads();  // mag_s / za are rewritten by the next frame
   }
-  // ---- split post-pass: X[k] = (Z[k] + conj(Z[H-k]))/2 - i e^{-2 pi i k/N} (Z[k] - conj(Z[H-k]))/2 ----
-  for (int k = tid; k <= H; k += blockDim.x) {
-    const float2 zk = src[k % H];
-    const float2 zc = src[(H - k) % H];
-    const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-    const float2 o = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
-    // -i * w * o, w = tw[k] (k = H: w = -1)
-    const float2 w = (k < H) ? tw_s[k] : make_float2(-1.f, 0.f);
-    const float2 wo = make_float2(w.x * o.x - w.y * o.y, w.x * o.y + w.y * o.x);
-    const float re = e.x + wo.y, im = e.y - wo.x;
-    mag_s[k] = sqrtf(re * re + im * im);
-  }
-  __syncthreads();
-  if (P.mag_out) {
-    for (int k = tid; k <= H; k += blockDim.x) P.mag_out[fi * (H + 1) + k] = mag_s[k];
-    return;
-  }
-  finish_frame(P, mag_s, fi);
 }
 
 // spectral subtraction, second pass: M' = max(M - mean_t(M)/10, 0) (Audio.py:45-46), then the usual tail
@@ -127,7 +159,7 @@ __global__ void __launch_bounds__(256) subtract_finish_kernel(const StftParams P
   for (int k = threadIdx.x; k < nb; k += blockDim.x)
     mag_s[k] = fmaxf(P.mag_in[fi * nb + k] - P.mag_mean[(size_t)b * nb + k] / 10.f, 0.f);
   __syncthreads();
-  finish_frame(P, mag_s, fi);
+  finish_frame(P, mag_s, fi, nullptr, nullptr);
 }
 
 // mean over frames of the magnitudes, one thread per (utterance, bin), fixed order
@@ -189,8 +221,33 @@ __global__ void stft_tables_kernel(const int4* tag, int n_fft, int win, int n_me
   }
 }
 
+// compact (non-zero) filter weights: off[m] = prefix sum of the range lengths, fbc[off[m] + k - lo] = fb[m][k]
+__global__ void stft_compact_kernel(const int4* tag, int n_fft, int win, int n_mels, int sr, const float* fb, const int* fb_range, int* fb_off,
+                                    float* fbc) {
+  {
+    const int4 t = *tag;
+    if (t.x == n_fft && t.y == win && t.z == n_mels && t.w == sr) return;
+  }
+  __shared__ int off_s[257];
+  const int nb = n_fft / 2 + 1;
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int m = 0; m < n_mels; ++m) {
+      off_s[m] = o;
+      o += fb_range[2 * m + 1] - fb_range[2 * m];
+    }
+    off_s[n_mels] = o;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m <= n_mels; m += blockDim.x) fb_off[m] = off_s[m];
+  for (int m = 0; m < n_mels; ++m) {
+    const int lo = fb_range[2 * m], hi = fb_range[2 * m + 1];
+    for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) fbc[off_s[m] + k - lo] = fb[(size_t)m * nb + k];
+  }
+}
+
 static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtract, size_t* o_tag, size_t* o_win, size_t* o_tw, size_t* o_fb,
-                             size_t* o_rng, size_t* o_mag, size_t* o_mean) {
+                             size_t* o_rng, size_t* o_mag, size_t* o_mean, size_t* o_fbc, size_t* o_off) {
   const size_t nb = n_fft / 2 + 1;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -203,6 +260,8 @@ static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtr
   *o_tw = take((size_t)n_fft / 2 * 8);
   *o_fb = take((size_t)n_mels * nb * 4);
   *o_rng = take((size_t)n_mels * 2 * 4);
+  *o_fbc = take((size_t)3 * nb * 4);
+  *o_off = take((size_t)(n_mels + 1) * 4);
   *o_mag = take(subtract ? (size_t)B * frames * nb * 4 : 0);
   *o_mean = take(subtract ? (size_t)B * nb * 4 : 0);
   return off;
@@ -210,8 +269,8 @@ static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtr
 
 extern "C" size_t mstts_stft_mel_workspace_bytes(int B, int S, int n_fft, int hop, int n_mels, int spectral_subtract) {
   if (B <= 0 || S <= 0 || n_fft <= 0 || hop <= 0) return 0;
-  size_t t, a, b2, c, d, e, f;
-  return stft_ws_layout(B, 1 + S / hop, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &t, &a, &b2, &c, &d, &e, &f);
+  size_t t, a, b2, c, d, e, f, g2, h2;
+  return stft_ws_layout(B, 1 + S / hop, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &t, &a, &b2, &c, &d, &e, &f, &g2, &h2);
 }
 
 extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop, int win, int n_mels, int sample_rate,
@@ -226,8 +285,8 @@ extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop
                 sample_rate);
   cudaStream_t s = (cudaStream_t)stream;
   const int frames = 1 + S / hop;
-  size_t o_tag, o_win, o_tw, o_fb, o_rng, o_mag, o_mean;
-  const size_t need = stft_ws_layout(B, frames, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &o_tag, &o_win, &o_tw, &o_fb, &o_rng, &o_mag, &o_mean);
+  size_t o_tag, o_win, o_tw, o_fb, o_rng, o_mag, o_mean, o_fbc, o_off;
+  const size_t need = stft_ws_layout(B, frames, n_fft, n_mels > 0 ? n_mels : 1, spectral_subtract, &o_tag, &o_win, &o_tw, &o_fb, &o_rng, &o_mag, &o_mean, &o_fbc, &o_off);
   MSTTS_REQUIRE(ws_bytes >= need, MSTTS_E_WORKSPACE, "stft_mel: workspace %zu < %zu", ws_bytes, need);
   char* ws = (char*)ws_;
   StftParams P;
@@ -237,23 +296,28 @@ extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop
   while ((1 << lg) < n_fft / 2) ++lg;
   P.log2h = lg;
   P.window = (float*)(ws + o_win); P.tw = (float2*)(ws + o_tw); P.fb = (float*)(ws + o_fb); P.fb_range = (int*)(ws + o_rng);
+  P.fbc = (float*)(ws + o_fbc); P.fb_off = (int*)(ws + o_off);
   P.max_abs = max_abs; P.mel_out = mel_out; P.spec_out = spec_out;
   {
     const int nm = n_mels > 0 ? n_mels : 1, sr = sample_rate > 0 ? sample_rate : 1;
     stft_tables_kernel<<<16, 128, 0, s>>>((const int4*)(ws + o_tag), n_fft, win, nm, sr, (float*)(ws + o_win), (float2*)(ws + o_tw),
                                           (float*)(ws + o_fb), (int*)(ws + o_rng));
+    stft_compact_kernel<<<1, 256, 0, s>>>((const int4*)(ws + o_tag), n_fft, win, nm, sr, (float*)(ws + o_fb), (int*)(ws + o_rng), (int*)(ws + o_off),
+                                          (float*)(ws + o_fbc));
     stft_tag_kernel<<<1, 1, 0, s>>>((int4*)(ws + o_tag), n_fft, win, nm, sr);
   }
-  const size_t smem = (size_t)(3 * (n_fft / 2)) * sizeof(float2) + (size_t)(n_fft / 2 + 1) * sizeof(float);
+  const size_t smem = (size_t)(3 * (n_fft / 2)) * sizeof(float2) + (size_t)n_fft * 4 + (size_t)(n_fft / 2 + 4) * 4 +
+                      (size_t)3 * (n_fft / 2 + 1) * 4 + (size_t)3 * 256 * 4;
   MSTTS_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t nframes = (size_t)B * frames;
   MSTTS_REQUIRE(nframes < (1ull << 31), MSTTS_E_INVALID, "stft_mel: too many frames");
+  const unsigned grid = (unsigned)(nframes < 148u * 8u ? nframes : 148u * 8u);  // persistent: 8 CTAs per SM
   if (!spectral_subtract) {
-    stft_mel_kernel<<<(unsigned)nframes, 256, smem, s>>>(P);
+    stft_mel_kernel<<<grid, 256, smem, s>>>(P, nframes);
   } else {
     StftParams Q = P;
     Q.mag_out = (float*)(ws + o_mag);
-    stft_mel_kernel<<<(unsigned)nframes, 256, smem, s>>>(Q);
+    stft_mel_kernel<<<grid, 256, smem, s>>>(Q, nframes);
     const int nb = n_fft / 2 + 1;
     mag_mean_kernel<<<(B * nb + 127) / 128, 128, 0, s>>>((float*)(ws + o_mag), B, frames, nb, (float*)(ws + o_mean));
     P.mag_in = (float*)(ws + o_mag);

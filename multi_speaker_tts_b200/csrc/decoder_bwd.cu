@@ -460,21 +460,35 @@ __global__ void gather_dproj_kernel(const float* __restrict__ dlin, const float*
   }
 }
 
-// out[c] = sum_r in[r][c]     (R x C row-major; one block per 32 columns, 8 row-lanes, fixed order)
-__global__ void colsum_kernel(const float* __restrict__ in, float* __restrict__ out, size_t R, int C) {
-  __shared__ float part[8][33];
+// out[c] = sum_r in[r][c]   (R x C row-major).  Two deterministic passes: kColsumSlices row slices per 32-column
+// group (coalesced 128-byte rows, fixed order inside a slice), then a fixed-order sum over the slices.
+constexpr int kColsumSlices = 64;
+__global__ void colsum_partial_kernel(const float* __restrict__ in, float* __restrict__ part, size_t R, int C) {
+  __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t r0 = R * blockIdx.y / kColsumSlices, r1 = R * (blockIdx.y + 1) / kColsumSlices;
   float s = 0.f;
   if (c < C)
-    for (size_t r = threadIdx.y; r < R; r += 8) s += in[r * C + c];
-  part[threadIdx.y][threadIdx.x] = s;
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) s += in[r * C + c];
+  sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
     float tot = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tot += part[j][threadIdx.x];
-    out[c] = tot;
+    for (int j = 0; j < 8; ++j) tot += sh[j][threadIdx.x];
+    part[(size_t)blockIdx.y * C + c] = tot;
   }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tot = 0.f;
+  for (int j = 0; j < kColsumSlices; ++j) tot += part[(size_t)j * C + c];
+  out[c] = tot;
+}
+static void colsum(cudaStream_t s, const float* in, float* out, size_t R, int C, float* scratch) {
+  colsum_partial_kernel<<<dim3((C + 31) / 32, kColsumSlices), dim3(32, 8), 0, s>>>(in, scratch, R, C);
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, out, C);
 }
 
 // prenet backward through relu + dropout: dz = 2 * dy * [y > 0]   (y = relu(z) * 2 * mask)
@@ -561,7 +575,7 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   if ((rc = gemm_rowmajor_ex(s, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return rc;
   if ((rc = gemm_rowmajor_ex(s, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
                              dw->proj_kernel + (size_t)kCell * NP, NP, 0.f))) return rc;
-  colsum_kernel<<<(NP + 31) / 32, dim3(32, 8), 0, s>>>(F(l.dproj_tm), dw->proj_bias, TB, NP);
+  colsum(s, F(l.dproj_tm), dw->proj_bias, TB, NP, F(l.colsum_scratch));
   // d m1 (projection part) and d ctx (projection part)
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kCell, NP, F(l.dproj_tm), NP, w->proj_kernel, NP, F(l.dm1_proj), kCell, 0.f))) return rc;
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, D, NP, F(l.dproj_tm), NP, w->proj_kernel + (size_t)kCell * NP, NP,
@@ -610,17 +624,17 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   // cell 1: rows [m0 | h1_prev]
   if ((rc = wgrad(F(l.m0), kCell, F(l.dG1), sg1, dw->cell1_kernel))) return rc;
   if ((rc = wgrad(F(l.hz1), kCell, F(l.dG1), sg1, dw->cell1_kernel + (size_t)kCell * kGates))) return rc;
-  colsum_kernel<<<kGates / 32, dim3(32, 8), 0, s>>>(F(l.dG1), dw->cell1_bias, TB, kGates);
+  colsum(s, F(l.dG1), dw->cell1_bias, TB, kGates, F(l.colsum_scratch));
   // cell 0: rows [prenet | ctx | ctx | h0_prev]
   if ((rc = wgrad(F(l.pre), kPrenet, F(l.dG0), sg0, dw->cell0_kernel))) return rc;
   float* dK0_ctx = dw->cell0_kernel + (size_t)kPrenet * kGates;
   if ((rc = wgrad(F(l.ctx), D, F(l.dG0), sg0, dK0_ctx))) return rc;
   copy_rows_kernel<<<ew_grid((size_t)D * kGates), 256, 0, s>>>(dK0_ctx, dK0_ctx + (size_t)D * kGates, (size_t)D * kGates);
   if ((rc = wgrad(F(l.hz0), kCell, F(l.dG0), sg0, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates))) return rc;
-  colsum_kernel<<<kGates / 32, dim3(32, 8), 0, s>>>(F(l.dG0), dw->cell0_bias, TB, kGates);
+  colsum(s, F(l.dG0), dw->cell0_bias, TB, kGates, F(l.colsum_scratch));
   // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
   if ((rc = gemm_rowmajor_ex(s, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
-  colsum_kernel<<<kAtt / 32, dim3(32, 8), 0, s>>>(F(l.dq), F(l.dfb), TB, kAtt);
+  colsum(s, F(l.dq), F(l.dfb), TB, kAtt, F(l.colsum_scratch));
   location_grads_kernel<<<1, 1024, 0, s>>>(F(l.dF), F(l.dfb), w->loc_conv_kernel, w->loc_conv_bias, w->loc_dense_kernel,
                                            dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
   MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -632,11 +646,11 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   }
   prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre), F(l.pre), TB * kPrenet);
   if ((rc = gemm_rowmajor_ex(s, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
-  colsum_kernel<<<kPrenet / 32, dim3(32, 8), 0, s>>>(F(l.dpre), dw->prenet1_bias, TB, kPrenet);
+  colsum(s, F(l.dpre), dw->prenet1_bias, TB, kPrenet, F(l.colsum_scratch));
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kPrenet, F(l.dpre), kPrenet, w->prenet1_kernel, kPrenet, F(l.dpre_h), kPrenet, 0.f))) return rc;
   prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre_h), F(l.pre_h), TB * kPrenet);
   if ((rc = gemm_rowmajor_ex(s, true, false, kMel, kPrenet, (int)TB, F(l.frames), kMel, F(l.dpre_h), kPrenet, dw->prenet0_kernel, kPrenet, 0.f))) return rc;
-  colsum_kernel<<<kPrenet / 32, dim3(32, 8), 0, s>>>(F(l.dpre_h), dw->prenet0_bias, TB, kPrenet);
+  colsum(s, F(l.dpre_h), dw->prenet0_bias, TB, kPrenet, F(l.colsum_scratch));
   // memory side: dvalues[b] = A_b^T dctx_b (over steps) + dkeys[b] @ Wm^T ; dWm = values^T dkeys
   if ((rc = gemm_rowmajor_batched(s, true, false, Te, D, T, F(l.align_tm), B * Te, Te, F(l.dctx), B * D, D, F(l.dvalues), D,
                                   (long long)Te * D, 0.f, B))) return rc;

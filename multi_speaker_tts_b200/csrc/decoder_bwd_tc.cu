@@ -41,7 +41,7 @@ struct DecBwdTcParams {
 };
 
 struct TcBwdSmem {
-  uint32_t ring, xbuf, recv, scratch, wq, xs, cum_s, a_s, da_s, de_s, dcum_s, e_loc, g_loc, e_parts1, e_parts2, dctx_s, ehalf, qred,
+  uint32_t ring, xbuf, recv, scratch, s_s, wq, xs, cum_s, a_s, da_s, de_s, dcum_s, e_loc, g_loc, e_parts1, e_parts2, dctx_s, ehalf, qred,
       bred, bars, total;
 };
 
@@ -59,6 +59,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int NS, int Te, int D) {
   s.recv = take(2 * kDecCluster * kTcN * kRecvStride * 4);  // two accumulators
   const uint32_t dps_bytes = (TeP + 32) * 32 * 4, dq_bytes = kTcN * (kAtt + 4) * 4;
   s.scratch = take(dps_bytes > dq_bytes ? dps_bytes : dq_bytes);  // d pre-activations (phase C') / dq rows (phase B'e)
+  s.s_s = take(16 * kTcCompute * 4);  // tanh(keys + q + loc) of the coming attention' step, [16 positions][256 threads]
   s.wq = take(kUnitsPerCta * (kAtt + 4) * 4);
   s.xs = take(4 * 2 * kTcN * 8 * 2);
   s.cum_s = take((TeP + 32) * 4);
@@ -98,6 +99,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   uint8_t* xbuf = smem + L.xbuf;  // [0]: dG0 slice (JA jobs), [1]: dG1 slice (JB jobs)
   float* recv = reinterpret_cast<float*>(smem + L.recv);  // [acc 2][src 4][batch 32][40]
   float* scratch = reinterpret_cast<float*>(smem + L.scratch);
+  float* s_s = reinterpret_cast<float*>(smem + L.s_s);
   float* wq_s = reinterpret_cast<float*>(smem + L.wq);    // [8][132]
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + L.xs);  // [gate 4][hi/lo][32][8]
   float* cum_s = reinterpret_cast<float*>(smem + L.cum_s);
@@ -366,25 +368,58 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       }
     };
 
+    // Stages everything of attention'(t) that depends only on saved forward data: alignment, cumulative alignment
+    // (shifted by 15, zero borders), zero borders of the d pre-activation buffer, and s = tanh(keys + q + loc) of this
+    // warp's 16 positions.  Runs inside the barrier wait that precedes phase C'(t).
+    float de_keep[16];
+    auto attention_prologue = [&](int t) {
+      if (cid >= B) return;
+      const int bb = cid;
+      const float* al = P.align_tm + ((size_t)t * B + bb) * Te;
+      const float* cum_prev = P.cum + ((size_t)t * B + bb) * Te;
+      for (int i = tid; i < TeP + 32; i += kTcCompute) {
+        const int x = i - 15;
+        cum_s[i] = (x >= 0 && x < Te) ? cum_prev[x] : 0.f;
+      }
+      for (int x = tid; x < TeP; x += kTcCompute) a_s[x] = (x < Te) ? al[x] : 0.f;
+      for (int i = tid; i < 15 * 32; i += kTcCompute) dps[i] = 0.f;
+      for (int i = (15 + tl) * 32 + tid; i < (TeP + 32) * 32; i += kTcCompute) dps[i] = 0.f;
+      const float qf = P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane];
+      ptx::bar_sync(1, kTcCompute);
+      const int t0 = warp * 16;
+      if (t0 < tl) {
+        float acc[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16 + kConvK - 1; ++c) {
+          const float cv = cum_s[t0 + c];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int k = c - p;
+            if (k >= 0 && k < kConvK) acc[p] = fmaf(cv, F_reg[k], acc[p]);
+          }
+        }
+        uint32_t kv[16];
+        ptx::tmem_ld16(tmem_keys + ((uint32_t)(q4 * 32) << 16) + half * 16, kv);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int p = 0; p < 16; ++p) s_s[p * kTcCompute + tid] = tanhf(__uint_as_float(kv[p]) + qf + acc[p]);
+      }
+    };
+    attention_prologue(T - 1);
+    ptx::bar_sync(1, kTcCompute);
+
     for (int t = T - 1; t >= 0; --t) {
       const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
       const uint32_t sp = (uint32_t)(T - 1 - t) & 1u;
       const bool last = (t == T - 1);
       STAMP(0);
       // ================= phase C': attention backward, batch row = cluster index =================
+      // (alignment, cumulative alignment and tanh(keys + q + loc) of this step were staged by attention_prologue(t)
+      //  inside the previous barrier wait: they depend only on saved forward data)
       if (cid < B) {
         const int bb = cid;
-        const float* al = P.align_tm + ((size_t)t * B + bb) * Te;
-        const float* cum_prev = P.cum + ((size_t)t * B + bb) * Te;
-        for (int i = tid; i < TeP + 32; i += kTcCompute) {
-          const int x = i - 15;
-          cum_s[i] = (x >= 0 && x < Te) ? cum_prev[x] : 0.f;
-        }
-        for (int x = tid; x < TeP; x += kTcCompute) a_s[x] = (x < Te) ? al[x] : 0.f;
-        // rows 15..15+tl of the d pre-activation buffer are rewritten below; only its zero borders need clearing
-        // (the buffer doubles as the dq staging area of phase B'e)
-        for (int i = tid; i < 15 * 32; i += kTcCompute) dps[i] = 0.f;
-        for (int i = (15 + tl) * 32 + tid; i < (TeP + 32) * 32; i += kTcCompute) dps[i] = 0.f;
         if (tid < Dq) {  // total gradient w.r.t. ctx_t: projection part + the 4 K-quarter partials of JA1(t+1)
           const size_t gi = ((size_t)t * B + bb) * D + crank * Dq + tid;
           float v = P.dctx[gi];
@@ -395,7 +430,6 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           }
           dctx_s[tid] = v;
         }
-        const float qf = P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane];
         ptx::bar_sync(1, kTcCompute);
         {  // partial d a[x] over this CTA's context dims: thread = text position, columns = dims (two halves of warps)
           const int x = q4 * 32 + lane;
@@ -423,7 +457,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         }
         mbar_wait_warp(e_bar, e_parity);
         e_parity ^= 1u;
-        // softmax backward (every warp reduces all positions redundantly: Te <= 128 -> 4 per lane)
+        // softmax backward (every warp reduces all positions redundantly: Te <= 128 -> 4 per lane); this warp's
+        // 16 positions of d e stay in registers (position t0 + p comes from lane (t0 + p) & 31, slot (t0 + p) >> 5)
+        float de_blk[16];
         {
           float dav[4], ldot = 0.f;
 #pragma unroll
@@ -436,66 +472,33 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             }
           }
           ldot = warp_sum(ldot);
-          if (warp == 0) {
+          float dev[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int x = lane + 32 * j;
-              if (x < TeP) de_s[x] = (x < tl) ? a_s[x] * (dav[j] - ldot) : 0.f;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const int x = lane + 32 * j;
+            dev[j] = (x < tl) ? a_s[x] * (dav[j] - ldot) : 0.f;
           }
+          const int t0 = warp * 16;
+          const float mine = dev[0] * (float)((t0 >> 5) == 0) + dev[1] * (float)((t0 >> 5) == 1) + dev[2] * (float)((t0 >> 5) == 2) +
+                             dev[3] * (float)((t0 >> 5) == 3);
+#pragma unroll
+          for (int p = 0; p < 16; ++p) de_blk[p] = __shfl_sync(0xffffffffu, mine, (t0 + p) & 31);
         }
-        ptx::bar_sync(1, kTcCompute);
-        // energy backward over this CTA's 32 attention units: warp = 16-position block, lane = unit
-        float dq_acc = 0.f;
+        // d pre-activation of the energy for this CTA's 32 attention units: warp = 16-position block, lane = unit
         {
           const int t0 = warp * 16;
+          float dq_acc = 0.f;
           if (t0 < tl) {
-            float acc[16], dp[16];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) acc[p] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 16 + kConvK - 1; ++c) {
-              const float cv = cum_s[t0 + c];
-#pragma unroll
-              for (int p = 0; p < 16; ++p) {
-                const int k = c - p;
-                if (k >= 0 && k < kConvK) acc[p] = fmaf(cv, F_reg[k], acc[p]);
-              }
-            }
-            uint32_t kv[16], dk[16];
-            const uint32_t ka = ((uint32_t)(q4 * 32) << 16) + half * 16;
-            ptx::tmem_ld16(tmem_keys + ka, kv);
-            ptx::tmem_ld16(tmem_dkeys + ka, dk);
-            ptx::tmem_wait_ld();
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
-              const int x = t0 + p;
-              float dpre = 0.f;
-              if (x < tl) {
-                const float s = tanhf(__uint_as_float(kv[p]) + qf + acc[p]);
-                const float de = de_s[x];
-                dpre = de * sw_l * (1.f - s * s);
-                dsw_acc = fmaf(de, s, dsw_acc);
-                dq_acc += dpre;
-                dk[p] = __float_as_uint(__uint_as_float(dk[p]) + dpre);
-                dps[(15 + x) * 32 + lane] = dpre;
-              }
-              dp[p] = dpre;
+              const float sv = s_s[p * kTcCompute + tid];
+              const float dpre = (t0 + p < tl) ? de_blk[p] * sw_l * (1.f - sv * sv) : 0.f;
+              dq_acc += dpre;
+              dps[(15 + t0 + p) * 32 + lane] = dpre;
             }
-            ptx::tmem_st16(tmem_dkeys + ka, dk);
-#pragma unroll
-            for (int c = 0; c < 16 + kConvK - 1; ++c) {
-              const float cv = cum_s[t0 + c];
-#pragma unroll
-              for (int p = 0; p < 16; ++p) {
-                const int k = c - p;
-                if (k >= 0 && k < kConvK) dF_reg[k] = fmaf(cv, dp[p], dF_reg[k]);
-              }
-            }
-            ptx::tmem_wait_st();
           }
+          qred[warp * 32 + lane] = dq_acc;
         }
-        qred[warp * 32 + lane] = dq_acc;
         ptx::bar_sync(1, kTcCompute);
         if (tid < 32) {
           float s = 0.f;
@@ -503,44 +506,70 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
           P.dq[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s;
         }
-        // conv transpose: gradient reaching cum_{t-1} through the location features (partial over this CTA's units)
-        {
-          const int t0 = warp * 16;
-          if (t0 < tl) {
-            float G[16];
+        // keep d e for the deferred part
 #pragma unroll
-            for (int p = 0; p < 16; ++p) G[p] = 0.f;
+        for (int p = 0; p < 16; ++p) de_keep[p] = de_blk[p];
+      }
+      STAMP(1);
+      grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+      // ---- inside the barrier wait: everything of attention' that only feeds later steps / weight gradients ----
+      if (cid < B) {
+        const int t0 = warp * 16;
+        if (t0 < tl) {
+          float dp[16];
+          uint32_t dk[16];
+          const uint32_t ka = ((uint32_t)(q4 * 32) << 16) + half * 16;
+          ptx::tmem_ld16(tmem_dkeys + ka, dk);
+          ptx::tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 16 + kConvK - 1; ++c) {
-              const float v = dps[(t0 + c) * 32 + lane];
+          for (int p = 0; p < 16; ++p) {
+            const float sv = s_s[p * kTcCompute + tid];
+            const bool ok = t0 + p < tl;
+            dp[p] = ok ? de_keep[p] * sw_l * (1.f - sv * sv) : 0.f;
+            if (ok) dsw_acc = fmaf(de_keep[p], sv, dsw_acc);
+            dk[p] = __float_as_uint(__uint_as_float(dk[p]) + dp[p]);
+          }
+          ptx::tmem_st16(tmem_dkeys + ka, dk);
 #pragma unroll
-              for (int p = 0; p < 16; ++p) {
-                const int k = p + (kConvK - 1) - c;
-                if (k >= 0 && k < kConvK) G[p] = fmaf(v, F_reg[k], G[p]);
-              }
+          for (int c = 0; c < 16 + kConvK - 1; ++c) {
+            const float cv = cum_s[t0 + c];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int k = c - p;
+              if (k >= 0 && k < kConvK) dF_reg[k] = fmaf(cv, dp[p], dF_reg[k]);
             }
-            const float tot = warp_sum16(G, lane);
-            if ((lane & 1) == 0) g_loc[t0 + warp_sum16_index(lane)] = tot;
           }
-        }
-        ptx::bar_sync(1, kTcCompute);
-        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
-        {
-          const uint32_t ep = ptx::smem_u32(e_parts2) + (uint32_t)(crank * TeP * 4);
-          const uint32_t eb = ptx::smem_u32(e_bar);
-          for (int x = tid; x < tl; x += kTcCompute) {
-            const float v = g_loc[x];
+          // conv transpose: gradient reaching cum_{t-1} through the location features (partial over this CTA's units)
+          float G[16];
 #pragma unroll
-            for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst) + x * 4, v, ptx::mapa(eb, dst));
+          for (int p = 0; p < 16; ++p) G[p] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16 + kConvK - 1; ++c) {
+            const float v = dps[(t0 + c) * 32 + lane];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int k = p + (kConvK - 1) - c;
+              if (k >= 0 && k < kConvK) G[p] = fmaf(v, F_reg[k], G[p]);
+            }
           }
+          const float tot = warp_sum16(G, lane);
+          if ((lane & 1) == 0) {
+            const int x = t0 + warp_sum16_index(lane);
+            if (x < tl) {
+              const uint32_t ep = ptx::smem_u32(e_parts2) + (uint32_t)((crank * TeP + x) * 4);
+              const uint32_t eb = ptx::smem_u32(e_bar);
+#pragma unroll
+              for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), tot, ptx::mapa(eb, dst));
+            }
+          }
+          ptx::tmem_wait_st();
         }
+        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
         mbar_wait_warp(e_bar, e_parity);
         e_parity ^= 1u;
         for (int x = tid; x < tl; x += kTcCompute)
           dcum_s[x] += ((e_parts2[x] + e_parts2[TeP + x]) + e_parts2[2 * TeP + x]) + e_parts2[3 * TeP + x];
       }
-      STAMP(1);
-      grid_arrive_compute(P.barrier, bar_target, gridDim.x);
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(2);
 
@@ -640,6 +669,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       drain(isctx ? &job_done[2] : &job_done[1], sp, isctx ? P.pctx : nullptr, D, P.ph1, kCell);
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+      attention_prologue(t - 1);
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(10);
     }

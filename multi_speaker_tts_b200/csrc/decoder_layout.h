@@ -47,6 +47,7 @@ struct DecLayout {
   size_t dcum;      // [B,Te]
   size_t dpre;      // [T,B,256]
   size_t dpre_h;    // [T,B,256]
+  size_t colsum_scratch;  // [64][4096] partial column sums (bias gradients)
   // ---- bf16x3 reverse kernel only ----
   size_t wimg_b;                         // [128 CTAs][16 tiles][32 KB] reverse weight stream
   size_t ximg_g1, ximg_g0, ximg_g_end;   // [64 k-tiles][8 KB] operand images of dG1_t / dG0_t
@@ -127,6 +128,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dcum = take((size_t)B * Te);
   l.dpre = take(TB * kPrenet);
   l.dpre_h = take(TB * kPrenet);
+  l.colsum_scratch = take((size_t)64 * kGates);
   l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = off;
   l.sp_g0_hi = l.sp_g0_lo = l.sp_g1_hi = l.sp_g1_lo = l.sp_left_hi = l.sp_left_lo = l.sp_w_hi = l.sp_w_lo = off;
   if (mode == MSTTS_MODE_BF16X3) {

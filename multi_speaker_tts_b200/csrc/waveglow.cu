@@ -25,13 +25,13 @@ static inline int ew_grid(size_t n, int per = 256) {
 }
 
 // ---- weight norm + split: v [k*in, out] (out fastest), g [out] (NULL: plain kernel) -> hi/lo [k*in, out] ----
-// pass 1: scale[o] = g[o] / sqrt(max(sum_r v[r][o]^2, 1e-5)); one block per 32 output channels, 8 row lanes, fixed order
+// pass 1: scale[o] = g[o] / sqrt(max(sum_r v[r][o]^2, 1e-5)); one block per 32 output channels, 32 row lanes, fixed order
 __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, int kin, int out, float* __restrict__ scale) {
-  __shared__ float part[8][33];
+  __shared__ float part[32][33];
   const int o = blockIdx.x * 32 + threadIdx.x;
   float ss = 0.f;
   if (o < out)
-    for (int r = threadIdx.y; r < kin; r += 8) {
+    for (int r = threadIdx.y; r < kin; r += 32) {
       const float x = v[(size_t)r * out + o];
       ss = fmaf(x, x, ss);
     }
@@ -40,7 +40,7 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
   if (threadIdx.y == 0 && o < out) {
     float tot = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tot += part[j][threadIdx.x];
+    for (int j = 0; j < 32; ++j) tot += part[j][threadIdx.x];
     scale[o] = g[o] * rsqrtf(fmaxf(tot, 1e-5f));
   }
 }
@@ -60,8 +60,10 @@ __global__ void wn_apply_kernel(const float* __restrict__ v, const float* __rest
 
 // ---- ConvTranspose1d 80->80, k=1024, stride 256, VALID (WaveGlow/Modules.py:198-208) ----
 // out[n, p, co] = bias[co] + sum_{t: 0 <= p-256t < 1024} sum_ci mel[n,t,ci] * K[p-256t, co, ci]
-__global__ void upsample_mel_kernel(const float* __restrict__ mel, const float* __restrict__ K, const float* __restrict__ bias,
-                                    float* __restrict__ out, int N, int Tm, int Lout, int Lkeep) {
+// Step 1 (library SGEMM, fp32): C[n*Tm+t][k*80+co] = sum_ci mel[n,t,ci] K[k,co,ci]   ([N*Tm,80] x [81920,80]^T)
+// Step 2 (this kernel): overlap-add of the <= 4 frames that reach output position p, + bias
+__global__ void upsample_overlap_add_kernel(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ out, int N,
+                                            int Tm, int Lkeep) {
   const size_t n_out = (size_t)N * Lkeep * 80;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_out; i += (size_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % 80);
@@ -69,16 +71,9 @@ __global__ void upsample_mel_kernel(const float* __restrict__ mel, const float* 
     const int p = (int)(np % Lkeep), n = (int)(np / Lkeep);
     float s = bias[co];
     const int t_hi = min(Tm - 1, p / 256), t_lo = max(0, (p - 1023 + 255) / 256);
-    for (int t = t_lo; t <= t_hi; ++t) {
-      const int k = p - 256 * t;
-      const float* kr = K + ((size_t)k * 80 + co) * 80;
-      const float* mr = mel + ((size_t)n * Tm + t) * 80;
-#pragma unroll 8
-      for (int ci = 0; ci < 80; ++ci) s = fmaf(mr[ci], kr[ci], s);
-    }
+    for (int t = t_lo; t <= t_hi; ++t) s += C[((size_t)n * Tm + t) * (1024 * 80) + (size_t)(p - 256 * t) * 80 + co];
     out[i] = s;
   }
-  (void)Lout;
 }
 
 // mel [N,T,640] fp32 -> padded hi/lo [N][Tp][640]
@@ -372,7 +367,7 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
     int slot = 0;
     auto prep = [&](const float* v, const float* g, int kin, int outc, __nv_bfloat16* hi, __nv_bfloat16* lo, float* eff) {
       float* sc = FP(l.wscale) + (size_t)(slot++) * 2 * kWnCh;
-      wn_scale_kernel<<<(outc + 31) / 32, dim3(32, 8), 0, s>>>(v, g, kin, outc, sc);
+      wn_scale_kernel<<<(outc + 31) / 32, dim3(32, 32), 0, s>>>(v, g, kin, outc, sc);
       wn_apply_kernel<<<ew_grid((size_t)kin * outc), 256, 0, s>>>(v, sc, (size_t)kin * outc, outc, hi, lo, eff);
     };
     for (int f = 0; f < kWgFlows; ++f) {
@@ -469,13 +464,22 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
   return MSTTS_OK;
 }
 
-extern "C" int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias, int N, int Tm, int keep, float* out,
-                                  void* stream) {
-  MSTTS_REQUIRE(mel && kernel && bias && out, MSTTS_E_INVALID, "upsample_mel: null pointer");
+extern "C" size_t mstts_upsample_mel_workspace_bytes(int N, int Tm) {
+  if (N <= 0 || Tm <= 0) return 0;
+  return (size_t)N * Tm * 1024 * 80 * sizeof(float);
+}
+
+extern "C" int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias, int N, int Tm, int keep, float* out, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  MSTTS_REQUIRE(mel && kernel && bias && out && ws, MSTTS_E_INVALID, "upsample_mel: null pointer");
   const int Lout = (Tm - 1) * 256 + 1024;
   MSTTS_REQUIRE(keep >= 1 && keep <= Lout, MSTTS_E_INVALID, "upsample_mel: keep=%d outside [1,%d] (the reference's tf.slice would fail)", keep,
                 Lout);
-  upsample_mel_kernel<<<ew_grid((size_t)N * keep * 80), 256, 0, (cudaStream_t)stream>>>(mel, kernel, bias, out, N, Tm, Lout, keep);
+  MSTTS_REQUIRE(ws_bytes >= mstts_upsample_mel_workspace_bytes(N, Tm), MSTTS_E_WORKSPACE, "upsample_mel: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = gemm_rowmajor_ex(s, false, true, N * Tm, 1024 * 80, 80, mel, 80, kernel, 80, (float*)ws, 1024 * 80, 0.f);
+  if (rc) return rc;
+  upsample_overlap_add_kernel<<<ew_grid((size_t)N * keep * 80), 256, 0, s>>>((const float*)ws, bias, out, N, Tm, keep);
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }
