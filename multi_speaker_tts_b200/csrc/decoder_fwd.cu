@@ -1,4 +1,6 @@
-// Tacotron2 decoder loop, forward, as ONE persistent kernel (training / teacher-forced mode).
+// Tacotron2 decoder loop, forward, as ONE persistent kernel: teacher-forced (training) and free-running
+// (inference, Modules.py:212-237: the projected frame of step t is the prenet input of step t+1, the loop ends
+// when every row has emitted stop >= 0 or the step cap is reached).
 //
 // Replaces the tf.while_loop body of Modules.py:397-443 (Decoder_Dynamic_Decode) and everything it calls
 // per step: ZoneoutLSTMCell.call x2 (ZoneoutLSTMCell.py:228-264), Location_Sensitive_Attention.__call__
@@ -24,6 +26,11 @@ struct DecFwdParams {
   int B, Te, T, D, training, resident;
   const float *W0r, *W1, *b0, *b1, *Wq, *F, *fb, *sw;
   const float *g0pre, *keys, *values;
+  // free-running mode only: un-hoisted prenet + projection (Modules.py:222-255,309-321)
+  const float *K0pre, *Wp, *bp, *P0, *pb0, *P1, *pb1;
+  const uint8_t* prenet_mask;  // [T,2,B,256]
+  float *pre, *proj_tm;        // [T,B,256], [T,B,81] (bias-free; finish_outputs adds it)
+  int* steps_done;
   const int* text_len;
   const uint8_t* zone_mask;
   float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart, *qf;
@@ -102,7 +109,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
   float* e_parts = e_loc + TeP;                       // [4][TeP]  written by the 4 CTAs of the cluster
   float* a_s = e_parts + kDecCluster * TeP;           // [TeP]
   float* bred = a_s + TeP;                            // [16]
-  float* keys_s = bred + 16;                          // [Te][32]   (resident)
+  float* x_s = bred + 16;                             // [512]  free-running: [m1 slice (256) | ctx slice (Dq)]
+  float* pred = x_s + 512;                            // [8][96] projection partials per warp
+  float* pparts = pred + 8 * 96;                      // [4][96] projection partials per CTA of the cluster
+  float* frame_s = pparts + kDecCluster * 96;         // [96]   projected frame (+ stop logit at [80])
+  float* h1_s = frame_s + 96;                         // [256]  prenet layer 0 output
+  float* p2red = h1_s + kPrenet;                      // [4][64]
+  int* fin_s = reinterpret_cast<int*>(p2red + 256);   // [256]  free-running: finished flag per batch row
+  float* keys_s = p2red + 256 + 256;                  // [Te][32]   (resident)
   float* vals_s = keys_s + (P.resident ? Te * 32 : 0);// [Te][Dq]   (resident)
 
   // ---- one-time staging ----
@@ -120,20 +134,65 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
     for (int i = tid; i < Te * Dq; i += kDecThreads) vals_s[i] = vg[(size_t)(i / Dq) * D + crank * Dq + (i % Dq)];
   }
   for (int i = tid; i < TeP + 32; i += kDecThreads) cum_s[i] = 0.f;
+  fin_s[tid] = 0;
   __syncthreads();
 
   unsigned bar_target = 0;
   const size_t BC = (size_t)B * kCell, BG = (size_t)B * kGates;
+
+  // free-running mode: prenet of frame_s (this cluster's batch row b) -> pre[slot][b][:]; layer 0 is computed by every
+  // CTA of the cluster (80x256), layer 1 is split 64 outputs per CTA.  Dropout stays on (Modules.py:252).
+  auto prenet_row = [&](int b, int slot) {
+    {
+      float s = P.pb0[tid];
+      for (int k = 0; k < kMel; ++k) s = fmaf(frame_s[k], __ldg(P.P0 + k * kPrenet + tid), s);
+      const float mk = (float)P.prenet_mask[(((size_t)slot * 2 + 0) * B + b) * kPrenet + tid];
+      h1_s[tid] = (fmaxf(s, 0.f) / 0.5f) * mk;
+    }
+    __syncthreads();
+    {
+      const int j = crank * 64 + (tid & 63), kq = tid >> 6;
+      float s = 0.f;
+      for (int k = kq * 64; k < kq * 64 + 64; ++k) s = fmaf(h1_s[k], __ldg(P.P1 + k * kPrenet + j), s);
+      p2red[kq * 64 + (tid & 63)] = s;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const int j = crank * 64 + tid;
+      const float s = ((p2red[tid] + p2red[64 + tid]) + p2red[128 + tid]) + p2red[192 + tid] + P.pb1[j];
+      const float mk = (float)P.prenet_mask[(((size_t)slot * 2 + 1) * B + b) * kPrenet + j];
+      P.pre[((size_t)slot * B + b) * kPrenet + j] = (fmaxf(s, 0.f) / 0.5f) * mk;
+    }
+    __syncthreads();
+  };
+  if (!P.training) {  // first input = prenet(zeros) (Modules.py:178-185)
+    if (tid < 96) frame_s[tid] = 0.f;
+    __syncthreads();
+    for (int b = cid; b < B; b += nclusters) prenet_row(b, 0);
+    grid_barrier(P.barrier, bar_target, gridDim.x);
+  }
 
   for (int t = 0; t < P.T; ++t) {
     const uint8_t* zm = P.training ? P.zone_mask + (size_t)t * 4 * BC : nullptr;
     // ================= phase A: LSTM cell 0 =================
     for (int b0 = 0; b0 < B; b0 += NB) {
       const int nb = min(NB, B - b0);
-      lstm_gemv<NB>(P.W0r, D + kCell, P.ctx + ((size_t)t * B + b0) * D, D, P.hz0 + (size_t)t * BC + (size_t)b0 * kCell,
-                    kCell, nb, red, unit0);
+      if (P.training) {
+        lstm_gemv<NB>(P.W0r, D + kCell, P.ctx + ((size_t)t * B + b0) * D, D, P.hz0 + (size_t)t * BC + (size_t)b0 * kCell,
+                      kCell, nb, red, unit0);
+      } else {  // the prenet rows of cell 0's kernel are not hoisted: the frame is last step's projection
+        const int col = (lane >> 3) * kCell + unit0 + (lane & 7);
+        const int kslice = (D + kCell) >> 3;
+        float acc[NB], acc2[NB];
+        gemv_acc<NB>(P.W0r, kGates, col, warp * kslice, (warp + 1) * kslice, P.ctx + ((size_t)t * B + b0) * D, D,
+                     P.hz0 + (size_t)t * BC + (size_t)b0 * kCell, kCell, nb, acc);
+        gemv_acc<NB>(P.K0pre, kGates, col, warp * (kPrenet / 8), (warp + 1) * (kPrenet / 8),
+                     P.pre + ((size_t)t * B + b0) * kPrenet, kPrenet, nullptr, 0, nb, acc2);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) red[(warp * NB + b) * kRedStride + lane] = acc[b] + acc2[b];
+      }
       __syncthreads();
-      lstm_epilogue<NB>(red, nb, unit0, P.g0pre + (size_t)t * BG + (size_t)b0 * kGates, P.b0,
+      lstm_epilogue<NB>(red, nb, unit0, P.training ? P.g0pre + (size_t)t * BG + (size_t)b0 * kGates : nullptr, P.b0,
                         P.cz0 + (size_t)t * BC + (size_t)b0 * kCell, P.hz0 + (size_t)t * BC + (size_t)b0 * kCell,
                         zm ? zm + (size_t)b0 * kCell : nullptr, zm ? zm + BC + (size_t)b0 * kCell : nullptr,
                         P.act0 + (size_t)t * BG + (size_t)b0 * kGates, P.c0n + (size_t)t * BC + (size_t)b0 * kCell,
@@ -266,10 +325,60 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
         float s = 0.f;
         for (int x = 0; x < tl; ++x) s = fmaf(a_s[x], vals_b[(size_t)x * vstride + tid], s);
         P.ctx[((size_t)(t + 1) * B + b) * D + crank * Dq + tid] = s;
+        if (!P.training) x_s[256 + tid] = s;
       }
-      if (b + nclusters < B) cluster.sync();  // e_parts is reused by the next row
+      if (!P.training) {
+        // ---- projection [m1 | ctx] @ Wp (Modules.py:309-321), K split over the cluster, then the next prenet ----
+        x_s[tid] = __ldcg(P.m1 + ((size_t)t * B + b) * kCell + crank * 256 + tid);
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        const int nrow = 256 + Dq;
+        for (int r = warp; r < nrow; r += 8) {
+          const int grow = r < 256 ? crank * 256 + r : kCell + crank * Dq + (r - 256);
+          const float* wr = P.Wp + (size_t)grow * (kMel + 1);
+          const float xv = x_s[r];
+          a0 = fmaf(xv, __ldg(wr + lane), a0);
+          a1 = fmaf(xv, __ldg(wr + 32 + lane), a1);
+          if (lane < kMel + 1 - 64) a2 = fmaf(xv, __ldg(wr + 64 + lane), a2);
+        }
+        pred[warp * 96 + lane] = a0;
+        pred[warp * 96 + 32 + lane] = a1;
+        pred[warp * 96 + 64 + lane] = a2;
+        __syncthreads();
+        if (tid < 96) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) s += pred[w * 96 + tid];
+#pragma unroll
+          for (int dst = 0; dst < kDecCluster; ++dst) cluster.map_shared_rank(pparts, dst)[crank * 96 + tid] = s;
+        }
+        cluster.sync();
+        if (tid < kMel + 1) {
+          const float s = ((pparts[tid] + pparts[96 + tid]) + pparts[192 + tid]) + pparts[288 + tid];
+          if (crank == 0) P.proj_tm[((size_t)t * B + b) * (kMel + 1) + tid] = s;
+          frame_s[tid] = s + P.bp[tid];
+        }
+        __syncthreads();
+        if (t + 1 < P.T) prenet_row(b, t + 1);
+        cluster.sync();  // pparts / e_parts are reused by the next row
+      } else if (b + nclusters < B) {
+        cluster.sync();  // e_parts is reused by the next row
+      }
     }
     grid_barrier(P.barrier, bar_target, gridDim.x);
+    if (!P.training) {
+      // finished |= stop >= 0 (Modules.py:216-219, OR-ed at :409); every CTA evaluates the same data => uniform exit.
+      // The step cap (time >= Max_Inference_Length) is the loop bound T = cap + 1.
+      int all = 1;
+      for (int b = tid; b < B; b += kDecThreads) {
+        const float st = __ldcg(P.proj_tm + ((size_t)t * B + b) * (kMel + 1) + kMel) + P.bp[kMel];
+        if (st >= 0.f) fin_s[b] = 1;
+        all &= fin_s[b];
+      }
+      all = __syncthreads_and(all);
+      if (blockIdx.x == 0 && tid == 0) *P.steps_done = t + 1;
+      if (all) break;
+    }
   }
 }
 
@@ -277,7 +386,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
 size_t dec_fwd_smem_bytes(int NB, int Te, int D, int resident) {
   const int TeP = (Te + 15) & ~15;
   size_t f = (size_t)8 * NB * kRedStride + kUnitsPerCta * kAtt + NB * kUnitsPerCta + 8 * 32 + 32 + (TeP + 32) + TeP +
-             kDecCluster * TeP + TeP + 16;
+             kDecCluster * TeP + TeP + 16 + (512 + 8 * 96 + kDecCluster * 96 + 96 + kPrenet + 256 + 256);
   if (resident) f += (size_t)Te * 32 + (size_t)Te * (D / kDecCluster);
   return f * sizeof(float);
 }
@@ -330,7 +439,10 @@ int dec_fwd_persistent_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO*
   P.W0r = F(l.W0r); P.W1 = w->cell1_kernel; P.b0 = w->cell0_bias; P.b1 = w->cell1_bias; P.Wq = w->query_kernel;
   P.F = F(l.locF); P.fb = F(l.locFb); P.sw = w->score_w;
   P.g0pre = F(l.g0pre); P.keys = F(l.keys); P.values = F(l.values);
-  P.text_len = io->text_len; P.zone_mask = io->zone_mask;
+  P.text_len = io->text_len; P.zone_mask = io->is_training ? io->zone_mask : nullptr;
+  P.K0pre = w->cell0_kernel; P.Wp = w->proj_kernel; P.bp = w->proj_bias; P.P0 = w->prenet0_kernel; P.pb0 = w->prenet0_bias;
+  P.P1 = w->prenet1_kernel; P.pb1 = w->prenet1_bias; P.prenet_mask = io->prenet_mask; P.pre = F(l.pre);
+  P.proj_tm = F(l.proj_tm); P.steps_done = io->steps_done;
   P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n);
   P.cz0 = F(l.cz0); P.hz0 = F(l.hz0); P.cz1 = F(l.cz1); P.hz1 = F(l.hz1);
   P.m0 = F(l.m0); P.m1 = F(l.m1); P.ctx = F(l.ctx); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.qpart = F(l.qpart); P.qf = F(l.qf);

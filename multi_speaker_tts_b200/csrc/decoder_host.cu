@@ -149,15 +149,54 @@ static int check_io(const MsttsDecoderWeights* w, const MsttsDecoderIO* io) {
   return MSTTS_OK;
 }
 
+// Free-running (inference) decode, Modules.py:212-237: nothing can be hoisted except the memory layer; the persistent
+// fp32 kernel computes projection -> prenet -> cells -> attention per step and stops when every row is finished.
+// n_steps = step cap + 1 (Max_Inference_Length + 1); outputs beyond *steps_done are zero.
+static int decoder_fwd_free_running(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes,
+                                    cudaStream_t s) {
+  MSTTS_REQUIRE(io->mode == MSTTS_MODE_FP32, MSTTS_E_UNSUPPORTED,
+                "decoder: free-running mode runs on the fp32 kernel only (mode=%d)", io->mode);
+  MSTTS_REQUIRE(io->steps_done, MSTTS_E_INVALID, "decoder: free-running mode needs steps_done");
+  const int B = io->B, Te = io->Te, D = io->D, T = io->n_steps;
+  const DecLayout l = dec_layout(B, Te, io->L, D, T, io->mode);
+  MSTTS_REQUIRE(ws_ && ws_bytes >= l.total, MSTTS_E_WORKSPACE, "decoder: workspace %zu < %zu", ws_bytes, l.total);
+  MSTTS_REQUIRE(((uintptr_t)ws_ & 255) == 0, MSTTS_E_INVALID, "decoder: workspace must be 256-byte aligned");
+  char* ws = (char*)ws_;
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  const size_t TB = (size_t)T * B;
+  mask_memory_kernel<<<ew_grid((size_t)B * Te * D), 256, 0, s>>>(io->memory, io->text_len, F(l.values), B, Te, D);
+  int rc = gemm_rowmajor(s, B * Te, kAtt, D, F(l.values), D, w->memory_kernel, kAtt, F(l.keys), kAtt, 0.f);
+  if (rc) return rc;
+  fold_cell0_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, F(l.W0r), D);
+  compose_location_kernel<<<32, kAtt, 0, s>>>(w->loc_conv_kernel, w->loc_conv_bias, w->loc_dense_kernel, w->score_b,
+                                              F(l.locF), F(l.locFb));
+  const size_t BC = (size_t)B * kCell * sizeof(float);
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.cz0, 0, BC, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.hz0, 0, BC, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.cz1, 0, BC, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.hz1, 0, BC, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.ctx, 0, (size_t)B * D * sizeof(float), s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.cum, 0, (size_t)B * Te * sizeof(float), s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.barrier, 0, 64, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.proj_tm, 0, TB * (kMel + 1) * sizeof(float), s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.align_tm, 0, TB * Te * sizeof(float), s));
+  MSTTS_CUDA(cudaMemsetAsync(io->steps_done, 0, sizeof(int), s));
+  rc = dec_fwd_persistent_entry(w, io, l, ws, s);
+  if (rc) return rc;
+  finish_outputs_kernel<<<ew_grid(TB * (kMel + 1 + Te)), 256, 0, s>>>(F(l.proj_tm), w->proj_bias, F(l.align_tm), io->linear,
+                                                                    io->stop, io->align, B, T, Te);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
 extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes,
                                  void* stream_) {
   int rc = check_io(w, io);
   if (rc) return rc;
-  MSTTS_REQUIRE(io->is_training, MSTTS_E_UNSUPPORTED,
-                "decoder: free-running (inference) mode is not implemented yet; teacher-forced only");
+  cudaStream_t s = (cudaStream_t)stream_;
+  if (!io->is_training) return decoder_fwd_free_running(w, io, ws_, ws_bytes, s);
   MSTTS_REQUIRE(io->mel && io->mel_len && io->zone_mask, MSTTS_E_INVALID, "decoder: training needs mel/mel_len/zone_mask");
   MSTTS_REQUIRE(io->n_steps <= io->L + 1, MSTTS_E_INVALID, "decoder: n_steps=%d > L+1=%d", io->n_steps, io->L + 1);
-  cudaStream_t s = (cudaStream_t)stream_;
   const int B = io->B, Te = io->Te, L = io->L, D = io->D, T = io->n_steps;
   const DecLayout l = dec_layout(B, Te, L, D, T, io->mode);
   MSTTS_REQUIRE(ws_ && ws_bytes >= l.total, MSTTS_E_WORKSPACE, "decoder: workspace %zu < %zu", ws_bytes, l.total);

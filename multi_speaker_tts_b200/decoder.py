@@ -40,19 +40,31 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
 
     weights: dict (keys as synthetic.decoder_weight_shapes) of fp32 CUDA tensors in TF layouts.
     Returns (linear [B,T,80], stop [B,T], align [B,T,Te], state).
+
+    ``is_training=False`` is the free-running decode of Modules.py:212-237 (``mel`` / ``mel_len`` / ``zone_mask`` are
+    ignored and may be None): ``n_steps`` is the step cap + 1 (default Max_Inference_Length + 1 = 1001), the loop
+    stops once every row has emitted ``stop >= 0`` and the outputs are cut to the executed steps (one host sync).
+    It always runs on the fp32 kernel.
     """
-    _require_cuda(memory, text_len, mel, mel_len, prenet_mask, zone_mask)
+    _require_cuda(memory, text_len, prenet_mask)
     lib = _lib.lib()
     B, Te, D = memory.shape
-    L = mel.shape[1]
-    if n_steps is None:
-        n_steps = int(mel_len.max().item()) + 1 if is_training else 1001
-    T = n_steps
     dev = memory.device
+    if not is_training:
+        mel, mel_len, zone_mask, mode = None, None, None, "fp32"
+        if n_steps is None:
+            n_steps = 1001
+    else:
+        _require_cuda(mel, mel_len, zone_mask)
+    L = mel.shape[1] if mel is not None else 0
+    if n_steps is None:
+        n_steps = int(mel_len.max().item()) + 1
+    T = n_steps
     memory = memory.contiguous().float()
-    mel = mel.contiguous().float()
     text_len = text_len.contiguous().to(torch.int32)
-    mel_len = mel_len.contiguous().to(torch.int32)
+    if mel is not None:
+        mel = mel.contiguous().float()
+        mel_len = mel_len.contiguous().to(torch.int32)
     prenet_mask = prenet_mask.contiguous()
     assert prenet_mask.dtype == torch.uint8 and tuple(prenet_mask.shape) == (T, 2, B, 256), prenet_mask.shape
     if zone_mask is not None:
@@ -69,7 +81,8 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
     wstruct, keep = pack_weights(weights)
     io = _lib.MsttsDecoderIO(
         B=B, Te=Te, L=L, D=D, n_steps=T, is_training=int(bool(is_training)), mode=m,
-        memory=memory.data_ptr(), text_len=text_len.data_ptr(), mel=mel.data_ptr(), mel_len=mel_len.data_ptr(),
+        memory=memory.data_ptr(), text_len=text_len.data_ptr(), mel=mel.data_ptr() if mel is not None else None,
+        mel_len=mel_len.data_ptr() if mel_len is not None else None,
         prenet_mask=prenet_mask.data_ptr(), zone_mask=zone_mask.data_ptr() if zone_mask is not None else None,
         linear=linear.data_ptr(), stop=stop.data_ptr(), align=align.data_ptr(), steps_done=steps_done.data_ptr())
     s = stream if stream is not None else torch.cuda.current_stream(dev)
@@ -81,6 +94,9 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
     st.io, st.ws, st.wstruct = io, workspace, wstruct
     st.keep = keep + [memory, text_len, mel, mel_len, prenet_mask, zone_mask, steps_done]
     st.shape = (B, Te, L, D, T)
+    if not is_training:
+        n = int(steps_done.item())
+        linear, stop, align = linear[:, :n].contiguous(), stop[:, :n].contiguous(), align[:, :n].contiguous()
     return linear, stop, align, st
 
 
