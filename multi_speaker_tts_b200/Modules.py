@@ -1,0 +1,244 @@
+"""Modules surface of the reference (Modules.py) on torch CUDA tensors.
+
+``Decoder_LSTM`` -- the hot path -- dispatches the whole tf.while_loop of Modules.py:76-119,148-472 (helper, two
+ZoneoutLSTMCells, location-sensitive attention, projection, dynamic decode) to the persistent sm_100a kernels through the
+C ABI (``decoder.py`` -> ``libmstts_b200.so``), as one ``torch.autograd.Function`` whose backward is the persistent
+reverse-time kernel.  There is no CPU path: non-CUDA tensors raise.
+
+``Encoder_Embedding / Encoder_Conv / Encoder_BiLSTM / Decoder_Conv`` are the callers either side of the decoder (SURVEY
+8f rank 1).  First pass, as the survey prescribes: library ops (cuDNN convolutions, cuBLAS) composed with the
+reference's exact semantics (TF batch-norm statistics over padding, dropout/zoneout conventions, sequence-length
+handling of stack_bidirectional_dynamic_rnn), with explicit variable dicts instead of TF variable scopes.
+"""
+from collections import namedtuple
+
+import torch
+import torch.nn.functional as F
+
+from . import Hyper_Parameters as hp
+from . import _lib
+from .decoder import decoder_forward, decoder_backward, fill_mask
+from .ZoneoutLSTMCell import ZoneoutLSTMCell  # noqa: F401  (re-exported like the reference module does)
+from .Location_Sensitive_Attention import Location_Sensitive_Attention, VARIABLE_KEYS as _ATT_KEYS
+
+# fp32 parity gate (mel L_inf < 1e-3 against the fp32 reference): cuDNN convolutions, forward and backward, stay in fp32
+torch.backends.cudnn.allow_tf32 = False
+
+DECODER_KEYS = [key for _, key in _lib.DECODER_WEIGHT_FIELDS]
+DECODER_OWN_KEYS = [k for k in DECODER_KEYS if k not in _ATT_KEYS]  # prenet, cells, projection
+
+
+class Decoder_Output(namedtuple('Decoder_Output', ('linear', 'stop'))):
+    pass
+
+
+class Alignment_History(object):
+    """stands in for the TensorArray in AttentionWrapperState.alignment_history: ``stack()`` -> [T, B, Te]"""
+
+    def __init__(self, align_btx):
+        self._a = align_btx  # [B, T, Te]
+
+    def stack(self):
+        return self._a.transpose(0, 1)
+
+
+class Decoder_State(namedtuple('Decoder_State', ('time', 'alignment_history'))):
+    pass
+
+
+_WORKSPACE = {}
+
+
+def _workspace(dev, nbytes):
+    """One cached decoder workspace per device (3.6 GB at B=32, Te=128, L=800 in bf16x3 mode): the saved activations of
+    the latest forward live in it until its backward ran, so at most one decoder call may be in flight per device."""
+    ws = _WORKSPACE.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        _WORKSPACE[dev] = ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    return ws
+
+
+class _DecoderFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, memory, text_len, mel, mel_len, prenet_mask, zone_mask, n_steps, mode, *weights):
+        w = dict(zip(DECODER_KEYS, weights))
+        B, Te, D = memory.shape
+        m = _lib.MODES[mode]
+        nbytes = _lib.lib().mstts_decoder_workspace_bytes(B, Te, mel.shape[1], D, n_steps, m)
+        lin, stop, align, st = decoder_forward(w, memory, text_len, mel, mel_len, prenet_mask, zone_mask, True, n_steps,
+                                               mode, workspace=_workspace(memory.device, nbytes))
+        ctx.state, ctx.weights = st, w
+        ctx.mark_non_differentiable(align)
+        return lin, stop, align
+
+    @staticmethod
+    def backward(ctx, d_linear, d_stop, _d_align):
+        grads, d_memory = decoder_backward(ctx.state, ctx.weights, d_linear.contiguous(), d_stop.contiguous(),
+                                           want_d_memory=ctx.needs_input_grad[0])
+        return (d_memory, None, None, None, None, None, None, None) + tuple(grads[k] for k in DECODER_KEYS)
+
+
+def decoder_mode(B, Te, D):
+    """tensor-core (bf16x3) loop where its tiling applies, the fp32 SIMT loop otherwise (both meet the 1e-3 gate)"""
+    return "bf16x3" if (B <= 32 and Te <= 128 and D in (256, 512, 768)) else "fp32"
+
+
+def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False, variables=None, masks=None, mode=None,
+                 seed=0):
+    """Modules.py:76-119.  inputs = Mel [B, L, 80] and sequence_length = Mel_Length [B] (ignored at inference),
+    attention_mechanism = Location_Sensitive_Attention (memory, memory_length and the attention variables),
+    variables = the decoder's own variables (prenet_*, cell_*, projection/*; short keys of synthetic.TF_VARIABLE_NAMES).
+    masks = (prenet_mask [T,2,B,256] u8, zone_mask [T,2,2,B,1024] u8) or None (drawn on device from ``seed``).
+    Returns (Decoder_Output(linear [B,T,80], stop [B,T,1]), state) with state.alignment_history.stack() -> [T,B,Te];
+    T = max(Mel_Length) + 1 in training, the executed steps at inference."""
+    att = attention_mechanism
+    if not isinstance(att, Location_Sensitive_Attention):
+        raise TypeError("attention_mechanism must be a Location_Sensitive_Attention")
+    if variables is None:
+        raise ValueError("Decoder_LSTM needs the decoder variables (there are no implicit TF variable scopes here)")
+    w = dict(att.variables)
+    w.update({k: variables[k] for k in DECODER_OWN_KEYS})
+    memory, text_len = att.memory, att.memory_length
+    B, Te, D = memory.shape
+    dev = memory.device
+    training = bool(is_training)
+    T = int(sequence_length.max().item()) + 1 if training else hp.Decoder.LSTM.Max_Inference_Length + 1
+    if masks is None:
+        pm = torch.empty(T, 2, B, 256, device=dev, dtype=torch.uint8)
+        fill_mask(pm, 1.0 - hp.Decoder.PreNet.Dropout_Rate, seed * 4 + 1)
+        zm = None
+        if training:
+            zm = torch.empty(T, 2, 2, B, 1024, device=dev, dtype=torch.uint8)
+            fill_mask(zm, 1.0 - hp.Decoder.LSTM.Zoneout_Rate, seed * 4 + 2)
+    else:
+        pm, zm = masks
+    if training:
+        mode = mode or decoder_mode(B, Te, D)
+        lin, stop, align = _DecoderFunction.apply(memory, text_len, inputs, sequence_length, pm, zm, T, mode,
+                                                  *[w[k] for k in DECODER_KEYS])
+    else:
+        with torch.no_grad():
+            lin, stop, align, _ = decoder_forward(w, memory, text_len, None, None, pm, None, False, T, "fp32")
+    return (Decoder_Output(linear=lin, stop=stop.unsqueeze(-1)),
+            Decoder_State(time=lin.shape[1], alignment_history=Alignment_History(align)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# callers either side of the decoder (library ops, reference semantics)
+# ------------------------------------------------------------------------------------------------------------------
+def _dropout(x, rate, training, mask):
+    """tf.layers.dropout: keep-prob 1-rate, kept values scaled by 1/(1-rate); identity when not training"""
+    if not training:
+        return x
+    if mask is None:
+        mask = torch.floor(torch.rand_like(x) + (1.0 - rate))
+    return x / (1.0 - rate) * mask
+
+
+def _batch_norm(x, v, prefix, training, momentum=0.99, eps=1e-3):
+    """tf.layers.batch_normalization on [B,T,C] (axis -1): biased batch statistics over (B,T) *including padding* in
+    training, moving statistics otherwise; moving stats are updated in place (the UPDATE_OPS group, MSTTS_SV.py:178)."""
+    gamma, beta = v[prefix + '/gamma'], v[prefix + '/beta']
+    if training:
+        var, mean = torch.var_mean(x, dim=(0, 1), unbiased=False)
+        with torch.no_grad():
+            v[prefix + '/moving_mean'].mul_(momentum).add_(mean, alpha=1.0 - momentum)
+            v[prefix + '/moving_variance'].mul_(momentum).add_(var, alpha=1.0 - momentum)
+    else:
+        mean, var = v[prefix + '/moving_mean'], v[prefix + '/moving_variance']
+    return (x - mean) * torch.rsqrt(var + eps) * gamma + beta
+
+
+def _conv1d_same(x, kernel, bias):
+    """tf.layers.conv1d(padding='same', stride 1) on [B,T,C] with a TF-layout kernel [k, in, out]"""
+    k = kernel.shape[0]
+    y = F.conv1d(x.transpose(1, 2), kernel.permute(2, 1, 0), bias, padding=k // 2)
+    return y.transpose(1, 2)
+
+
+def Encoder_Embedding(inputs, variables):
+    """Modules.py:15-23"""
+    return F.embedding(inputs.long(), variables['encoder/embedding_variable'])
+
+
+def Encoder_Conv(inputs, is_training=False, variables=None, masks=None):
+    """Modules.py:25-47: conv -> ReLU -> batch norm -> dropout, x3"""
+    x = inputs
+    for i in range(hp.Encoder.Conv.Nums):
+        p = 'encoder/conv_%d' % i
+        x = torch.relu(_conv1d_same(x, variables[p + '/conv1d/kernel'], variables[p + '/conv1d/bias']))
+        x = _batch_norm(x, variables, p + '/batch_normalization', is_training)
+        x = _dropout(x, hp.Encoder.Conv.Dropout_Rate, is_training, None if masks is None else masks[i])
+    return x
+
+
+def _reverse_sequence(x, lengths):
+    """tf.reverse_sequence over axis 1: the first lengths[b] entries of row b are reversed, the rest stay"""
+    T = x.shape[1]
+    t = torch.arange(T, device=x.device)[None, :]
+    ln = lengths.long()[:, None]
+    idx = torch.where(t < ln, ln - 1 - t, t)
+    return torch.gather(x, 1, idx[:, :, None].expand_as(x))
+
+
+def zoneout_lstm_sequence(inputs, lengths, kernel, bias, is_training, zoneout_rate, masks=None, residual=False):
+    """tf.nn.dynamic_rnn over a ZoneoutLSTMCell with sequence_length: beyond lengths[b] the output is zero and the state
+    is carried through.  The input rows of the kernel are applied to all steps in one GEMM; the loop keeps h @ K_h.
+    masks: [T, 2, B, H] 0/1 (c, h) or None.  residual: tf ResidualWrapper (output = m + input)."""
+    B, T, In = inputs.shape
+    H = kernel.shape[1] // 4
+    xk = inputs @ kernel[:In] + bias
+    kh = kernel[In:]
+    c = inputs.new_zeros(B, H)
+    h = inputs.new_zeros(B, H)
+    keep = 1.0 - zoneout_rate
+    outs = []
+    ln = lengths.long()
+    for t in range(T):
+        g = xk[:, t] + h @ kh
+        i, j, f, o = torch.split(g, H, dim=1)
+        cn = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+        m = torch.sigmoid(o) * torch.tanh(cn)
+        dc, dm = cn - c, m - h
+        if is_training:
+            if masks is None:
+                dc = dc * torch.floor(torch.rand_like(dc) + keep)
+                dm = dm * torch.floor(torch.rand_like(dm) + keep)
+            else:
+                dc, dm = dc * masks[t, 0], dm * masks[t, 1]
+        live = (t < ln)[:, None]
+        out = m + inputs[:, t] if residual else m
+        outs.append(torch.where(live, out, torch.zeros_like(out)))
+        c = torch.where(live, keep * dc + c, c)
+        h = torch.where(live, keep * dm + h, h)
+    return torch.stack(outs, 1), (c, h)
+
+
+def Encoder_BiLSTM(inputs, lengths, is_training=False, variables=None, masks=None):
+    """Modules.py:49-73: stack_bidirectional_dynamic_rnn of ZoneoutLSTMCells (1 layer x 256 units per direction)"""
+    x = inputs
+    for n in range(hp.Encoder.BiLSTM.Nums):
+        p = 'encoder/bilstm/stack_bidirectional_rnn/cell_%d/bidirectional_rnn' % n
+        mf = mb = None
+        if masks is not None:
+            mf, mb = masks[n]
+        fw, _ = zoneout_lstm_sequence(x, lengths, variables[p + '/fw/zoneout_lstm_cell/kernel'],
+                                      variables[p + '/fw/zoneout_lstm_cell/bias'], is_training,
+                                      hp.Encoder.BiLSTM.Zoneout_Rate, mf)
+        bw, _ = zoneout_lstm_sequence(_reverse_sequence(x, lengths), lengths, variables[p + '/bw/zoneout_lstm_cell/kernel'],
+                                      variables[p + '/bw/zoneout_lstm_cell/bias'], is_training,
+                                      hp.Encoder.BiLSTM.Zoneout_Rate, mb)
+        x = torch.cat([fw, _reverse_sequence(bw, lengths)], dim=-1)
+    return x
+
+
+def Decoder_Conv(inputs, is_training=False, variables=None, masks=None):
+    """Modules.py:121-143 (postnet): conv -> tanh -> batch norm -> dropout on all 5 layers incl. the last; the dropout
+    rate is read from hp.Encoder.Conv (quirk B-10)"""
+    x = inputs
+    for i in range(hp.Decoder.Conv.Nums):
+        p = 'decoder/conv_%d' % i
+        x = torch.tanh(_conv1d_same(x, variables[p + '/conv1d/kernel'], variables[p + '/conv1d/bias']))
+        x = _batch_norm(x, variables, p + '/batch_normalization', is_training)
+        x = _dropout(x, hp.Encoder.Conv.Dropout_Rate, is_training, None if masks is None else masks[i])
+    return x

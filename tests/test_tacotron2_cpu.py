@@ -1,0 +1,134 @@
+"""Host-side surface (MSTTS_SV / Feeder / Modules callers either side of the decoder) on the CPU: the batched library-op
+implementations in multi_speaker_tts_b200.Modules against the row-by-row oracle, the variable inventory, the
+weight-regularisation name filter and the Feeder contracts.  (Decoder_LSTM itself needs the GPU: tests/test_tacotron2_gpu.py.)"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from multi_speaker_tts_b200 import Feeder, Hyper_Parameters as hp
+
+
+def _variables(seed=0, dtype=torch.float64):
+    from multi_speaker_tts_b200 import MSTTS_SV as M
+    gen = torch.Generator().manual_seed(seed)
+    v = {}
+    for k, (s, kind) in M.variable_shapes().items():
+        t = M._init(s, kind, gen).to(dtype)
+        if kind in ('zeros', 'ones', 'moving_mean', 'moving_variance'):  # make every bias / BN term matter
+            t = t + 0.1 * torch.randn(s, generator=gen, dtype=dtype) if kind != 'moving_variance' else \
+                t + 0.3 * torch.rand(s, generator=gen, dtype=dtype)
+        v[k] = t
+    return v
+
+
+def test_variable_inventory_and_regularised_set():
+    from multi_speaker_tts_b200 import MSTTS_SV as M
+    s = M.variable_shapes()
+    n = sum(math.prod(v[0]) for k, v in s.items() if M.is_trainable(k, v[1]))
+    assert n == 30278977  # "~30.3 M params" in the Tacotron2 trainable set
+    wr = [k for k, v in s.items() if M.is_trainable(k, v[1]) and M.in_weight_regularization(k)]
+    assert 'attention/memory_layer/kernel' in wr and 'encoder/conv_0/batch_normalization/beta' in wr
+    for k in wr:  # MSTTS_SV.py:145-159
+        assert not any(x in k.lower() for x in ('bias', 'embedding', 'lstm', 'rnn', 'weight_w', 'projection'))
+    assert not any('multi_rnn_cell' in k or 'linear_projection' in k for k in wr)
+    assert s['decoder/decoder/attention_wrapper/multi_rnn_cell/cell_0/zoneout_lstm_cell/kernel'][0] == (2816, 4096)
+
+
+def test_feeder_contracts():
+    f = Feeder.Feeder(is_Training=True, synthetic=True, synthetic_shape=(3, 20, 50))
+    p = f.placeholder_Dict
+    assert set(p) == {"Is_Training", "Token", "Token_Length", "Mel", "Mel_Length", "Speaker_Embedding_Mel"}
+    d = f.Get_Train_Pattern()
+    assert d[p['Token']].dtype == np.int32 and d[p['Token']].shape == (3, 20)
+    assert (d[p['Token']][:, 0] == 0).all() and (d[p['Token']][:, -1] == 1).all()      # <S> ... <E>
+    assert d[p['Mel']].shape == (3, 50, 80) and d[p['Mel']].dtype == np.float32
+    assert d[p['Speaker_Embedding_Mel']].shape == (15, 64, 80)
+    g = Feeder.Feeder(is_Training=False, synthetic=True)
+    q = g.Get_Inference_Pattern(['nowhere_a.wav', 'nowhere_b.wav'], ['Hello, world!', 'Hi.'])
+    tok = q[g.placeholder_Dict['Token']]
+    assert tok.shape == (2, 15) and (tok[1, 5:] == 1).all()                           # padded with <E> (Feeder.py:155)
+    assert q[g.placeholder_Dict['Mel']].shape == (2, 1, 80) and (q[g.placeholder_Dict['Mel_Length']] == 0).all()
+    assert q[g.placeholder_Dict['Token_Length']].tolist() == [15, 5]
+
+
+def test_speaker_embedding_windows():
+    f = Feeder.Feeder(is_Training=False, synthetic=True)
+    long = np.arange(400 * 80, dtype=np.float32).reshape(400, 80)
+    short = np.ones((30, 80), np.float32)
+    w = f.Speaker_Embedding_Mel([long, short]).reshape(2, 5, 64, 80)
+    start = int((400 - 192) / 2)
+    for s in range(5):
+        assert np.array_equal(w[0, s], long[start + 32 * s:start + 32 * s + 64])
+    assert (w[1, :, :30] == 1).all() and (w[1, :, 30:] == 0).all()
+
+
+def test_trim_drops_quiet_edges():
+    y = np.concatenate([np.zeros(320), np.sin(np.arange(1600) * 0.3), np.zeros(480)]).astype(np.float32)
+    t = Feeder._trim(y)
+    assert 1500 <= t.shape[0] <= 1700 and abs(t).max() > 0.9
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_encoder_and_postnet_match_oracle(training):
+    from oracle import tacotron2_oracle as O
+    from multi_speaker_tts_b200 import Modules
+    torch.manual_seed(0)
+    v = _variables()
+    B, Te, T = 3, 11, 9
+    tok = torch.randint(2, 42, (B, Te), dtype=torch.int32)
+    tl = torch.tensor([11, 7, 4], dtype=torch.int32)
+    masks_c = [(torch.rand(B, Te, 512) < 0.5).double() for _ in range(3)]
+    mf = (torch.rand(Te, 2, B, 256) < 0.9).double()
+    mb = (torch.rand(Te, 2, B, 256) < 0.9).double()
+    # batched library-op path
+    va = {k: t.clone() for k, t in v.items()}
+    x = Modules.Encoder_Embedding(tok, va)
+    x = Modules.Encoder_Conv(x, training, va, masks_c)
+    x = Modules.Encoder_BiLSTM(x, tl, training, va, [(mf, mb)])
+    # oracle
+    y = v['encoder/embedding_variable'][tok.long()]
+    y = O.conv_bn_stack(y, v, 'encoder', 3, torch.relu, training, 0.5, masks_c)
+    p = 'encoder/bilstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn'
+    fw = O.dynamic_rnn(y, tl, v[p + '/fw/zoneout_lstm_cell/kernel'], v[p + '/fw/zoneout_lstm_cell/bias'], training, mf)
+    bw = O.dynamic_rnn(O.reverse_rows(y, tl), tl, v[p + '/bw/zoneout_lstm_cell/kernel'], v[p + '/bw/zoneout_lstm_cell/bias'],
+                       training, mb)
+    y = torch.cat([fw, O.reverse_rows(bw, tl)], dim=-1)
+    assert x.shape == (B, Te, 512) and (x - y).abs().max() < 1e-10
+    assert (x[1, 7:] == 0).all() and (x[2, 4:] == 0).all()  # zero beyond Token_Length
+    if training:  # moving statistics moved by (1 - 0.99) towards the batch statistics
+        assert not torch.equal(va['encoder/conv_0/batch_normalization/moving_mean'],
+                               v['encoder/conv_0/batch_normalization/moving_mean'])
+    lin = torch.randn(B, T, 80, dtype=torch.float64)
+    masks_p = [(torch.rand(B, T, 512 if i < 4 else 80) < 0.5).double() for i in range(5)]
+    a = Modules.Decoder_Conv(lin, training, va, masks_p)
+    b = O.conv_bn_stack(lin, v, 'decoder', 5, torch.tanh, training, 0.5, masks_p)
+    assert (a - b).abs().max() < 1e-10
+
+
+def test_speaker_embedding_matches_oracle_and_is_normalised_over_the_batch():
+    from oracle import tacotron2_oracle as O
+    from multi_speaker_tts_b200.Speaker_Embedding import Modules as S
+    v = _variables()
+    se = torch.randn(2 * 5, 12, 80, dtype=torch.float64)
+    x = S.Restructure(se, v)
+    x = S.Stack_LSTM(x, torch.full((10,), 12), False, v)
+    e = S.Inference(x)
+    ref = O.speaker_embedding(v, se)
+    assert e.shape == (2, 256) and (e - ref).abs().max() < 1e-10
+    assert abs(float((e * e).sum()) - 1.0) < 1e-9  # whole-tensor l2 norm (quirk B-4), not per row
+
+
+def test_zoneout_cell_class_matches_oracle_cell():
+    from oracle import decoder_oracle as D
+    from multi_speaker_tts_b200.ZoneoutLSTMCell import ZoneoutLSTMCell
+    g = torch.Generator().manual_seed(1)
+    cell = ZoneoutLSTMCell(16, is_training=True, cell_zoneout_rate=0.1, output_zoneout_rate=0.1, input_size=8, generator=g)
+    x, c, h = torch.randn(4, 8), torch.randn(4, 16), torch.randn(4, 16)
+    mc, mh = (torch.rand(4, 16) < 0.9).float(), (torch.rand(4, 16) < 0.9).float()
+    m, (c2, h2) = cell(x, (c, h), masks=(mc, mh))
+    rm, rc, rh = D.lstm_cell(x, c, h, cell.kernel, cell.bias, mc, mh)
+    assert torch.allclose(m, rm, atol=1e-6) and torch.allclose(c2, rc, atol=1e-6) and torch.allclose(h2, rh, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        ZoneoutLSTMCell(16, num_proj=8)
