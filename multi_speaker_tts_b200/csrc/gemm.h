@@ -30,3 +30,8 @@ struct Bf16Pair {
 int split_bf16_matrix(cudaStream_t s, const float* src, size_t rows, size_t cols, size_t ld, Bf16Pair dst);
 int gemm_rowmajor_x3(cudaStream_t s, bool transA, bool transB, int M, int N, int K, Bf16Pair A, int lda, Bf16Pair B, int ldb,
                      float* C, int ldc, float beta);
+
+// one bf16 x bf16 -> fp32 tensor-core GEMM (row-major, no transposes): C = A B + beta C.  Callers that fold the three
+// bf16x3 partial products into K (A rows [hi|lo|hi], B rows [hi;hi;lo]) get the bf16x3 result from a single call.
+int gemm_rowmajor_bf16(cudaStream_t s, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
+                       float* C, int ldc, float beta);

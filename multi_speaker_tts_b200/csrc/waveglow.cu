@@ -1,9 +1,12 @@
 // WaveGlow affine-coupling flows (WaveGlow/Modules.py:210-371, WaveGlow/Inv1x1.py:9-32), forward (training direction,
 // with the log-likelihood sums) and reverse (synthesis direction).
 //
-// Round-1 structure: the dense contractions of the WN stack (dilated k=3 conv 512->1024, mel conditioning 640->1024,
-// res/skip 512->1024) run as bf16x3 tensor-core GEMMs through cuBLAS (gemm.h: hi/lo split operands, fp32 accumulation,
-// same numerics contract as the decoder kernels); everything around them is hand-written and fused:
+// Structure: the dense contractions of the WN stack (dilated k=3 conv 512->1024, mel conditioning 640->1024, res/skip
+// 512->1024) run as bf16x3 tensor-core GEMMs through cuBLAS with fp32 accumulation (same numerics contract as the
+// decoder kernels).  The three partial products of bf16x3 are folded into the K dimension: every activation row is stored
+// as [hi | lo | hi] and every weight as [W_hi ; W_hi ; W_lo], so a product is ONE bf16 GEMM with K tripled instead of three
+// GEMMs that each read-modify-write the 65 MB fp32 pre-activation (which made the K=512 calls HBM-bound: 29 us measured vs
+// 12.5 us of tensor work).  Everything around the GEMMs is hand-written and fused:
 //   wn_scale / wn_apply weight norm g*v/sqrt(max(sum v^2,1e-5)) -> bf16 hi/lo weight operands
 //   flow_pre_kernel     invertible 1x1 (or plain split in reverse) + the K<=4 start conv -> bf16 hi/lo activations
 //   gate_kernel         bias + tanh * sigmoid -> fp32 + bf16 hi/lo
@@ -24,38 +27,71 @@ static inline int ew_grid(size_t n, int per = 256) {
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
-// ---- weight norm + split: v [k*in, out] (out fastest), g [out] (NULL: plain kernel) -> hi/lo [k*in, out] ----
-// pass 1: scale[o] = g[o] / sqrt(max(sum_r v[r][o]^2, 1e-5)); one block per 32 output channels, 32 row lanes, fixed order
-__global__ void wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, int kin, int out, float* __restrict__ scale) {
+// ---- weight norm + split, batched: one launch handles every weight tensor of a flow ----
+// v [k*in, out] (out fastest), g [out] -> effective w = g * v / sqrt(max(sum_r v[r][o]^2, 1e-5)) (WaveGlow/Modules.py:31-33)
+// written as the stacked bf16 operand [W_hi ; W_hi ; W_lo] per tap (seg rows per tap), or as fp32 (start conv).
+struct WnJob {
+  const float* v;
+  const float* g;
+  float* eff;             // fp32 destination (start conv) or NULL
+  __nv_bfloat16* dst;     // stacked bf16 destination or NULL
+  int kin, out, seg;      // seg = rows per tap (kin for 1x1 convs, kin/3 for the k=3 conv)
+};
+constexpr int kWnJobsPerFlow = 1 + 3 * 8;
+struct WnJobs {
+  WnJob j[kWnJobsPerFlow];
+  float* scale;  // [kWnJobsPerFlow][1024]
+};
+
+// pass 1: scale[o] = g[o] / sqrt(max(sum_r v[r][o]^2, 1e-5)); block = 32 output channels x 32 row lanes, fixed order
+__global__ void wn_scale_kernel(const WnJobs J) {
   __shared__ float part[32][33];
+  const WnJob& job = J.j[blockIdx.y];
   const int o = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x * 32 >= job.out) return;
   float ss = 0.f;
-  if (o < out)
-    for (int r = threadIdx.y; r < kin; r += 32) {
-      const float x = v[(size_t)r * out + o];
+  if (o < job.out)
+    for (int r = threadIdx.y; r < job.kin; r += 32) {
+      const float x = job.v[(size_t)r * job.out + o];
       ss = fmaf(x, x, ss);
     }
   part[threadIdx.y][threadIdx.x] = ss;
   __syncthreads();
-  if (threadIdx.y == 0 && o < out) {
+  if (threadIdx.y == 0 && o < job.out) {
     float tot = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) tot += part[j][threadIdx.x];
-    scale[o] = g[o] * rsqrtf(fmaxf(tot, 1e-5f));
+    J.scale[blockIdx.y * 1024 + o] = job.g[o] * rsqrtf(fmaxf(tot, 1e-5f));
   }
 }
-// pass 2: w = v * scale -> fp32 (eff) and/or bf16 hi/lo
-__global__ void wn_apply_kernel(const float* __restrict__ v, const float* __restrict__ scale, size_t n, int out,
-                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ eff) {
+// pass 2: w = v * scale -> fp32 (eff) or the stacked bf16 operand
+__global__ void wn_apply_kernel(const WnJobs J) {
+  const WnJob& job = J.j[blockIdx.y];
+  const float* scale = J.scale + blockIdx.y * 1024;
+  const size_t n = (size_t)job.kin * job.out;
+  const size_t tap_stride = (size_t)3 * job.seg * job.out, seg_stride = (size_t)job.seg * job.out;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float w = v[i] * scale[i % out];
-    if (eff) eff[i] = w;
-    if (hi) {
+    const int o = (int)(i % job.out);
+    const int r = (int)(i / job.out);
+    const float w = job.v[i] * scale[o];
+    if (job.eff) job.eff[i] = w;
+    if (job.dst) {
+      const int tap = r / job.seg, rr = r - tap * job.seg;
       const __nv_bfloat16 h = __float2bfloat16_rn(w);
-      hi[i] = h;
-      lo[i] = __float2bfloat16_rn(w - __bfloat162float(h));
+      __nv_bfloat16* d = job.dst + tap * tap_stride + (size_t)rr * job.out + o;
+      d[0] = h;
+      d[seg_stride] = h;
+      d[2 * seg_stride] = __float2bfloat16_rn(w - __bfloat162float(h));
     }
   }
+}
+
+// activation row in the K-stacked operand layout: [hi (C) | lo (C) | hi (C)]
+__device__ __forceinline__ void store_x3(__nv_bfloat16* row, int C, int c, float x) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  row[c] = h;
+  row[C + c] = __float2bfloat16_rn(x - __bfloat162float(h));
+  row[2 * C + c] = h;
 }
 
 // ---- ConvTranspose1d 80->80, k=1024, stride 256, VALID (WaveGlow/Modules.py:198-208) ----
@@ -76,28 +112,23 @@ __global__ void upsample_overlap_add_kernel(const float* __restrict__ C, const f
   }
 }
 
-// mel [N,T,640] fp32 -> padded hi/lo [N][Tp][640]
-__global__ void pad_split_kernel(const float* __restrict__ src, int N, int T, int C, __nv_bfloat16* __restrict__ hi,
-                                 __nv_bfloat16* __restrict__ lo) {
+// mel [N,T,640] fp32 -> padded stacked operand [N][Tp][3*640]
+__global__ void pad_split_kernel(const float* __restrict__ src, int N, int T, int C, __nv_bfloat16* __restrict__ dst) {
   const int Tp = T + 2 * kWgPad;
   const size_t n = (size_t)N * T * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const size_t nt = i / C;
     const int t = (int)(nt % T), b = (int)(nt / T);
-    const float x = src[i];
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const size_t o = ((size_t)b * Tp + kWgPad + t) * C + c;
-    hi[o] = h;
-    lo[o] = __float2bfloat16_rn(x - __bfloat162float(h));
+    store_x3(dst + ((size_t)b * Tp + kWgPad + t) * 3 * C, C, c, src[i]);
   }
 }
 
 // ---- flow prologue: y = x W (forward) or y = x (reverse); start conv h = y[:half] Ws + bs -> hi/lo padded ----
 // x [N,T,c] -> y [N,T,c] fp32 (coupling input kept for the epilogue); Wm [c,c] row-major (y_j = sum_i x_i Wm[i][j])
 __global__ void flow_pre_kernel(const float* __restrict__ x, const float* __restrict__ Wm, const float* __restrict__ Ws,
-                                const float* __restrict__ bs, float* __restrict__ y, __nv_bfloat16* __restrict__ h_hi,
-                                __nv_bfloat16* __restrict__ h_lo, int N, int T, int c, int apply_w) {
+                                const float* __restrict__ bs, float* __restrict__ y, __nv_bfloat16* __restrict__ h3, int N, int T,
+                                int c, int apply_w) {
   __shared__ float w_s[64], ws_s[4 * kWnCh], bs_s[kWnCh];
   const int half = c / 2, Tp = T + 2 * kWgPad;
   for (int i = threadIdx.x; i < c * c; i += blockDim.x) w_s[i] = Wm[i];
@@ -121,20 +152,18 @@ __global__ void flow_pre_kernel(const float* __restrict__ x, const float* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) x0[j] = __shfl_sync(0xffffffffu, yv, j);
     const int b = (int)(r / T), t = (int)(r % T);
-    const size_t o = ((size_t)b * Tp + kWgPad + t) * kWnCh;
+    __nv_bfloat16* hrow = h3 + ((size_t)b * Tp + kWgPad + t) * 3 * kWnCh;
     for (int ch = lane; ch < kWnCh; ch += 32) {
       float s = bs_s[ch];
       for (int j = 0; j < half; ++j) s = fmaf(x0[j], ws_s[j * kWnCh + ch], s);
-      const __nv_bfloat16 h = __float2bfloat16_rn(s);
-      h_hi[o + ch] = h;
-      h_lo[o + ch] = __float2bfloat16_rn(s - __bfloat162float(h));
+      store_x3(hrow, kWnCh, ch, s);
     }
   }
 }
 
 // ---- gate: g = tanh(a[:, :512] + b1[:512] + b2[:512]) * sigmoid(a[:, 512:] + ...) over the valid rows ----
 __global__ void gate_kernel(const float* __restrict__ a, const float* __restrict__ b_in, const float* __restrict__ b_cond,
-                            float* __restrict__ g, __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, int N, int T) {
+                            float* __restrict__ g, __nv_bfloat16* __restrict__ g3, int N, int T) {
   const int Tp = T + 2 * kWgPad;
   const size_t n = (size_t)N * T * kWnCh;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -145,16 +174,13 @@ __global__ void gate_kernel(const float* __restrict__ a, const float* __restrict
     const float as = a[row * 2 * kWnCh + kWnCh + ch] + b_in[kWnCh + ch] + b_cond[kWnCh + ch];
     const float v = tanhf(at) * (1.f / (1.f + expf(-as)));
     g[row * kWnCh + ch] = v;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    g_hi[row * kWnCh + ch] = h;
-    g_lo[row * kWnCh + ch] = __float2bfloat16_rn(v - __bfloat162float(h));
+    store_x3(g3 + row * 3 * kWnCh, kWnCh, ch, v);
   }
 }
 
 // ---- residual + skip: h = g + rs[:, :512] + b[:512] (-> hi/lo), skip (+)= rs[:, 512:] + b[512:]; last layer: skip += rs + b ----
 __global__ void resskip_kernel(const float* __restrict__ rs, const float* __restrict__ b_res, const float* __restrict__ g,
-                               __nv_bfloat16* __restrict__ h_hi, __nv_bfloat16* __restrict__ h_lo, float* __restrict__ skip, int N,
-                               int T, int first, int lastl) {
+                               __nv_bfloat16* __restrict__ h3, float* __restrict__ skip, int N, int T, int first, int lastl) {
   const int Tp = T + 2 * kWgPad;
   const int ldr = lastl ? kWnCh : 2 * kWnCh;
   const size_t n = (size_t)N * T * kWnCh;
@@ -165,9 +191,7 @@ __global__ void resskip_kernel(const float* __restrict__ rs, const float* __rest
     float sk;
     if (!lastl) {
       const float hv = g[row * kWnCh + ch] + (rs[row * ldr + ch] + b_res[ch]);
-      const __nv_bfloat16 h = __float2bfloat16_rn(hv);
-      h_hi[row * kWnCh + ch] = h;
-      h_lo[row * kWnCh + ch] = __float2bfloat16_rn(hv - __bfloat162float(h));
+      store_x3(h3 + row * 3 * kWnCh, kWnCh, ch, hv);
       sk = rs[row * ldr + kWnCh + ch] + b_res[kWnCh + ch];
     } else {
       sk = rs[row * ldr + ch] + b_res[ch];
@@ -289,12 +313,12 @@ __global__ void copy_channels_kernel(const float* __restrict__ src, int sc, int 
 
 // ---------------------------------------------------------------------------------------------------------------
 struct WgLayout {
-  size_t w_hi, w_lo;        // per flow: in[8] (3*512*1024) | cond[8] (640*1024) | res[7] (512*1024) + res[7] (512*512)
+  size_t wq;                // stacked bf16 weights, per flow: {in (3 taps x [1536,1024]) | cond [1920,1024] | res [1536,1024 or 512]} x 8
   size_t start_eff;         // [12][4*512] effective start kernels (fp32)
   size_t wscale;            // [12][25][1024] weight-norm scales
   size_t mel_up;            // [N, S, 80] = [N, T, 640]
-  size_t mel_hi, mel_lo;    // padded [N][Tp][640]
-  size_t h_hi, h_lo, g_hi, g_lo;  // padded [N][Tp][512]
+  size_t mel3;              // padded stacked [N][Tp][3*640]
+  size_t h3, g3;            // padded stacked [N][Tp][3*512]
   size_t g, skip;           // padded fp32 [N][Tp][512]
   size_t a;                 // padded fp32 [N][Tp][1024]
   size_t y, xa, xb;         // [N,T,8]
@@ -313,17 +337,13 @@ static WgLayout wg_layout(int N, int T) {
     return o;
   };
   const size_t rows_p = (size_t)N * (T + 2 * kWgPad);
-  l.w_hi = take(kWgFlowW * kWgFlows * 2);
-  l.w_lo = take(kWgFlowW * kWgFlows * 2);
+  l.wq = take(kWgFlowW * kWgFlows * 3 * 2);
   l.start_eff = take((size_t)kWgFlows * 4 * kWnCh * 4);
-  l.wscale = take((size_t)kWgFlows * 25 * 2 * kWnCh * 4);
+  l.wscale = take((size_t)kWgFlows * kWnJobsPerFlow * 1024 * 4);
   l.mel_up = take((size_t)N * T * kWnMel * 4);
-  l.mel_hi = take(rows_p * kWnMel * 2);
-  l.mel_lo = take(rows_p * kWnMel * 2);
-  l.h_hi = take(rows_p * kWnCh * 2);
-  l.h_lo = take(rows_p * kWnCh * 2);
-  l.g_hi = take(rows_p * kWnCh * 2);
-  l.g_lo = take(rows_p * kWnCh * 2);
+  l.mel3 = take(rows_p * 3 * kWnMel * 2);
+  l.h3 = take(rows_p * 3 * kWnCh * 2);
+  l.g3 = take(rows_p * 3 * kWnCh * 2);
   l.g = take(rows_p * kWnCh * 4);
   l.skip = take(rows_p * kWnCh * 4);
   l.a = take(rows_p * 2 * kWnCh * 4);
@@ -363,34 +383,32 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
   int rc;
 
   // ---- effective weights (weight norm is part of the per-step graph in the reference, Modules.py:31-33) ----
-  {
-    int slot = 0;
-    auto prep = [&](const float* v, const float* g, int kin, int outc, __nv_bfloat16* hi, __nv_bfloat16* lo, float* eff) {
-      float* sc = FP(l.wscale) + (size_t)(slot++) * 2 * kWnCh;
-      wn_scale_kernel<<<(outc + 31) / 32, dim3(32, 32), 0, s>>>(v, g, kin, outc, sc);
-      wn_apply_kernel<<<ew_grid((size_t)kin * outc), 256, 0, s>>>(v, sc, (size_t)kin * outc, outc, hi, lo, eff);
-    };
-    for (int f = 0; f < kWgFlows; ++f) {
-      size_t wo = (size_t)f * kWgFlowW;
-      const int half = flow_c(f) / 2;
-      prep(w->start_v[f], w->start_g[f], half, kWnCh, nullptr, nullptr, FP(l.start_eff) + (size_t)f * 4 * kWnCh);
-      for (int i = 0; i < kWnLayers; ++i) {
-        prep(w->in_v[f][i], w->in_g[f][i], 3 * kWnCh, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo, nullptr);
-        wo += (size_t)3 * kWnCh * 2 * kWnCh;
-        prep(w->cond_v[f][i], w->cond_g[f][i], kWnMel, 2 * kWnCh, BF(l.w_hi) + wo, BF(l.w_lo) + wo, nullptr);
-        wo += (size_t)kWnMel * 2 * kWnCh;
-        const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
-        prep(w->res_v[f][i], w->res_g[f][i], kWnCh, rout, BF(l.w_hi) + wo, BF(l.w_lo) + wo, nullptr);
-        wo += (size_t)kWnCh * rout;
-      }
+  for (int f = 0; f < kWgFlows; ++f) {
+    WnJobs J;
+    memset(&J, 0, sizeof(J));
+    J.scale = FP(l.wscale) + (size_t)f * kWnJobsPerFlow * 1024;
+    __nv_bfloat16* wq = BF(l.wq) + (size_t)f * kWgFlowW * 3;
+    const int half = flow_c(f) / 2;
+    int nj = 0;
+    J.j[nj++] = WnJob{w->start_v[f], w->start_g[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, nullptr, half, kWnCh, half};
+    size_t wo = 0;
+    for (int i = 0; i < kWnLayers; ++i) {
+      J.j[nj++] = WnJob{w->in_v[f][i], w->in_g[f][i], nullptr, wq + wo, 3 * kWnCh, 2 * kWnCh, kWnCh};
+      wo += (size_t)9 * kWnCh * 2 * kWnCh;
+      J.j[nj++] = WnJob{w->cond_v[f][i], w->cond_g[f][i], nullptr, wq + wo, kWnMel, 2 * kWnCh, kWnMel};
+      wo += (size_t)3 * kWnMel * 2 * kWnCh;
+      const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
+      J.j[nj++] = WnJob{w->res_v[f][i], w->res_g[f][i], nullptr, wq + wo, kWnCh, rout, kWnCh};
+      wo += (size_t)3 * kWnCh * rout;
     }
+    wn_scale_kernel<<<dim3(32, kWnJobsPerFlow), dim3(32, 32), 0, s>>>(J);
+    wn_apply_kernel<<<dim3(64, kWnJobsPerFlow), 256, 0, s>>>(J);
   }
   // ---- conditioning operand + zeroed pads ----
-  MSTTS_CUDA(cudaMemsetAsync(ws + l.mel_hi, 0, rows_p * kWnMel * 2, s));
-  MSTTS_CUDA(cudaMemsetAsync(ws + l.mel_lo, 0, rows_p * kWnMel * 2, s));
-  MSTTS_CUDA(cudaMemsetAsync(ws + l.h_hi, 0, rows_p * kWnCh * 2, s));
-  MSTTS_CUDA(cudaMemsetAsync(ws + l.h_lo, 0, rows_p * kWnCh * 2, s));
-  pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel_hi), BF(l.mel_lo));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.mel3, 0, rows_p * 3 * kWnMel * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.h3, 0, rows_p * 3 * kWnCh * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + l.g3, 0, rows_p * 3 * kWnCh * 2, s));
+  pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel3));
   if (direction == 0) MSTTS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
 
   const int M = (int)(rows_p - 2 * kWgPad);  // GEMM rows: everything except the outermost pads
@@ -411,32 +429,36 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
       xcur = nx;
       xsel ^= 1;
     }
-    flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], FP(l.y), BF(l.h_hi),
-                                            BF(l.h_lo), N, T, c, direction == 0 ? 1 : 0);
-    size_t wo = (size_t)f * kWgFlowW;
+    flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], FP(l.y), BF(l.h3), N,
+                                            T, c, direction == 0 ? 1 : 0);
+    const __nv_bfloat16* wq = BF(l.wq) + (size_t)f * kWgFlowW * 3;
+    size_t wo = 0;
     for (int i = 0; i < kWnLayers; ++i) {
       const int d = 1 << i;
-      const Bf16Pair Wc = {BF(l.w_hi) + wo + (size_t)3 * kWnCh * 2 * kWnCh, BF(l.w_lo) + wo + (size_t)3 * kWnCh * 2 * kWnCh};
+      const int K3 = 3 * kWnCh;
       float* a_out = FP(l.a) + (size_t)kWgPad * 2 * kWnCh;
-      // conditioning first (beta = 0), then the three taps accumulate
-      const Bf16Pair melp = {BF(l.mel_hi) + (size_t)kWgPad * kWnMel, BF(l.mel_lo) + (size_t)kWgPad * kWnMel};
-      if ((rc = gemm_rowmajor_x3(s, false, false, M, 2 * kWnCh, kWnMel, melp, kWnMel, Wc, 2 * kWnCh, a_out, 2 * kWnCh, 0.f))) return rc;
+      const __nv_bfloat16* Wtap = wq + wo;
+      const __nv_bfloat16* Wc = wq + wo + (size_t)3 * K3 * 2 * kWnCh;
+      // conditioning first (beta = 0), then the three taps accumulate: 4 GEMMs with K = 1920 / 1536
+      if ((rc = gemm_rowmajor_bf16(s, M, 2 * kWnCh, 3 * kWnMel, BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel, 3 * kWnMel, Wc, 2 * kWnCh, a_out,
+                                   2 * kWnCh, 0.f)))
+        return rc;
       for (int k = 0; k < 3; ++k) {
-        const long long shift = (long long)(kWgPad + (k - 1) * d) * kWnCh;
-        const Bf16Pair hp = {BF(l.h_hi) + shift, BF(l.h_lo) + shift};
-        const Bf16Pair Wk = {BF(l.w_hi) + wo + (size_t)k * kWnCh * 2 * kWnCh, BF(l.w_lo) + wo + (size_t)k * kWnCh * 2 * kWnCh};
-        if ((rc = gemm_rowmajor_x3(s, false, false, M, 2 * kWnCh, kWnCh, hp, kWnCh, Wk, 2 * kWnCh, a_out, 2 * kWnCh, 1.f))) return rc;
+        const long long shift = (long long)(kWgPad + (k - 1) * d) * K3;
+        if ((rc = gemm_rowmajor_bf16(s, M, 2 * kWnCh, K3, BF(l.h3) + shift, K3, Wtap + (size_t)k * K3 * 2 * kWnCh, 2 * kWnCh, a_out,
+                                     2 * kWnCh, 1.f)))
+          return rc;
       }
-      wo += (size_t)3 * kWnCh * 2 * kWnCh + (size_t)kWnMel * 2 * kWnCh;
-      gate_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->in_b[f][i], w->cond_b[f][i], FP(l.g), BF(l.g_hi), BF(l.g_lo), N, T);
+      wo += (size_t)3 * K3 * 2 * kWnCh + (size_t)3 * kWnMel * 2 * kWnCh;
+      gate_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->in_b[f][i], w->cond_b[f][i], FP(l.g), BF(l.g3), N, T);
       const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
-      const Bf16Pair gp = {BF(l.g_hi) + (size_t)kWgPad * kWnCh, BF(l.g_lo) + (size_t)kWgPad * kWnCh};
-      const Bf16Pair Wr = {BF(l.w_hi) + wo, BF(l.w_lo) + wo};
       // res/skip output reuses the pre-activation buffer (row stride = rout)
-      if ((rc = gemm_rowmajor_x3(s, false, false, M, rout, kWnCh, gp, kWnCh, Wr, rout, FP(l.a) + (size_t)kWgPad * rout, rout, 0.f))) return rc;
-      wo += (size_t)kWnCh * rout;
-      resskip_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->res_b[f][i], FP(l.g), BF(l.h_hi), BF(l.h_lo), FP(l.skip), N, T,
-                                                           i == 0, i == kWnLayers - 1);
+      if ((rc = gemm_rowmajor_bf16(s, M, rout, K3, BF(l.g3) + (size_t)kWgPad * K3, K3, wq + wo, rout, FP(l.a) + (size_t)kWgPad * rout, rout,
+                                   0.f)))
+        return rc;
+      wo += (size_t)K3 * rout;
+      resskip_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->res_b[f][i], FP(l.g), BF(l.h3), FP(l.skip), N, T, i == 0,
+                                                           i == kWnLayers - 1);
     }
     float* xnext = xbuf[xsel ^ 1];
     flow_post_kernel<<<nblk_post, 256, 0, s>>>(FP(l.skip), w->end_w[f], w->end_b[f], FP(l.y), w->inv_w[f], xnext, (double*)(ws + l.partial),
