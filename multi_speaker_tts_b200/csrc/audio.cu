@@ -149,6 +149,277 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const StftParams P, size_
   }
 }
 
+
+// =====================================================================================================================
+// Team kernel (the fast path): a "team" of H/8 threads owns one frame; a CTA of 256 threads runs 256/(H/8) consecutive
+// frames of one utterance at a time and loops persistently over such groups.
+//   * the raw segment the group needs (n_fft + (teams-1)*hop samples) is staged ONCE, coalesced, reflect-indexed and
+//     pre-emphasised, in shared memory: the 4x overlap of neighbouring frames never goes back to L2;
+//   * the n_fft/2-point complex FFT is a Stockham autosort with radix-8 butterflies held in registers (one radix-2/4 stage
+//     first when log2 is not a multiple of 3): 3 shared-memory round trips for n_fft = 1024 instead of 9, synchronised
+//     with named barriers per team, never the whole CTA;
+//   * shared arrays are padded (i + i/8) so the stride-8 scatter of the first stage is conflict free;
+//   * mel filters: one thread per filter over its non-zero bins (the triangles are 3..45 bins wide), then dB, clip, store.
+// =====================================================================================================================
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void bfly(float2& a, float2& b) {
+  const float2 t = a;
+  a = make_float2(t.x + b.x, t.y + b.y);
+  b = make_float2(t.x - b.x, t.y - b.y);
+}
+// forward DFTs (kernel e^{-2 pi i nk/R}), result in natural order in o[]
+template <int R>
+__device__ __forceinline__ void dft_regs(float2 (&v)[R], float2 (&o)[R]);
+template <>
+__device__ __forceinline__ void dft_regs<2>(float2 (&v)[2], float2 (&o)[2]) {
+  bfly(v[0], v[1]);
+  o[0] = v[0];
+  o[1] = v[1];
+}
+__device__ __forceinline__ void dft4_inplace(float2& a, float2& b, float2& c, float2& d) {  // -> X0, X1, X2, X3 in a, b, c, d
+  bfly(a, c);
+  bfly(b, d);
+  d = make_float2(d.y, -d.x);  // * -i
+  bfly(a, b);                  // a = X0, b = X2
+  bfly(c, d);                  // c = X1, d = X3
+  const float2 t = b;
+  b = c;
+  c = t;
+}
+template <>
+__device__ __forceinline__ void dft_regs<4>(float2 (&v)[4], float2 (&o)[4]) {
+  dft4_inplace(v[0], v[1], v[2], v[3]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) o[r] = v[r];
+}
+template <>
+__device__ __forceinline__ void dft_regs<8>(float2 (&v)[8], float2 (&o)[8]) {
+  constexpr float kS = 0.70710678118654752f;
+  bfly(v[0], v[4]);
+  bfly(v[1], v[5]);
+  bfly(v[2], v[6]);
+  bfly(v[3], v[7]);
+  v[5] = make_float2((v[5].x + v[5].y) * kS, (v[5].y - v[5].x) * kS);    // * w8^1
+  v[6] = make_float2(v[6].y, -v[6].x);                                   // * w8^2 = -i
+  v[7] = make_float2((v[7].y - v[7].x) * kS, (-v[7].x - v[7].y) * kS);   // * w8^3
+  dft4_inplace(v[0], v[1], v[2], v[3]);  // X0 X2 X4 X6
+  dft4_inplace(v[4], v[5], v[6], v[7]);  // X1 X3 X5 X7
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    o[2 * r] = v[r];
+    o[2 * r + 1] = v[4 + r];
+  }
+}
+
+template <int TEAM>
+__device__ __forceinline__ void team_sync(int team) {
+  if (TEAM == 32)
+    __syncwarp();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TEAM) : "memory");
+}
+
+// one Stockham stage of radix R over H points: thread j handles inputs j + r H/R, outputs (j/Ns) Ns R + j%Ns + r Ns
+template <int R, int H, int TEAM>
+__device__ __forceinline__ void fft_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ twN,
+                                          const int Ns, const int ltid) {
+#pragma unroll
+  for (int j = ltid; j < H / R; j += TEAM) {
+    float2 v[R], o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = src[padi(j + r * (H / R))];
+    const int k = j & (Ns - 1);
+    if (Ns > 1) {
+      const int step = k * (2 * H / (Ns * R));  // twN[i] = exp(-2 pi i * i / (2H)), i < H; twN[i + H] = -twN[i]
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        const int i = r * step;
+        float2 w = twN[i & (H - 1)];
+        if (i & H) w = make_float2(-w.x, -w.y);
+        v[r] = cmulf(v[r], w);
+      }
+    }
+    dft_regs<R>(v, o);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[padi(base + r * Ns)] = o[r];
+  }
+}
+
+template <int LOG2H>
+__global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int groups_per_utt, int ngroups) {
+  constexpr int H = 1 << LOG2H, N = 2 * H;
+  constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
+  constexpr int TPC = 256 / TEAM;            // frames per CTA iteration
+  constexpr int ZP = H + H / 8 + 8;          // padded complex array length
+  extern __shared__ __align__(16) float smem_f[];
+  float2* tw_s = reinterpret_cast<float2*>(smem_f);              // [H]
+  float* win_s = reinterpret_cast<float*>(tw_s + H);             // [N]
+  float* fbc_s = win_s + N;                                      // [3*(H+1)] compact filter weights
+  int* rng_s = reinterpret_cast<int*>(fbc_s + 3 * (H + 1));      // [256][3]
+  constexpr int kTabFloats = (2 * H + N + 3 * (H + 1) + 3 * 256 + 1) & ~1;                 // keep the complex arrays 8-byte aligned
+  float2* z_all = reinterpret_cast<float2*>(smem_f + kTabFloats);
+  float* mag_all = reinterpret_cast<float*>(z_all + (size_t)TPC * 2 * ZP);  // [TPC][H+4]
+  float* raw_s = mag_all + TPC * (H + 4);                        // [N + (TPC-1)*hop]
+  const int tid = threadIdx.x, team = tid / TEAM, ltid = tid % TEAM;
+  float2* za = z_all + (size_t)team * 2 * ZP;
+  float2* zb = za + ZP;
+  float* mag_s = mag_all + team * (H + 4);
+
+  for (int i = tid; i < H; i += 256) tw_s[i] = P.tw[i];
+  for (int i = tid; i < N; i += 256) win_s[i] = P.window[i];
+  if (P.mel_out) {
+    const int nnz = P.fb_off[P.n_mels];
+    for (int i = tid; i < nnz; i += 256) fbc_s[i] = P.fbc[i];
+    for (int m = tid; m < P.n_mels; m += 256) {
+      rng_s[3 * m] = P.fb_range[2 * m];
+      rng_s[3 * m + 1] = P.fb_range[2 * m + 1];
+      rng_s[3 * m + 2] = P.fb_off[m];
+    }
+  }
+  __syncthreads();
+  const int rawlen = N + (TPC - 1) * P.hop;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int b = g / groups_per_utt, fr0 = (g % groups_per_utt) * TPC;
+    const float* x = P.wav + (size_t)b * P.S;
+    // ---- stage the pre-emphasised, reflect-padded segment (librosa pads AFTER Audio.preemphasis ran) ----
+    for (int i = tid; i < rawlen; i += 256) {
+      int j = fr0 * P.hop + i - H;
+      if (j < 0) j = -j;
+      if (j >= P.S) j = 2 * (P.S - 1) - j;
+      j = min(max(j, 0), P.S - 1);
+      const float x0 = __ldg(x + j), x1 = __ldg(x + max(j - 1, 0));
+      raw_s[i] = (j > 0) ? x0 - 0.97f * x1 : x0;
+    }
+    __syncthreads();
+    const int fr = fr0 + team;
+    const bool live = fr < P.frames;
+    if (live) {
+      const float* rw = raw_s + team * P.hop;
+#pragma unroll 4
+      for (int k = ltid; k < H; k += TEAM) {
+        const float2 wv = *reinterpret_cast<const float2*>(win_s + 2 * k);
+        za[padi(k)] = make_float2(rw[2 * k] * wv.x, rw[2 * k + 1] * wv.y);
+      }
+    }
+    __syncthreads();  // raw_s may be overwritten by the next group from here on; teams run independently below
+    if (!live) continue;
+    // ---- complex FFT of size H ----
+    float2* src = za;
+    float2* dst = zb;
+    int Ns = 1;
+    if (LOG2H % 3 == 1) {
+      fft_stage<2, H, TEAM>(src, dst, tw_s, 1, ltid);
+      Ns = 2;
+    } else if (LOG2H % 3 == 2) {
+      fft_stage<4, H, TEAM>(src, dst, tw_s, 1, ltid);
+      Ns = 4;
+    }
+    if (Ns > 1) {
+      float2* t = src; src = dst; dst = t;
+      team_sync<TEAM>(team);
+    }
+#pragma unroll
+    for (int it = 0; it < LOG2H / 3; ++it) {
+      fft_stage<8, H, TEAM>(src, dst, tw_s, Ns, ltid);
+      Ns *= 8;
+      float2* t = src; src = dst; dst = t;
+      team_sync<TEAM>(team);
+    }
+    // ---- split post-pass: X[k] = (Z[k] + conj(Z[H-k]))/2 - i e^{-2 pi i k/N} (Z[k] - conj(Z[H-k]))/2, magnitude ----
+    for (int k = ltid; k <= H; k += TEAM) {
+      const float2 zk = src[padi(k & (H - 1))];
+      const float2 zc = src[padi((H - k) & (H - 1))];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 o = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
+      const float2 w = (k < H) ? tw_s[k] : make_float2(-1.f, 0.f);
+      const float2 wo = cmulf(w, o);
+      const float re = e.x + wo.y, im = e.y - wo.x;
+      mag_s[k] = sqrtf(re * re + im * im);
+    }
+    team_sync<TEAM>(team);
+    const size_t fi = (size_t)b * P.frames + fr;
+    if (P.mag_out) {
+      for (int k = ltid; k <= H; k += TEAM) P.mag_out[fi * (H + 1) + k] = mag_s[k];
+    } else {
+      if (P.mel_out) {
+        for (int m = ltid; m < P.n_mels; m += TEAM) {
+          const int lo = rng_s[3 * m], hi = rng_s[3 * m + 1];
+          const float* wts = fbc_s + rng_s[3 * m + 2] - lo;
+          float s = 0.f;
+          for (int k = lo; k < hi; ++k) s = fmaf(wts[k], mag_s[k], s);
+          const float db = amp_to_db(s);
+          float v;
+          if (P.max_abs > 0.f)
+            v = fminf(fmaxf((2.f * P.max_abs) * ((db + 100.f) / 100.f) - P.max_abs, -P.max_abs), P.max_abs);
+          else
+            v = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+          P.mel_out[fi * P.n_mels + m] = v;
+        }
+      }
+      if (P.spec_out) {
+        for (int k = ltid; k <= H; k += TEAM)
+          P.spec_out[fi * (H + 1) + k] = fminf(fmaxf((amp_to_db(mag_s[k]) - 20.f + 100.f) / 100.f, 0.f), 1.f);
+      }
+    }
+    team_sync<TEAM>(team);  // mag_s / za are rewritten by this team's next frame
+  }
+}
+
+template <int LOG2H>
+static size_t stft_team_smem(int hop) {
+  constexpr int H = 1 << LOG2H, N = 2 * H;
+  constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
+  constexpr int TPC = 256 / TEAM, ZP = H + H / 8 + 8;
+  return (size_t)H * 8 + (size_t)N * 4 + (size_t)3 * (H + 1) * 4 + (size_t)(3 * 256 + 2) * 4 + (size_t)TPC * 2 * ZP * 8 +
+         (size_t)TPC * (H + 4) * 4 + (size_t)(N + (TPC - 1) * hop) * 4 + 16;
+}
+
+// returns 1 if launched, 0 if this shape is left to the generic kernel, <0 on error
+template <int LOG2H>
+static int stft_team_launch(const StftParams& P, cudaStream_t s) {
+  constexpr int H = 1 << LOG2H;
+  constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
+  constexpr int TPC = 256 / TEAM;
+  const size_t smem = stft_team_smem<LOG2H>(P.hop);
+  int dev = 0, max_optin = 0;
+  MSTTS_CUDA(cudaGetDevice(&dev));
+  MSTTS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem > (size_t)max_optin || P.n_mels > 256) return 0;
+  MSTTS_CUDA(cudaFuncSetAttribute(stft_team_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int gpu = (P.frames + TPC - 1) / TPC;
+  const long long ngroups = (long long)P.B * gpu;
+  int per_sm = 1;
+  MSTTS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_team_kernel<LOG2H>, 256, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = 148LL * per_sm;
+  stft_team_kernel<LOG2H><<<(unsigned)(ngroups < cap ? ngroups : cap), 256, smem, s>>>(P, gpu, (int)ngroups);
+  MSTTS_CUDA(cudaGetLastError());
+  return 1;
+}
+
+static int stft_launch_main(const StftParams& P, cudaStream_t s, size_t nframes, size_t smem_generic) {
+  int done = 0;
+  if (P.hop <= P.n_fft) {
+    switch (P.log2h) {
+      case 7: done = stft_team_launch<7>(P, s); break;
+      case 8: done = stft_team_launch<8>(P, s); break;
+      case 9: done = stft_team_launch<9>(P, s); break;
+      case 10: done = stft_team_launch<10>(P, s); break;
+      case 11: done = stft_team_launch<11>(P, s); break;
+      default: break;
+    }
+  }
+  if (done < 0) return done;
+  if (!done) {  // generic radix-2 kernel: any power-of-two n_fft in [64, 4096], any hop
+    const unsigned grid = (unsigned)(nframes < 148u * 8u ? nframes : 148u * 8u);
+    stft_mel_kernel<<<grid, 256, smem_generic, s>>>(P, nframes);
+    MSTTS_CUDA(cudaGetLastError());
+  }
+  return MSTTS_OK;
+}
+
 // spectral subtraction, second pass: M' = max(M - mean_t(M)/10, 0) (Audio.py:45-46), then the usual tail
 __global__ void __launch_bounds__(256) subtract_finish_kernel(const StftParams P) {
   extern __shared__ __align__(16) float smem_f[];
@@ -311,13 +582,13 @@ extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop
   MSTTS_CUDA(cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t nframes = (size_t)B * frames;
   MSTTS_REQUIRE(nframes < (1ull << 31), MSTTS_E_INVALID, "stft_mel: too many frames");
-  const unsigned grid = (unsigned)(nframes < 148u * 8u ? nframes : 148u * 8u);  // persistent: 8 CTAs per SM
+  int rc;
   if (!spectral_subtract) {
-    stft_mel_kernel<<<grid, 256, smem, s>>>(P, nframes);
+    if ((rc = stft_launch_main(P, s, nframes, smem))) return rc;
   } else {
     StftParams Q = P;
     Q.mag_out = (float*)(ws + o_mag);
-    stft_mel_kernel<<<grid, 256, smem, s>>>(Q, nframes);
+    if ((rc = stft_launch_main(Q, s, nframes, smem))) return rc;
     const int nb = n_fft / 2 + 1;
     mag_mean_kernel<<<(B * nb + 127) / 128, 128, 0, s>>>((float*)(ws + o_mag), B, frames, nb, (float*)(ws + o_mean));
     P.mag_in = (float*)(ws + o_mag);
