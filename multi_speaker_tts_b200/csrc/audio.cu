@@ -222,7 +222,7 @@ __device__ __forceinline__ void team_sync(int team) {
 
 // one Stockham stage of radix R over H points: thread j handles inputs j + r H/R, outputs (j/Ns) Ns R + j%Ns + r Ns
 template <int R, int H, int TEAM>
-__device__ __forceinline__ void fft_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ twN,
+__device__ __forceinline__ void fft_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ twst,
                                           const int Ns, const int ltid) {
 #pragma unroll
   for (int j = ltid; j < H / R; j += TEAM) {
@@ -231,14 +231,10 @@ __device__ __forceinline__ void fft_stage(const float2* __restrict__ src, float2
     for (int r = 0; r < R; ++r) v[r] = src[padi(j + r * (H / R))];
     const int k = j & (Ns - 1);
     if (Ns > 1) {
-      const int step = k * (2 * H / (Ns * R));  // twN[i] = exp(-2 pi i * i / (2H)), i < H; twN[i + H] = -twN[i]
+      // per-stage table twst[(r-1) Ns + k] = exp(-2 pi i k r / (Ns R)): lanes of a warp have consecutive k, so the reads are
+      // conflict free (indexing the n_fft-th roots table directly is an 8-way conflict: stride 128 B between lanes)
 #pragma unroll
-      for (int r = 1; r < R; ++r) {
-        const int i = r * step;
-        float2 w = twN[i & (H - 1)];
-        if (i & H) w = make_float2(-w.x, -w.y);
-        v[r] = cmulf(v[r], w);
-      }
+      for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], twst[(r - 1) * Ns + k]);
     }
     dft_regs<R>(v, o);
     const int base = (j - k) * R + k;
@@ -261,7 +257,8 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
   constexpr int kTabFloats = (2 * H + N + 3 * (H + 1) + 3 * 256 + 1) & ~1;                 // keep the complex arrays 8-byte aligned
   float2* z_all = reinterpret_cast<float2*>(smem_f + kTabFloats);
   float* mag_all = reinterpret_cast<float*>(z_all + (size_t)TPC * 2 * ZP);  // [TPC][H+4]
-  float* raw_s = mag_all + TPC * (H + 4);                        // [N + (TPC-1)*hop]
+  float2* twst_s = reinterpret_cast<float2*>(mag_all + TPC * (H + 4));  // [H] per-stage twiddle tables (radix-8 stages)
+  float* raw_s = reinterpret_cast<float*>(twst_s + H);           // [N + (TPC-1)*hop]
   const int tid = threadIdx.x, team = tid / TEAM, ltid = tid % TEAM;
   float2* za = z_all + (size_t)team * 2 * ZP;
   float2* zb = za + ZP;
@@ -276,6 +273,23 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
       rng_s[3 * m] = P.fb_range[2 * m];
       rng_s[3 * m + 1] = P.fb_range[2 * m + 1];
       rng_s[3 * m + 2] = P.fb_off[m];
+    }
+  }
+  {
+    int Ns = (LOG2H % 3 == 1) ? 2 : (LOG2H % 3 == 2) ? 4 : 1, off = 0;
+#pragma unroll
+    for (int it = 0; it < LOG2H / 3; ++it) {
+      if (Ns > 1) {
+        for (int idx = tid; idx < 7 * Ns; idx += 256) {
+          const int r = idx / Ns + 1, k = idx % Ns;
+          const int i = r * k * (2 * H / (Ns * 8));  // P.tw[i] = exp(-2 pi i * i / (2H)), i < H; the other half is its negative
+          float2 w = P.tw[i & (H - 1)];
+          if (i & H) w = make_float2(-w.x, -w.y);
+          twst_s[off + idx] = w;
+        }
+        off += 7 * Ns;
+      }
+      Ns *= 8;
     }
   }
   __syncthreads();
@@ -309,11 +323,12 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
     float2* src = za;
     float2* dst = zb;
     int Ns = 1;
+    int twoff = 0;
     if (LOG2H % 3 == 1) {
-      fft_stage<2, H, TEAM>(src, dst, tw_s, 1, ltid);
+      fft_stage<2, H, TEAM>(src, dst, twst_s, 1, ltid);
       Ns = 2;
     } else if (LOG2H % 3 == 2) {
-      fft_stage<4, H, TEAM>(src, dst, tw_s, 1, ltid);
+      fft_stage<4, H, TEAM>(src, dst, twst_s, 1, ltid);
       Ns = 4;
     }
     if (Ns > 1) {
@@ -322,7 +337,8 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
     }
 #pragma unroll
     for (int it = 0; it < LOG2H / 3; ++it) {
-      fft_stage<8, H, TEAM>(src, dst, tw_s, Ns, ltid);
+      fft_stage<8, H, TEAM>(src, dst, twst_s + twoff, Ns, ltid);
+      if (Ns > 1) twoff += 7 * Ns;
       Ns *= 8;
       float2* t = src; src = dst; dst = t;
       team_sync<TEAM>(team);
@@ -373,7 +389,7 @@ static size_t stft_team_smem(int hop) {
   constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
   constexpr int TPC = 256 / TEAM, ZP = H + H / 8 + 8;
   return (size_t)H * 8 + (size_t)N * 4 + (size_t)3 * (H + 1) * 4 + (size_t)(3 * 256 + 2) * 4 + (size_t)TPC * 2 * ZP * 8 +
-         (size_t)TPC * (H + 4) * 4 + (size_t)(N + (TPC - 1) * hop) * 4 + 16;
+         (size_t)TPC * (H + 4) * 4 + (size_t)H * 8 + (size_t)(N + (TPC - 1) * hop) * 4 + 16;
 }
 
 // returns 1 if launched, 0 if this shape is left to the generic kernel, <0 on error
@@ -446,9 +462,10 @@ __global__ void mag_mean_kernel(const float* __restrict__ mag, int B, int frames
 // tables: periodic Hann(win) centred in n_fft, twiddles, slaney mel filter bank (librosa.filters.mel defaults)
 // The tables depend only on (n_fft, win, n_mels, sr): a tag in the workspace lets repeated calls with the same
 // workspace skip the rebuild (the reference rebuilds the mel basis on every call, Audio.py:78).
-__global__ void stft_tag_kernel(int4* tag, int n_fft, int win, int n_mels, int sr) { *tag = make_int4(n_fft, win, n_mels, sr); }
-
-__global__ void stft_tables_kernel(const int4* tag, int n_fft, int win, int n_mels, int sr, float* window, float2* tw, float* fb, int* fb_range) {
+// ONE single-block launch: returns at once when the tag matches (the steady state costs one ~2 us launch); otherwise builds
+// window / twiddles / filter bank, compacts the non-zero filter weights and writes the tag last.
+__global__ void __launch_bounds__(1024) stft_tables_kernel(int4* tag, int n_fft, int win, int n_mels, int sr, float* window, float2* tw,
+                                                           float* fb, int* fb_range, int* fb_off, float* fbc) {
   {
     const int4 t = *tag;
     if (t.x == n_fft && t.y == win && t.z == n_mels && t.w == sr) return;
@@ -490,17 +507,9 @@ __global__ void stft_tables_kernel(const int4* tag, int n_fft, int win, int n_me
     fb_range[2 * m] = lo;
     fb_range[2 * m + 1] = hi;
   }
-}
-
-// compact (non-zero) filter weights: off[m] = prefix sum of the range lengths, fbc[off[m] + k - lo] = fb[m][k]
-__global__ void stft_compact_kernel(const int4* tag, int n_fft, int win, int n_mels, int sr, const float* fb, const int* fb_range, int* fb_off,
-                                    float* fbc) {
-  {
-    const int4 t = *tag;
-    if (t.x == n_fft && t.y == win && t.z == n_mels && t.w == sr) return;
-  }
+  __syncthreads();
+  // compact (non-zero) filter weights: off[m] = prefix sum of the range lengths, fbc[off[m] + k - lo] = fb[m][k]
   __shared__ int off_s[257];
-  const int nb = n_fft / 2 + 1;
   if (threadIdx.x == 0) {
     int o = 0;
     for (int m = 0; m < n_mels; ++m) {
@@ -515,6 +524,8 @@ __global__ void stft_compact_kernel(const int4* tag, int n_fft, int win, int n_m
     const int lo = fb_range[2 * m], hi = fb_range[2 * m + 1];
     for (int k = lo + threadIdx.x; k < hi; k += blockDim.x) fbc[off_s[m] + k - lo] = fb[(size_t)m * nb + k];
   }
+  __syncthreads();
+  if (threadIdx.x == 0) *tag = make_int4(n_fft, win, n_mels, sr);
 }
 
 static size_t stft_ws_layout(int B, int frames, int n_fft, int n_mels, int subtract, size_t* o_tag, size_t* o_win, size_t* o_tw, size_t* o_fb,
@@ -571,11 +582,8 @@ extern "C" int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop
   P.max_abs = max_abs; P.mel_out = mel_out; P.spec_out = spec_out;
   {
     const int nm = n_mels > 0 ? n_mels : 1, sr = sample_rate > 0 ? sample_rate : 1;
-    stft_tables_kernel<<<16, 128, 0, s>>>((const int4*)(ws + o_tag), n_fft, win, nm, sr, (float*)(ws + o_win), (float2*)(ws + o_tw),
-                                          (float*)(ws + o_fb), (int*)(ws + o_rng));
-    stft_compact_kernel<<<1, 256, 0, s>>>((const int4*)(ws + o_tag), n_fft, win, nm, sr, (float*)(ws + o_fb), (int*)(ws + o_rng), (int*)(ws + o_off),
-                                          (float*)(ws + o_fbc));
-    stft_tag_kernel<<<1, 1, 0, s>>>((int4*)(ws + o_tag), n_fft, win, nm, sr);
+    stft_tables_kernel<<<1, 1024, 0, s>>>((int4*)(ws + o_tag), n_fft, win, nm, sr, (float*)(ws + o_win), (float2*)(ws + o_tw),
+                                          (float*)(ws + o_fb), (int*)(ws + o_rng), (int*)(ws + o_off), (float*)(ws + o_fbc));
   }
   const size_t smem = (size_t)(3 * (n_fft / 2)) * sizeof(float2) + (size_t)n_fft * 4 + (size_t)(n_fft / 2 + 4) * 4 +
                       (size_t)3 * (n_fft / 2 + 1) * 4 + (size_t)3 * 256 * 4;

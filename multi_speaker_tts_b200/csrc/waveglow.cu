@@ -161,42 +161,76 @@ __global__ void flow_pre_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
-// ---- gate: g = tanh(a[:, :512] + b1[:512] + b2[:512]) * sigmoid(a[:, 512:] + ...) over the valid rows ----
+// four consecutive channels of an activation row in the K-stacked layout [hi | lo | hi]: 8-byte stores
+__device__ __forceinline__ void store_x3_vec4(__nv_bfloat16* row, int C, int c4, const float (&x)[4]) {
+  __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(x[j]);
+    l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+  }
+  const uint2 hv = *reinterpret_cast<const uint2*>(h), lv = *reinterpret_cast<const uint2*>(l);
+  *reinterpret_cast<uint2*>(row + c4) = hv;
+  *reinterpret_cast<uint2*>(row + C + c4) = lv;
+  *reinterpret_cast<uint2*>(row + 2 * C + c4) = hv;
+}
+
+// ---- gate: g = tanh(a[:, :512] + b1[:512] + b2[:512]) * sigmoid(a[:, 512:] + ...) over the valid rows; 4 channels/thread ----
 __global__ void gate_kernel(const float* __restrict__ a, const float* __restrict__ b_in, const float* __restrict__ b_cond,
                             float* __restrict__ g, __nv_bfloat16* __restrict__ g3, int N, int T) {
   const int Tp = T + 2 * kWgPad;
-  const size_t n = (size_t)N * T * kWnCh;
+  constexpr int C4 = kWnCh / 4;
+  const size_t n = (size_t)N * T * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % kWnCh);
-    const size_t nt = i / kWnCh;
+    const int ch = (int)(i % C4) * 4;
+    const size_t nt = i / C4;
     const size_t row = (nt / T) * Tp + kWgPad + (nt % T);
-    const float at = a[row * 2 * kWnCh + ch] + b_in[ch] + b_cond[ch];
-    const float as = a[row * 2 * kWnCh + kWnCh + ch] + b_in[kWnCh + ch] + b_cond[kWnCh + ch];
-    const float v = tanhf(at) * (1.f / (1.f + expf(-as)));
-    g[row * kWnCh + ch] = v;
-    store_x3(g3 + row * 3 * kWnCh, kWnCh, ch, v);
+    const float4 at = *reinterpret_cast<const float4*>(a + row * 2 * kWnCh + ch);
+    const float4 as = *reinterpret_cast<const float4*>(a + row * 2 * kWnCh + kWnCh + ch);
+    const float4 bt1 = *reinterpret_cast<const float4*>(b_in + ch), bt2 = *reinterpret_cast<const float4*>(b_cond + ch);
+    const float4 bs1 = *reinterpret_cast<const float4*>(b_in + kWnCh + ch), bs2 = *reinterpret_cast<const float4*>(b_cond + kWnCh + ch);
+    const float t4[4] = {at.x + bt1.x + bt2.x, at.y + bt1.y + bt2.y, at.z + bt1.z + bt2.z, at.w + bt1.w + bt2.w};
+    const float s4[4] = {as.x + bs1.x + bs2.x, as.y + bs1.y + bs2.y, as.z + bs1.z + bs2.z, as.w + bs1.w + bs2.w};
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = tanhf(t4[j]) * (1.f / (1.f + expf(-s4[j])));
+    *reinterpret_cast<float4*>(g + row * kWnCh + ch) = make_float4(v[0], v[1], v[2], v[3]);
+    store_x3_vec4(g3 + row * 3 * kWnCh, kWnCh, ch, v);
   }
 }
 
-// ---- residual + skip: h = g + rs[:, :512] + b[:512] (-> hi/lo), skip (+)= rs[:, 512:] + b[512:]; last layer: skip += rs + b ----
+// ---- residual + skip: h = g + rs[:, :512] + b[:512] (-> stacked bf16), skip (+)= rs[:, 512:] + b[512:]; last layer: skip += rs + b ----
 __global__ void resskip_kernel(const float* __restrict__ rs, const float* __restrict__ b_res, const float* __restrict__ g,
                                __nv_bfloat16* __restrict__ h3, float* __restrict__ skip, int N, int T, int first, int lastl) {
   const int Tp = T + 2 * kWgPad;
   const int ldr = lastl ? kWnCh : 2 * kWnCh;
-  const size_t n = (size_t)N * T * kWnCh;
+  constexpr int C4 = kWnCh / 4;
+  const size_t n = (size_t)N * T * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % kWnCh);
-    const size_t nt = i / kWnCh;
+    const int ch = (int)(i % C4) * 4;
+    const size_t nt = i / C4;
     const size_t row = (nt / T) * Tp + kWgPad + (nt % T);
-    float sk;
+    float4 sk;
     if (!lastl) {
-      const float hv = g[row * kWnCh + ch] + (rs[row * ldr + ch] + b_res[ch]);
-      store_x3(h3 + row * 3 * kWnCh, kWnCh, ch, hv);
-      sk = rs[row * ldr + kWnCh + ch] + b_res[kWnCh + ch];
+      const float4 gv = *reinterpret_cast<const float4*>(g + row * kWnCh + ch);
+      const float4 r0 = *reinterpret_cast<const float4*>(rs + row * ldr + ch);
+      const float4 b0 = *reinterpret_cast<const float4*>(b_res + ch);
+      const float hv[4] = {gv.x + (r0.x + b0.x), gv.y + (r0.y + b0.y), gv.z + (r0.z + b0.z), gv.w + (r0.w + b0.w)};
+      store_x3_vec4(h3 + row * 3 * kWnCh, kWnCh, ch, hv);
+      const float4 r1 = *reinterpret_cast<const float4*>(rs + row * ldr + kWnCh + ch);
+      const float4 b1 = *reinterpret_cast<const float4*>(b_res + kWnCh + ch);
+      sk = make_float4(r1.x + b1.x, r1.y + b1.y, r1.z + b1.z, r1.w + b1.w);
     } else {
-      sk = rs[row * ldr + ch] + b_res[ch];
+      const float4 r0 = *reinterpret_cast<const float4*>(rs + row * ldr + ch);
+      const float4 b0 = *reinterpret_cast<const float4*>(b_res + ch);
+      sk = make_float4(r0.x + b0.x, r0.y + b0.y, r0.z + b0.z, r0.w + b0.w);
     }
-    skip[row * kWnCh + ch] = first ? sk : skip[row * kWnCh + ch] + sk;
+    float4* sp = reinterpret_cast<float4*>(skip + row * kWnCh + ch);
+    if (!first) {
+      const float4 o = *sp;
+      sk = make_float4(o.x + sk.x, o.y + sk.y, o.z + sk.z, o.w + sk.w);
+    }
+    *sp = sk;
   }
 }
 
@@ -450,14 +484,14 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
           return rc;
       }
       wo += (size_t)3 * K3 * 2 * kWnCh + (size_t)3 * kWnMel * 2 * kWnCh;
-      gate_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->in_b[f][i], w->cond_b[f][i], FP(l.g), BF(l.g3), N, T);
+      gate_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(FP(l.a), w->in_b[f][i], w->cond_b[f][i], FP(l.g), BF(l.g3), N, T);
       const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
       // res/skip output reuses the pre-activation buffer (row stride = rout)
       if ((rc = gemm_rowmajor_bf16(s, M, rout, K3, BF(l.g3) + (size_t)kWgPad * K3, K3, wq + wo, rout, FP(l.a) + (size_t)kWgPad * rout, rout,
                                    0.f)))
         return rc;
       wo += (size_t)K3 * rout;
-      resskip_kernel<<<ew_grid(rows * kWnCh), 256, 0, s>>>(FP(l.a), w->res_b[f][i], FP(l.g), BF(l.h3), FP(l.skip), N, T, i == 0,
+      resskip_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(FP(l.a), w->res_b[f][i], FP(l.g), BF(l.h3), FP(l.skip), N, T, i == 0,
                                                            i == kWnLayers - 1);
     }
     float* xnext = xbuf[xsel ^ 1];
