@@ -174,6 +174,29 @@ size_t mstts_waveglow_workspace_bytes(int N, int T);
 int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
                          int direction, const float* const* early_noise, float* out, double* sums, void* ws,
                          size_t ws_bytes, void* stream);
+/* Training (WaveGlow/WaveGlow.py:48-70): forward in the training direction that keeps every layer's operands in the workspace,
+ * and the reverse pass for L = -sum(log_s)/n - sum(logdet W)/n + sum(z^2)/(2 sigma^2 n), n = N*T*8 (Modules.py:373-384).
+ * Gradients are written (not accumulated) in the layouts of the raw variables; the logdet term of the twelve c x c kernels is
+ * host math for the caller, as in the forward direction.  d_mel_nt640 (may be NULL): gradient w.r.t. the conditioning
+ * [N,T,640], i.e. w.r.t. the up-sampled mel [N, 8T, 80].  fwd and bwd must use the same workspace, back to back. */
+typedef struct MsttsWaveGlowGrads {
+  float* inv_w[12];
+  float* start_g[12];   float* start_v[12];   float* start_b[12];
+  float* in_g[12][8];   float* in_v[12][8];   float* in_b[12][8];
+  float* cond_g[12][8]; float* cond_v[12][8]; float* cond_b[12][8];
+  float* res_g[12][8];  float* res_v[12][8];  float* res_b[12][8];
+  float* end_w[12];     float* end_b[12];
+} MsttsWaveGlowGrads;
+size_t mstts_waveglow_train_workspace_bytes(int N, int T);
+int mstts_waveglow_train_fwd(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T, float* z,
+                             double* sums, void* ws, size_t ws_bytes, void* stream);
+int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const MsttsWaveGlowGrads* dw, const float* z, int N, int T, float sigma,
+                             float* d_mel_nt640, void* ws, size_t ws_bytes, void* stream);
+/* Upsample_Mel backward: d_up [N, keep, 80] -> d_kernel [1024, out, in], d_bias [80] */
+size_t mstts_upsample_mel_bwd_workspace_bytes(int N, int Tm);
+int mstts_upsample_mel_bwd(const float* mel, const float* d_up, int N, int Tm, int keep, float* d_kernel, float* d_bias, void* ws,
+                           size_t ws_bytes, void* stream);
+
 /* Upsample_Mel (Modules.py:198-208): ConvTranspose1d 80->80, k=1024, stride 256, VALID; kernel [1024, out, in];
  * writes the first `keep` of the (Tm-1)*256+1024 output frames: out [N, keep, 80]. */
 size_t mstts_upsample_mel_workspace_bytes(int N, int Tm);

@@ -36,10 +36,10 @@ class WaveGlowParams(object):
         self.up_kernel, self.up_bias = dev(up_kernel), dev(up_bias)
         self.device = device
 
-    def struct(self, inverse):
-        s = _lib.MsttsWaveGlowWeights()
+    def struct(self, inverse, raws=None, cls=None):
+        s = (cls or _lib.MsttsWaveGlowWeights)()
         keep = []
-        for f, r in enumerate(self.raws):
+        for f, r in enumerate(raws if raws is not None else self.raws):
             W = r['inv_w']
             if inverse:
                 W = torch.linalg.inv(W.double()).float().contiguous()  # tf.linalg.inv(kernel), Inv1x1.py:31
@@ -158,3 +158,76 @@ def Reshaped_Mel(mel_Tensor):
     if pad:
         mel_Tensor = torch.cat([mel_Tensor, mel_Tensor.new_zeros(B, pad, D)], dim=1)
     return mel_Tensor.reshape(B * (mel_Tensor.shape[1] // L), L, D)
+
+
+# ---- training: forward with saved activations + reverse pass (WaveGlow/WaveGlow.py:48-70) ---------------------------------
+_TRAIN_WS = {}
+
+
+def zeros_like_raws(raws):
+    """gradient holders with the structure of ``WaveGlowParams.raws``"""
+    def z(t):
+        return torch.zeros_like(t)
+    return [{'start': {k: z(v) for k, v in r['start'].items()},
+             'in': [{k: z(v) for k, v in x.items()} for x in r['in']],
+             'cond': [{k: z(v) for k, v in x.items()} for x in r['cond']],
+             'res': [{k: z(v) for k, v in x.items()} for x in r['res']],
+             'end_w': z(r['end_w']), 'end_b': z(r['end_b']), 'inv_w': z(r['inv_w'])} for r in raws]
+
+
+def Glow_Train_Backward(audio_Tensor, mel_Tensor, params, sigma=1.0, grads=None, want_d_mel=True):
+    """Glow_Train + Glow_Loss + their gradients.  Returns (z, (log_S_Loss, log_Det_W_Loss, audio_Loss), grads, d_mel) where
+    ``grads`` mirrors ``params.raws`` (gradient of the sum of the three loss terms w.r.t. every raw variable g / v / bias /
+    end conv / invertible 1x1 kernel) and d_mel [N,T,640] is the gradient w.r.t. the folded up-sampled conditioning."""
+    lib = _lib.lib()
+    x = audio_Tensor.contiguous().float()
+    mel = mel_Tensor.contiguous().float()
+    assert x.is_cuda and mel.is_cuda, "no CPU fallback"
+    N, T, _ = x.shape
+    dev = x.device
+    nbytes = lib.mstts_waveglow_train_workspace_bytes(N, T)
+    ws = _TRAIN_WS.get(dev)
+    if ws is None or ws.numel() < nbytes:
+        _TRAIN_WS[dev] = ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    z = torch.empty(N, T, hp.WaveGlow.Groups, device=dev)
+    sums = torch.zeros(2, device=dev, dtype=torch.float64)
+    wstruct, keep = params.struct(inverse=False)
+    if grads is None:
+        grads = zeros_like_raws(params.raws)
+    gstruct, _ = params.struct(inverse=False, raws=grads, cls=_lib.MsttsWaveGlowGrads)
+    d_mel = torch.empty(N, T, hp.WaveGlow.Groups * hp.Sound.Mel_Dim, device=dev) if want_d_mel else None
+    with torch.cuda.device(dev):
+        rc = lib.mstts_waveglow_train_fwd(C.byref(wstruct), _lib.ptr(x), _lib.ptr(mel), N, T, _lib.ptr(z), _lib.ptr(sums),
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), _stream(x))
+        _lib.check(rc, "mstts_waveglow_train_fwd")
+        rc = lib.mstts_waveglow_train_bwd(C.byref(wstruct), C.byref(gstruct), _lib.ptr(z), N, T, float(sigma), _lib.ptr(d_mel),
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), _stream(x))
+        _lib.check(rc, "mstts_waveglow_train_bwd")
+    n = float(z.numel())
+    # log-det term of the invertible 1x1 kernels: host-side c x c math in float64 (Inv1x1.py:25-27), forward and gradient
+    log_dets = []
+    for r, gr in zip(params.raws, grads):
+        W = r['inv_w'].double()
+        c = W.shape[0]
+        det3 = torch.linalg.det(W * 1e3)
+        log_dets.append(((torch.log(det3 + 1e-6)).float() - math.log(1e3) * c) * float(N * T))
+        gr['inv_w'].add_((-(float(N * T) / n) * (det3 / (det3 + 1e-6)) * torch.linalg.inv(W).t()).float())
+    losses = Glow_Loss(z, sums[0], log_dets, sums[1], sigma)
+    return z, losses, grads, d_mel
+
+
+def Upsample_Mel_Backward(mels, d_up, params):
+    """gradients of Upsample_Mel's kernel [1024,80,80] and bias [80] given d_up [N, keep, 80]"""
+    lib = _lib.lib()
+    N, Tm, _ = mels.shape
+    keep = d_up.shape[1]
+    x = mels.contiguous().float()
+    d = d_up.contiguous().float()
+    dk = torch.empty_like(params.up_kernel)
+    db = torch.empty_like(params.up_bias)
+    ws = torch.empty(lib.mstts_upsample_mel_bwd_workspace_bytes(N, Tm), device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        rc = lib.mstts_upsample_mel_bwd(_lib.ptr(x), _lib.ptr(d), N, Tm, keep, _lib.ptr(dk), _lib.ptr(db), C.c_void_p(ws.data_ptr()),
+                                        ws.numel(), _stream(x))
+    _lib.check(rc, "mstts_upsample_mel_bwd")
+    return dk, db

@@ -55,6 +55,10 @@ class MsttsWaveGlowWeights(C.Structure):
                 [("end_w", _fp * 12), ("end_b", _fp * 12)])
 
 
+class MsttsWaveGlowGrads(C.Structure):
+    _fields_ = MsttsWaveGlowWeights._fields_
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "mstts_version": (C.c_int, []),
@@ -72,6 +76,12 @@ EXPORTS = {
     "mstts_waveglow_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mstts_waveglow_flows": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp,
                                        C.c_size_t, _fp]),
+    "mstts_waveglow_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mstts_waveglow_train_fwd": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), _fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "mstts_waveglow_train_bwd": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), C.POINTER(MsttsWaveGlowGrads), _fp, C.c_int, C.c_int,
+                                           C.c_float, _fp, _fp, C.c_size_t, _fp]),
+    "mstts_upsample_mel_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "mstts_upsample_mel_bwd": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     "mstts_upsample_mel_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mstts_upsample_mel": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "mstts_stft_mel_workspace_bytes": (C.c_size_t, [C.c_int] * 6),

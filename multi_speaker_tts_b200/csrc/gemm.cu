@@ -142,3 +142,25 @@ int gemm_rowmajor_bf16(cudaStream_t s, int M, int N, int K, const __nv_bfloat16*
   }
   return MSTTS_OK;
 }
+
+int gemm_bf16_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B,
+                 int ldb, float* C, int ldc, float beta) {
+  int rc;
+  cublasHandle_t h = get_handle(&rc);
+  if (!h) return rc;
+  cublasStatus_t st = cublasSetStream(h, s);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
+    return MSTTS_E_CUDA;
+  }
+  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+  const float one = 1.f;
+  st = cublasGemmEx(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &one, B, CUDA_R_16BF, ldb, A,
+                    CUDA_R_16BF, lda, &beta, C, CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasGemmEx bf16 (M=%d,N=%d,K=%d,tA=%d,tB=%d) failed (%d)", M, N, K, (int)transA, (int)transB, (int)st);
+    return MSTTS_E_CUDA;
+  }
+  return MSTTS_OK;
+}

@@ -35,3 +35,6 @@ int gemm_rowmajor_x3(cudaStream_t s, bool transA, bool transB, int M, int N, int
 // bf16x3 partial products into K (A rows [hi|lo|hi], B rows [hi;hi;lo]) get the bf16x3 result from a single call.
 int gemm_rowmajor_bf16(cudaStream_t s, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                        float* C, int ldc, float beta);
+// general form: C[M,N] = op(A) op(B) + beta C with op(A) M x K (stored K x M when transA), op(B) K x N (stored N x K when transB)
+int gemm_bf16_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B,
+                 int ldb, float* C, int ldc, float beta);

@@ -355,6 +355,7 @@ struct WgLayout {
   size_t h3, g3;            // padded stacked [N][Tp][3*512]
   size_t g, skip;           // padded fp32 [N][Tp][512]
   size_t a;                 // padded fp32 [N][Tp][1024]
+  size_t rs;                // padded fp32 [N][Tp][1024]: res/skip output when the pre-activations are being saved
   size_t y, xa, xb;         // [N,T,8]
   size_t partial;           // doubles
   size_t total;
@@ -381,6 +382,7 @@ static WgLayout wg_layout(int N, int T) {
   l.g = take(rows_p * kWnCh * 4);
   l.skip = take(rows_p * kWnCh * 4);
   l.a = take(rows_p * 2 * kWnCh * 4);
+  l.rs = take(rows_p * 2 * kWnCh * 4);
   l.y = take((size_t)N * T * 8 * 4);
   l.xa = take((size_t)N * T * 8 * 4);
   l.xb = take((size_t)N * T * 8 * 4);
@@ -394,14 +396,42 @@ extern "C" size_t mstts_waveglow_workspace_bytes(int N, int T) {
   return wg_layout(N, T).total;
 }
 
+// Saved activations of a training-direction forward (what the reverse pass reads).  180 GB of HBM makes keeping every
+// layer's operands (163 MB per layer, 15.7 GB at config 3) cheaper than recomputing the WN stack through the inverse flow.
+struct WgSave {
+  size_t xin, y;       // per flow [rows, 8] fp32: flow input (after the early split) / after the invertible 1x1
+  size_t skip;         // per flow [rows_p, 512] fp32 (padded layout)
+  size_t h3, g3;       // per (flow, layer) stacked bf16 [rows_p, 1536]: layer input / gated activation
+  size_t a;            // per (flow, layer) fp32 [rows_p, 1024]: pre-activations without the biases
+  size_t total;
+};
+static WgSave wg_save_layout(int N, int T, size_t base) {
+  WgSave v;
+  size_t off = base;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  const size_t rows = (size_t)N * T, rows_p = (size_t)N * (T + 2 * kWgPad);
+  v.xin = take(kWgFlows * rows * 8 * 4);
+  v.y = take(kWgFlows * rows * 8 * 4);
+  v.skip = take(kWgFlows * rows_p * kWnCh * 4);
+  v.h3 = take((size_t)kWgFlows * kWnLayers * rows_p * 3 * kWnCh * 2);
+  v.g3 = take((size_t)kWgFlows * kWnLayers * rows_p * 3 * kWnCh * 2);
+  v.a = take((size_t)kWgFlows * kWnLayers * rows_p * 2 * kWnCh * 4);
+  v.total = off;
+  return v;
+}
+
 static inline int flow_c(int f) { return 8 - 2 * (f / 4); }
 
 // Runs all 12 flows.  direction 0: training direction x -> z with sums[0] = sum(log_s), sums[1] = sum(z^2);
 // direction 1: synthesis z -> x (early_noise[2]: the two [N,T,2] noise tensors injected before flows 7 and 3 are run,
 // i.e. after undoing flows 8 and 4; inv_w then holds the INVERSE 1x1 kernels).
-extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
-                                    int direction, const float* const* early_noise, float* out, double* sums, void* ws_, size_t ws_bytes,
-                                    void* stream_) {
+static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
+                               int direction, const float* const* early_noise, float* out, double* sums, void* ws_, size_t ws_bytes,
+                               void* stream_, const WgSave* save) {
   MSTTS_REQUIRE(w && audio_in && mel_nt640 && out && ws_, MSTTS_E_INVALID, "waveglow: null argument");
   MSTTS_REQUIRE(N >= 1 && T >= 1, MSTTS_E_INVALID, "waveglow: N=%d T=%d", N, T);
   MSTTS_REQUIRE(direction == 0 || (early_noise && early_noise[0] && early_noise[1]), MSTTS_E_INVALID, "waveglow: reverse needs early noise");
@@ -442,6 +472,13 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
   MSTTS_CUDA(cudaMemsetAsync(ws + l.mel3, 0, rows_p * 3 * kWnMel * 2, s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.h3, 0, rows_p * 3 * kWnCh * 2, s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.g3, 0, rows_p * 3 * kWnCh * 2, s));
+  if (save) MSTTS_CUDA(cudaMemsetAsync(ws + save->skip, 0, save->a - save->skip, s));  // saved skip / h3 / g3 slots: pads must read 0
+  const size_t slot3 = rows_p * 3 * kWnCh * 2, slota = rows_p * 2 * kWnCh * 4;
+  auto H3 = [&](int f, int i) { return save ? BF(save->h3 + ((size_t)f * kWnLayers + i) * slot3) : BF(l.h3); };
+  auto G3 = [&](int f, int i) { return save ? BF(save->g3 + ((size_t)f * kWnLayers + i) * slot3) : BF(l.g3); };
+  auto APRE = [&](int f, int i) { return save ? FP(save->a + ((size_t)f * kWnLayers + i) * slota) : FP(l.a); };
+  auto SKIP = [&](int f) { return save ? FP(save->skip + (size_t)f * rows_p * kWnCh * 4) : FP(l.skip); };
+  auto YBUF = [&](int f) { return save ? FP(save->y + (size_t)f * rows * 8 * 4) : FP(l.y); };
   pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel3));
   if (direction == 0) MSTTS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
 
@@ -463,14 +500,15 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
       xcur = nx;
       xsel ^= 1;
     }
-    flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], FP(l.y), BF(l.h3), N,
+    if (save) MSTTS_CUDA(cudaMemcpyAsync(ws + save->xin + (size_t)f * rows * 8 * 4, xcur, rows * c * 4, cudaMemcpyDeviceToDevice, s));
+    flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], YBUF(f), H3(f, 0), N,
                                             T, c, direction == 0 ? 1 : 0);
     const __nv_bfloat16* wq = BF(l.wq) + (size_t)f * kWgFlowW * 3;
     size_t wo = 0;
     for (int i = 0; i < kWnLayers; ++i) {
       const int d = 1 << i;
       const int K3 = 3 * kWnCh;
-      float* a_out = FP(l.a) + (size_t)kWgPad * 2 * kWnCh;
+      float* a_out = APRE(f, i) + (size_t)kWgPad * 2 * kWnCh;
       const __nv_bfloat16* Wtap = wq + wo;
       const __nv_bfloat16* Wc = wq + wo + (size_t)3 * K3 * 2 * kWnCh;
       // conditioning first (beta = 0), then the three taps accumulate: 4 GEMMs with K = 1920 / 1536
@@ -479,23 +517,24 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
         return rc;
       for (int k = 0; k < 3; ++k) {
         const long long shift = (long long)(kWgPad + (k - 1) * d) * K3;
-        if ((rc = gemm_rowmajor_bf16(s, M, 2 * kWnCh, K3, BF(l.h3) + shift, K3, Wtap + (size_t)k * K3 * 2 * kWnCh, 2 * kWnCh, a_out,
+        if ((rc = gemm_rowmajor_bf16(s, M, 2 * kWnCh, K3, H3(f, i) + shift, K3, Wtap + (size_t)k * K3 * 2 * kWnCh, 2 * kWnCh, a_out,
                                      2 * kWnCh, 1.f)))
           return rc;
       }
       wo += (size_t)3 * K3 * 2 * kWnCh + (size_t)3 * kWnMel * 2 * kWnCh;
-      gate_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(FP(l.a), w->in_b[f][i], w->cond_b[f][i], FP(l.g), BF(l.g3), N, T);
+      gate_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(APRE(f, i), w->in_b[f][i], w->cond_b[f][i], FP(l.g), G3(f, i), N, T);
       const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
-      // res/skip output reuses the pre-activation buffer (row stride = rout)
-      if ((rc = gemm_rowmajor_bf16(s, M, rout, K3, BF(l.g3) + (size_t)kWgPad * K3, K3, wq + wo, rout, FP(l.a) + (size_t)kWgPad * rout, rout,
+      // res/skip output: the scratch pre-activation buffer when the pre-activations are saved elsewhere, else in place
+      float* rsbuf = save ? FP(l.rs) : FP(l.a);
+      if ((rc = gemm_rowmajor_bf16(s, M, rout, K3, G3(f, i) + (size_t)kWgPad * K3, K3, wq + wo, rout, rsbuf + (size_t)kWgPad * rout, rout,
                                    0.f)))
         return rc;
       wo += (size_t)K3 * rout;
-      resskip_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(FP(l.a), w->res_b[f][i], FP(l.g), BF(l.h3), FP(l.skip), N, T, i == 0,
-                                                           i == kWnLayers - 1);
+      resskip_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(rsbuf, w->res_b[f][i], FP(l.g), H3(f, i < kWnLayers - 1 ? i + 1 : i), SKIP(f), N,
+                                                           T, i == 0, i == kWnLayers - 1);
     }
     float* xnext = xbuf[xsel ^ 1];
-    flow_post_kernel<<<nblk_post, 256, 0, s>>>(FP(l.skip), w->end_w[f], w->end_b[f], FP(l.y), w->inv_w[f], xnext, (double*)(ws + l.partial),
+    flow_post_kernel<<<nblk_post, 256, 0, s>>>(SKIP(f), w->end_w[f], w->end_b[f], YBUF(f), w->inv_w[f], xnext, (double*)(ws + l.partial),
                                                N, T, c, direction);
     if (direction == 0) finish_sum_kernel<<<1, 32, 0, s>>>((double*)(ws + l.partial), nblk_post, sums);
     xcur = xnext;
@@ -520,6 +559,12 @@ extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* 
   return MSTTS_OK;
 }
 
+extern "C" int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
+                                    int direction, const float* const* early_noise, float* out, double* sums, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  return waveglow_flows_impl(w, audio_in, mel_nt640, N, T, direction, early_noise, out, sums, ws, ws_bytes, stream, nullptr);
+}
+
 extern "C" size_t mstts_upsample_mel_workspace_bytes(int N, int Tm) {
   if (N <= 0 || Tm <= 0) return 0;
   return (size_t)N * Tm * 1024 * 80 * sizeof(float);
@@ -536,6 +581,627 @@ extern "C" int mstts_upsample_mel(const float* mel, const float* kernel, const f
   int rc = gemm_rowmajor_ex(s, false, true, N * Tm, 1024 * 80, 80, mel, 80, kernel, 80, (float*)ws, 1024 * 80, 0.f);
   if (rc) return rc;
   upsample_overlap_add_kernel<<<ew_grid((size_t)N * keep * 80), 256, 0, s>>>((const float*)ws, bias, out, N, Tm, keep);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+// =====================================================================================================================
+// Training: forward with saved activations + reverse pass (what tf.gradients builds for WaveGlow/WaveGlow.py:48-70).
+//   L = -sum(log_s)/n - sum(logdet_W)/n + sum(z^2)/(2 sigma^2 n),  n = N*T*8  (WaveGlow/Modules.py:373-384)
+// The logdet term only touches the twelve c x c kernels and stays host math, like in the forward direction.
+// Every dense product is again a bf16 GEMM with the bf16x3 terms folded into K (activation gradients [hi|lo|hi] against
+// column-stacked weights [W_hi | W_hi | W_lo]); weight gradients contract over the 16 000 positions with a small fp32
+// output, so their three partial products are three accumulating GEMM calls.
+// =====================================================================================================================
+struct WgBwdLayout {
+  size_t wqc;                  // column-stacked bf16 weights, per flow per layer: in taps 3 x [512, 3072] | cond [640, 3072] | res [512, 3*rout]
+  size_t dh[2];                // fp32 [rows_p, 512] gradient w.r.t. a layer input (ping-pong)
+  size_t dskip;                // fp32 [rows_p, 512]
+  size_t drs3;                 // stacked bf16 [rows_p, 3*1024]
+  size_t drs3_last;            // stacked bf16 [rows_p, 3*512] (last layer: res conv has 512 outputs)
+  size_t dg;                   // fp32 [rows_p, 512]
+  size_t da;                   // fp32 [rows_p, 1024]
+  size_t da3;                  // stacked bf16 [rows_p, 3*1024]
+  size_t dmel;                 // fp32 [rows_p, 640] accumulated over all layers and flows
+  size_t dopad;                // fp32 [rows_p, 8] gradient w.r.t. the end-conv output (padded layout)
+  size_t dy, dx, dx2;          // [rows, 8] fp32
+  size_t dw_eff;               // fp32 [3*512*1024] gradient w.r.t. one effective weight tensor
+  size_t part;                 // fp32 partial sums (colsum / small reductions)
+  size_t total;
+};
+constexpr size_t kWgFlowWc = kWgFlowW;  // same element count per flow as the row-stacked image (x3 copies)
+constexpr int kWgPartSlices = 64;
+
+static WgBwdLayout wg_bwd_layout(int N, int T, size_t base) {
+  WgBwdLayout b;
+  size_t off = base;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes, 256);
+    return o;
+  };
+  const size_t rows = (size_t)N * T, rows_p = (size_t)N * (T + 2 * kWgPad);
+  b.wqc = take(kWgFlowWc * kWgFlows * 3 * 2);
+  b.dh[0] = take(rows_p * kWnCh * 4);
+  b.dh[1] = take(rows_p * kWnCh * 4);
+  b.dskip = take(rows_p * kWnCh * 4);
+  b.drs3 = take(rows_p * 3 * 2 * kWnCh * 2);
+  b.drs3_last = take(rows_p * 3 * kWnCh * 2);
+  b.dg = take(rows_p * kWnCh * 4);
+  b.da = take(rows_p * 2 * kWnCh * 4);
+  b.da3 = take(rows_p * 3 * 2 * kWnCh * 2);
+  b.dmel = take(rows_p * kWnMel * 4);
+  b.dopad = take(rows_p * 8 * 4);
+  b.dy = take(rows * 8 * 4);
+  b.dx = take(rows * 8 * 4);
+  b.dx2 = take(rows * 8 * 4);
+  b.dw_eff = take((size_t)3 * kWnCh * 2 * kWnCh * 4);
+  b.part = take((size_t)kWgPartSlices * 4 * 2 * kWnCh * 4 + 148 * 8 * 4 * kWnCh * 4);
+  b.total = off;
+  return b;
+}
+
+extern "C" size_t mstts_waveglow_train_workspace_bytes(int N, int T) {
+  if (N <= 0 || T <= 0) return 0;
+  const WgSave v = wg_save_layout(N, T, wg_layout(N, T).total);
+  return wg_bwd_layout(N, T, v.total).total;
+}
+
+extern "C" int mstts_waveglow_train_fwd(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T, float* z,
+                                        double* sums, void* ws, size_t ws_bytes, void* stream) {
+  MSTTS_REQUIRE(N >= 1 && T >= 1, MSTTS_E_INVALID, "waveglow: N=%d T=%d", N, T);
+  MSTTS_REQUIRE(ws_bytes >= mstts_waveglow_train_workspace_bytes(N, T), MSTTS_E_WORKSPACE, "waveglow train: workspace %zu < %zu", ws_bytes,
+                mstts_waveglow_train_workspace_bytes(N, T));
+  const WgSave v = wg_save_layout(N, T, wg_layout(N, T).total);
+  return waveglow_flows_impl(w, audio_in, mel_nt640, N, T, 0, nullptr, z, sums, ws, ws_bytes, stream, &v);
+}
+
+// ---- column-stacked weights for the transposed products: dst[r][s*out + o], s = 0,1 -> hi, s = 2 -> lo (per tap) ----
+__global__ void wn_apply_cols_kernel(const WnJobs J) {
+  const WnJob& job = J.j[blockIdx.y];
+  if (!job.dst) return;
+  const float* scale = J.scale + blockIdx.y * 1024;
+  const size_t n = (size_t)job.kin * job.out;
+  const size_t tap_stride = (size_t)3 * job.seg * job.out;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % job.out);
+    const int r = (int)(i / job.out);
+    const float wv = job.v[i] * scale[o];
+    const int tap = r / job.seg, rr = r - tap * job.seg;
+    const __nv_bfloat16 h = __float2bfloat16_rn(wv);
+    __nv_bfloat16* d = job.dst + tap * tap_stride + (size_t)rr * 3 * job.out + o;
+    d[0] = h;
+    d[job.out] = h;
+    d[2 * job.out] = __float2bfloat16_rn(wv - __bfloat162float(h));
+  }
+}
+
+// weight-norm backward for one tensor: w = g v / sqrt(max(ss, 1e-5)), ss = sum_r v^2 per output channel
+//   dg = sum_r dw v / sqrt(.) ;  dv = g dw / sqrt(.) - [ss > 1e-5] g v (sum_r dw v) / sqrt(.)^3
+__global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ dw, int kin, int out,
+                              float* __restrict__ dg, float* __restrict__ dv) {
+  __shared__ float p_ss[32][33], p_dot[32][33];
+  const int o = blockIdx.x * 32 + threadIdx.x;
+  float ss = 0.f, dot = 0.f;
+  if (o < out)
+    for (int r = threadIdx.y; r < kin; r += 32) {
+      const float x = v[(size_t)r * out + o];
+      ss = fmaf(x, x, ss);
+      dot = fmaf(dw[(size_t)r * out + o], x, dot);
+    }
+  p_ss[threadIdx.y][threadIdx.x] = ss;
+  p_dot[threadIdx.y][threadIdx.x] = dot;
+  __syncthreads();
+  ss = 0.f;
+  dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    ss += p_ss[j][threadIdx.x];
+    dot += p_dot[j][threadIdx.x];
+  }
+  if (o >= out) return;
+  const float inv = rsqrtf(fmaxf(ss, 1e-5f));
+  const float gv = g[o];
+  if (threadIdx.y == 0) dg[o] = dot * inv;
+  const float c2 = ss > 1e-5f ? gv * dot * inv * inv * inv : 0.f;
+  for (int r = threadIdx.y; r < kin; r += 32) {
+    const size_t i = (size_t)r * out + o;
+    dv[i] = gv * inv * dw[i] - c2 * v[i];
+  }
+}
+
+// column sums over the VALID rows of a padded-layout fp32 matrix [N][Tp][C] (ld = C): deterministic two passes
+__global__ void colsum_valid_partial_kernel(const float* __restrict__ in, int ld, float* __restrict__ part, int N, int T, int C) {
+  __shared__ float sh[8][33];
+  const int Tp = T + 2 * kWgPad;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t R = (size_t)N * T;
+  const size_t r0 = R * blockIdx.y / kWgPartSlices, r1 = R * (blockIdx.y + 1) / kWgPartSlices;
+  float s = 0.f;
+  if (c < C)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) s += in[((r / T) * Tp + kWgPad + (r % T)) * ld + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += sh[j][threadIdx.x];
+    part[(size_t)blockIdx.y * C + c] = tot;
+  }
+}
+__global__ void sum_partials_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tot = 0.f;
+  for (int j = 0; j < nparts; ++j) tot += part[(size_t)j * C + c];
+  out[c] = accumulate ? out[c] + tot : tot;
+}
+
+// dz = z / (sigma^2 n): rows [rows, 8] -> the three channel groups of the flow chain
+__global__ void dz_kernel(const float* __restrict__ z, float scale, size_t n, float* __restrict__ dz) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dz[i] = z[i] * scale;
+}
+
+// coupling + end conv backward, one warp per row.
+//   recompute o = skip We + be -> (log_s_raw, b); ls = min(log_s_raw, 8); x1' = exp(ls) x1 + b
+//   in : dxo [rows, c] gradient w.r.t. the flow output [x0, x1'], y = [x0, x1] (after the 1x1)
+//   out: dy [rows, c] = [dxo_x0 (the WN path is added later), dx1' exp(ls)], do_pad [rows_p, 8] = [d log_s, d b, 0...],
+//        dskip [rows_p, 512] = do We^T
+__global__ void coupling_bwd_kernel(const float* __restrict__ skip, const float* __restrict__ We, const float* __restrict__ be,
+                                    const float* __restrict__ y, const float* __restrict__ dxo, float coef_ls, float* __restrict__ dy,
+                                    float* __restrict__ do_pad, float* __restrict__ dskip, int N, int T, int c) {
+  __shared__ float we_s[kWnCh * 8];
+  const int half = c / 2, Tp = T + 2 * kWgPad;
+  for (int i = threadIdx.x; i < kWnCh * c; i += blockDim.x) we_s[i] = We[i];
+  __syncthreads();
+  const size_t rows = (size_t)N * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (size_t r = (size_t)blockIdx.x * wpb + warp; r < rows; r += (size_t)gridDim.x * wpb) {
+    const size_t prow = (r / T) * Tp + kWgPad + (r % T);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < kWnCh; k += 32) {
+      const float sv = skip[prow * kWnCh + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < c) acc[j] = fmaf(sv, we_s[k * c + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = warp_sum(acc[j]);
+    // every lane now holds o (without bias) for all c outputs; lane j < half handles coupling channel j
+    float dov[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dov[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < half) {
+        const float ls_raw = acc[j] + be[j];
+        const float ls = fminf(ls_raw, 8.0f);
+        const float e = expf(ls);
+        const float x1 = y[r * c + half + j];
+        const float dx1p = dxo[r * c + half + j];
+        dov[j] = ls_raw <= 8.0f ? dx1p * e * x1 + coef_ls : 0.f;  // d log_s (the clamp passes no gradient)
+        dov[half + j] = dx1p;                                     // d b
+        if (lane == 0) {
+          dy[r * c + half + j] = dx1p * e;
+          dy[r * c + j] = dxo[r * c + j];
+        }
+      }
+    }
+    if (lane < 8) {
+      float vsel = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j == lane) vsel = dov[j];
+      do_pad[prow * 8 + lane] = lane < c ? vsel : 0.f;
+    }
+    for (int k = lane; k < kWnCh; k += 32) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < c) sacc = fmaf(dov[j], we_s[k * c + j], sacc);
+      dskip[prow * kWnCh + k] = sacc;
+    }
+  }
+}
+
+// d rs of a layer in the stacked operand layout: [d_h | d_skip] (R = 1024) or d_skip alone (last layer, R = 512); valid rows
+__global__ void stack_drs_kernel(const float* __restrict__ dh, const float* __restrict__ dskip, __nv_bfloat16* __restrict__ drs3, int N, int T,
+                                 int lastl) {
+  const int Tp = T + 2 * kWgPad;
+  const int R = lastl ? kWnCh : 2 * kWnCh;
+  const int R4 = R / 4;
+  const size_t n = (size_t)N * T * R4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % R4) * 4;
+    const size_t nt = i / R4;
+    const size_t row = (nt / T) * Tp + kWgPad + (nt % T);
+    float4 v;
+    if (!lastl && ch < kWnCh)
+      v = *reinterpret_cast<const float4*>(dh + row * kWnCh + ch);
+    else
+      v = *reinterpret_cast<const float4*>(dskip + row * kWnCh + (lastl ? ch : ch - kWnCh));
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    store_x3_vec4(drs3 + row * 3 * R, R, ch, x);
+  }
+}
+
+// gate backward over the valid rows: g = tanh(at) sigmoid(as), at/as = a + b_in + b_cond;
+// dg_tot = dg (through the res/skip conv) + dh (direct residual path, layers < 7)  ->  da fp32 + stacked bf16
+__global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b_in, const float* __restrict__ b_cond,
+                                const float* __restrict__ dg, const float* __restrict__ dh, float* __restrict__ da,
+                                __nv_bfloat16* __restrict__ da3, int N, int T) {
+  const int Tp = T + 2 * kWgPad;
+  constexpr int C4 = kWnCh / 4;
+  const size_t n = (size_t)N * T * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C4) * 4;
+    const size_t nt = i / C4;
+    const size_t row = (nt / T) * Tp + kWgPad + (nt % T);
+    const float4 at = *reinterpret_cast<const float4*>(a + row * 2 * kWnCh + ch);
+    const float4 as = *reinterpret_cast<const float4*>(a + row * 2 * kWnCh + kWnCh + ch);
+    const float4 bt1 = *reinterpret_cast<const float4*>(b_in + ch), bt2 = *reinterpret_cast<const float4*>(b_cond + ch);
+    const float4 bs1 = *reinterpret_cast<const float4*>(b_in + kWnCh + ch), bs2 = *reinterpret_cast<const float4*>(b_cond + kWnCh + ch);
+    float4 d = *reinterpret_cast<const float4*>(dg + row * kWnCh + ch);
+    if (dh) {
+      const float4 e = *reinterpret_cast<const float4*>(dh + row * kWnCh + ch);
+      d = make_float4(d.x + e.x, d.y + e.y, d.z + e.z, d.w + e.w);
+    }
+    const float t4[4] = {at.x + bt1.x + bt2.x, at.y + bt1.y + bt2.y, at.z + bt1.z + bt2.z, at.w + bt1.w + bt2.w};
+    const float s4[4] = {as.x + bs1.x + bs2.x, as.y + bs1.y + bs2.y, as.z + bs1.z + bs2.z, as.w + bs1.w + bs2.w};
+    const float d4[4] = {d.x, d.y, d.z, d.w};
+    float dt[4], ds[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float th = tanhf(t4[j]);
+      const float sg = 1.f / (1.f + expf(-s4[j]));
+      dt[j] = d4[j] * sg * (1.f - th * th);
+      ds[j] = d4[j] * th * sg * (1.f - sg);
+    }
+    *reinterpret_cast<float4*>(da + row * 2 * kWnCh + ch) = make_float4(dt[0], dt[1], dt[2], dt[3]);
+    *reinterpret_cast<float4*>(da + row * 2 * kWnCh + kWnCh + ch) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+    store_x3_vec4(da3 + row * 3 * 2 * kWnCh, 2 * kWnCh, ch, dt);
+    store_x3_vec4(da3 + row * 3 * 2 * kWnCh, 2 * kWnCh, kWnCh + ch, ds);
+  }
+}
+
+// start conv backward, one warp per row: dx0[j] += sum_ch dh0[ch] Ws[j][ch]; per-block partials of dWs[j][ch] = sum x0[j] dh0[ch]
+__global__ void start_bwd_kernel(const float* __restrict__ dh0, const float* __restrict__ Ws, const float* __restrict__ y, float* __restrict__ dy,
+                                 float* __restrict__ part, int N, int T, int c) {
+  __shared__ float ws_s[4 * kWnCh];
+  __shared__ float red[8][4 * kWnCh / 8];  // reused in 8 chunks
+  const int half = c / 2, Tp = T + 2 * kWgPad;
+  for (int i = threadIdx.x; i < half * kWnCh; i += blockDim.x) ws_s[i] = Ws[i];
+  __syncthreads();
+  const size_t rows = (size_t)N * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float accw[4][16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) accw[j][k] = 0.f;
+  for (size_t r = (size_t)blockIdx.x * wpb + warp; r < rows; r += (size_t)gridDim.x * wpb) {
+    const size_t prow = (r / T) * Tp + kWgPad + (r % T);
+    float x0[4], dx0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x0[j] = j < half ? y[r * c + j] : 0.f;
+      dx0[j] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int ch = lane + 32 * k;
+      const float d = dh0[prow * kWnCh + ch];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < half) {
+          dx0[j] = fmaf(d, ws_s[j * kWnCh + ch], dx0[j]);
+          accw[j][k] = fmaf(x0[j], d, accw[j][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tot = warp_sum(dx0[j]);
+      if (lane == 0 && j < half) dy[r * c + j] += tot;
+    }
+  }
+  // block reduction of the dWs partials, fixed order over the 8 warps
+  float* sh = &red[0][0];  // [8 warps][32 lanes] per (j, k)
+  for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 16; ++k) {
+      __syncthreads();
+      sh[warp * 32 + lane] = accw[j][k];
+      __syncthreads();
+      if (warp == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) tot += sh[w2 * 32 + lane];
+        part[(size_t)blockIdx.x * 4 * kWnCh + j * kWnCh + lane + 32 * k] = tot;
+      }
+    }
+}
+
+// invertible 1x1 backward: dx = dy W^T; per-block partials of dW[i][j] = sum_rows x[row][i] dy[row][j]
+__global__ void inv1x1_bwd_kernel(const float* __restrict__ xin, const float* __restrict__ dy, const float* __restrict__ Wm,
+                                  float* __restrict__ dx, float* __restrict__ part, size_t rows, int c) {
+  __shared__ float w_s[64];
+  __shared__ float red[256];
+  for (int i = threadIdx.x; i < c * c; i += blockDim.x) w_s[i] = Wm[i];
+  __syncthreads();
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+    float xv[8], dv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xv[i] = i < c ? xin[r * c + i] : 0.f;
+      dv[i] = i < c ? dy[r * c + i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < c) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < c) sacc = fmaf(dv[j], w_s[i * c + j], sacc);
+        dx[r * c + i] = sacc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fmaf(xv[i], dv[j], acc[i * 8 + j]);
+      }
+    }
+  }
+  for (int e = 0; e < 64; ++e) {
+    __syncthreads();
+    red[threadIdx.x] = acc[e];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int t2 = 0; t2 < (int)blockDim.x; ++t2) tot += red[t2];
+      part[(size_t)blockIdx.x * 64 + e] = tot;
+    }
+  }
+}
+// dW[i][j] (c x c) from the [nblk][64] partials (8-wide rows)
+__global__ void inv1x1_dw_final_kernel(const float* __restrict__ part, int nblk, int c, float* __restrict__ dW) {
+  const int e = threadIdx.x;
+  if (e >= 64) return;
+  const int i = e / 8, j = e % 8;
+  if (i >= c || j >= c) return;
+  float tot = 0.f;
+  for (int b = 0; b < nblk; ++b) tot += part[(size_t)b * 64 + e];
+  dW[i * c + j] = tot;
+}
+
+// padded [rows_p, C] valid rows -> dense [rows, C]
+__global__ void unpad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int T, int C) {
+  const int Tp = T + 2 * kWgPad;
+  const size_t n = (size_t)N * T * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % C);
+    const size_t nt = i / C;
+    dst[i] = src[((nt / T) * Tp + kWgPad + (nt % T)) * C + cc];
+  }
+}
+
+static void colsum_valid(cudaStream_t s, const float* in, int ld, int C, float* out, float* out2, float* part, int N, int T) {
+  colsum_valid_partial_kernel<<<dim3((C + 31) / 32, kWgPartSlices), dim3(32, 8), 0, s>>>(in, ld, part, N, T, C);
+  sum_partials_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, kWgPartSlices, C, out, 0);
+  if (out2) sum_partials_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, kWgPartSlices, C, out2, 0);
+}
+
+// dW = A_hi^T B_hi + A_lo^T B_hi + A_hi^T B_lo over `rows` rows of two stacked operands (block widths ka / nb)
+static int wgrad_x3(cudaStream_t s, int ka, int nb, int rows, const __nv_bfloat16* A3, int lda, const __nv_bfloat16* B3, int ldb, float* C) {
+  int rc;
+  if ((rc = gemm_bf16_ex(s, true, false, ka, nb, rows, A3, lda, B3, ldb, C, nb, 0.f))) return rc;
+  if ((rc = gemm_bf16_ex(s, true, false, ka, nb, rows, A3 + ka, lda, B3, ldb, C, nb, 1.f))) return rc;
+  return gemm_bf16_ex(s, true, false, ka, nb, rows, A3, lda, B3 + nb, ldb, C, nb, 1.f);
+}
+
+extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const MsttsWaveGlowGrads* dwt, const float* z, int N, int T,
+                                        float sigma, float* d_mel_nt640, void* ws_, size_t ws_bytes, void* stream_) {
+  MSTTS_REQUIRE(w && dwt && z && ws_, MSTTS_E_INVALID, "waveglow bwd: null argument");
+  MSTTS_REQUIRE(N >= 1 && T >= 1 && sigma > 0.f, MSTTS_E_INVALID, "waveglow bwd: N=%d T=%d sigma=%g", N, T, sigma);
+  const WgLayout l = wg_layout(N, T);
+  const WgSave v = wg_save_layout(N, T, l.total);
+  const WgBwdLayout b = wg_bwd_layout(N, T, v.total);
+  MSTTS_REQUIRE(ws_bytes >= b.total, MSTTS_E_WORKSPACE, "waveglow bwd: workspace %zu < %zu", ws_bytes, b.total);
+  cudaStream_t s = (cudaStream_t)stream_;
+  char* ws = (char*)ws_;
+  const int Tp = T + 2 * kWgPad;
+  const size_t rows = (size_t)N * T, rows_p = (size_t)N * Tp;
+  auto BF = [&](size_t off) { return (__nv_bfloat16*)(ws + off); };
+  auto FP = [&](size_t off) { return (float*)(ws + off); };
+  const size_t slot3 = rows_p * 3 * kWnCh * 2, slota = rows_p * 2 * kWnCh * 4;
+  auto H3 = [&](int f, int i) { return BF(v.h3 + ((size_t)f * kWnLayers + i) * slot3); };
+  auto G3 = [&](int f, int i) { return BF(v.g3 + ((size_t)f * kWnLayers + i) * slot3); };
+  auto APRE = [&](int f, int i) { return FP(v.a + ((size_t)f * kWnLayers + i) * slota); };
+  auto SKIP = [&](int f) { return FP(v.skip + (size_t)f * rows_p * kWnCh * 4); };
+  auto YBUF = [&](int f) { return FP(v.y + (size_t)f * rows * 8 * 4); };
+  auto XIN = [&](int f) { return FP(v.xin + (size_t)f * rows * 8 * 4); };
+  int rc;
+  const int Mr = (int)(rows_p - 2 * kWgPad);
+  const int K3 = 3 * kWnCh, A3 = 3 * 2 * kWnCh;  // stacked widths of 512- and 1024-wide rows
+  const float n_el = (float)rows * 8.f;
+
+  // ---- column-stacked effective weights (the scales are still in the workspace from the forward pass) ----
+  for (int f = 0; f < kWgFlows; ++f) {
+    WnJobs J;
+    memset(&J, 0, sizeof(J));
+    J.scale = FP(l.wscale) + (size_t)f * kWnJobsPerFlow * 1024;
+    __nv_bfloat16* wq = BF(b.wqc) + (size_t)f * kWgFlowW * 3;
+    int nj = 0;
+    J.j[nj++] = WnJob{w->start_v[f], w->start_g[f], nullptr, nullptr, flow_c(f) / 2, kWnCh, flow_c(f) / 2};
+    size_t wo = 0;
+    for (int i = 0; i < kWnLayers; ++i) {
+      J.j[nj++] = WnJob{w->in_v[f][i], w->in_g[f][i], nullptr, wq + wo, 3 * kWnCh, 2 * kWnCh, kWnCh};
+      wo += (size_t)9 * kWnCh * 2 * kWnCh;
+      J.j[nj++] = WnJob{w->cond_v[f][i], w->cond_g[f][i], nullptr, wq + wo, kWnMel, 2 * kWnCh, kWnMel};
+      wo += (size_t)3 * kWnMel * 2 * kWnCh;
+      const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
+      J.j[nj++] = WnJob{w->res_v[f][i], w->res_g[f][i], nullptr, wq + wo, kWnCh, rout, kWnCh};
+      wo += (size_t)3 * kWnCh * rout;
+    }
+    wn_apply_cols_kernel<<<dim3(64, kWnJobsPerFlow), 256, 0, s>>>(J);
+  }
+  MSTTS_CUDA(cudaMemsetAsync(ws + b.drs3, 0, rows_p * A3 * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + b.drs3_last, 0, rows_p * K3 * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + b.da3, 0, rows_p * A3 * 2, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + b.dmel, 0, rows_p * kWnMel * 4, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + b.dopad, 0, rows_p * 8 * 4, s));
+  MSTTS_CUDA(cudaMemsetAsync(ws + b.dskip, 0, rows_p * kWnCh * 4, s));
+
+  float* dz = FP(l.xa);  // forward scratch, free now
+  dz_kernel<<<ew_grid(rows * 8), 256, 0, s>>>(z, 1.f / (sigma * sigma * n_el), rows * 8, dz);
+  float* dxcur = FP(b.dx2);
+  copy_channels_kernel<<<ew_grid(rows * 4), 256, 0, s>>>(dz, 8, 4, dxcur, 4, 0, 4, rows);
+  const int nblk_small = 148 * 2;
+
+  for (int f = kWgFlows - 1; f >= 0; --f) {
+    const int c = flow_c(f), half = c / 2;
+    const __nv_bfloat16* wqc = BF(b.wqc) + (size_t)f * kWgFlowW * 3;
+    coupling_bwd_kernel<<<148 * 2, 256, 0, s>>>(SKIP(f), w->end_w[f], w->end_b[f], YBUF(f), dxcur, -1.f / n_el, FP(b.dy), FP(b.dopad),
+                                               FP(b.dskip), N, T, c);
+    // end conv: dWe = skip^T do, dbe = colsum(do)   (fp32 library GEMM: 512 x c output)
+    if ((rc = gemm_rowmajor_ex(s, true, false, kWnCh, c, (int)rows_p, SKIP(f), kWnCh, FP(b.dopad), 8, dwt->end_w[f], c, 0.f))) return rc;
+    colsum_valid(s, FP(b.dopad), 8, c, dwt->end_b[f], nullptr, FP(b.part), N, T);
+    int cur = 0;
+    // per-layer offsets inside the flow's stacked weight image
+    size_t wo_layer[kWnLayers];
+    {
+      size_t wo = 0;
+      for (int i = 0; i < kWnLayers; ++i) {
+        wo_layer[i] = wo;
+        wo += (size_t)9 * kWnCh * 2 * kWnCh + (size_t)3 * kWnMel * 2 * kWnCh + (size_t)3 * kWnCh * (i < kWnLayers - 1 ? 2 * kWnCh : kWnCh);
+      }
+    }
+    for (int i = kWnLayers - 1; i >= 0; --i) {
+      const int d = 1 << i;
+      const bool lastl = i == kWnLayers - 1;
+      const int R = lastl ? kWnCh : 2 * kWnCh;
+      const float* dh_in = lastl ? nullptr : FP(b.dh[cur]);
+      const __nv_bfloat16* Wtap_c = wqc + wo_layer[i];
+      const __nv_bfloat16* Wc_c = Wtap_c + (size_t)9 * kWnCh * 2 * kWnCh;
+      const __nv_bfloat16* Wr_c = Wc_c + (size_t)3 * kWnMel * 2 * kWnCh;
+      __nv_bfloat16* drs3 = lastl ? BF(b.drs3_last) : BF(b.drs3);
+      stack_drs_kernel<<<ew_grid(rows * R / 4), 256, 0, s>>>(dh_in, FP(b.dskip), drs3, N, T, lastl ? 1 : 0);
+      // d res bias = colsum of d rs = [colsum(dh) | colsum(dskip)]
+      if (!lastl) {
+        colsum_valid(s, dh_in, kWnCh, kWnCh, dwt->res_b[f][i], nullptr, FP(b.part), N, T);
+        colsum_valid(s, FP(b.dskip), kWnCh, kWnCh, dwt->res_b[f][i] + kWnCh, nullptr, FP(b.part), N, T);
+      } else {
+        colsum_valid(s, FP(b.dskip), kWnCh, kWnCh, dwt->res_b[f][i], nullptr, FP(b.part), N, T);
+      }
+      // d W_res (effective) = g^T d rs ; then through the weight norm
+      if ((rc = wgrad_x3(s, kWnCh, R, Mr, G3(f, i) + (size_t)kWgPad * K3, K3, drs3 + (size_t)kWgPad * 3 * R, 3 * R, FP(b.dw_eff)))) return rc;
+      wn_bwd_kernel<<<(R + 31) / 32, dim3(32, 32), 0, s>>>(w->res_v[f][i], w->res_g[f][i], FP(b.dw_eff), kWnCh, R, dwt->res_g[f][i],
+                                                          dwt->res_v[f][i]);
+      // d g = d rs W_res^T
+      if ((rc = gemm_bf16_ex(s, false, true, Mr, kWnCh, 3 * R, drs3 + (size_t)kWgPad * 3 * R, 3 * R, Wr_c, 3 * R,
+                             FP(b.dg) + (size_t)kWgPad * kWnCh, kWnCh, 0.f)))
+        return rc;
+      gate_bwd_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(APRE(f, i), w->in_b[f][i], w->cond_b[f][i], FP(b.dg), dh_in, FP(b.da), BF(b.da3),
+                                                            N, T);
+      colsum_valid(s, FP(b.da), 2 * kWnCh, 2 * kWnCh, dwt->in_b[f][i], dwt->cond_b[f][i], FP(b.part), N, T);
+      const __nv_bfloat16* da3p = BF(b.da3) + (size_t)kWgPad * A3;
+      // conditioning conv: d W_cond = mel^T d a ; d mel += d a W_cond^T
+      if ((rc = wgrad_x3(s, kWnMel, 2 * kWnCh, Mr, BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel, 3 * kWnMel, da3p, A3, FP(b.dw_eff)))) return rc;
+      wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->cond_v[f][i], w->cond_g[f][i], FP(b.dw_eff), kWnMel, 2 * kWnCh,
+                                                                  dwt->cond_g[f][i], dwt->cond_v[f][i]);
+      if (d_mel_nt640)
+        if ((rc = gemm_bf16_ex(s, false, true, Mr, kWnMel, A3, da3p, A3, Wc_c, A3, FP(b.dmel) + (size_t)kWgPad * kWnMel, kWnMel, 1.f))) return rc;
+      // dilated conv: d W_in[k] = h(t + (k-1) d)^T d a(t) ; d h(u) = sum_k d a(u - (k-1) d) W_in[k]^T
+      for (int k = 0; k < 3; ++k) {
+        const long long sh = (long long)(kWgPad + (k - 1) * d) * K3;
+        if ((rc = wgrad_x3(s, kWnCh, 2 * kWnCh, Mr, H3(f, i) + sh, K3, da3p, A3, FP(b.dw_eff) + (size_t)k * kWnCh * 2 * kWnCh))) return rc;
+      }
+      wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->in_v[f][i], w->in_g[f][i], FP(b.dw_eff), 3 * kWnCh, 2 * kWnCh,
+                                                                  dwt->in_g[f][i], dwt->in_v[f][i]);
+      const int nxt = cur ^ 1;
+      for (int k = 0; k < 3; ++k) {
+        const long long sh = (long long)(kWgPad - (k - 1) * d) * A3;
+        if ((rc = gemm_bf16_ex(s, false, true, Mr, kWnCh, A3, BF(b.da3) + sh, A3, Wtap_c + (size_t)k * kWnCh * A3, A3,
+                               FP(b.dh[nxt]) + (size_t)kWgPad * kWnCh, kWnCh, k == 0 ? 0.f : 1.f)))
+          return rc;
+      }
+      cur = nxt;
+    }
+    // ---- start conv (weight-normed 1x1, c/2 -> 512) ----
+    const float* dh0 = FP(b.dh[cur]);
+    colsum_valid(s, dh0, kWnCh, kWnCh, dwt->start_b[f], nullptr, FP(b.part), N, T);
+    float* part2 = FP(b.part) + (size_t)kWgPartSlices * 4 * 2 * kWnCh;
+    start_bwd_kernel<<<nblk_small, 256, 0, s>>>(dh0, FP(l.start_eff) + (size_t)f * 4 * kWnCh, YBUF(f), FP(b.dy), part2, N, T, c);
+    sum_partials_kernel<<<(4 * kWnCh + 127) / 128, 128, 0, s>>>(part2, nblk_small, 4 * kWnCh, FP(b.dw_eff), 0);
+    wn_bwd_kernel<<<(kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->start_v[f], w->start_g[f], FP(b.dw_eff), half, kWnCh, dwt->start_g[f],
+                                                            dwt->start_v[f]);
+    // ---- invertible 1x1 ----
+    inv1x1_bwd_kernel<<<nblk_small, 256, 0, s>>>(XIN(f), FP(b.dy), w->inv_w[f], FP(b.dx), part2, rows, c);
+    inv1x1_dw_final_kernel<<<1, 64, 0, s>>>(part2, nblk_small, c, dwt->inv_w[f]);
+    dxcur = FP(b.dx);
+    if (f % 4 == 0 && f > 0) {  // the two early-output channels rejoin the chain (Modules.py:334-336 in reverse)
+      float* nx = FP(b.dx2);
+      copy_channels_kernel<<<ew_grid(rows * 2), 256, 0, s>>>(dz, 8, f == 8 ? 2 : 0, nx, c + 2, 0, 2, rows);
+      copy_channels_kernel<<<ew_grid(rows * c), 256, 0, s>>>(dxcur, c, 0, nx, c + 2, 2, c, rows);
+      dxcur = nx;
+    }
+  }
+  if (d_mel_nt640) unpad_rows_kernel<<<ew_grid(rows * kWnMel), 256, 0, s>>>(FP(b.dmel), d_mel_nt640, N, T, kWnMel);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+// Upsample_Mel backward: d kernel [1024, out, in], d bias [80] from d up [N, keep, 80] (zero beyond keep)
+extern "C" size_t mstts_upsample_mel_bwd_workspace_bytes(int N, int Tm) {
+  if (N <= 0 || Tm <= 0) return 0;
+  return (size_t)N * ((size_t)(Tm - 1) * 256 + 1024) * 80 * sizeof(float) + 64 * 80 * sizeof(float) + 256;
+}
+__global__ void pad_dup_kernel(const float* __restrict__ dup, float* __restrict__ dst, int N, int keep, int Lfull) {
+  const size_t n = (size_t)N * Lfull * 80;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % 80);
+    const size_t np = i / 80;
+    const int p = (int)(np % Lfull), nn = (int)(np / Lfull);
+    dst[i] = p < keep ? dup[((size_t)nn * keep + p) * 80 + co] : 0.f;
+  }
+}
+__global__ void colsum_dense_partial_kernel(const float* __restrict__ in, float* __restrict__ part, size_t R, int C) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const size_t r0 = R * blockIdx.y / 64, r1 = R * (blockIdx.y + 1) / 64;
+  float sacc = 0.f;
+  if (c < C)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) sacc += in[r * C + c];
+  sh[threadIdx.y][threadIdx.x] = sacc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += sh[j][threadIdx.x];
+    part[(size_t)blockIdx.y * C + c] = tot;
+  }
+}
+extern "C" int mstts_upsample_mel_bwd(const float* mel, const float* d_up, int N, int Tm, int keep, float* d_kernel, float* d_bias, void* ws_,
+                                      size_t ws_bytes, void* stream) {
+  MSTTS_REQUIRE(mel && d_up && d_kernel && d_bias && ws_, MSTTS_E_INVALID, "upsample_mel_bwd: null pointer");
+  const int Lfull = (Tm - 1) * 256 + 1024;
+  MSTTS_REQUIRE(keep >= 1 && keep <= Lfull, MSTTS_E_INVALID, "upsample_mel_bwd: keep=%d outside [1,%d]", keep, Lfull);
+  MSTTS_REQUIRE(ws_bytes >= mstts_upsample_mel_bwd_workspace_bytes(N, Tm), MSTTS_E_WORKSPACE, "upsample_mel_bwd: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* dpad = (float*)ws_;
+  float* part = dpad + (size_t)N * Lfull * 80;
+  pad_dup_kernel<<<ew_grid((size_t)N * Lfull * 80), 256, 0, s>>>(d_up, dpad, N, keep, Lfull);
+  colsum_dense_partial_kernel<<<dim3(3, 64), dim3(32, 8), 0, s>>>(dpad, part, (size_t)N * Lfull, 80);
+  sum_partials_kernel<<<1, 128, 0, s>>>(part, 64, 80, d_bias, 0);
+  // dK[(k,co), ci] = sum_{n,t} dpad[n, 256 t + k, co] mel[n, t, ci].  With k = 256 q + r the padded gradient of one utterance
+  // is a [(Tm+3), 256*80] matrix and quarter q of the kernel contracts its rows q .. q+Tm-1 with mel: 4 GEMMs per utterance.
+  int rc;
+  for (int n = 0; n < N; ++n)
+    for (int q = 0; q < 4; ++q)
+      if ((rc = gemm_rowmajor_ex(s, true, false, 256 * 80, 80, Tm, dpad + ((size_t)n * Lfull + 256 * q) * 80, 256 * 80,
+                                 mel + (size_t)n * Tm * 80, 80, d_kernel + (size_t)q * 256 * 80 * 80, 80, n == 0 ? 0.f : 1.f)))
+        return rc;
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }

@@ -1,0 +1,79 @@
+"""GPU parity of the WaveGlow reverse pass (C ABI) against torch.autograd through the fp64 CPU oracle: gradients of
+L = -sum(log_s)/n - sum(logdet W)/n + sum(z^2)/(2 sigma^2 n) w.r.t. every raw variable (weight-norm g / v / bias, end
+conv, invertible 1x1 kernels) and, through the conditioning, the up-sampling kernel.  Gate: 2e-3 of max|ref| per tensor."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def _rel(a, b):
+    return (a.double().cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("N,S,Tm,seed", [(1, 8 * 40, 2, 0), (2, 8 * 301, 8, 1)])
+def test_gradients_match_autograd(cuda_dev, N, S, Tm, seed):
+    from oracle import waveglow_oracle as W
+    from multi_speaker_tts_b200.WaveGlow import Modules as M
+    raws, upk, upb = W.init_waveglow(seed, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
+    audio, mel = W.synthetic_batch(N, S, Tm)
+    params = M.WaveGlowParams(raws, upk, upb, cuda_dev)
+    a, m = M.Restructure_Train_Data(audio.to(cuda_dev), mel.to(cuda_dev), params)
+    z, losses, grads, d_mel = M.Glow_Train_Backward(a, m, params)
+    S8 = (S // 8) * 8
+    dk, db = M.Upsample_Mel_Backward(mel.to(cuda_dev), d_mel.reshape(N, S8, 80), params)
+    torch.cuda.synchronize()
+    # ---- fp64 oracle with autograd over the raw variables ----
+    leaves = []
+
+    def leaf(t):
+        t = t.double().clone().requires_grad_(True)
+        leaves.append(t)
+        return t
+
+    raws64 = [{'start': {k: leaf(v) for k, v in r['start'].items()},
+               'in': [{k: leaf(v) for k, v in x.items()} for x in r['in']],
+               'cond': [{k: leaf(v) for k, v in x.items()} for x in r['cond']],
+               'res': [{k: leaf(v) for k, v in x.items()} for x in r['res']],
+               'end_w': leaf(r['end_w']), 'end_b': leaf(r['end_b']), 'inv_w': leaf(r['inv_w'])} for r in raws]
+    upk64, upb64 = leaf(upk), leaf(upb)
+    flows = [W.effective_params(r) for r in raws64]
+    a_ref, m_ref = W.restructure_train_data(audio.double(), mel.double(), upk64, upb64)
+    z_ref, ls, ld = W.glow_train(a_ref, m_ref, flows)
+    l_ref = W.glow_loss(z_ref, ls, [x.double() for x in ld])
+    sum(l_ref).backward()
+    for got, ref in zip(losses, l_ref):
+        assert abs(float(got) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+    worst = {}
+    for f in range(12):
+        r64, g = raws64[f], grads[f]
+        pairs = [('inv_w', g['inv_w'], r64['inv_w']), ('end_w', g['end_w'], r64['end_w']), ('end_b', g['end_b'], r64['end_b'])]
+        for k in ('g', 'v', 'b'):
+            pairs.append(('start/' + k, g['start'][k], r64['start'][k]))
+            for i in range(8):
+                for grp in ('in', 'cond', 'res'):
+                    pairs.append(('%s_%d/%s' % (grp, i, k), g[grp][i][k], r64[grp][i][k]))
+        for name, mine, ref in pairs:
+            e = _rel(mine, ref.grad)
+            key = name.split('_')[0] + '/' + name.split('/')[-1] if '/' in name else name
+            worst[key] = max(worst.get(key, 0.0), e)
+            assert e < TOL, "flow %d %s: rel err %.3e" % (f, name, e)
+    print({k: "%.1e" % v for k, v in worst.items()})
+    assert _rel(dk, upk64.grad) < TOL and _rel(db, upb64.grad) < TOL
+
+
+def test_forward_values_unchanged_by_saving(cuda_dev):
+    """the training forward (activations kept for the reverse pass) returns the same z and sums as Glow_Train"""
+    from oracle import waveglow_oracle as W
+    from multi_speaker_tts_b200.WaveGlow import Modules as M
+    raws, upk, upb = W.init_waveglow(2, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
+    audio, mel = W.synthetic_batch(2, 8 * 120, 4)
+    params = M.WaveGlowParams(raws, upk, upb, cuda_dev)
+    a, m = M.Restructure_Train_Data(audio.to(cuda_dev), mel.to(cuda_dev), params)
+    z0, ls0, ld0, ss0 = M.Glow_Train(a, m, params)
+    z1, losses, _, _ = M.Glow_Train_Backward(a, m, params, want_d_mel=False)
+    assert torch.equal(z0, z1)
+    l0 = M.Glow_Loss(z0, ls0, ld0, ss0)
+    for x, y in zip(l0, losses):
+        assert float(x) == float(y)
