@@ -58,6 +58,29 @@ def bench_waveglow(args, pk, src):
            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": src,
                         "note": "algorithmic FLOPs (1x); the bf16x3 split executes 3x of them on the tensor pipe"}}
+    # ---- the same workload as a full training step (forward with saved activations, reverse pass, clip, TF Adam) ----
+    try:
+        from multi_speaker_tts_b200.WaveGlow import WaveGlow as WG
+        del params
+        torch.cuda.empty_cache()
+        feeder = WG.Feeder(seed=1, batch_size=N, signal_length=S)
+        model = WG.WaveGlow(device=dev, feeder=feeder, seed=0)
+        pat = feeder.Get_Train_Pattern()
+        for _ in range(2):
+            model.Run_Train_Step(pat)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            model.Run_Train_Step(pat)
+        torch.cuda.synchronize()
+        tms = (time.perf_counter() - t0) / args.steps * 1e3
+        out["train_step"] = {"ms_per_step": tms, "samples_per_s": N * S / (tms * 1e-3),
+                             "tensor_tflops_1x": 3 * flops / (tms * 1e-3) / 1e12,
+                             "note": "fwd + bwd ~ 3x the forward FLOPs; host pinned->device copies and the loss read inside"}
+        del model
+        torch.cuda.empty_cache()
+    except Exception as e:  # keep the forward line even if the trainer cannot allocate
+        out["train_step"] = {"error": repr(e)}
     if not args.no_cpu:
         flows = [W.effective_params(r) for r in raws]
         torch.set_num_threads(os.cpu_count() or 1)
