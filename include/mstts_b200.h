@@ -204,6 +204,20 @@ int mstts_upsample_mel(const float* mel, const float* kernel, const float* bias,
                        void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Zoneout LSTM over a whole sequence (H = 256): the recurrence of tf.nn.dynamic_rnn / stack_bidirectional_dynamic_rnn over
+ * ZoneoutLSTMCell.call (ZoneoutLSTMCell.py:188-271) as used by the encoder BiLSTM (Modules.py:49-73) and the speaker-embedding
+ * stack (Speaker_Embedding/Modules.py:12-37).  xk = x Kx + bias for all steps is the caller's GEMM; kh = the h rows of the cell
+ * kernel [H,4H], gate order i j f o.  masks [T,2,B,H] u8 (c, h; indexed by loop step) or NULL (inference: no mask, the (1-rate)
+ * factor stays).  reverse = 1 walks every row from its last valid frame down.  Outputs beyond lengths[b] are zero.
+ * fwd saves acts [B,T,4H], c_prev, h_prev [B,T,H] when acts != NULL (pre-zeroed by the caller);
+ * bwd returns dxk [B,T,4H] = gradient w.r.t. the gate pre-activations given dout [B,T,H] (w.r.t. the cell output m).
+ * ---------------------------------------------------------------------------------------------- */
+int mstts_zlstm_fwd(const float* xk, const float* kh, const int32_t* lengths, const uint8_t* masks, const float* x_res, int B, int T,
+                    int H, int reverse, float keep, float* out, float* acts, float* c_prev, float* h_prev, void* stream);
+int mstts_zlstm_bwd(const float* dout, const float* kh, const int32_t* lengths, const uint8_t* masks, const float* acts,
+                    const float* c_prev, int B, int T, int H, int reverse, float keep, float* dxk, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Audio features.  Replaces Audio.melspectrogram / spectrogram / spectrogram_and_mel (Audio.py:19-48,62-96):
  * pre-emphasis 0.97, librosa.stft (centre, reflect padding, periodic Hann(win) centred in n_fft), magnitude, optional
  * spectral subtraction, slaney mel filter bank (librosa.filters.mel defaults), 20 log10(max(1e-5,.)), clip to

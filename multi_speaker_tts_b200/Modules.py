@@ -181,12 +181,76 @@ def _reverse_sequence(x, lengths):
     return torch.gather(x, 1, idx[:, :, None].expand_as(x))
 
 
-def zoneout_lstm_sequence(inputs, lengths, kernel, bias, is_training, zoneout_rate, masks=None, residual=False):
+class _ZlstmFunction(torch.autograd.Function):
+    """the recurrence of a zoneout-LSTM sequence on the GPU (csrc/zlstm.cu): one launch per sequence, forward and reverse"""
+
+    @staticmethod
+    def forward(ctx, xk, kh, x_res, lengths, masks, reverse, keep):
+        import ctypes as C
+        lib = _lib.lib()
+        B, T, G = xk.shape
+        H = G // 4
+        xk, kh = xk.contiguous(), kh.contiguous()
+        out = torch.empty(B, T, H, device=xk.device)
+        need = xk.requires_grad or kh.requires_grad or (x_res is not None and x_res.requires_grad)
+        acts = torch.zeros(B, T, G, device=xk.device) if need else None
+        cp = torch.zeros(B, T, H, device=xk.device) if need else None
+        hp_ = torch.zeros(B, T, H, device=xk.device) if need else None
+        xr = x_res.contiguous() if x_res is not None else None
+        with torch.cuda.device(xk.device):
+            rc = lib.mstts_zlstm_fwd(_lib.ptr(xk), _lib.ptr(kh), _lib.ptr(lengths), _lib.ptr(masks), _lib.ptr(xr), B, T, H, int(reverse),
+                                     float(keep), _lib.ptr(out), _lib.ptr(acts), _lib.ptr(cp), _lib.ptr(hp_),
+                                     C.c_void_p(torch.cuda.current_stream(xk.device).cuda_stream))
+        _lib.check(rc, "mstts_zlstm_fwd")
+        ctx.save_for_backward(kh, lengths, masks, acts, cp, hp_)
+        ctx.meta = (B, T, H, int(reverse), float(keep), x_res is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        kh, lengths, masks, acts, cp, hp_ = ctx.saved_tensors
+        B, T, H, reverse, keep, has_res = ctx.meta
+        dout = dout.contiguous()
+        dxk = torch.empty(B, T, 4 * H, device=dout.device)
+        with torch.cuda.device(dout.device):
+            rc = _lib.lib().mstts_zlstm_bwd(_lib.ptr(dout), _lib.ptr(kh), _lib.ptr(lengths), _lib.ptr(masks), _lib.ptr(acts), _lib.ptr(cp),
+                                            B, T, H, reverse, keep, _lib.ptr(dxk),
+                                            C.c_void_p(torch.cuda.current_stream(dout.device).cuda_stream))
+        _lib.check(rc, "mstts_zlstm_bwd")
+        dkh = hp_.reshape(B * T, H).t() @ dxk.reshape(B * T, 4 * H)
+        dres = None
+        if has_res:
+            live = torch.arange(T, device=dout.device)[None, :] < lengths[:, None]
+            dres = dout * live[:, :, None]
+        return dxk, dkh, dres, None, None, None, None
+
+
+def zoneout_lstm_sequence(inputs, lengths, kernel, bias, is_training, zoneout_rate, masks=None, residual=False, reverse=False):
     """tf.nn.dynamic_rnn over a ZoneoutLSTMCell with sequence_length: beyond lengths[b] the output is zero and the state
-    is carried through.  The input rows of the kernel are applied to all steps in one GEMM; the loop keeps h @ K_h.
-    masks: [T, 2, B, H] 0/1 (c, h) or None.  residual: tf ResidualWrapper (output = m + input)."""
+    is carried through.  The input rows of the kernel are applied to all steps in one GEMM; the recurrence (h @ K_h, gates,
+    zoneout) is one persistent cluster kernel per sequence on CUDA fp32 tensors with 256 units (csrc/zlstm.cu); other shapes /
+    dtypes / devices run the same math step by step with library ops.
+    masks: [T, 2, B, H] 0/1 (c, h; indexed by loop step) or None.  residual: tf ResidualWrapper (output = m + input).
+    reverse: walk every row from its last valid frame down (reverse_sequence -> rnn -> reverse_sequence)."""
     B, T, In = inputs.shape
     H = kernel.shape[1] // 4
+    if inputs.is_cuda and inputs.dtype == torch.float32 and H == 256:
+        keep = 1.0 - zoneout_rate
+        xk = inputs @ kernel[:In] + bias
+        m8 = None
+        if is_training:
+            if masks is None:
+                m8 = torch.empty(T, 2, B, H, device=inputs.device, dtype=torch.uint8)
+                fill_mask(m8, keep, int(torch.randint(0, 2 ** 62, (1,)).item()))
+            else:
+                m8 = masks.to(torch.uint8).contiguous()
+        out = _ZlstmFunction.apply(xk, kernel[In:], inputs if residual else None, lengths.to(torch.int32).contiguous(), m8, reverse, keep)
+        return out, None
+    if reverse:
+        out, st = zoneout_lstm_sequence(_reverse_sequence(inputs, lengths), lengths, kernel, bias, is_training, zoneout_rate, masks,
+                                        residual, False)
+        return _reverse_sequence(out, lengths), st
     xk = inputs @ kernel[:In] + bias
     kh = kernel[In:]
     c = inputs.new_zeros(B, H)
@@ -225,10 +289,10 @@ def Encoder_BiLSTM(inputs, lengths, is_training=False, variables=None, masks=Non
         fw, _ = zoneout_lstm_sequence(x, lengths, variables[p + '/fw/zoneout_lstm_cell/kernel'],
                                       variables[p + '/fw/zoneout_lstm_cell/bias'], is_training,
                                       hp.Encoder.BiLSTM.Zoneout_Rate, mf)
-        bw, _ = zoneout_lstm_sequence(_reverse_sequence(x, lengths), lengths, variables[p + '/bw/zoneout_lstm_cell/kernel'],
+        bw, _ = zoneout_lstm_sequence(x, lengths, variables[p + '/bw/zoneout_lstm_cell/kernel'],
                                       variables[p + '/bw/zoneout_lstm_cell/bias'], is_training,
-                                      hp.Encoder.BiLSTM.Zoneout_Rate, mb)
-        x = torch.cat([fw, _reverse_sequence(bw, lengths)], dim=-1)
+                                      hp.Encoder.BiLSTM.Zoneout_Rate, mb, reverse=True)
+        x = torch.cat([fw, bw], dim=-1)
     return x
 
 

@@ -87,6 +87,8 @@ EXPORTS = {
     "mstts_stft_mel_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "mstts_stft_mel": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp,
                                  _fp, C.c_size_t, _fp]),
+    "mstts_zlstm_fwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, _fp]),
+    "mstts_zlstm_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp]),
     "mstts_fill_mask": (C.c_int, [_fp, C.c_size_t, C.c_float, C.c_uint64, _fp]),
     "mstts_adam_tf": (C.c_int, [_fp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _fp]),
