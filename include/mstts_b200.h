@@ -228,6 +228,15 @@ size_t mstts_stft_mel_workspace_bytes(int B, int S, int n_fft, int hop, int n_me
 int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop, int win, int n_mels, int sample_rate, float max_abs,
                    int spectral_subtract, float* mel_out, float* spec_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Hand-written tcgen05 GEMM (csrc/tc_gemm.cu): C[M,N] fp32 = A[M,K] . B[K,N] over bf16 operand images pre-tiled in the
+ * tensor core's shared-memory layout (A: [M/128][K/64][128 x 64], B: [N/256][K/64][256 x 64], element (r,k) of a tile at
+ * byte (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2).  N % 256 == 0, K % 64 == 0.
+ * mstts_tc_gemm_test tiles fp32 row-major A [M,K] and Bt [N,K] into the workspace first (bf16 rounding) -- the parity hook.
+ * ---------------------------------------------------------------------------------------------- */
+int mstts_tc_gemm_tiled(const void* A_tiled, const void* B_tiled, int M, int N, int K, float* C, int ldc, void* stream);
+int mstts_tc_gemm_test(const float* A, const float* Bt, int M, int N, int K, float* C, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

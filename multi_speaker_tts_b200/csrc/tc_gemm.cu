@@ -1,0 +1,191 @@
+// Hand-written tcgen05 GEMM for the WaveGlow WN contractions (bf16 operands, fp32 accumulation in TMEM).
+//
+//   C[M, N] = A[M, K] . B[K, N]        A, B pre-tiled in global memory exactly as the tensor core reads shared memory
+//
+// Operand images (bf16, K-major canonical layout without swizzle, the same format the decoder kernels stream):
+//   A: [M/128 m-tiles][K/64 k-blocks][128 rows x 64 k]  (16 KB per tile)
+//   B: [N/256 n-tiles][K/64 k-blocks][256 cols x 64 k]  (32 KB per tile; "column" = output channel)
+//   element (r, k) of a tile at byte (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2  =>  LBO = 128 (K), SBO = 1024 (M/N)
+// so one pipeline stage is two contiguous bulk async copies (no tensor map, no swizzle), and the producers of the
+// activations write their outputs directly in this layout (8 consecutive rows x 16 B = one 128-byte line).
+//
+// Kernel: persistent, one CTA per SM, 192 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
+// thread, M = 128, N = 256, K = 16 per instruction), warps 2-5 = epilogue (one TMEM lane quarter each).  4-stage smem ring
+// (48 KB / stage), two 256-column accumulators in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tc_gemm.h"
+
+constexpr int kGemmStages = 4;
+constexpr uint32_t kGemmATile = 128 * 64 * 2, kGemmBTile = 256 * 64 * 2, kGemmStage = kGemmATile + kGemmBTile;
+constexpr int kGemmThreads = 192;
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmParams P) {
+  extern __shared__ __align__(1024) uint8_t gsm[];
+  uint8_t* ring = gsm;
+  uint64_t* full = reinterpret_cast<uint64_t*>(gsm + kGemmStages * kGemmStage);
+  uint64_t* empty = full + kGemmStages;
+  uint64_t* acc_full = empty + kGemmStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kGemmStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ntiles = P.Mt * P.Nt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = tile / P.Nt, nt = tile % P.Nt;
+        const uint8_t* a = P.A + (size_t)mt * P.Kb * kGemmATile;
+        const uint8_t* b = P.B + (size_t)nt * P.Kb * kGemmBTile;
+        for (int kb = 0; kb < P.Kb; ++kb, ++it) {
+          const int s = it % kGemmStages, round = it / kGemmStages;
+          if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
+          ptx::mbar_arrive_expect_tx(&full[s], kGemmStage);
+          uint8_t* dst = ring + (size_t)s * kGemmStage;
+          ptx::bulk_g2s(dst, a + (size_t)kb * kGemmATile, kGemmATile, &full[s]);
+          ptx::bulk_g2s(dst + kGemmATile, b + (size_t)kb * kGemmBTile, kGemmBTile, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, 256);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+        const int ab = ti & 1, use = ti >> 1;
+        if (use > 0) ptx::mbar_wait(&acc_empty[ab], (use - 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem + (uint32_t)ab * 256;
+        for (int kb = 0; kb < P.Kb; ++kb, ++it) {
+          const int s = it % kGemmStages, round = it / kGemmStages;
+          ptx::mbar_wait(&full[s], round & 1);
+          ptx::tc_fence_after();
+          const uint32_t abase = ptx::smem_u32(ring + (size_t)s * kGemmStage), bbase = abase + kGemmATile;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ptx::umma_desc(abase + k * 256, 128, 1024);
+            const uint64_t bd = ptx::umma_desc(bbase + k * 256, 128, 1024);
+            ptx::umma_bf16(d, ad, bd, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+          }
+          ptx::umma_commit(&empty[s]);
+        }
+        ptx::umma_commit(&acc_full[ab]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue warps: TMEM lane quarter q = warp & 3 holds rows 32q .. 32q+31 of the tile ----
+    const int q = warp & 3;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int mt = tile / P.Nt, nt = tile % P.Nt;
+      const int ab = ti & 1, use = ti >> 1;
+      ptx::mbar_wait(&acc_full[ab], use & 1);
+      ptx::tc_fence_after();
+      const int row = mt * 128 + q * 32 + lane;
+      const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * 256;
+      tc_gemm_epilogue<MODE>(P, ta, row, nt);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// ---- epilogues --------------------------------------------------------------------------------------------------
+// MODE 0: plain fp32 store C[row, nt*256 + c]
+template <>
+__device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint32_t ta, int row, int nt) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(ta + c0, v);
+    ptx::tmem_wait_ld();
+    if (row < P.M) {
+      float* dst = P.C + (size_t)row * P.ldc + nt * 256 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dst + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  }
+}
+
+static size_t tc_gemm_smem() { return (size_t)kGemmStages * kGemmStage + 256; }
+
+template <int MODE>
+static int tc_gemm_launch(const TcGemmParams& P, cudaStream_t s) {
+  const size_t smem = tc_gemm_smem();
+  MSTTS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ntiles = P.Mt * P.Nt;
+  tc_gemm_kernel<MODE><<<ntiles < 148 ? ntiles : 148, kGemmThreads, smem, s>>>(P);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, float* C, int M, int N, int K, int ldc) {
+  MSTTS_REQUIRE(N % 256 == 0 && K % 64 == 0 && M >= 1, MSTTS_E_INVALID, "tc_gemm: M=%d N=%d K=%d (N %% 256, K %% 64)", M, N, K);
+  TcGemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.A = (const uint8_t*)A_tiled; P.B = (const uint8_t*)B_tiled; P.C = C; P.M = M; P.Mt = (M + 127) / 128; P.Nt = N / 256; P.Kb = K / 64;
+  P.ldc = ldc;
+  return tc_gemm_launch<0>(P, s);
+}
+
+// ---- operand tiling (tests, and the one-off conversion of weights): src row-major [R, K] fp32 (ld) -> tiled bf16 image
+//      with TR rows per tile (128 for A, 256 for B given as [N, K], i.e. B transposed); rows >= R are zero ----
+__global__ void tile_rows_kernel(const float* __restrict__ src, int R, int K, int ld, int TR, __nv_bfloat16* __restrict__ dst) {
+  const int Rt = (R + TR - 1) / TR, Kb = K / 64;
+  const size_t n = (size_t)Rt * TR * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const size_t r = i / K;
+    const int rt = (int)(r / TR), rr = (int)(r % TR);
+    const float x = r < (size_t)R ? src[r * ld + k] : 0.f;
+    const size_t tile = (size_t)rt * Kb + k / 64;
+    const int kk = k % 64;
+    dst[tile * TR * 64 + (size_t)(rr / 8) * 512 + (kk / 8) * 64 + (rr % 8) * 8 + (kk % 8)] = __float2bfloat16_rn(x);
+  }
+}
+
+extern "C" int mstts_tc_gemm_test(const float* A, const float* Bt, int M, int N, int K, float* C, void* ws, size_t ws_bytes, void* stream) {
+  // A [M,K] fp32, Bt [N,K] fp32 (B transposed) -> C [M,N] = bf16(A) . bf16(Bt)^T through the hand-written kernel
+  const size_t Mt = (M + 127) / 128, Nt = N / 256;
+  const size_t abytes = Mt * 128 * (size_t)K * 2, bbytes = Nt * 256 * (size_t)K * 2;
+  MSTTS_REQUIRE(A && Bt && C && ws, MSTTS_E_INVALID, "tc_gemm_test: null pointer");
+  MSTTS_REQUIRE(N % 256 == 0 && K % 64 == 0, MSTTS_E_INVALID, "tc_gemm_test: N %% 256, K %% 64");
+  MSTTS_REQUIRE(ws_bytes >= abytes + bbytes + 2048, MSTTS_E_WORKSPACE, "tc_gemm_test: workspace %zu < %zu", ws_bytes, abytes + bbytes + 2048);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* a = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  uint8_t* b = a + abytes;
+  tile_rows_kernel<<<148 * 8, 256, 0, s>>>(A, M, K, K, 128, (__nv_bfloat16*)a);
+  tile_rows_kernel<<<148 * 8, 256, 0, s>>>(Bt, N, K, K, 256, (__nv_bfloat16*)b);
+  return tc_gemm_plain(s, a, b, C, M, N, K, N);
+}
+
+extern "C" int mstts_tc_gemm_tiled(const void* A_tiled, const void* B_tiled, int M, int N, int K, float* C, int ldc, void* stream) {
+  MSTTS_REQUIRE(A_tiled && B_tiled && C, MSTTS_E_INVALID, "tc_gemm_tiled: null pointer");
+  return tc_gemm_plain((cudaStream_t)stream, A_tiled, B_tiled, C, M, N, K, ldc);
+}
