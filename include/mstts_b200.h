@@ -174,6 +174,10 @@ size_t mstts_waveglow_workspace_bytes(int N, int T);
 int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
                          int direction, const float* const* early_noise, float* out, double* sums, void* ws,
                          size_t ws_bytes, void* stream);
+/* A/B switch for measurements: 1 = run the WN contractions of mstts_waveglow_flows as library (cuBLAS) bf16 GEMMs with separate
+ * gate / residual-skip kernels instead of the hand-written tcgen05 GEMMs with fused epilogues (default 0). */
+int mstts_waveglow_set_path(int library_gemm);
+
 /* Training (WaveGlow/WaveGlow.py:48-70): forward in the training direction that keeps every layer's operands in the workspace,
  * and the reverse pass for L = -sum(log_s)/n - sum(logdet W)/n + sum(z^2)/(2 sigma^2 n), n = N*T*8 (Modules.py:373-384).
  * Gradients are written (not accumulated) in the layouts of the raw variables; the logdet term of the twelve c x c kernels is

@@ -76,6 +76,7 @@ EXPORTS = {
     "mstts_waveglow_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mstts_waveglow_flows": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, _fp,
                                        C.c_size_t, _fp]),
+    "mstts_waveglow_set_path": (C.c_int, [C.c_int]),
     "mstts_waveglow_train_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "mstts_waveglow_train_fwd": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), _fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     "mstts_waveglow_train_bwd": (C.c_int, [C.POINTER(MsttsWaveGlowWeights), C.POINTER(MsttsWaveGlowGrads), _fp, C.c_int, C.c_int,

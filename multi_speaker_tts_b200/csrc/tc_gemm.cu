@@ -9,8 +9,8 @@
 // so one pipeline stage is two contiguous bulk async copies (no tensor map, no swizzle), and the producers of the
 // activations write their outputs directly in this layout (8 consecutive rows x 16 B = one 128-byte line).
 //
-// Kernel: persistent, one CTA per SM, 192 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
-// thread, M = 128, N = 256, K = 16 per instruction), warps 2-5 = epilogue (one TMEM lane quarter each).  4-stage smem ring
+// Kernel: persistent, one CTA per SM, 320 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
+// thread, M = 128, N = 256, K = 16 per instruction), warps 2-9 = epilogue (two per TMEM lane quarter).  4-stage smem ring
 // (48 KB / stage), two 256-column accumulators in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -18,7 +18,7 @@
 
 constexpr int kGemmStages = 4;
 constexpr uint32_t kGemmATile = 128 * 64 * 2, kGemmBTile = 256 * 64 * 2, kGemmStage = kGemmATile + kGemmBTile;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // producer, MMA, 8 epilogue warps (two per TMEM lane quarter, half the columns each)
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmParams P) {
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&acc_full[i], 1);
-      ptx::mbar_init(&acc_empty[i], 4);
+      ptx::mbar_init(&acc_empty[i], 8);
     }
     ptx::fence_mbar_init();
   }
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
     __syncwarp();
   } else {
     // ---- epilogue warps: TMEM lane quarter q = warp & 3 holds rows 32q .. 32q+31 of the tile ----
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     int ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
       const int mt = tile / P.Nt, nt = tile % P.Nt;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
       ptx::tc_fence_after();
       const int row = mt * 128 + q * 32 + lane;
       const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * 256;
-      tc_gemm_epilogue<MODE>(P, ta, row, nt);
+      tc_gemm_epilogue<MODE>(P, ta, row, nt, half);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[ab]);
@@ -117,9 +117,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
 // ---- epilogues --------------------------------------------------------------------------------------------------
 // MODE 0: plain fp32 store C[row, nt*256 + c]
 template <>
-__device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint32_t ta, int row, int nt) {
+__device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < 256; c0 += 32) {
+  for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
     uint32_t v[32];
     ptx::tmem_ld32(ta + c0, v);
     ptx::tmem_wait_ld();
@@ -129,6 +129,84 @@ __device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint3
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(dst + j) =
             make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  }
+}
+
+// MODE 1 (WN gate): columns [0,128) = tanh pre-activations of channels 128 nt + c, [128,256) = the matching sigmoid ones
+template <>
+__device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half) {
+  const int t = row % P.Tp;
+  const bool valid = row < P.M && t < P.T;
+#pragma unroll 1
+  for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
+    uint32_t va[16], vs[16];
+    ptx::tmem_ld16(ta + c0, va);
+    ptx::tmem_ld16(ta + 128 + c0, vs);
+    ptx::tmem_wait_ld();
+    if (valid) {
+      const int ch0 = nt * 128 + c0;
+      float g[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float at = __uint_as_float(va[j]) + P.bias0[ch0 + j] + P.bias1[ch0 + j];
+        const float as = __uint_as_float(vs[j]) + P.bias0[512 + ch0 + j] + P.bias1[512 + ch0 + j];
+        g[j] = tanhf(at) * (1.f / (1.f + expf(-as)));
+      }
+      const float g0[8] = {g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7]};
+      const float g1[8] = {g[8], g[9], g[10], g[11], g[12], g[13], g[14], g[15]};
+      wn_store_x3(P.out_img, row, kWnK2 / 64, 0, 512, ch0, g0);
+      wn_store_x3(P.out_img, row, kWnK2 / 64, 0, 512, ch0 + 8, g1);
+    }
+  }
+}
+
+// MODE 2 (WN res/skip): layers < 7: n-tiles 0,1 = residual channels, 2,3 = skip channels; last layer: both tiles are skip
+template <>
+__device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half) {
+  const int t = row % P.Tp;
+  const bool valid = row < P.M && t < P.T;
+  const size_t prow = (size_t)row + 128;
+  const bool is_res = !P.lastl && nt < 2;
+  const int chb = is_res ? nt * 256 : (P.lastl ? nt * 256 : (nt - 2) * 256);  // first channel of this tile
+  const int bofs = is_res || P.lastl ? 0 : 512;                               // bias offset of the skip half
+#pragma unroll 1
+  for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld16(ta + c0, v);
+    ptx::tmem_wait_ld();
+    if (!valid) continue;
+    const int ch0 = chb + c0;
+    float x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + P.bias0[bofs + ch0 + j];
+    if (is_res) {
+      // the gated activation this residual is added to: its hi + lo halves from the A operand image (coalesced 16-byte
+      // chunks; g to 16 mantissa bits, the same value the tensor core multiplied)
+#pragma unroll
+      for (int c8 = 0; c8 < 16; c8 += 8) {
+        const uint4 hv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + c8, kWnK2 / 64));
+        const uint4 lv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, 512 + ch0 + c8, kWnK2 / 64));
+        const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hv);
+        const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&lv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[c8 + j] += __bfloat162float(hp[j]) + __bfloat162float(lp[j]);
+      }
+      const float h0[8] = {x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]};
+      const float h1[8] = {x[8], x[9], x[10], x[11], x[12], x[13], x[14], x[15]};
+      wn_store_taps(P.out_img, row, t, P.T, P.dil, ch0, h0);
+      wn_store_taps(P.out_img, row, t, P.T, P.dil, ch0 + 8, h1);
+    } else {
+      float* sp = P.skip + prow * 512 + ch0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 o = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        if (!P.first) {
+          const float4 old = *reinterpret_cast<const float4*>(sp + j);
+          o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
+        }
+        *reinterpret_cast<float4*>(sp + j) = o;
+      }
     }
   }
 }
@@ -152,6 +230,25 @@ int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, floa
   P.A = (const uint8_t*)A_tiled; P.B = (const uint8_t*)B_tiled; P.C = C; P.M = M; P.Mt = (M + 127) / 128; P.Nt = N / 256; P.Kb = K / 64;
   P.ldc = ldc;
   return tc_gemm_launch<0>(P, s);
+}
+
+int tc_gemm_wn_gate(cudaStream_t s, const void* A1, const void* B1, int M, const float* b_in, const float* b_cond, float* g_f32, void* A2,
+                    int T, int Tp) {
+  TcGemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.A = (const uint8_t*)A1; P.B = (const uint8_t*)B1; P.M = M; P.Mt = (M + 127) / 128; P.Nt = 4; P.Kb = kWnK1 / 64;
+  P.bias0 = b_in; P.bias1 = b_cond; P.out_f32 = g_f32; P.out_img = (uint8_t*)A2; P.T = T; P.Tp = Tp;
+  return tc_gemm_launch<1>(P, s);
+}
+
+int tc_gemm_wn_res(cudaStream_t s, const void* A2, const void* B2, int M, const float* b_res, const float* g_f32, float* skip, void* A1_next,
+                   int T, int Tp, int dil_next, int first, int lastl) {
+  TcGemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.A = (const uint8_t*)A2; P.B = (const uint8_t*)B2; P.M = M; P.Mt = (M + 127) / 128; P.Nt = lastl ? 2 : 4; P.Kb = kWnK2 / 64;
+  P.bias0 = b_res; P.g_in = g_f32; P.skip = skip; P.out_img = (uint8_t*)A1_next; P.T = T; P.Tp = Tp; P.dil = dil_next; P.first = first;
+  P.lastl = lastl;
+  return tc_gemm_launch<2>(P, s);
 }
 
 // ---- operand tiling (tests, and the one-off conversion of weights): src row-major [R, K] fp32 (ld) -> tiled bf16 image

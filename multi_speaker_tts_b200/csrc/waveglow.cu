@@ -18,6 +18,7 @@
 // A single fused tcgen05 kernel per flow is the planned replacement ("what comes next").
 #include "common.cuh"
 #include "gemm.h"
+#include "tc_gemm.h"
 
 constexpr int kWnCh = 512, kWnLayers = 8, kWnMel = 640, kWgPad = 128, kWgFlows = 12;
 
@@ -345,6 +346,120 @@ __global__ void copy_channels_kernel(const float* __restrict__ src, int sc, int 
   }
 }
 
+// =====================================================================================================================
+// tcgen05 path (forward / inverse without saved activations): operands live in the tensor core's tile layout (tc_gemm.h)
+// =====================================================================================================================
+// effective weight -> tiled B image.  Each thread takes 8 consecutive K rows of one output channel: one 16-byte chunk per
+// copy of the (hi ; hi ; lo) stack.  perm = 1: gate permutation (n-tile j = tanh channels 128j.. | sigmoid channels 128j..)
+struct WnTileJob {
+  const float* v;
+  const float* g_unused;
+  __nv_bfloat16* dst;
+  int kin, out, seg, Kb, kbase, perm;
+};
+struct WnTileJobs {
+  WnTileJob j[24];
+  const float* scale[24];
+};
+__global__ void wn_apply_tiled_kernel(const WnTileJobs J) {
+  const WnTileJob& job = J.j[blockIdx.y];
+  const float* scale = J.scale[blockIdx.y];
+  const int r8n = job.kin / 8;
+  const size_t n = (size_t)r8n * job.out;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % job.out);
+    const int r0 = (int)(i / job.out) * 8;
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    const float sc = scale[o];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float wv = job.v[(size_t)(r0 + q) * job.out + o] * sc;
+      hi[q] = __float2bfloat16_rn(wv);
+      lo[q] = __float2bfloat16_rn(wv - __bfloat162float(hi[q]));
+    }
+    int jt, c;
+    if (job.perm) {
+      const int oo = o < 512 ? o : o - 512;
+      jt = oo >> 7;
+      c = (oo & 127) + (o < 512 ? 0 : 128);
+    } else {
+      jt = o >> 8;
+      c = o & 255;
+    }
+    const int tap = r0 / job.seg, rr = r0 - tap * job.seg;
+    const int k0 = job.kbase + tap * 3 * job.seg + rr;
+    auto off = [&](int k) {  // bf16 element offset of the 8-element chunk (column c, K index k)
+      return ((size_t)jt * job.Kb + (k >> 6)) * (256 * 64) + (size_t)(c >> 3) * 512 + (size_t)((k & 63) >> 3) * 64 + (size_t)(c & 7) * 8;
+    };
+    const uint4 hv = *reinterpret_cast<const uint4*>(hi), lv = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(job.dst + off(k0)) = hv;
+    *reinterpret_cast<uint4*>(job.dst + off(k0 + job.seg)) = hv;
+    *reinterpret_cast<uint4*>(job.dst + off(k0 + 2 * job.seg)) = lv;
+  }
+}
+
+// conditioning [N,T,640] -> the mel K range of the im2col image (written once per call; the layers only rewrite the taps)
+__global__ void mel_tiled_kernel(const float* __restrict__ src, int N, int T, uint8_t* __restrict__ img) {
+  const int Tp = T + 2 * kWgPad;
+  const size_t n = (size_t)N * T * (kWnMel / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % (kWnMel / 8)) * 8;
+    const size_t nt = i / (kWnMel / 8);
+    const int m = (int)((nt / T) * Tp + (nt % T));
+    const float4 a = *reinterpret_cast<const float4*>(src + nt * kWnMel + ch), b = *reinterpret_cast<const float4*>(src + nt * kWnMel + ch + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    wn_store_x3(img, m, kWnK1 / 64, 9 * kWnCh, kWnMel, ch, x);
+  }
+}
+
+// flow prologue for the tiled path: y = x W (or x), start conv h0 = y[:half] Ws + bs -> taps of the first layer (dilation 1)
+__global__ void flow_pre_tiled_kernel(const float* __restrict__ x, const float* __restrict__ Wm, const float* __restrict__ Ws,
+                                      const float* __restrict__ bs, float* __restrict__ y, uint8_t* __restrict__ img, int N, int T, int c,
+                                      int apply_w) {
+  __shared__ float w_s[64], ws_s[4 * kWnCh], bs_s[kWnCh];
+  const int half = c / 2, Tp = T + 2 * kWgPad;
+  for (int i = threadIdx.x; i < c * c; i += blockDim.x) w_s[i] = Wm[i];
+  for (int i = threadIdx.x; i < half * kWnCh; i += blockDim.x) ws_s[i] = Ws[i];
+  for (int i = threadIdx.x; i < kWnCh; i += blockDim.x) bs_s[i] = bs[i];
+  __syncthreads();
+  const size_t n = (size_t)N * T * (kWnCh / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % (kWnCh / 8)) * 8;
+    const size_t r = i / (kWnCh / 8);
+    const int t = (int)(r % T);
+    const int m = (int)((r / T) * Tp + t);
+    float xin[8], yv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xin[j] = j < c ? x[r * c + j] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sacc = 0.f;
+      if (j < c) {
+        if (apply_w) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < c) sacc = fmaf(xin[q], w_s[q * c + j], sacc);
+        } else {
+          sacc = xin[j];
+        }
+      }
+      yv[j] = sacc;
+    }
+    if (ch == 0)
+      for (int j = 0; j < c; ++j) y[r * c + j] = yv[j];
+    float h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float sacc = bs_s[ch + q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < half) sacc = fmaf(yv[j], ws_s[j * kWnCh + ch + q], sacc);
+      h[q] = sacc;
+    }
+    wn_store_taps(img, m, t, T, 1, ch, h);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 struct WgLayout {
   size_t wq;                // stacked bf16 weights, per flow: {in (3 taps x [1536,1024]) | cond [1920,1024] | res [1536,1024 or 512]} x 8
@@ -356,12 +471,18 @@ struct WgLayout {
   size_t g, skip;           // padded fp32 [N][Tp][512]
   size_t a;                 // padded fp32 [N][Tp][1024]
   size_t rs;                // padded fp32 [N][Tp][1024]: res/skip output when the pre-activations are being saved
+  size_t wqt;               // tcgen05 path: tiled weight images, per flow per layer {gate B [4][102][32 KB] | res B [4|2][24][32 KB]}
+  size_t a1, a2;            // tcgen05 path: im2col image [Mt][102][16 KB], gated-activation image [Mt][24][16 KB]
   size_t y, xa, xb;         // [N,T,8]
   size_t partial;           // doubles
   size_t total;
 };
 constexpr size_t kWgFlowW = (size_t)kWnLayers * (3 * kWnCh * 2 * kWnCh + kWnMel * 2 * kWnCh) + (size_t)(kWnLayers - 1) * kWnCh * 2 * kWnCh +
                             (size_t)kWnCh * kWnCh;
+
+// bytes of tiled weight images per flow: 8 gate images (4 x 102 x 32 KB) + 7 res images (4 x 24 x 32 KB) + 1 (2 x 24 x 32 KB)
+constexpr size_t kWgGateImg = (size_t)4 * (kWnK1 / 64) * 32768, kWgResImg = (size_t)4 * (kWnK2 / 64) * 32768;
+constexpr size_t kWgFlowWt = 8 * kWgGateImg + 7 * kWgResImg + kWgResImg / 2;
 
 static WgLayout wg_layout(int N, int T) {
   WgLayout l;
@@ -383,6 +504,12 @@ static WgLayout wg_layout(int N, int T) {
   l.skip = take(rows_p * kWnCh * 4);
   l.a = take(rows_p * 2 * kWnCh * 4);
   l.rs = take(rows_p * 2 * kWnCh * 4);
+  {
+    const size_t Mt = (rows_p - 2 * kWgPad + 127) / 128;
+    l.wqt = take(kWgFlowWt * kWgFlows + 1024);
+    l.a1 = take(Mt * (kWnK1 / 64) * 16384 + 1024);
+    l.a2 = take(Mt * (kWnK2 / 64) * 16384 + 1024);
+  }
   l.y = take((size_t)N * T * 8 * 4);
   l.xa = take((size_t)N * T * 8 * 4);
   l.xb = take((size_t)N * T * 8 * 4);
@@ -429,6 +556,12 @@ static inline int flow_c(int f) { return 8 - 2 * (f / 4); }
 // Runs all 12 flows.  direction 0: training direction x -> z with sums[0] = sum(log_s), sums[1] = sum(z^2);
 // direction 1: synthesis z -> x (early_noise[2]: the two [N,T,2] noise tensors injected before flows 7 and 3 are run,
 // i.e. after undoing flows 8 and 4; inv_w then holds the INVERSE 1x1 kernels).
+static bool g_waveglow_force_library = false;  // A/B switch for tools/bench_secondary.py (mstts_waveglow_set_path)
+extern "C" int mstts_waveglow_set_path(int library_gemm) {
+  g_waveglow_force_library = library_gemm != 0;
+  return MSTTS_OK;
+}
+
 static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
                                int direction, const float* const* early_noise, float* out, double* sums, void* ws_, size_t ws_bytes,
                                void* stream_, const WgSave* save) {
@@ -446,6 +579,9 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   auto FP = [&](size_t off) { return (float*)(ws + off); };
   int rc;
 
+  // The hand-written tcgen05 GEMMs with fused gate / residual-skip epilogues run the forward and inverse directions; the
+  // training forward that keeps every layer's operands for the reverse pass stays on the stacked row-major path.
+  const bool use_tc = save == nullptr && !g_waveglow_force_library;
   // ---- effective weights (weight norm is part of the per-step graph in the reference, Modules.py:31-33) ----
   for (int f = 0; f < kWgFlows; ++f) {
     WnJobs J;
@@ -466,7 +602,27 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
       wo += (size_t)3 * kWnCh * rout;
     }
     wn_scale_kernel<<<dim3(32, kWnJobsPerFlow), dim3(32, 32), 0, s>>>(J);
-    wn_apply_kernel<<<dim3(64, kWnJobsPerFlow), 256, 0, s>>>(J);
+    if (!use_tc) {
+      wn_apply_kernel<<<dim3(64, kWnJobsPerFlow), 256, 0, s>>>(J);
+    } else {
+      wn_apply_kernel<<<dim3(64, 1), 256, 0, s>>>(J);  // job 0: the start conv's fp32 effective kernel
+      WnTileJobs TJ;
+      memset(&TJ, 0, sizeof(TJ));
+      __nv_bfloat16* img = (__nv_bfloat16*)(ws + l.wqt + (size_t)f * kWgFlowWt);
+      size_t io = 0;  // byte offset inside this flow's images
+      for (int i = 0; i < kWnLayers; ++i) {
+        __nv_bfloat16* gate_img = (__nv_bfloat16*)((char*)img + io);
+        io += kWgGateImg;
+        __nv_bfloat16* res_img = (__nv_bfloat16*)((char*)img + io);
+        const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
+        io += i < kWnLayers - 1 ? kWgResImg : kWgResImg / 2;
+        TJ.j[3 * i + 0] = WnTileJob{w->in_v[f][i], nullptr, gate_img, 3 * kWnCh, 2 * kWnCh, kWnCh, kWnK1 / 64, 0, 1};
+        TJ.j[3 * i + 1] = WnTileJob{w->cond_v[f][i], nullptr, gate_img, kWnMel, 2 * kWnCh, kWnMel, kWnK1 / 64, 9 * kWnCh, 1};
+        TJ.j[3 * i + 2] = WnTileJob{w->res_v[f][i], nullptr, res_img, kWnCh, rout, kWnCh, kWnK2 / 64, 0, 0};
+        for (int q = 0; q < 3; ++q) TJ.scale[3 * i + q] = J.scale + (size_t)(1 + 3 * i + q) * 1024;
+      }
+      wn_apply_tiled_kernel<<<dim3(48, 24), 256, 0, s>>>(TJ);
+    }
   }
   // ---- conditioning operand + zeroed pads ----
   MSTTS_CUDA(cudaMemsetAsync(ws + l.mel3, 0, rows_p * 3 * kWnMel * 2, s));
@@ -479,7 +635,14 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   auto APRE = [&](int f, int i) { return save ? FP(save->a + ((size_t)f * kWnLayers + i) * slota) : FP(l.a); };
   auto SKIP = [&](int f) { return save ? FP(save->skip + (size_t)f * rows_p * kWnCh * 4) : FP(l.skip); };
   auto YBUF = [&](int f) { return save ? FP(save->y + (size_t)f * rows * 8 * 4) : FP(l.y); };
-  pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel3));
+  if (use_tc) {
+    const size_t Mt = (rows_p - 2 * kWgPad + 127) / 128;
+    MSTTS_CUDA(cudaMemsetAsync(ws + l.a1, 0, Mt * (kWnK1 / 64) * 16384, s));
+    MSTTS_CUDA(cudaMemsetAsync(ws + l.a2, 0, Mt * (kWnK2 / 64) * 16384, s));
+    mel_tiled_kernel<<<ew_grid((size_t)rows * kWnMel / 8), 256, 0, s>>>(mel_nt640, N, T, (uint8_t*)(ws + l.a1));
+  } else {
+    pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel3));
+  }
   if (direction == 0) MSTTS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
 
   const int M = (int)(rows_p - 2 * kWgPad);  // GEMM rows: everything except the outermost pads
@@ -501,11 +664,29 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
       xsel ^= 1;
     }
     if (save) MSTTS_CUDA(cudaMemcpyAsync(ws + save->xin + (size_t)f * rows * 8 * 4, xcur, rows * c * 4, cudaMemcpyDeviceToDevice, s));
-    flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], YBUF(f), H3(f, 0), N,
-                                            T, c, direction == 0 ? 1 : 0);
+    if (use_tc)
+      flow_pre_tiled_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], YBUF(f),
+                                                    (uint8_t*)(ws + l.a1), N, T, c, direction == 0 ? 1 : 0);
+    else
+      flow_pre_kernel<<<148 * 4, 256, 0, s>>>(xcur, w->inv_w[f], FP(l.start_eff) + (size_t)f * 4 * kWnCh, w->start_b[f], YBUF(f), H3(f, 0), N,
+                                              T, c, direction == 0 ? 1 : 0);
     const __nv_bfloat16* wq = BF(l.wq) + (size_t)f * kWgFlowW * 3;
     size_t wo = 0;
-    for (int i = 0; i < kWnLayers; ++i) {
+    if (use_tc) {
+      const char* img = ws + l.wqt + (size_t)f * kWgFlowWt;
+      size_t io = 0;
+      for (int i = 0; i < kWnLayers; ++i) {
+        const char* gate_img = img + io;
+        io += kWgGateImg;
+        const char* res_img = img + io;
+        const bool lastl = i == kWnLayers - 1;
+        io += lastl ? kWgResImg / 2 : kWgResImg;
+        if ((rc = tc_gemm_wn_gate(s, ws + l.a1, gate_img, M, w->in_b[f][i], w->cond_b[f][i], FP(l.g), ws + l.a2, T, Tp))) return rc;
+        if ((rc = tc_gemm_wn_res(s, ws + l.a2, res_img, M, w->res_b[f][i], FP(l.g), SKIP(f), ws + l.a1, T, Tp, 2 << i, i == 0, lastl ? 1 : 0)))
+          return rc;
+      }
+    }
+    for (int i = 0; i < (use_tc ? 0 : kWnLayers); ++i) {
       const int d = 1 << i;
       const int K3 = 3 * kWnCh;
       float* a_out = APRE(f, i) + (size_t)kWgPad * 2 * kWnCh;

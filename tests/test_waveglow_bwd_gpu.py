@@ -64,7 +64,8 @@ def test_gradients_match_autograd(cuda_dev, N, S, Tm, seed):
 
 
 def test_forward_values_unchanged_by_saving(cuda_dev):
-    """the training forward (activations kept for the reverse pass) returns the same z and sums as Glow_Train"""
+    """the training forward (activations kept for the reverse pass; library GEMMs over row-major stacked operands) and Glow_Train
+    (hand-written tcgen05 GEMMs over tiled operands) compute the same bf16x3 products in a different summation order"""
     from oracle import waveglow_oracle as W
     from multi_speaker_tts_b200.WaveGlow import Modules as M
     raws, upk, upb = W.init_waveglow(2, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
@@ -73,10 +74,10 @@ def test_forward_values_unchanged_by_saving(cuda_dev):
     a, m = M.Restructure_Train_Data(audio.to(cuda_dev), mel.to(cuda_dev), params)
     z0, ls0, ld0, ss0 = M.Glow_Train(a, m, params)
     z1, losses, _, _ = M.Glow_Train_Backward(a, m, params, want_d_mel=False)
-    assert torch.equal(z0, z1)
+    assert (z0 - z1).abs().max().item() < 1e-4
     l0 = M.Glow_Loss(z0, ls0, ld0, ss0)
     for x, y in zip(l0, losses):
-        assert float(x) == float(y)
+        assert abs(float(x) - float(y)) <= 1e-6 * max(1.0, abs(float(y)))
 
 
 def test_trainer_step_clip_and_adam(cuda_dev, capsys):
