@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int mt = tile / P.Nt, nt = tile % P.Nt;
+        const int mt = tile / P.Nt, nt = (tile % P.Nt + mt) % P.Nt;  // rotated: every CTA gets a mix of n-tiles
         const uint8_t* a = P.A + (size_t)mt * P.Kb * kGemmATile;
         const uint8_t* b = P.B + (size_t)nt * P.Kb * kGemmBTile;
         for (int kb = 0; kb < P.Kb; ++kb, ++it) {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
     const int q = warp & 3, half = (warp - 2) >> 2;
     int ti = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
-      const int mt = tile / P.Nt, nt = tile % P.Nt;
+      const int mt = tile / P.Nt, nt = (tile % P.Nt + mt) % P.Nt;
       const int ab = ti & 1, use = ti >> 1;
       ptx::mbar_wait(&acc_full[ab], use & 1);
       ptx::tc_fence_after();
@@ -136,8 +136,7 @@ __device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint3
 // MODE 1 (WN gate): columns [0,128) = tanh pre-activations of channels 128 nt + c, [128,256) = the matching sigmoid ones
 template <>
 __device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half) {
-  const int t = row % P.Tp;
-  const bool valid = row < P.M && t < P.T;
+  const bool valid = row < P.M;  // rows are compact: m = n * T + t
 #pragma unroll 1
   for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
     uint32_t va[16], vs[16];
@@ -164,9 +163,9 @@ __device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint3
 // MODE 2 (WN res/skip): layers < 7: n-tiles 0,1 = residual channels, 2,3 = skip channels; last layer: both tiles are skip
 template <>
 __device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half) {
-  const int t = row % P.Tp;
-  const bool valid = row < P.M && t < P.T;
-  const size_t prow = (size_t)row + 128;
+  const int t = row % P.T;
+  const bool valid = row < P.M;
+  const size_t prow = (size_t)(row / P.T) * P.Tp + 128 + t;  // row of the padded fp32 layout the flow epilogue reads
   const bool is_res = !P.lastl && nt < 2;
   const int chb = is_res ? nt * 256 : (P.lastl ? nt * 256 : (nt - 2) * 256);  // first channel of this tile
   const int bofs = is_res || P.lastl ? 0 : 512;                               // bias offset of the skip half

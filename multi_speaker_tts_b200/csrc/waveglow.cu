@@ -405,7 +405,7 @@ __global__ void mel_tiled_kernel(const float* __restrict__ src, int N, int T, ui
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % (kWnMel / 8)) * 8;
     const size_t nt = i / (kWnMel / 8);
-    const int m = (int)((nt / T) * Tp + (nt % T));
+    const int m = (int)nt;  // compact rows: m = n * T + t
     const float4 a = *reinterpret_cast<const float4*>(src + nt * kWnMel + ch), b = *reinterpret_cast<const float4*>(src + nt * kWnMel + ch + 4);
     const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     wn_store_x3(img, m, kWnK1 / 64, 9 * kWnCh, kWnMel, ch, x);
@@ -427,7 +427,7 @@ __global__ void flow_pre_tiled_kernel(const float* __restrict__ x, const float* 
     const int ch = (int)(i % (kWnCh / 8)) * 8;
     const size_t r = i / (kWnCh / 8);
     const int t = (int)(r % T);
-    const int m = (int)((r / T) * Tp + t);
+    const int m = (int)r;  // compact rows
     float xin[8], yv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) xin[j] = j < c ? x[r * c + j] : 0.f;
@@ -505,7 +505,7 @@ static WgLayout wg_layout(int N, int T) {
   l.a = take(rows_p * 2 * kWnCh * 4);
   l.rs = take(rows_p * 2 * kWnCh * 4);
   {
-    const size_t Mt = (rows_p - 2 * kWgPad + 127) / 128;
+    const size_t Mt = ((size_t)N * T + 127) / 128;  // the tiled path has no pad rows: the im2col taps carry the zero borders
     l.wqt = take(kWgFlowWt * kWgFlows + 1024);
     l.a1 = take(Mt * (kWnK1 / 64) * 16384 + 1024);
     l.a2 = take(Mt * (kWnK2 / 64) * 16384 + 1024);
@@ -636,7 +636,7 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   auto SKIP = [&](int f) { return save ? FP(save->skip + (size_t)f * rows_p * kWnCh * 4) : FP(l.skip); };
   auto YBUF = [&](int f) { return save ? FP(save->y + (size_t)f * rows * 8 * 4) : FP(l.y); };
   if (use_tc) {
-    const size_t Mt = (rows_p - 2 * kWgPad + 127) / 128;
+    const size_t Mt = (rows + 127) / 128;
     MSTTS_CUDA(cudaMemsetAsync(ws + l.a1, 0, Mt * (kWnK1 / 64) * 16384, s));
     MSTTS_CUDA(cudaMemsetAsync(ws + l.a2, 0, Mt * (kWnK2 / 64) * 16384, s));
     mel_tiled_kernel<<<ew_grid((size_t)rows * kWnMel / 8), 256, 0, s>>>(mel_nt640, N, T, (uint8_t*)(ws + l.a1));
@@ -681,8 +681,8 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
         const char* res_img = img + io;
         const bool lastl = i == kWnLayers - 1;
         io += lastl ? kWgResImg / 2 : kWgResImg;
-        if ((rc = tc_gemm_wn_gate(s, ws + l.a1, gate_img, M, w->in_b[f][i], w->cond_b[f][i], FP(l.g), ws + l.a2, T, Tp))) return rc;
-        if ((rc = tc_gemm_wn_res(s, ws + l.a2, res_img, M, w->res_b[f][i], FP(l.g), SKIP(f), ws + l.a1, T, Tp, 2 << i, i == 0, lastl ? 1 : 0)))
+        if ((rc = tc_gemm_wn_gate(s, ws + l.a1, gate_img, (int)rows, w->in_b[f][i], w->cond_b[f][i], FP(l.g), ws + l.a2, T, Tp))) return rc;
+        if ((rc = tc_gemm_wn_res(s, ws + l.a2, res_img, (int)rows, w->res_b[f][i], FP(l.g), SKIP(f), ws + l.a1, T, Tp, 2 << i, i == 0, lastl ? 1 : 0)))
           return rc;
       }
     }
