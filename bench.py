@@ -235,13 +235,21 @@ def main():
     bwd_alg = (fwd_bytes_per_step(B, TE, s_w, 4) + saved_bytes_per_step(B, TE)) * T
     fwd_avg, bwd_avg = fwd_ms / max(nf, 1), bwd_ms / max(nb, 1)
 
-    def roof(alg, avg_ms, name):
+    # dram__bytes_read + dram__bytes_write per launch from the committed `ncu --set full` capture of this command at the
+    # default workload (profiles/r1_traffic.json); null for any other shape / mode
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.mode == "bf16x3" and (B, TE, L) == (32, 128, 800):
+        tj = json.load(open(tpath))
+        traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj.items() if isinstance(v, dict)}
+
+    def roof(alg, avg_ms, name, tkey):
         ach = alg / (avg_ms * 1e-3) / 1e9
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                "traffic": None, "peak_source": peak_kind, "avg_launch_ms": avg_ms, "algorithmic_bytes": alg}
+                "traffic": traffic.get(tkey), "peak_source": peak_kind, "avg_launch_ms": avg_ms, "algorithmic_bytes": alg}
 
-    r_f = roof(fwd_alg, fwd_avg, "decoder_fwd_kernel (forward loop, %d steps/launch)" % T)
-    r_b = roof(bwd_alg, bwd_avg, "decoder_bwd_kernel (reverse loop, %d steps/launch)" % T)
+    r_f = roof(fwd_alg, fwd_avg, "decoder_fwd_kernel (forward loop, %d steps/launch)" % T, "decoder_fwd_tc_kernel")
+    r_b = roof(bwd_alg, bwd_avg, "decoder_bwd_kernel (reverse loop, %d steps/launch)" % T, "decoder_bwd_tc_kernel")
     dominant, other = (r_b, r_f) if bwd_avg >= fwd_avg else (r_f, r_b)
 
     if rank == 0:
