@@ -609,7 +609,8 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   const Bf16Pair sg0 = {(__nv_bfloat16*)(ws + l.sp_g0_hi), (__nv_bfloat16*)(ws + l.sp_g0_lo)};
   const Bf16Pair sg1 = {(__nv_bfloat16*)(ws + l.sp_g1_hi), (__nv_bfloat16*)(ws + l.sp_g1_lo)};
   const Bf16Pair sl = {(__nv_bfloat16*)(ws + l.sp_left_hi), (__nv_bfloat16*)(ws + l.sp_left_lo)};
-  const Bf16Pair sw = {(__nv_bfloat16*)(ws + l.sp_w_hi), (__nv_bfloat16*)(ws + l.sp_w_lo)};
+  // the forward call left the prenet rows of cell0_kernel stacked (hi ; hi ; lo) in sp_w3: block 0 = hi, block 2 = lo
+  const Bf16Pair sw = {(__nv_bfloat16*)(ws + l.sp_w3), (__nv_bfloat16*)(ws + l.sp_w3) + (size_t)2 * kPrenet * kGates};
   if (tc) {
     if ((rc = split_bf16_matrix(s, F(l.dG0), TB, kGates, kGates, sg0))) return rc;
     if ((rc = split_bf16_matrix(s, F(l.dG1), TB, kGates, kGates, sg1))) return rc;

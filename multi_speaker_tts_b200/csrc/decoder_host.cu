@@ -221,11 +221,13 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   if (rc) return rc;
   prenet_act_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.pre), w->prenet1_bias, io->prenet_mask, 1, B, TB * kPrenet);
   if (io->mode == MSTTS_MODE_BF16X3) {  // 54 GFLOP at config 2: tensor cores, bf16x3
-    const Bf16Pair a = {(__nv_bfloat16*)(ws + l.sp_left_hi), (__nv_bfloat16*)(ws + l.sp_left_lo)};
-    const Bf16Pair b = {(__nv_bfloat16*)(ws + l.sp_w_hi), (__nv_bfloat16*)(ws + l.sp_w_lo)};
-    if ((rc = split_bf16_matrix(s, F(l.pre), TB, kPrenet, kPrenet, a))) return rc;
-    if ((rc = split_bf16_matrix(s, w->cell0_kernel, kPrenet, kGates, kGates, b))) return rc;
-    rc = gemm_rowmajor_x3(s, false, false, (int)TB, kGates, kPrenet, a, kPrenet, b, kGates, F(l.g0pre), kGates, 0.f);
+    // one bf16 GEMM with the three bf16x3 products folded into K (768): g0pre [TB,4096] is written once instead of being
+    // read-modify-written by three K=256 calls (420 MB each way)
+    __nv_bfloat16* a3 = (__nv_bfloat16*)(ws + l.sp_left_hi);  // [TB, 768] fits the [TB, 1024] split buffer
+    __nv_bfloat16* b3 = (__nv_bfloat16*)(ws + l.sp_w3);       // [768, 4096]
+    if ((rc = split_bf16_stack(s, F(l.pre), TB, kPrenet, kPrenet, a3, false))) return rc;
+    if ((rc = split_bf16_stack(s, w->cell0_kernel, kPrenet, kGates, kGates, b3, true))) return rc;
+    rc = gemm_rowmajor_bf16(s, (int)TB, kGates, 3 * kPrenet, a3, 3 * kPrenet, b3, kGates, F(l.g0pre), kGates, 0.f);
   } else {
     rc = gemm_rowmajor(s, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
   }

@@ -57,6 +57,7 @@ struct DecLayout {
   size_t sp_g0_hi, sp_g0_lo, sp_g1_hi, sp_g1_lo;   // [T*B,4096] dG0 / dG1
   size_t sp_left_hi, sp_left_lo;                   // [T*B,1024] the activation operand of the current GEMM
   size_t sp_w_hi, sp_w_lo;                         // [256,4096] prenet rows of cell0_kernel
+  size_t sp_w3;                                    // [768,4096] the same rows stacked (hi;hi;lo) for the one-call forward product
   size_t total;
 };
 
@@ -130,7 +131,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dpre_h = take(TB * kPrenet);
   l.colsum_scratch = take((size_t)64 * kGates);
   l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = off;
-  l.sp_g0_hi = l.sp_g0_lo = l.sp_g1_hi = l.sp_g1_lo = l.sp_left_hi = l.sp_left_lo = l.sp_w_hi = l.sp_w_lo = off;
+  l.sp_g0_hi = l.sp_g0_lo = l.sp_g1_hi = l.sp_g1_lo = l.sp_left_hi = l.sp_left_lo = l.sp_w_hi = l.sp_w_lo = l.sp_w3 = off;
   if (mode == MSTTS_MODE_BF16X3) {
     auto take_bytes = [&](size_t nbytes) {
       size_t o = off;
@@ -154,6 +155,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
     l.sp_left_lo = take_bytes(TB * kCell * 2);
     l.sp_w_hi = take_bytes((size_t)kPrenet * kGates * 2);
     l.sp_w_lo = take_bytes((size_t)kPrenet * kGates * 2);
+    l.sp_w3 = take_bytes((size_t)3 * kPrenet * kGates * 2);
   }
   l.total = off;
   return l;

@@ -28,6 +28,8 @@ struct Bf16Pair {
 };
 // dst.{hi,lo}[r*cols + c] = split(src[r*ld + c])
 int split_bf16_matrix(cudaStream_t s, const float* src, size_t rows, size_t cols, size_t ld, Bf16Pair dst);
+// stacked single-buffer split for a one-call bf16x3 product: A side [rows, 3*cols] = [hi|lo|hi], B side [3*rows, cols] = [hi;hi;lo]
+int split_bf16_stack(cudaStream_t s, const float* src, size_t rows, size_t cols, size_t ld, __nv_bfloat16* dst, bool b_side);
 int gemm_rowmajor_x3(cudaStream_t s, bool transA, bool transB, int M, int N, int K, Bf16Pair A, int lda, Bf16Pair B, int ldb,
                      float* C, int ldc, float beta);
 
