@@ -1268,10 +1268,11 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
       const __nv_bfloat16* Wr_c = Wc_c + (size_t)3 * kWnMel * 2 * kWnCh;
       __nv_bfloat16* drs3 = lastl ? BF(b.drs3_last) : BF(b.drs3);
       stack_drs_kernel<<<ew_grid(rows * R / 4), 256, 0, s>>>(dh_in, FP(b.dskip), drs3, N, T, lastl ? 1 : 0);
-      // d res bias = colsum of d rs = [colsum(dh) | colsum(dskip)]
+      // d res bias = colsum of d rs = [colsum(dh) | colsum(dskip)]; d skip is the same for all 8 layers of the flow: its
+      // column sums are computed once (last layer) and copied
       if (!lastl) {
         colsum_valid(s, dh_in, kWnCh, kWnCh, dwt->res_b[f][i], nullptr, FP(b.part), N, T);
-        colsum_valid(s, FP(b.dskip), kWnCh, kWnCh, dwt->res_b[f][i] + kWnCh, nullptr, FP(b.part), N, T);
+        MSTTS_CUDA(cudaMemcpyAsync(dwt->res_b[f][i] + kWnCh, dwt->res_b[f][kWnLayers - 1], kWnCh * sizeof(float), cudaMemcpyDeviceToDevice, s));
       } else {
         colsum_valid(s, FP(b.dskip), kWnCh, kWnCh, dwt->res_b[f][i], nullptr, FP(b.part), N, T);
       }
