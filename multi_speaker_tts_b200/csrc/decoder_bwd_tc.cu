@@ -286,7 +286,18 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     float* dps = scratch;   // [(TeP+32)][32]
     float* dq_s = scratch;  // [32][128]
     long long* dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
-#define STAMP(k) do { if (dbg) dbg[(size_t)(T - 1 - t) * 32 + (k)] = clock64(); } while (0)
+    // profiling aid: CTA 0 stamps every step with its SM clock; at the middle step EVERY CTA also stamps the global timer
+    // (rows 0..127 of the same buffer, one row per CTA) so that tools/phase_times.py can show the arrival spread at each barrier
+    long long* dbg_all = (P.dbg && tid == 0) ? P.dbg + (size_t)blockIdx.x * 32 : nullptr;
+#define STAMP(k)                                                                 \
+  do {                                                                           \
+    if (dbg && t != T / 2) dbg[(size_t)(T - 1 - t) * 32 + (k)] = clock64();      \
+    if (dbg_all && t == T / 2) {                                                 \
+      unsigned long long gt;                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                     \
+      dbg_all[(k)] = (long long)gt;                                              \
+    }                                                                            \
+  } while (0)
 
     // Drains both accumulators (acc 0 = lanes 0-15, acc 1 = lanes 16-31 of every TMEM lane quarter), adds the hi/lo
     // quadrants, reduces the cluster's 4 K-slices through DSMEM and writes this CTA's 32 rows of each to the partial

@@ -30,6 +30,15 @@ names_f = ["start", "J0 done", "reduceA done", "epiA done", "barA done", "J1 don
 order_f = [0, 1, 2, 3, 4, 5, 6, 7, 8, 14, 15, 11, 12, 13, 9, 10]
 sel = stamps[T // 4: 3 * T // 4]
 if which == "bwd":
+    # rows 0..127: global-timer stamps (ns) of every CTA at the middle step -> arrival spread at the phase ends
+    allc = stamps[:128, :11]
+    if (allc > 0).all():
+        base = allc[:, 0].min()
+        print("middle step, all 128 CTAs, global timer (ns since the first CTA started the step): min / median / max over CTAs")
+        for k in range(11):
+            col = allc[:, k] - base
+            print("  %-16s %8.0f %8.0f %8.0f   slowest CTA %d" % (names_b[k], col.min().item(), col.median().item(), col.max().item(),
+                                                                   int(col.argmax())))
     prev = sel[:, 0]
     print("reverse kernel, cycles per step (mean over the middle half of the steps), CTA 0:")
     for k in range(11):
