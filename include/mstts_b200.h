@@ -222,6 +222,17 @@ int mstts_zlstm_bwd(const float* dout, const float* kh, const int32_t* lengths, 
                     const float* c_prev, int B, int T, int H, int reverse, float keep, float* dxk, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * tf.layers.conv1d(padding='same', stride 1) and its gradients as bf16x3 tensor-core GEMMs: encoder and postnet convolutions
+ * (Modules.py:25-47,121-143).  x [B,T,Cin], kernel [k,Cin,Cout] (TF layout), y [B,T,Cout]; odd k <= 15, channels % 8 == 0.
+ * bwd: dx (may be NULL) and dkernel are overwritten; the bias gradient is a column sum the caller owns.
+ * ---------------------------------------------------------------------------------------------- */
+size_t mstts_conv1d_workspace_bytes(int B, int T, int Cin, int Cout, int k);
+int mstts_conv1d_fwd(const float* x, const float* kernel, const float* bias, int B, int T, int Cin, int Cout, int k, float* y, void* ws,
+                     size_t ws_bytes, void* stream);
+int mstts_conv1d_bwd(const float* x, const float* kernel, const float* dy, int B, int T, int Cin, int Cout, int k, float* dx,
+                     float* dkernel, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Audio features.  Replaces Audio.melspectrogram / spectrogram / spectrogram_and_mel (Audio.py:19-48,62-96):
  * pre-emphasis 0.97, librosa.stft (centre, reflect padding, periodic Hann(win) centred in n_fft), magnitude, optional
  * spectral subtraction, slaney mel filter bank (librosa.filters.mel defaults), 20 log10(max(1e-5,.)), clip to

@@ -149,9 +149,51 @@ def _batch_norm(x, v, prefix, training, momentum=0.99, eps=1e-3):
     return (x - mean) * torch.rsqrt(var + eps) * gamma + beta
 
 
+class _Conv1dFunction(torch.autograd.Function):
+    """conv1d 'same' + gradients as bf16x3 tensor-core GEMMs (csrc/conv1d.cu)"""
+
+    @staticmethod
+    def _ws(x, B, T, Cin, Cout, k):
+        return torch.empty(_lib.lib().mstts_conv1d_workspace_bytes(B, T, Cin, Cout, k), device=x.device, dtype=torch.uint8)
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias):
+        import ctypes as C
+        B, T, Cin = x.shape
+        k, _, Cout = kernel.shape
+        x, kernel, bias = x.contiguous(), kernel.contiguous(), bias.contiguous()
+        y = torch.empty(B, T, Cout, device=x.device)
+        ws = _Conv1dFunction._ws(x, B, T, Cin, Cout, k)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().mstts_conv1d_fwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(bias), B, T, Cin, Cout, k, _lib.ptr(y),
+                                             C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _lib.check(rc, "mstts_conv1d_fwd")
+        ctx.save_for_backward(x, kernel)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes as C
+        x, kernel = ctx.saved_tensors
+        B, T, Cin = x.shape
+        k, _, Cout = kernel.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dk = torch.empty_like(kernel)
+        ws = _Conv1dFunction._ws(x, B, T, Cin, Cout, k)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().mstts_conv1d_bwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(dy), B, T, Cin, Cout, k, _lib.ptr(dx), _lib.ptr(dk),
+                                             C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _lib.check(rc, "mstts_conv1d_bwd")
+        return dx, dk, dy.sum(dim=(0, 1))
+
+
 def _conv1d_same(x, kernel, bias):
-    """tf.layers.conv1d(padding='same', stride 1) on [B,T,C] with a TF-layout kernel [k, in, out]"""
+    """tf.layers.conv1d(padding='same', stride 1) on [B,T,C] with a TF-layout kernel [k, in, out]: bf16x3 tensor-core GEMMs on
+    CUDA fp32 tensors (csrc/conv1d.cu), the library convolution otherwise"""
     k = kernel.shape[0]
+    if x.is_cuda and x.dtype == torch.float32 and k % 2 == 1 and k <= 15 and kernel.shape[1] % 8 == 0 and kernel.shape[2] % 8 == 0:
+        return _Conv1dFunction.apply(x, kernel, bias)
     y = F.conv1d(x.transpose(1, 2), kernel.permute(2, 1, 0), bias, padding=k // 2)
     return y.transpose(1, 2)
 

@@ -224,3 +224,25 @@ int gemm_bf16_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, 
   }
   return MSTTS_OK;
 }
+
+int gemm_bf16_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, long long sA,
+                      const __nv_bfloat16* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch) {
+  int rc;
+  cublasHandle_t h = get_handle(&rc);
+  if (!h) return rc;
+  cublasStatus_t st = cublasSetStream(h, s);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
+    return MSTTS_E_CUDA;
+  }
+  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+  const float one = 1.f;
+  st = cublasGemmStridedBatchedEx(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &one, B, CUDA_R_16BF, ldb,
+                                  sB, A, CUDA_R_16BF, lda, sA, &beta, C, CUDA_R_32F, ldc, sC, batch, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+  if (st != CUBLAS_STATUS_SUCCESS) {
+    mstts_set_error("gemm: cublasGemmStridedBatchedEx bf16 (M=%d,N=%d,K=%d,batch=%d) failed (%d)", M, N, K, batch, (int)st);
+    return MSTTS_E_CUDA;
+  }
+  return MSTTS_OK;
+}

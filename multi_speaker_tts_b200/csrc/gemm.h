@@ -40,3 +40,6 @@ int gemm_rowmajor_bf16(cudaStream_t s, int M, int N, int K, const __nv_bfloat16*
 // general form: C[M,N] = op(A) op(B) + beta C with op(A) M x K (stored K x M when transA), op(B) K x N (stored N x K when transB)
 int gemm_bf16_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B,
                  int ldb, float* C, int ldc, float beta);
+// strided-batched form (element strides sA / sB / sC between batches; sB = 0 shares B)
+int gemm_bf16_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, long long sA,
+                      const __nv_bfloat16* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch);
