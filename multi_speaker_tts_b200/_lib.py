@@ -90,7 +90,7 @@ EXPORTS = {
                                  _fp, C.c_size_t, _fp]),
     "mstts_zlstm_fwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, _fp]),
     "mstts_zlstm_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp]),
-    "mstts_tc_gemm_tiled": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp]),
+    "mstts_tc_gemm_tiled": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp]),
     "mstts_tc_gemm_test": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "mstts_conv1d_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "mstts_conv1d_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),

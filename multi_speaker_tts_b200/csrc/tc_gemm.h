@@ -13,10 +13,17 @@ struct TcGemmParams {
   uint8_t* out_img;
   const float* g_in;
   int T, Tp, dil, first, lastl;
+  // split-K tail: the first n_full tiles run whole; each of the remaining n_split tiles is computed as two K halves on two
+  // CTAs of the same round (the writer parks its fp32 accumulator in `partial`, the finisher adds it in its epilogue)
+  int n_full, n_split;
+  float* partial;     // [n_split][256 cols][128 rows]
+  unsigned* flags;    // [n_split], zeroed before the launch; the 8 writer warps each add 1
 };
+// scratch bytes a caller must provide for the split-K tail (partials + flags)
+constexpr size_t kTcGemmScratchBytes = (size_t)74 * 256 * 128 * 4 + 1024;
 
 template <int MODE>
-__device__ __forceinline__ void tc_gemm_epilogue(const TcGemmParams& P, uint32_t ta, int row, int nt, int half);
+__device__ __forceinline__ void tc_gemm_epilogue(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part);
 
 // WaveGlow WN layer, fused epilogues (tc_gemm.cu):
 //   gate : A = im2col image [3 taps x (hi|lo|hi) x 512 | mel (hi|lo|hi) x 640] (K = 6528), B columns permuted so that n-tile j
@@ -25,9 +32,9 @@ __device__ __forceinline__ void tc_gemm_epilogue(const TcGemmParams& P, uint32_t
 //   res  : A = that image, B = res/skip kernel (N = 1024, or 512 in the last layer); epilogue = residual onto the gated
 //          activation -> the NEXT layer's im2col taps (dilation dil), and skip accumulation
 int tc_gemm_wn_gate(cudaStream_t s, const void* A1, const void* B1, int M, const float* b_in, const float* b_cond, float* g_f32, void* A2,
-                    int T, int Tp);
+                    int T, int Tp, void* scratch);
 int tc_gemm_wn_res(cudaStream_t s, const void* A2, const void* B2, int M, const float* b_res, const float* g_f32, float* skip, void* A1_next,
-                   int T, int Tp, int dil_next, int first, int lastl);
+                   int T, int Tp, int dil_next, int first, int lastl, void* scratch);
 constexpr int kWnK1 = 3 * 3 * 512 + 3 * 640;  // 6528
 constexpr int kWnK2 = 3 * 512;                // 1536
 // byte offset of the 16-byte chunk (row m, K index k with k % 8 == 0) inside an A image with Kb k-blocks per m-tile
@@ -78,4 +85,4 @@ __device__ __forceinline__ void wn_store_x3(uint8_t* img, int m, int Kb, int k0,
 }
 #endif
 
-int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, float* C, int M, int N, int K, int ldc);
+int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, float* C, int M, int N, int K, int ldc, void* scratch);

@@ -473,6 +473,7 @@ struct WgLayout {
   size_t rs;                // padded fp32 [N][Tp][1024]: res/skip output when the pre-activations are being saved
   size_t wqt;               // tcgen05 path: tiled weight images, per flow per layer {gate B [4][102][32 KB] | res B [4|2][24][32 KB]}
   size_t a1, a2;            // tcgen05 path: im2col image [Mt][102][16 KB], gated-activation image [Mt][24][16 KB]
+  size_t tcscr;             // tcgen05 path: split-K tail scratch (tc_gemm.h)
   size_t y, xa, xb;         // [N,T,8]
   size_t partial;           // doubles
   size_t total;
@@ -509,6 +510,7 @@ static WgLayout wg_layout(int N, int T) {
     l.wqt = take(kWgFlowWt * kWgFlows + 1024);
     l.a1 = take(Mt * (kWnK1 / 64) * 16384 + 1024);
     l.a2 = take(Mt * (kWnK2 / 64) * 16384 + 1024);
+    l.tcscr = take(kTcGemmScratchBytes);
   }
   l.y = take((size_t)N * T * 8 * 4);
   l.xa = take((size_t)N * T * 8 * 4);
@@ -681,8 +683,8 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
         const char* res_img = img + io;
         const bool lastl = i == kWnLayers - 1;
         io += lastl ? kWgResImg / 2 : kWgResImg;
-        if ((rc = tc_gemm_wn_gate(s, ws + l.a1, gate_img, (int)rows, w->in_b[f][i], w->cond_b[f][i], FP(l.g), ws + l.a2, T, Tp))) return rc;
-        if ((rc = tc_gemm_wn_res(s, ws + l.a2, res_img, (int)rows, w->res_b[f][i], FP(l.g), SKIP(f), ws + l.a1, T, Tp, 2 << i, i == 0, lastl ? 1 : 0)))
+        if ((rc = tc_gemm_wn_gate(s, ws + l.a1, gate_img, (int)rows, w->in_b[f][i], w->cond_b[f][i], FP(l.g), ws + l.a2, T, Tp, ws + l.tcscr))) return rc;
+        if ((rc = tc_gemm_wn_res(s, ws + l.a2, res_img, (int)rows, w->res_b[f][i], FP(l.g), SKIP(f), ws + l.a1, T, Tp, 2 << i, i == 0, lastl ? 1 : 0, ws + l.tcscr)))
           return rc;
       }
     }

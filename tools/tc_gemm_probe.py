@@ -17,7 +17,7 @@ A = torch.randn(M, K, device=dev, generator=g)
 Bt = torch.randn(N, K, device=dev, generator=g)
 Cm = torch.zeros(M, N, device=dev)
 Mt, Nt = (M + 127) // 128, N // 256
-nbytes = Mt * 128 * K * 2 + Nt * 256 * K * 2 + 4096
+nbytes = Mt * 128 * K * 2 + Nt * 256 * K * 2 + 4096 + 74 * 256 * 128 * 4 + 1024
 ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 _lib.check(lib.mstts_tc_gemm_test(_lib.ptr(A), _lib.ptr(Bt), M, N, K, _lib.ptr(Cm), C.c_void_p(ws.data_ptr()), ws.numel(), st), "tc_gemm_test")
@@ -42,7 +42,11 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 
-ms = timeit(lambda: lib.mstts_tc_gemm_tiled(a_t, b_t, M, N, K, _lib.ptr(Cm), N, st))
+scr = C.c_void_p(base + Mt * 128 * K * 2 + Nt * 256 * K * 2 + 256)
+ms0 = timeit(lambda: lib.mstts_tc_gemm_tiled(a_t, b_t, M, N, K, _lib.ptr(Cm), N, None, st))
+ms = timeit(lambda: lib.mstts_tc_gemm_tiled(a_t, b_t, M, N, K, _lib.ptr(Cm), N, scr, st))
+err2 = (Cm - ref).abs().max().item() / ref.abs().max().item()
+print('split-K tail: %.3f ms (whole tiles only: %.3f ms), max rel err %.3e' % (ms, ms0, err2))
 Bn = Bb.t().contiguous()
 out = torch.empty(M, N, device=dev)
 ms_ref = timeit(lambda: torch.matmul(Ab, Bn))
