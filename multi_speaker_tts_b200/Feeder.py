@@ -39,7 +39,9 @@ class Feeder(object):
         self.Placeholder_Generate()
         self._rng = np.random.default_rng(seed + rank)
         self._synthetic_shape = synthetic_shape  # (B, Te, L) or None: hp.Train.Batch_Size and ragged lengths
-        meta = os.path.join(hp.Train.Pattern_Path, hp.Train.Metadata_File.upper()).replace("\\", "/")
+        self._pattern_path = hp.Train.Pattern_Path  # captured: the generator thread outlives later changes of hp
+        self._batch_size = hp.Train.Batch_Size
+        meta = os.path.join(self._pattern_path, hp.Train.Metadata_File.upper()).replace("\\", "/")
         self.synthetic = (not os.path.exists(meta)) if synthetic is None else synthetic
         self.Metadata_Load()
         if self.is_Training and not self.synthetic:
@@ -68,7 +70,7 @@ class Feeder(object):
     def Metadata_Load(self):
         """Feeder.py:43-62"""
         if self.is_Training and not self.synthetic:
-            with open(os.path.join(hp.Train.Pattern_Path, hp.Train.Metadata_File.upper()).replace("\\", "/"), 'rb') as f:
+            with open(os.path.join(self._pattern_path, hp.Train.Metadata_File.upper()).replace("\\", "/"), 'rb') as f:
                 self.metadata_Dict = pickle.load(f)
             if not all([
                     len(self.metadata_Dict['Token_Index_Dict']) == hp.Encoder.Embedding.Token_Size,
@@ -132,7 +134,7 @@ class Feeder(object):
         while True:
             if not hp.Train.Pattern_Sorting_by_Mel_Length:
                 shuffle(path_List)
-            batches = [path_List[x:x + hp.Train.Batch_Size] for x in range(0, len(path_List), hp.Train.Batch_Size)]
+            batches = [path_List[x:x + self._batch_size] for x in range(0, len(path_List), self._batch_size)]
             shuffle(batches)
             i = 0
             while i < len(batches):
@@ -141,7 +143,7 @@ class Feeder(object):
                     continue
                 token_List, mel_List = [], []
                 for file_Path in batches[i]:
-                    with open(os.path.join(hp.Train.Pattern_Path, file_Path).replace("\\", "/"), "rb") as f:
+                    with open(os.path.join(self._pattern_path, file_Path).replace("\\", "/"), "rb") as f:
                         pattern_Dict = pickle.load(f)
                     token_List.append(np.hstack([S, pattern_Dict['Token'], E]).astype(np.int32))
                     mel_List.append(pattern_Dict['Mel'])

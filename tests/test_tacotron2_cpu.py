@@ -132,3 +132,41 @@ def test_zoneout_cell_class_matches_oracle_cell():
     assert torch.allclose(m, rm, atol=1e-6) and torch.allclose(c2, rc, atol=1e-6) and torch.allclose(h2, rh, atol=1e-6)
     with pytest.raises(NotImplementedError):
         ZoneoutLSTMCell(16, num_proj=8)
+
+
+def test_feeder_reads_the_reference_pickle_dataset(tmp_path):
+    """the on-disk format of Pattern_Generate.py:66-76,245-272: one pickle per utterance ('Token', 'Mel', 'Text', 'Dataset') and
+    METADATA.PICKLE with the length / dataset dictionaries; the Feeder thread batches, pads with <E> and adds <S>/<E>"""
+    import pickle
+    rng = np.random.default_rng(0)
+    files, mel_len, tok_len, dataset = [], {}, {}, {}
+    for i in range(5):
+        name = 'VCTK.UTT%d.PICKLE' % i
+        T = 45 + 7 * i  # frames; Use_Wav_Length_Range (500..9000 ms) / Frame_Shift 12.5 ms => 40..720 frames
+        pat = {'Token': rng.integers(2, 42, size=6 + i).astype(np.int32), 'Mel': rng.standard_normal((T, 80)).astype(np.float32),
+               'Text': 'X' * (6 + i), 'Dataset': 'VCTK'}
+        with open(tmp_path / name, 'wb') as f:
+            pickle.dump(pat, f, protocol=2)
+        files.append(name)
+        mel_len[name], tok_len[name], dataset[name] = T, 6 + i, 'VCTK'
+    meta = {'Token_Index_Dict': dict(Feeder.TOKEN_INDEX_DICT), 'Spectrogram_Dim': hp.Sound.Spectrogram_Dim, 'Mel_Dim': hp.Sound.Mel_Dim,
+            'Frame_Shift': hp.Sound.Frame_Shift, 'Frame_Length': hp.Sound.Frame_Length, 'Sample_Rate': hp.Sound.Sample_Rate,
+            'File_List': files, 'Token_Length_Dict': tok_len, 'Mel_Length_Dict': mel_len, 'Dataset_Dict': dataset}
+    with open(tmp_path / 'METADATA.PICKLE', 'wb') as f:
+        pickle.dump(meta, f, protocol=2)
+    old = (hp.Train.Pattern_Path, hp.Train.Batch_Size)
+    hp.Train.Pattern_Path, hp.Train.Batch_Size = str(tmp_path), 3
+    try:
+        f = Feeder.Feeder(is_Training=True)
+        assert not f.synthetic
+        d = f.Get_Train_Pattern()
+    finally:
+        hp.Train.Pattern_Path, hp.Train.Batch_Size = old
+    p = f.placeholder_Dict
+    tok, tl, mel, ml = d[p['Token']], d[p['Token_Length']], d[p['Mel']], d[p['Mel_Length']]
+    assert tok.shape[0] in (2, 3) and tok.dtype == np.int32 and mel.shape[2] == 80
+    for b in range(tok.shape[0]):
+        assert tok[b, 0] == 0 and tok[b, tl[b] - 1] == 1 and (tok[b, tl[b]:] == 1).all()   # <S> ... <E>, <E> padding
+        assert (mel[b, ml[b]:] == 0).all()
+    assert list(ml) == sorted(ml)                                                            # Pattern_Sorting_by_Mel_Length
+    assert d[p['Speaker_Embedding_Mel']].shape == (tok.shape[0] * 5, 64, 80)
