@@ -31,7 +31,7 @@ enum {
   MSTTS_OK = 0,
   MSTTS_E_INVALID = -1,     /* bad argument (null pointer, size out of range) */
   MSTTS_E_WORKSPACE = -2,   /* workspace too small */
-  MSTTS_E_CUDA = -3,        /* a CUDA runtime / cuBLAS / cuFFT call failed */
+  MSTTS_E_CUDA = -3,        /* a CUDA runtime / cuBLAS call failed */
   MSTTS_E_UNSUPPORTED = -4, /* configuration not implemented (e.g. conv stride != 1) */
   MSTTS_E_DEVICE = -5       /* device is not sm_100 or cannot co-schedule the persistent grid */
 };

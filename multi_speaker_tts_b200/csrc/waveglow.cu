@@ -1,21 +1,22 @@
 // WaveGlow affine-coupling flows (WaveGlow/Modules.py:210-371, WaveGlow/Inv1x1.py:9-32), forward (training direction,
 // with the log-likelihood sums) and reverse (synthesis direction).
 //
-// Structure: the dense contractions of the WN stack (dilated k=3 conv 512->1024, mel conditioning 640->1024, res/skip
-// 512->1024) run as bf16x3 tensor-core GEMMs through cuBLAS with fp32 accumulation (same numerics contract as the
-// decoder kernels).  The three partial products of bf16x3 are folded into the K dimension: every activation row is stored
-// as [hi | lo | hi] and every weight as [W_hi ; W_hi ; W_lo], so a product is ONE bf16 GEMM with K tripled instead of three
-// GEMMs that each read-modify-write the 65 MB fp32 pre-activation (which made the K=512 calls HBM-bound: 29 us measured vs
-// 12.5 us of tensor work).  Everything around the GEMMs is hand-written and fused:
-//   wn_scale / wn_apply weight norm g*v/sqrt(max(sum v^2,1e-5)) -> bf16 hi/lo weight operands
-//   flow_pre_kernel     invertible 1x1 (or plain split in reverse) + the K<=4 start conv -> bf16 hi/lo activations
-//   gate_kernel         bias + tanh * sigmoid -> fp32 + bf16 hi/lo
-//   resskip_kernel      residual onto the GATED activation (reference quirk) + skip accumulation
-//   flow_post_kernel    512->c end conv + affine transform (clamp log_s at 8 in forward only) + sum(log_s), or the
-//                       inverse transform followed by the inverse 1x1
-// Activations live in a time-padded layout [N][T+2P][C], P = 128 zero rows on both sides of every utterance, so the
-// dilated conv is three GEMMs over row-shifted views of one buffer (no im2col, no per-utterance launches).
-// A single fused tcgen05 kernel per flow is the planned replacement ("what comes next").
+// Numerics: bf16x3 as in the decoder kernels (operands split hi + lo, fp32 accumulation), with the three partial products
+// folded into the K dimension: every activation row is stored as [hi | lo | hi] and every weight as [W_hi ; W_hi ; W_lo], so a
+// product is ONE bf16 GEMM with K tripled (three K=512 calls each read-modify-wrote the 65 MB fp32 pre-activation and were
+// HBM-bound: 29 us measured vs 12.5 us of tensor work).
+//
+// Two paths share the flow prologue / epilogue kernels:
+//   * forward / inverse without saved activations (Glow_Train for evaluation, Glow_Inference): the hand-written tcgen05 GEMMs of
+//     tc_gemm.cu.  Operands live in the tensor core's tile layout; the gate GEMM (K = 6528: im2col taps of the dilated conv +
+//     conditioning) applies bias + tanh * sigmoid in its epilogue and writes the operand of the res/skip GEMM, whose epilogue
+//     adds the residual onto the GATED activation (reference quirk B-6), writes the next layer's taps and accumulates the skip.
+//     wn_apply_tiled_kernel / mel_tiled_kernel / flow_pre_tiled_kernel produce the tile images.
+//   * training forward that keeps every layer's operands + the reverse pass (second half of this file): library bf16 GEMMs over
+//     row-major stacked operands in a time-padded layout [N][T+2P][C] (P = 128 zero rows per utterance side, so the dilated conv
+//     is three GEMMs over row-shifted views), with gate_kernel / resskip_kernel and their backward counterparts.
+// Shared: wn_scale (weight norm g*v/sqrt(max(sum v^2,1e-5))), flow_post_kernel (512->c end conv + affine transform with log_s
+// clamped at 8 in forward only + sum(log_s) in double, or the inverse transform followed by the inverse 1x1), mel upsampling.
 #include "common.cuh"
 #include "gemm.h"
 #include "tc_gemm.h"
