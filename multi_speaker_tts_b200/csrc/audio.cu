@@ -158,10 +158,14 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const StftParams P, size_
 //   * the n_fft/2-point complex FFT is a Stockham autosort with radix-8 butterflies held in registers (one radix-2/4 stage
 //     first when log2 is not a multiple of 3): 3 shared-memory round trips for n_fft = 1024 instead of 9, synchronised
 //     with named barriers per team, never the whole CTA;
-//   * shared arrays are padded (i + i/8) so the stride-8 scatter of the first stage is conflict free;
+//   * shared arrays are XOR-swizzled so both the stride-8 scatter of the first stage and every consecutive access are conflict free;
 //   * mel filters: one thread per filter over its non-zero bins (the triangles are 3..45 bins wide), then dB, clip, store.
 // =====================================================================================================================
-__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+// XOR swizzle of the complex work arrays: slot = i ^ ((i >> 4) & 15).  Consecutive accesses stay a permutation inside an
+// aligned group of 16 (ideal wavefronts, no padding), and the stride-8 scatter of the first radix-8 stage (i = 8j + t) lands
+// in 16 distinct 8-byte banks per half-warp.  (Padding i + i/8 fixed the scatter but doubled the wavefronts of every
+// consecutive access: 32 float2 then span 36 slots.)
+__device__ __forceinline__ int padi(int i) { return i ^ ((i >> 4) & 15); }
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ void bfly(float2& a, float2& b) {
   const float2 t = a;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
   constexpr int H = 1 << LOG2H, N = 2 * H;
   constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
   constexpr int TPC = 256 / TEAM;            // frames per CTA iteration
-  constexpr int ZP = H + H / 8 + 8;          // padded complex array length
+  constexpr int ZP = H;                      // complex array length (XOR swizzle, no padding)
   extern __shared__ __align__(16) float smem_f[];
   float2* tw_s = reinterpret_cast<float2*>(smem_f);              // [H]
   float* win_s = reinterpret_cast<float*>(tw_s + H);             // [N]
@@ -311,10 +315,19 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
     const bool live = fr < P.frames;
     if (live) {
       const float* rw = raw_s + team * P.hop;
+      if (((team * P.hop) & 1) == 0) {  // even offset: the pair (x[2k], x[2k+1]) is one aligned 8-byte load
 #pragma unroll 4
-      for (int k = ltid; k < H; k += TEAM) {
-        const float2 wv = *reinterpret_cast<const float2*>(win_s + 2 * k);
-        za[padi(k)] = make_float2(rw[2 * k] * wv.x, rw[2 * k + 1] * wv.y);
+        for (int k = ltid; k < H; k += TEAM) {
+          const float2 wv = *reinterpret_cast<const float2*>(win_s + 2 * k);
+          const float2 xv = *reinterpret_cast<const float2*>(rw + 2 * k);
+          za[padi(k)] = make_float2(xv.x * wv.x, xv.y * wv.y);
+        }
+      } else {
+#pragma unroll 4
+        for (int k = ltid; k < H; k += TEAM) {
+          const float2 wv = *reinterpret_cast<const float2*>(win_s + 2 * k);
+          za[padi(k)] = make_float2(rw[2 * k] * wv.x, rw[2 * k + 1] * wv.y);
+        }
       }
     }
     __syncthreads();  // raw_s may be overwritten by the next group from here on; teams run independently below
@@ -387,7 +400,7 @@ template <int LOG2H>
 static size_t stft_team_smem(int hop) {
   constexpr int H = 1 << LOG2H, N = 2 * H;
   constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
-  constexpr int TPC = 256 / TEAM, ZP = H + H / 8 + 8;
+  constexpr int TPC = 256 / TEAM, ZP = H;
   return (size_t)H * 8 + (size_t)N * 4 + (size_t)3 * (H + 1) * 4 + (size_t)(3 * 256 + 2) * 4 + (size_t)TPC * 2 * ZP * 8 +
          (size_t)TPC * (H + 4) * 4 + (size_t)H * 8 + (size_t)(N + (TPC - 1) * hop) * 4 + 16;
 }
