@@ -244,13 +244,14 @@ int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop, int win, 
                    int spectral_subtract, float* mel_out, float* spec_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Hand-written tcgen05 GEMM (csrc/tc_gemm.cu): C[M,N] fp32 = A[M,K] . B[K,N] over bf16 operand images pre-tiled in the
- * tensor core's shared-memory layout (A: [M/128][K/64][128 x 64], B: [N/256][K/64][256 x 64], element (r,k) of a tile at
- * byte (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2).  N % 256 == 0, K % 64 == 0.
+ * Hand-written tcgen05 GEMM (csrc/tc_gemm.cu): C[M,N] fp32 = A[M,K] . B[K,N] as bf16x3 (A_hi B_hi + A_lo B_hi + A_hi B_lo, the
+ * hi/lo tiles staged once in shared memory and multiplied three times) over operand images pre-tiled in the tensor core's
+ * shared-memory layout: A [M/128][K/64][hi|lo][128 x 64], B [N/256][K/64][hi|lo][256 x 64], element (r,k) of a tile at byte
+ * (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2.  N % 256 == 0, K % 64 == 0.
  * scratch (may be NULL; 9.7 MB = 74*256*128*4 + 1024 bytes): enables the split-K tail -- when the last round of the persistent
  * grid holds r <= 74 tiles they run as 2r half-K work items and are combined through this buffer.
- * mstts_tc_gemm_test tiles fp32 row-major A [M,K] and Bt [N,K] into the workspace first (bf16 rounding) -- the parity hook;
- * its workspace = tiled A + tiled B + 9.7 MB scratch + 2 KB.
+ * mstts_tc_gemm_test tiles fp32 row-major A [M,K] and Bt [N,K] into the workspace first -- the parity hook; its workspace =
+ * tiled A (4 bytes/element) + tiled B + 9.7 MB scratch + 2 KB.
  * ---------------------------------------------------------------------------------------------- */
 int mstts_tc_gemm_tiled(const void* A_tiled, const void* B_tiled, int M, int N, int K, float* C, int ldc, void* scratch, void* stream);
 int mstts_tc_gemm_test(const float* A, const float* Bt, int M, int N, int K, float* C, void* ws, size_t ws_bytes, void* stream);

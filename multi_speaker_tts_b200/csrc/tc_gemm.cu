@@ -1,23 +1,28 @@
-// Hand-written tcgen05 GEMM for the WaveGlow WN contractions (bf16 operands, fp32 accumulation in TMEM).
+// Hand-written tcgen05 GEMM for the WaveGlow WN contractions: bf16x3 (both operands split hi + lo, fp32 accumulation in TMEM)
+// with the split done ON CHIP -- each operand tile is staged once and multiplied three times.
 //
-//   C[M, N] = A[M, K] . B[K, N]        A, B pre-tiled in global memory exactly as the tensor core reads shared memory
+//   C[M, N] = A[M, K] . B[K, N]  ~  A_hi B_hi + A_lo B_hi + A_hi B_lo
 //
-// Operand images (bf16, K-major canonical layout without swizzle, the same format the decoder kernels stream):
-//   A: [M/128 m-tiles][K/64 k-blocks][128 rows x 64 k]  (16 KB per tile)
-//   B: [N/256 n-tiles][K/64 k-blocks][256 cols x 64 k]  (32 KB per tile; "column" = output channel)
+// Operand images (bf16, K-major canonical layout without swizzle, the same format the decoder kernels stream), per 64-wide
+// k-block a "chunk" holding the hi tile followed by the lo tile:
+//   A: [M/128 m-tiles][K/64 k-blocks][hi | lo][128 rows x 64 k]  (2 x 16 KB per chunk)
+//   B: [N/256 n-tiles][K/64 k-blocks][hi | lo][256 cols x 64 k]  (2 x 32 KB per chunk; "column" = output channel)
 //   element (r, k) of a tile at byte (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2  =>  LBO = 128 (K), SBO = 1024 (M/N)
-// so one pipeline stage is two contiguous bulk async copies (no tensor map, no swizzle), and the producers of the
-// activations write their outputs directly in this layout (8 consecutive rows x 16 B = one 128-byte line).
+// so one pipeline stage is two contiguous bulk async copies (96 KB, no tensor map, no swizzle) feeding 12 MMAs, and the
+// producers of the activations write their outputs directly in this layout (8 consecutive rows x 16 B = one 128-byte line).
+// Compared with folding the three products into K ([hi|lo|hi] x [hi;hi;lo], the library-GEMM form used elsewhere in this
+// repository) this moves a third less operand data per FLOP and the producers write two copies of every value instead of three.
 //
 // Kernel: persistent, one CTA per SM, 320 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
-// thread, M = 128, N = 256, K = 16 per instruction), warps 2-9 = epilogue (two per TMEM lane quarter).  4-stage smem ring
-// (48 KB / stage), two 256-column accumulators in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// thread, M = 128, N = 256, K = 16 per instruction), warps 2-9 = epilogue (two per TMEM lane quarter).  2-stage smem ring
+// (96 KB / stage), two 256-column accumulators in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tc_gemm.h"
 
-constexpr int kGemmStages = 4;
-constexpr uint32_t kGemmATile = 128 * 64 * 2, kGemmBTile = 256 * 64 * 2, kGemmStage = kGemmATile + kGemmBTile;
+constexpr int kGemmStages = 2;
+constexpr uint32_t kGemmATile = 128 * 64 * 2, kGemmBTile = 256 * 64 * 2;                 // one hi or lo tile
+constexpr uint32_t kGemmAChunk = 2 * kGemmATile, kGemmBChunk = 2 * kGemmBTile, kGemmStage = kGemmAChunk + kGemmBChunk;
 constexpr int kGemmThreads = 320;  // producer, MMA, 8 epilogue warps (two per TMEM lane quarter, half the columns each)
 
 // work item i -> (tile, K-block range, role): role 0 = whole tile, 1 = writer (first K half), 2 = finisher (second half)
@@ -70,15 +75,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const TcItem w = tc_item(P, item);
         const int mt = w.tile / P.Nt, nt = (w.tile % P.Nt + mt) % P.Nt;  // rotated: every CTA gets a mix of n-tiles
-        const uint8_t* a = P.A + (size_t)mt * P.Kb * kGemmATile;
-        const uint8_t* b = P.B + (size_t)nt * P.Kb * kGemmBTile;
+        const uint8_t* a = P.A + (size_t)mt * P.Kb * kGemmAChunk;
+        const uint8_t* b = P.B + (size_t)nt * P.Kb * kGemmBChunk;
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
           const int s = it % kGemmStages, round = it / kGemmStages;
           if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
           ptx::mbar_arrive_expect_tx(&full[s], kGemmStage);
           uint8_t* dst = ring + (size_t)s * kGemmStage;
-          ptx::bulk_g2s(dst, a + (size_t)kb * kGemmATile, kGemmATile, &full[s]);
-          ptx::bulk_g2s(dst + kGemmATile, b + (size_t)kb * kGemmBTile, kGemmBTile, &full[s]);
+          ptx::bulk_g2s(dst, a + (size_t)kb * kGemmAChunk, kGemmAChunk, &full[s]);
+          ptx::bulk_g2s(dst + kGemmAChunk, b + (size_t)kb * kGemmBChunk, kGemmBChunk, &full[s]);
         }
       }
     }
@@ -97,12 +102,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
           const int s = it % kGemmStages, round = it / kGemmStages;
           ptx::mbar_wait(&full[s], round & 1);
           ptx::tc_fence_after();
-          const uint32_t abase = ptx::smem_u32(ring + (size_t)s * kGemmStage), bbase = abase + kGemmATile;
+          const uint32_t a_hi = ptx::smem_u32(ring + (size_t)s * kGemmStage), a_lo = a_hi + kGemmATile;
+          const uint32_t b_hi = a_hi + kGemmAChunk, b_lo = b_hi + kGemmBTile;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = ptx::umma_desc(abase + k * 256, 128, 1024);
-            const uint64_t bd = ptx::umma_desc(bbase + k * 256, 128, 1024);
-            ptx::umma_bf16(d, ad, bd, idesc, (kb == w.kb0 && k == 0) ? 0u : 1u);
+            const uint64_t ah = ptx::umma_desc(a_hi + k * 256, 128, 1024), al = ptx::umma_desc(a_lo + k * 256, 128, 1024);
+            const uint64_t bh = ptx::umma_desc(b_hi + k * 256, 128, 1024), bl = ptx::umma_desc(b_lo + k * 256, 128, 1024);
+            ptx::umma_bf16(d, al, bh, idesc, (kb == w.kb0 && k == 0) ? 0u : 1u);  // small terms first
+            ptx::umma_bf16(d, ah, bl, idesc, 1u);
+            ptx::umma_bf16(d, ah, bh, idesc, 1u);
           }
           ptx::umma_commit(&empty[s]);
         }
@@ -208,8 +216,8 @@ __device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint3
       }
       const float g0[8] = {g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7]};
       const float g1[8] = {g[8], g[9], g[10], g[11], g[12], g[13], g[14], g[15]};
-      wn_store_x3(P.out_img, row, kWnK2 / 64, 0, 512, ch0, g0);
-      wn_store_x3(P.out_img, row, kWnK2 / 64, 0, 512, ch0 + 8, g1);
+      wn_store_hl(P.out_img, row, kWnK2 / 64, ch0, g0);
+      wn_store_hl(P.out_img, row, kWnK2 / 64, ch0 + 8, g1);
     }
   }
 }
@@ -242,8 +250,8 @@ __device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint3
       // chunks; g to 16 mantissa bits, the same value the tensor core multiplied)
 #pragma unroll
       for (int c8 = 0; c8 < 16; c8 += 8) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + c8, kWnK2 / 64));
-        const uint4 lv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, 512 + ch0 + c8, kWnK2 / 64));
+        const uint4 hv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + c8, 0, kWnK2 / 64));
+        const uint4 lv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + c8, 1, kWnK2 / 64));
         const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hv);
         const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&lv);
 #pragma unroll
@@ -281,7 +289,7 @@ static int tc_gemm_launch(const TcGemmParams& P0, cudaStream_t s, void* scratch)
   const int r = ntiles % ncta;
   P.n_full = ntiles;
   P.n_split = 0;
-  if (scratch && ntiles > ncta && r > 0 && 2 * r <= ncta && P.Kb >= 8) {
+  if (scratch && ntiles > ncta && r > 0 && 2 * r <= ncta && P.Kb >= 4) {
     P.n_full = ntiles - r;
     P.n_split = r;
     P.partial = (float*)scratch;
@@ -332,16 +340,19 @@ __global__ void tile_rows_kernel(const float* __restrict__ src, int R, int K, in
     const size_t r = i / K;
     const int rt = (int)(r / TR), rr = (int)(r % TR);
     const float x = r < (size_t)R ? src[r * ld + k] : 0.f;
-    const size_t tile = (size_t)rt * Kb + k / 64;
+    const size_t chunk = (size_t)rt * Kb + k / 64;  // [hi tile | lo tile]
     const int kk = k % 64;
-    dst[tile * TR * 64 + (size_t)(rr / 8) * 512 + (kk / 8) * 64 + (rr % 8) * 8 + (kk % 8)] = __float2bfloat16_rn(x);
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const size_t e = chunk * 2 * TR * 64 + (size_t)(rr / 8) * 512 + (kk / 8) * 64 + (rr % 8) * 8 + (kk % 8);
+    dst[e] = h;
+    dst[e + (size_t)TR * 64] = __float2bfloat16_rn(x - __bfloat162float(h));
   }
 }
 
 extern "C" int mstts_tc_gemm_test(const float* A, const float* Bt, int M, int N, int K, float* C, void* ws, size_t ws_bytes, void* stream) {
-  // A [M,K] fp32, Bt [N,K] fp32 (B transposed) -> C [M,N] = bf16(A) . bf16(Bt)^T through the hand-written kernel
+  // A [M,K] fp32, Bt [N,K] fp32 (B transposed) -> C [M,N] = A . Bt^T as bf16x3 (hi/lo split on chip) through the hand-written kernel
   const size_t Mt = (M + 127) / 128, Nt = N / 256;
-  const size_t abytes = Mt * 128 * (size_t)K * 2, bbytes = Nt * 256 * (size_t)K * 2;
+  const size_t abytes = Mt * 128 * (size_t)K * 4, bbytes = Nt * 256 * (size_t)K * 4;  // hi + lo tiles
   MSTTS_REQUIRE(A && Bt && C && ws, MSTTS_E_INVALID, "tc_gemm_test: null pointer");
   MSTTS_REQUIRE(N % 256 == 0 && K % 64 == 0, MSTTS_E_INVALID, "tc_gemm_test: N %% 256, K %% 64");
   MSTTS_REQUIRE(ws_bytes >= abytes + bbytes + 2048 + kTcGemmScratchBytes, MSTTS_E_WORKSPACE, "tc_gemm_test: workspace %zu < %zu", ws_bytes,

@@ -350,8 +350,8 @@ __global__ void copy_channels_kernel(const float* __restrict__ src, int sc, int 
 // =====================================================================================================================
 // tcgen05 path (forward / inverse without saved activations): operands live in the tensor core's tile layout (tc_gemm.h)
 // =====================================================================================================================
-// effective weight -> tiled B image.  Each thread takes 8 consecutive K rows of one output channel: one 16-byte chunk per
-// copy of the (hi ; hi ; lo) stack.  perm = 1: gate permutation (n-tile j = tanh channels 128j.. | sigmoid channels 128j..)
+// effective weight -> tiled B image (hi tile and lo tile per k-block).  Each thread takes 8 consecutive K rows of one output
+// channel: one 16-byte chunk per tile.  perm = 1: gate permutation (n-tile j = tanh channels 128j.. | sigmoid channels 128j..)
 struct WnTileJob {
   const float* v;
   const float* g_unused;
@@ -387,15 +387,12 @@ __global__ void wn_apply_tiled_kernel(const WnTileJobs J) {
       jt = o >> 8;
       c = o & 255;
     }
-    const int tap = r0 / job.seg, rr = r0 - tap * job.seg;
-    const int k0 = job.kbase + tap * 3 * job.seg + rr;
-    auto off = [&](int k) {  // bf16 element offset of the 8-element chunk (column c, K index k)
-      return ((size_t)jt * job.Kb + (k >> 6)) * (256 * 64) + (size_t)(c >> 3) * 512 + (size_t)((k & 63) >> 3) * 64 + (size_t)(c & 7) * 8;
-    };
-    const uint4 hv = *reinterpret_cast<const uint4*>(hi), lv = *reinterpret_cast<const uint4*>(lo);
-    *reinterpret_cast<uint4*>(job.dst + off(k0)) = hv;
-    *reinterpret_cast<uint4*>(job.dst + off(k0 + job.seg)) = hv;
-    *reinterpret_cast<uint4*>(job.dst + off(k0 + 2 * job.seg)) = lv;
+    const int k0 = job.kbase + r0;  // K index inside the GEMM (taps are consecutive 512-row segments of the conv kernel)
+    // bf16 element offset of the 8-element chunk (column c, K index k0) in the hi tile; the lo tile follows 256*64 elements later
+    const size_t off = (((size_t)jt * job.Kb + (k0 >> 6)) * 2) * (256 * 64) + (size_t)(c >> 3) * 512 + (size_t)((k0 & 63) >> 3) * 64 +
+                       (size_t)(c & 7) * 8;
+    *reinterpret_cast<uint4*>(job.dst + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(job.dst + off + 256 * 64) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -409,7 +406,7 @@ __global__ void mel_tiled_kernel(const float* __restrict__ src, int N, int T, ui
     const int m = (int)nt;  // compact rows: m = n * T + t
     const float4 a = *reinterpret_cast<const float4*>(src + nt * kWnMel + ch), b = *reinterpret_cast<const float4*>(src + nt * kWnMel + ch + 4);
     const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    wn_store_x3(img, m, kWnK1 / 64, 9 * kWnCh, kWnMel, ch, x);
+    wn_store_hl(img, m, kWnK1 / 64, 3 * kWnCh + ch, x);
   }
 }
 
@@ -472,8 +469,8 @@ struct WgLayout {
   size_t g, skip;           // padded fp32 [N][Tp][512]
   size_t a;                 // padded fp32 [N][Tp][1024]
   size_t rs;                // padded fp32 [N][Tp][1024]: res/skip output when the pre-activations are being saved
-  size_t wqt;               // tcgen05 path: tiled weight images, per flow per layer {gate B [4][102][32 KB] | res B [4|2][24][32 KB]}
-  size_t a1, a2;            // tcgen05 path: im2col image [Mt][102][16 KB], gated-activation image [Mt][24][16 KB]
+  size_t wqt;               // tcgen05 path: tiled weight images, per flow per layer {gate B [4][34][2 x 32 KB] | res B [4|2][8][2 x 32 KB]}
+  size_t a1, a2;            // tcgen05 path: im2col image [Mt][34][2 x 16 KB], gated-activation image [Mt][8][2 x 16 KB]
   size_t tcscr;             // tcgen05 path: split-K tail scratch (tc_gemm.h)
   size_t y, xa, xb;         // [N,T,8]
   size_t partial;           // doubles
@@ -482,8 +479,8 @@ struct WgLayout {
 constexpr size_t kWgFlowW = (size_t)kWnLayers * (3 * kWnCh * 2 * kWnCh + kWnMel * 2 * kWnCh) + (size_t)(kWnLayers - 1) * kWnCh * 2 * kWnCh +
                             (size_t)kWnCh * kWnCh;
 
-// bytes of tiled weight images per flow: 8 gate images (4 x 102 x 32 KB) + 7 res images (4 x 24 x 32 KB) + 1 (2 x 24 x 32 KB)
-constexpr size_t kWgGateImg = (size_t)4 * (kWnK1 / 64) * 32768, kWgResImg = (size_t)4 * (kWnK2 / 64) * 32768;
+// bytes of tiled weight images per flow: 8 gate images (4 x 34 x 64 KB) + 7 res images (4 x 8 x 64 KB) + 1 (2 x 8 x 64 KB)
+constexpr size_t kWgGateImg = (size_t)4 * (kWnK1 / 64) * 65536, kWgResImg = (size_t)4 * (kWnK2 / 64) * 65536;
 constexpr size_t kWgFlowWt = 8 * kWgGateImg + 7 * kWgResImg + kWgResImg / 2;
 
 static WgLayout wg_layout(int N, int T) {
@@ -509,8 +506,8 @@ static WgLayout wg_layout(int N, int T) {
   {
     const size_t Mt = ((size_t)N * T + 127) / 128;  // the tiled path has no pad rows: the im2col taps carry the zero borders
     l.wqt = take(kWgFlowWt * kWgFlows + 1024);
-    l.a1 = take(Mt * (kWnK1 / 64) * 16384 + 1024);
-    l.a2 = take(Mt * (kWnK2 / 64) * 16384 + 1024);
+    l.a1 = take(Mt * (kWnK1 / 64) * 32768 + 1024);
+    l.a2 = take(Mt * (kWnK2 / 64) * 32768 + 1024);
     l.tcscr = take(kTcGemmScratchBytes);
   }
   l.y = take((size_t)N * T * 8 * 4);
@@ -620,7 +617,7 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
         const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
         io += i < kWnLayers - 1 ? kWgResImg : kWgResImg / 2;
         TJ.j[3 * i + 0] = WnTileJob{w->in_v[f][i], nullptr, gate_img, 3 * kWnCh, 2 * kWnCh, kWnCh, kWnK1 / 64, 0, 1};
-        TJ.j[3 * i + 1] = WnTileJob{w->cond_v[f][i], nullptr, gate_img, kWnMel, 2 * kWnCh, kWnMel, kWnK1 / 64, 9 * kWnCh, 1};
+        TJ.j[3 * i + 1] = WnTileJob{w->cond_v[f][i], nullptr, gate_img, kWnMel, 2 * kWnCh, kWnMel, kWnK1 / 64, 3 * kWnCh, 1};
         TJ.j[3 * i + 2] = WnTileJob{w->res_v[f][i], nullptr, res_img, kWnCh, rout, kWnCh, kWnK2 / 64, 0, 0};
         for (int q = 0; q < 3; ++q) TJ.scale[3 * i + q] = J.scale + (size_t)(1 + 3 * i + q) * 1024;
       }
@@ -640,8 +637,8 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   auto YBUF = [&](int f) { return save ? FP(save->y + (size_t)f * rows * 8 * 4) : FP(l.y); };
   if (use_tc) {
     const size_t Mt = (rows + 127) / 128;
-    MSTTS_CUDA(cudaMemsetAsync(ws + l.a1, 0, Mt * (kWnK1 / 64) * 16384, s));
-    MSTTS_CUDA(cudaMemsetAsync(ws + l.a2, 0, Mt * (kWnK2 / 64) * 16384, s));
+    MSTTS_CUDA(cudaMemsetAsync(ws + l.a1, 0, Mt * (kWnK1 / 64) * 32768, s));
+    MSTTS_CUDA(cudaMemsetAsync(ws + l.a2, 0, Mt * (kWnK2 / 64) * 32768, s));
     mel_tiled_kernel<<<ew_grid((size_t)rows * kWnMel / 8), 256, 0, s>>>(mel_nt640, N, T, (uint8_t*)(ws + l.a1));
   } else {
     pad_split_kernel<<<ew_grid((size_t)rows * kWnMel), 256, 0, s>>>(mel_nt640, N, T, kWnMel, BF(l.mel3));
