@@ -27,7 +27,9 @@ METRIC = "decoder mel-frames/s (train step)"
 UNIT = "frames/s"
 B_PER_GPU, TE, L, D = 32, 128, 800, 768
 W_STEP = 20299345  # parameters touched per decoder step
-MY_KERNELS_PER_STEP = 31  # fill_mask 2, fwd 9, loss 1, bwd 17 (incl. the reverse loop), adam 2 -- see DESIGN.md
+MY_KERNELS_PER_STEP = 44  # counted in profiles/r1_launches_bf16x3.csv between two forward loops: the 2 persistent loops, 2 mask fills,
+# 9 hi/lo split kernels, 12 column-sum kernels, 4 prenet activation kernels, loss, Adam x2 and 12 prep / epilogue kernels
+# (library GEMMs -- 48 launches per step -- are not counted)
 
 
 def fwd_bytes_per_step(B, Te, s_w=4, s_kv=4):

@@ -222,7 +222,9 @@ __device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint3
   }
 }
 
-// MODE 2 (WN res/skip): layers < 7: n-tiles 0,1 = residual channels, 2,3 = skip channels; last layer: both tiles are skip
+// MODE 2 (WN res/skip): layers < 7: n-tiles 0,1 = residual channels, 2,3 = skip channels; last layer: both tiles are skip.
+// 32 columns per iteration; everything the chunk needs from memory (bias, the gated activation's hi/lo chunks or the old skip
+// values) is requested before the TMEM load is waited for, so the three latencies overlap instead of chaining.
 template <>
 __device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part) {
   const int t = row % P.T;
@@ -232,45 +234,59 @@ __device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint3
   const int chb = is_res ? nt * 256 : (P.lastl ? nt * 256 : (nt - 2) * 256);  // first channel of this tile
   const int bofs = is_res || P.lastl ? 0 : 512;                               // bias offset of the skip half
 #pragma unroll 1
-  for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 16) {
-    uint32_t v[16];
-    ptx::tmem_ld16(ta + c0, v);
+  for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(ta + c0, v);
+    const int ch0 = chb + c0;
+    float4 bias[8], old[8];
+    uint4 ghi[4], glo[4];
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bias[j] = __ldg(reinterpret_cast<const float4*>(P.bias0 + bofs + ch0) + j);
+      if (is_res) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          ghi[c8] = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + 8 * c8, 0, kWnK2 / 64));
+          glo[c8] = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + 8 * c8, 1, kWnK2 / 64));
+        }
+      } else if (!P.first) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) old[j] = *(reinterpret_cast<const float4*>(P.skip + prow * 512 + ch0) + j);
+      }
+    }
     ptx::tmem_wait_ld();
     if (part) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(part + (size_t)(c0 + j) * 128));
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(part + (size_t)(c0 + j) * 128));
     }
     if (!valid) continue;
-    const int ch0 = chb + c0;
-    float x[16];
+    float x[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + P.bias0[bofs + ch0 + j];
+    for (int j = 0; j < 8; ++j) {
+      x[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bias[j].x;
+      x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bias[j].y;
+      x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bias[j].z;
+      x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bias[j].w;
+    }
     if (is_res) {
-      // the gated activation this residual is added to: its hi + lo halves from the A operand image (coalesced 16-byte
-      // chunks; g to 16 mantissa bits, the same value the tensor core multiplied)
+      // the gated activation this residual is added to: hi + lo from the A operand image (g to 16 mantissa bits, the same
+      // value the tensor core multiplied)
 #pragma unroll
-      for (int c8 = 0; c8 < 16; c8 += 8) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + c8, 0, kWnK2 / 64));
-        const uint4 lv = *reinterpret_cast<const uint4*>(P.A + tc_a_chunk_offset(row, ch0 + c8, 1, kWnK2 / 64));
-        const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hv);
-        const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&lv);
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&ghi[c8]);
+        const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&glo[c8]);
+        float h[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[c8 + j] += __bfloat162float(hp[j]) + __bfloat162float(lp[j]);
+        for (int j = 0; j < 8; ++j) h[j] = x[8 * c8 + j] + (__bfloat162float(hp[j]) + __bfloat162float(lp[j]));
+        wn_store_taps(P.out_img, row, t, P.T, P.dil, ch0 + 8 * c8, h);
       }
-      const float h0[8] = {x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]};
-      const float h1[8] = {x[8], x[9], x[10], x[11], x[12], x[13], x[14], x[15]};
-      wn_store_taps(P.out_img, row, t, P.T, P.dil, ch0, h0);
-      wn_store_taps(P.out_img, row, t, P.T, P.dil, ch0 + 8, h1);
     } else {
-      float* sp = P.skip + prow * 512 + ch0;
+      float4* sp = reinterpret_cast<float4*>(P.skip + prow * 512 + ch0);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 o = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-        if (!P.first) {
-          const float4 old = *reinterpret_cast<const float4*>(sp + j);
-          o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
-        }
-        *reinterpret_cast<float4*>(sp + j) = o;
+      for (int j = 0; j < 8; ++j) {
+        float4 o = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        if (!P.first) o = make_float4(o.x + old[j].x, o.y + old[j].y, o.z + old[j].z, o.w + old[j].w);
+        sp[j] = o;
       }
     }
   }
