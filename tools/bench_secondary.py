@@ -58,6 +58,16 @@ def bench_waveglow(args, pk, src):
            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": src,
                         "note": "algorithmic FLOPs (1x); the bf16x3 split executes 3x of them on the tensor pipe"}}
+    # ---- synthesis direction (Glow_Inference): the same 12 flows inverted, 4 + 2 + 2 noise channels in, audio out ----
+    try:
+        zin = torch.randn(N, S // 8, 4, device=dev)
+        noise = {f: torch.randn(N, S // 8, 2, device=dev) for f in (8, 4)}
+        a0, m0 = M.Restructure_Train_Data(ad, md, params)
+        ims = time_gpu(lambda: M.Glow_Inference(zin, m0, params, sigma=0.6, early_noise=noise), args.steps)
+        out["inference"] = {"ms_per_step": ims, "samples_per_s": N * S / (ims * 1e-3),
+                            "note": "Glow_Inference on the up-sampled conditioning of the same batch (tcgen05 path)"}
+    except Exception as e:
+        out["inference"] = {"error": repr(e)}
     # ---- the same workload as a full training step (forward with saved activations, reverse pass, clip, TF Adam) ----
     try:
         from multi_speaker_tts_b200.WaveGlow import WaveGlow as WG
