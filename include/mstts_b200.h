@@ -233,6 +233,20 @@ int mstts_conv1d_bwd(const float* x, const float* kernel, const float* dy, int B
                      float* dkernel, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * activation (0 relu / 1 tanh) -> tf.layers.batch_normalization -> tf.layers.dropout of the encoder / postnet conv stacks, fused
+ * (Modules.py:29-45,125-141).  x, y [R, C] with R = B*T rows (padding included in the batch statistics, as in the reference);
+ * training: biased batch statistics, moving <- moving * momentum + batch * (1 - momentum) updated in place, mask [R,C] u8 with
+ * y scaled by 1/keep; inference: moving statistics, no dropout.  stats [2,C] (mean, rstd) and a_saved [R,C] (activation
+ * output) feed the reverse pass, which overwrites dx, dgamma, dbeta.
+ * ---------------------------------------------------------------------------------------------- */
+size_t mstts_act_bn_dropout_workspace_bytes(int C);
+int mstts_act_bn_dropout_fwd(const float* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                             const uint8_t* mask, long long R, int C, int act, int training, float keep, float momentum, float eps, float* y,
+                             float* a_saved, float* stats, void* ws, size_t ws_bytes, void* stream);
+int mstts_act_bn_dropout_bwd(const float* dy, const float* a_saved, const float* stats, const float* gamma, const uint8_t* mask, long long R,
+                             int C, int act, float keep, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Audio features.  Replaces Audio.melspectrogram / spectrogram / spectrogram_and_mel (Audio.py:19-48,62-96):
  * pre-emphasis 0.97, librosa.stft (centre, reflect padding, periodic Hann(win) centred in n_fft), magnitude, optional
  * spectral subtraction, slaney mel filter bank (librosa.filters.mel defaults), 20 log10(max(1e-5,.)), clip to

@@ -188,6 +188,70 @@ class _Conv1dFunction(torch.autograd.Function):
         return dx, dk, dy.sum(dim=(0, 1))
 
 
+class _ActBnDropoutFunction(torch.autograd.Function):
+    """activation -> batch norm -> dropout of a conv layer, fused (csrc/act_bn_dropout.cu)"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, moving_mean, moving_var, mask, act, training, rate):
+        import ctypes as C
+        lib = _lib.lib()
+        B, T, Cc = x.shape
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        stats = torch.empty(2, Cc, device=x.device)
+        a_saved = torch.empty_like(x) if training else None
+        ws = torch.empty(lib.mstts_act_bn_dropout_workspace_bytes(Cc), device=x.device, dtype=torch.uint8)
+        keep = 1.0 - rate
+        with torch.cuda.device(x.device):
+            rc = lib.mstts_act_bn_dropout_fwd(_lib.ptr(x), _lib.ptr(gamma.contiguous()), _lib.ptr(beta.contiguous()), _lib.ptr(moving_mean),
+                                              _lib.ptr(moving_var), _lib.ptr(mask), B * T, Cc, act, int(training), keep, 0.99, 1e-3,
+                                              _lib.ptr(y), _lib.ptr(a_saved), _lib.ptr(stats), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                              C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _lib.check(rc, "mstts_act_bn_dropout_fwd")
+        if training:
+            ctx.save_for_backward(a_saved, stats, gamma, mask)
+        ctx.meta = (B, T, Cc, act, keep)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes as C
+        lib = _lib.lib()
+        a_saved, stats, gamma, mask = ctx.saved_tensors
+        B, T, Cc, act, keep = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        dgamma = torch.empty(Cc, device=dy.device)
+        dbeta = torch.empty(Cc, device=dy.device)
+        ws = torch.empty(lib.mstts_act_bn_dropout_workspace_bytes(Cc), device=dy.device, dtype=torch.uint8)
+        with torch.cuda.device(dy.device):
+            rc = lib.mstts_act_bn_dropout_bwd(_lib.ptr(dy), _lib.ptr(a_saved), _lib.ptr(stats), _lib.ptr(gamma.contiguous()), _lib.ptr(mask),
+                                              B * T, Cc, act, keep, _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                              C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+        _lib.check(rc, "mstts_act_bn_dropout_bwd")
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+def _act_bn_dropout(x, v, prefix, act, training, rate, mask):
+    """act (0 relu / 1 tanh) -> tf.layers.batch_normalization -> tf.layers.dropout: one fused kernel pair on CUDA fp32 tensors,
+    the library-op composition otherwise (CPU tests, other dtypes)"""
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or v[prefix + '/gamma'].requires_grad or v[prefix + '/beta'].requires_grad)
+    if x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % 4 == 0 and (training or not needs_grad):
+        # (gradients through the inference-mode normalisation -- moving statistics -- take the library composition below)
+        m8 = None
+        if training:
+            if mask is None:
+                m8 = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+                fill_mask(m8, 1.0 - rate, int(torch.randint(0, 2 ** 62, (1,)).item()))
+            else:
+                m8 = mask.to(torch.uint8).contiguous()
+        return _ActBnDropoutFunction.apply(x, v[prefix + '/gamma'], v[prefix + '/beta'], v[prefix + '/moving_mean'],
+                                           v[prefix + '/moving_variance'], m8, act, bool(training), rate)
+    a = torch.relu(x) if act == 0 else torch.tanh(x)
+    a = _batch_norm(a, v, prefix, training)
+    return _dropout(a, rate, training, mask)
+
+
 def _conv1d_same(x, kernel, bias):
     """tf.layers.conv1d(padding='same', stride 1) on [B,T,C] with a TF-layout kernel [k, in, out]: bf16x3 tensor-core GEMMs on
     CUDA fp32 tensors (csrc/conv1d.cu), the library convolution otherwise"""
@@ -208,9 +272,9 @@ def Encoder_Conv(inputs, is_training=False, variables=None, masks=None):
     x = inputs
     for i in range(hp.Encoder.Conv.Nums):
         p = 'encoder/conv_%d' % i
-        x = torch.relu(_conv1d_same(x, variables[p + '/conv1d/kernel'], variables[p + '/conv1d/bias']))
-        x = _batch_norm(x, variables, p + '/batch_normalization', is_training)
-        x = _dropout(x, hp.Encoder.Conv.Dropout_Rate, is_training, None if masks is None else masks[i])
+        x = _conv1d_same(x, variables[p + '/conv1d/kernel'], variables[p + '/conv1d/bias'])
+        x = _act_bn_dropout(x, variables, p + '/batch_normalization', 0, is_training, hp.Encoder.Conv.Dropout_Rate,
+                            None if masks is None else masks[i])
     return x
 
 
@@ -344,7 +408,7 @@ def Decoder_Conv(inputs, is_training=False, variables=None, masks=None):
     x = inputs
     for i in range(hp.Decoder.Conv.Nums):
         p = 'decoder/conv_%d' % i
-        x = torch.tanh(_conv1d_same(x, variables[p + '/conv1d/kernel'], variables[p + '/conv1d/bias']))
-        x = _batch_norm(x, variables, p + '/batch_normalization', is_training)
-        x = _dropout(x, hp.Encoder.Conv.Dropout_Rate, is_training, None if masks is None else masks[i])
+        x = _conv1d_same(x, variables[p + '/conv1d/kernel'], variables[p + '/conv1d/bias'])
+        x = _act_bn_dropout(x, variables, p + '/batch_normalization', 1, is_training, hp.Encoder.Conv.Dropout_Rate,
+                            None if masks is None else masks[i])
     return x

@@ -95,6 +95,11 @@ EXPORTS = {
     "mstts_conv1d_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "mstts_conv1d_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "mstts_conv1d_bwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "mstts_act_bn_dropout_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "mstts_act_bn_dropout_fwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                           C.c_float, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "mstts_act_bn_dropout_bwd": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_longlong, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp,
+                                           C.c_size_t, _fp]),
     "mstts_fill_mask": (C.c_int, [_fp, C.c_size_t, C.c_float, C.c_uint64, _fp]),
     "mstts_adam_tf": (C.c_int, [_fp, _fp, _fp, _fp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _fp]),
