@@ -146,3 +146,24 @@ def test_train_loop_prints_reference_line(cuda_dev, capsys):
     for key in ('Learning rate:', 'Linear loss:', 'Postnet loss:', 'Stop loss:', 'WR loss:'):
         assert key in lines[0]
     assert model.global_Step == 2
+
+
+def test_text_to_wave_with_waveglow_vocoder(cuda_dev):
+    """MSTTS_SV.Inference_WaveGlow (MSTTS_SV.py:325-389): free-running decode, postnet mel cut into Mel_Split_Length chunks, each
+    batch of chunks through Restructure_Inference_Data + Glow_Inference, waveforms re-joined per sentence"""
+    from multi_speaker_tts_b200 import MSTTS_SV as M
+    from multi_speaker_tts_b200.WaveGlow import WaveGlow as WG
+    feeder = Feeder.Feeder(is_Training=False, synthetic=True)
+    model = M.Tacotron2(is_Training=False, device=cuda_dev, seed=4, feeder=feeder)
+    model.waveglow_params = WG.WaveGlow(device=cuda_dev, seed=2).params      # what Vocoder_Load builds from a checkpoint
+    old = hp.Decoder.LSTM.Max_Inference_Length
+    hp.Decoder.LSTM.Max_Inference_Length = 95                                # 96 frames -> chunks of 40, 40, 16
+    try:
+        out = model.Inference(['spk_a.wav', 'spk_b.wav'], ['Hello.', 'Good morning!'])
+    finally:
+        hp.Decoder.LSTM.Max_Inference_Length = old
+    assert len(out['Wav']) == 2
+    for mel, wav in zip(out['Mel'], out['Wav']):
+        n_chunks = -(-mel.shape[0] // hp.WaveGlow.Inference.Mel_Split_Length)
+        per_chunk = ((hp.WaveGlow.Inference.Mel_Split_Length - 1) * 256 + 1024) // 8 * 8
+        assert wav.ndim == 1 and wav.shape[0] == n_chunks * per_chunk and np.isfinite(wav).all()
