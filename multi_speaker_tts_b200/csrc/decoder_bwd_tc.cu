@@ -291,7 +291,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     long long* dbg_all = (P.dbg && tid == 0) ? P.dbg + (size_t)blockIdx.x * 32 : nullptr;
 #define STAMP(k)                                                                 \
   do {                                                                           \
-    if (dbg && t != T / 2) dbg[(size_t)(T - 1 - t) * 32 + (k)] = clock64();      \
+    if (dbg) dbg[(size_t)(T - 1 - t) * 32 + (k)] = clock64();                    \
     if (dbg_all && t == T / 2) {                                                 \
       unsigned long long gt;                                                     \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                     \
