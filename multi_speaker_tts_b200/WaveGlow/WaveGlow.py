@@ -133,7 +133,7 @@ class WaveGlow(object):
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_g, group=self.pg)  # the single gradient all-reduce of the step
         # tf.clip_by_global_norm(gradients, 0.1) on the (mean) gradient; one host read per step (losses travel with it)
-        stats = torch.stack([self.flat_g.double().square().sum().sqrt() / self.world] + [x.double() for x in losses]).cpu().tolist()
+        stats = torch.stack([torch.linalg.vector_norm(self.flat_g, dtype=torch.float64) / self.world] + [x.double() for x in losses]).cpu().tolist()
         gnorm = stats[0]
         scale = (CLIP_NORM / max(gnorm, CLIP_NORM)) / self.world
         step = self.global_Step

@@ -556,6 +556,19 @@ static inline int flow_c(int f) { return 8 - 2 * (f / 4); }
 // Runs all 12 flows.  direction 0: training direction x -> z with sums[0] = sum(log_s), sums[1] = sum(z^2);
 // direction 1: synthesis z -> x (early_noise[2]: the two [N,T,2] noise tensors injected before flows 7 and 3 are run,
 // i.e. after undoing flows 8 and 4; inv_w then holds the INVERSE 1x1 kernels).
+// zero the pad rows (kWgPad leading / trailing rows per utterance) of `nslots` consecutive padded buffers [N][T+2P][row16 x 16 B]
+__global__ void zero_pad_rows_kernel(uint4* __restrict__ base, int nslots, size_t row16, int N, int T) {
+  const int Tp = T + 2 * kWgPad;
+  const size_t per_utt = (size_t)2 * kWgPad * row16, per_slot = (size_t)N * per_utt, n = (size_t)nslots * per_slot;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t slot = i / per_slot, r = i % per_slot;
+    const size_t u = r / per_utt, q = r % per_utt;
+    const size_t prow = q / row16, col = q % row16;
+    const size_t row = prow < (size_t)kWgPad ? prow : (size_t)T + prow;  // second half: rows T+P .. T+2P-1
+    base[((slot * N + u) * Tp + row) * row16 + col] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 static bool g_waveglow_force_library = false;  // A/B switch for tools/bench_secondary.py (mstts_waveglow_set_path)
 extern "C" int mstts_waveglow_set_path(int library_gemm) {
   g_waveglow_force_library = library_gemm != 0;
@@ -628,7 +641,12 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   MSTTS_CUDA(cudaMemsetAsync(ws + l.mel3, 0, rows_p * 3 * kWnMel * 2, s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.h3, 0, rows_p * 3 * kWnCh * 2, s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.g3, 0, rows_p * 3 * kWnCh * 2, s));
-  if (save) MSTTS_CUDA(cudaMemsetAsync(ws + save->skip, 0, save->a - save->skip, s));  // saved skip / h3 / g3 slots: pads must read 0
+  if (save) {
+    // saved skip / h3 / g3 slots: the pad rows must read 0 (shifted conv views, flat-row weight-gradient contractions); the
+    // valid rows are fully overwritten by the layers, so only the 2 x 128 pad rows per utterance are cleared (11 % of 11 GB)
+    zero_pad_rows_kernel<<<148 * 8, 256, 0, s>>>((uint4*)(ws + save->skip), kWgFlows, (size_t)kWnCh * 4 / 16, N, T);
+    zero_pad_rows_kernel<<<148 * 8, 256, 0, s>>>((uint4*)(ws + save->h3), 2 * kWgFlows * kWnLayers, (size_t)3 * kWnCh * 2 / 16, N, T);
+  }
   const size_t slot3 = rows_p * 3 * kWnCh * 2, slota = rows_p * 2 * kWnCh * 4;
   auto H3 = [&](int f, int i) { return save ? BF(save->h3 + ((size_t)f * kWnLayers + i) * slot3) : BF(l.h3); };
   auto G3 = [&](int f, int i) { return save ? BF(save->g3 + ((size_t)f * kWnLayers + i) * slot3) : BF(l.g3); };
