@@ -42,8 +42,9 @@ class WaveGlowParams(object):
         cache = getattr(self, '_struct_cache', None)
         if cache is None:
             cache = self._struct_cache = {}
-        key = (id(raws) if raws is not None else 0, cls)
-        if not inverse and key in cache:
+        key = cls
+        cacheable = not inverse and raws is None  # gradient trees are caller-owned and may be fresh per call: never cached
+        if cacheable and key in cache:
             return cache[key]
         s = (cls or _lib.MsttsWaveGlowWeights)()
         keep = []
@@ -59,8 +60,8 @@ class WaveGlowParams(object):
                 s.cond_g[f][i], s.cond_v[f][i], s.cond_b[f][i] = (r['cond'][i][k].data_ptr() for k in ('g', 'v', 'b'))
                 s.res_g[f][i], s.res_v[f][i], s.res_b[f][i] = (r['res'][i][k].data_ptr() for k in ('g', 'v', 'b'))
             s.end_w[f], s.end_b[f] = r['end_w'].data_ptr(), r['end_b'].data_ptr()
-        if not inverse:
-            cache[key] = (s, [raws if raws is not None else self.raws])  # keeps the tensors (and thus the pointers) alive
+        if cacheable:
+            cache[key] = (s, keep)
         return s, keep
 
     def log_det_w(self, n_positions):
