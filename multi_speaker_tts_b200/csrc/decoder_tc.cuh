@@ -140,16 +140,20 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void grid_arrive_compute(unsigned* counter, unsigned& target, unsigned nblocks) {
   asm volatile("fence.proxy.async.global;" ::: "memory");  // image writes (generic proxy) -> later bulk-copy reads
   ptx::bar_sync(1, kTcCompute);
-  if (threadIdx.x == 0) {
-    target += nblocks;
-    red_release_gpu_add(counter, 1u);  // release is cumulative over the writes ordered by the bar.sync above
-  }
+  target += nblocks;  // every thread tracks the target: the pollers of grid_wait_compute sit in four different warps
+  if (threadIdx.x == 0) red_release_gpu_add(counter, 1u);  // release is cumulative over the writes ordered by the bar.sync above
 }
+// Four lanes (one per warp 0..3) poll: their loops drift apart, so the counter update is seen about a fifth of an L2 round trip
+// after it lands instead of half of one; the first poller to see it publishes the (monotonically increasing) event number,
+// the others leave through the shared-memory word.
 __device__ __forceinline__ void grid_wait_compute(unsigned* counter, unsigned target, unsigned* ready_seq, unsigned event) {
-  if (threadIdx.x == 0) {
-    while (ld_acquire_gpu(counter) < target) {
+  if ((threadIdx.x & 31) == 0 && threadIdx.x < 128) {
+    while (ld_volatile_shared(ready_seq) < event) {
+      if (ld_acquire_gpu(counter) >= target) {
+        st_volatile_shared(ready_seq, event);
+        break;
+      }
     }
-    st_volatile_shared(ready_seq, event);
   }
   ptx::bar_sync(1, kTcCompute);
 }
