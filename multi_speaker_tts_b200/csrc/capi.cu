@@ -16,16 +16,21 @@ void mstts_set_error(const char* fmt, ...) {
 // ---- optional kernel timing (bench / roofline): events around the persistent kernels ----
 // With profiling on, every launch of a persistent kernel is bracketed by a fresh event pair on the caller's
 // stream (no synchronisation); mstts_kernel_ms(which) later waits for them and returns sum / count.
+// The timers are process-wide (guarded by a mutex), not thread-local: torch.autograd runs the reverse pass on its own
+// engine thread, and the caller reads the totals from the main thread.
+#include <mutex>
 #include <vector>
 static int g_profiling = 0;
+static std::mutex g_timer_mu;
 struct KernelTimer {
   std::vector<cudaEvent_t> ev;  // start0, stop0, start1, stop1, ...
   size_t used = 0;
 };
-static thread_local KernelTimer g_timers[2];  // 0 = decoder forward loop, 1 = decoder reverse loop
+static KernelTimer g_timers[2];  // 0 = decoder forward loop, 1 = decoder reverse loop
 
 void mstts_timer_start(int which, cudaStream_t s) {
   if (!g_profiling) return;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
   KernelTimer& t = g_timers[which];
   if (t.used + 2 > t.ev.size()) {
     cudaEvent_t a, b;
@@ -38,12 +43,14 @@ void mstts_timer_start(int which, cudaStream_t s) {
 }
 void mstts_timer_stop(int which, cudaStream_t s) {
   if (!g_profiling) return;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
   KernelTimer& t = g_timers[which];
   cudaEventRecord(t.ev[t.used + 1], s);
   t.used += 2;
 }
 
 extern "C" int mstts_set_profiling(int on) {
+  std::lock_guard<std::mutex> lk(g_timer_mu);
   g_profiling = on;
   g_timers[0].used = 0;
   g_timers[1].used = 0;
@@ -51,6 +58,7 @@ extern "C" int mstts_set_profiling(int on) {
 }
 extern "C" int mstts_kernel_ms(int which, float* sum_ms, int* count) {
   MSTTS_REQUIRE(which >= 0 && which < 2 && sum_ms && count, MSTTS_E_INVALID, "kernel_ms: bad argument");
+  std::lock_guard<std::mutex> lk(g_timer_mu);
   KernelTimer& t = g_timers[which];
   float total = 0.f;
   for (size_t i = 0; i + 1 < t.used; i += 2) {
