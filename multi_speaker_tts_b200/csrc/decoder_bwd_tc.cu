@@ -420,6 +420,11 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     };
     attention_prologue(T - 1);
     ptx::bar_sync(1, kTcCompute);
+    // Saved forward activations come from HBM (2.4 GB per launch, nothing of it is L2-resident): every phase issues the
+    // loads of its saved operands BEFORE the grid-barrier wait that precedes it, so their latency rides in the wait.
+    float pf_act[4] = {0.f, 0.f, 0.f, 0.f}, pf_cn = 0.f, pf_cz = 0.f, pf_mc = 0.f, pf_mh = 0.f, pf_dm = 0.f, pf_dh = 0.f;
+    float pf_dctx = 0.f;
+    if (cid < B && tid < Dq) pf_dctx = P.dctx[((size_t)(T - 1) * B + cid) * D + crank * Dq + tid];
 
     for (int t = T - 1; t >= 0; --t) {
       const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
@@ -433,7 +438,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         const int bb = cid;
         if (tid < Dq) {  // total gradient w.r.t. ctx_t: projection part + the 4 K-quarter partials of JA1(t+1)
           const size_t gi = ((size_t)t * B + bb) * D + crank * Dq + tid;
-          float v = P.dctx[gi];
+          float v = pf_dctx;
           if (!last) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) v += __ldcg(P.pctx + ((size_t)k4 * B + bb) * D + crank * Dq + tid);
@@ -581,6 +586,21 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         for (int x = tid; x < tl; x += kTcCompute)
           dcum_s[x] += ((e_parts2[x] + e_parts2[TeP + x]) + e_parts2[2 * TeP + x]) + e_parts2[3 * TeP + x];
       }
+      if (brow) {  // saved operands of phase B'e (d h1 partials of JB2(t+1) are complete since the last barrier of step t+1)
+        const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = P.act1[ai + gi * kCell];
+        pf_cn = P.c1n[(size_t)t * BC + si];
+        pf_cz = P.cz1[(size_t)t * BC + si];
+        pf_mc = (float)zm[2 * BC + si];
+        pf_mh = (float)zm[3 * BC + si];
+        pf_dm = P.dm1_proj[(size_t)t * BC + si];
+        pf_dh = dh1d;
+        if (!last) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) pf_dh += __ldcg(P.ph1 + ((size_t)k4 * B + b) * kCell + unit);
+        }
+      }
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(2);
 
@@ -588,11 +608,6 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       {
         for (int i = tid; i < B * (kAtt / 4); i += kTcCompute)  // rows padded to 132 floats: conflict-free float4 reads
           reinterpret_cast<float4*>(dq_s)[(i >> 5) * 33 + (i & 31)] = __ldcg(reinterpret_cast<const float4*>(P.dq + (size_t)t * B * kAtt) + i);
-        float dh = dh1d;
-        if (brow && !last) {
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) dh += __ldcg(P.ph1 + ((size_t)k4 * B + b) * kCell + unit);
-        }
         ptx::bar_sync(1, kTcCompute);
         CellGradTc g = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (brow) {
@@ -607,10 +622,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             s = fmaf(x4.z, w4.z, s);
             s = fmaf(x4.w, w4.w, s);
           }
-          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          const float dm_direct = P.dm1_proj[(size_t)t * BC + si] + s;
-          g = cell_backward_tc(dm_direct, dh, dc1, P.act1[ai], P.act1[ai + kCell], P.act1[ai + 2 * kCell], P.act1[ai + 3 * kCell],
-                               P.c1n[(size_t)t * BC + si], P.cz1[(size_t)t * BC + si], (float)zm[2 * BC + si], (float)zm[3 * BC + si]);
+          g = cell_backward_tc(pf_dm + s, pf_dh, dc1, pf_act[0], pf_act[1], pf_act[2], pf_act[3], pf_cn, pf_cz, pf_mc, pf_mh);
           dc1 = g.dc_prev;
           dh1d = g.dh_prev;
         }
@@ -632,6 +644,15 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       drain(&job_done[0], sp, P.pm0, kCell, last ? nullptr : P.ph0, kCell);
       STAMP(5);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+      if (brow) {  // saved operands of phase A'e
+        const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = P.act0[ai + gi * kCell];
+        pf_cn = P.c0n[(size_t)t * BC + si];
+        pf_cz = P.cz0[(size_t)t * BC + si];
+        pf_mc = (float)zm[si];
+        pf_mh = (float)zm[BC + si];
+      }
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(6);
 
@@ -646,9 +667,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) dh += __ldcg(P.ph0 + ((size_t)k4 * B + b) * kCell + unit);
           }
-          const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          g = cell_backward_tc(dm0, dh, dc0, P.act0[ai], P.act0[ai + kCell], P.act0[ai + 2 * kCell], P.act0[ai + 3 * kCell],
-                               P.c0n[(size_t)t * BC + si], P.cz0[(size_t)t * BC + si], (float)zm[si], (float)zm[BC + si]);
+          g = cell_backward_tc(dm0, dh, dc0, pf_act[0], pf_act[1], pf_act[2], pf_act[3], pf_cn, pf_cz, pf_mc, pf_mh);
           dc0 = g.dc_prev;
           dh0d = g.dh_prev;
         }
@@ -681,6 +700,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
       attention_prologue(t - 1);
+      if (cid < B && tid < Dq) pf_dctx = P.dctx[((size_t)(t - 1) * B + cid) * D + crank * Dq + tid];
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(10);
     }
