@@ -55,7 +55,7 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int NS, int Te, int D) {
     return o;
   };
   s.ring = take(NS * kWTileBytes);
-  s.xbuf = take(2 * 4 * kXTileBytes);
+  s.xbuf = take(4 * kXTileBytes);  // ONE dG slice: dG1_t (JB jobs) and dG0_t (JA jobs) take turns
   s.recv = take(2 * kDecCluster * kTcN * kRecvStride * 4);  // two accumulators
   const uint32_t dps_bytes = (TeP + 32) * 32 * 4, dq_bytes = kTcN * (kAtt + 4) * 4;
   s.scratch = take(dps_bytes > dq_bytes ? dps_bytes : dq_bytes);  // d pre-activations (phase C') / dq rows (phase B'e)
@@ -96,7 +96,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   const TcBwdSmem L = tc_bwd_smem(NS, Te, D);
 
   uint8_t* ring = smem + L.ring;
-  uint8_t* xbuf = smem + L.xbuf;  // [0]: dG0 slice (JA jobs), [1]: dG1 slice (JB jobs)
+  uint8_t* xbuf = smem + L.xbuf;  // dG1_t slice from barrier 2 until JB2(t) has read it, then dG0_t slice (JA jobs)
   float* recv = reinterpret_cast<float*>(smem + L.recv);  // [acc 2][src 4][batch 32][40]
   float* scratch = reinterpret_cast<float*>(smem + L.scratch);
   float* s_s = reinterpret_cast<float*>(smem + L.s_s);
@@ -219,15 +219,15 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     if (lane == 0) {
       for (int t = T - 1; t >= 0; --t) {
         const unsigned sidx = (unsigned)(T - 1 - t);
-        // dG1_t slice -> buffer 1 (readers of the previous use: JB2 of step t+1)
-        if (sidx > 0) ptx::mbar_wait(&job_done[1], (sidx - 1) & 1);
+        // dG1_t slice (the buffer's previous readers: JA1 / JA2 of step t+1, long finished)
+        if (sidx > 0) ptx::mbar_wait(&job_done[3], (sidx - 1) & 1);
         while (ld_volatile_shared(ready_seq) < 5u * sidx + 2) {
         }
         ptx::mbar_arrive_expect_tx(&xfull[1], 4 * kXTileBytes);
-        ptx::bulk_g2s(xbuf + 4 * kXTileBytes, P.ximg_g1 + (size_t)kslice * 4 * kXTileBytes, 4 * kXTileBytes, &xfull[1]);
+        ptx::bulk_g2s(xbuf, P.ximg_g1 + (size_t)kslice * 4 * kXTileBytes, 4 * kXTileBytes, &xfull[1]);
         if (t == 0) break;
-        // dG0_t slice -> buffer 0 (readers of the previous use: JA2 of step t+1)
-        if (sidx > 0) ptx::mbar_wait(&job_done[3], (sidx - 1) & 1);
+        // dG0_t slice (previous readers: JB1 / JB2 of this step; JB2 ends ~3 us before barrier 4 passes)
+        ptx::mbar_wait(&job_done[1], sidx & 1);
         while (ld_volatile_shared(ready_seq) < 5u * sidx + 4) {
         }
         ptx::mbar_arrive_expect_tx(&xfull[0], 4 * kXTileBytes);
@@ -252,7 +252,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             free_parity ^= 1u;
           }
           const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
-          const uint32_t xbase = ptx::smem_u32(xbuf + (size_t)(job < 2 ? 1 : 0) * 4 * kXTileBytes);
+          const uint32_t xbase = ptx::smem_u32(xbuf);
           for (int kt = 0; kt < 4; ++kt, ++i) {
             const int s = i % NS, round = i / NS;
             ptx::mbar_wait(&wfull[s], round & 1);
@@ -283,8 +283,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     float dc0 = 0.f, dh0d = 0.f, dc1 = 0.f, dh1d = 0.f;  // carries: d c (zoned) and the direct zoneout path of d h
     const int tl = (cid < B) ? min(P.text_len[cid], Te) : 0;
     const uint32_t recv_addr = ptx::smem_u32(recv);
-    float* dps = scratch;   // [(TeP+32)][32]
-    float* dq_s = scratch;  // [32][128]
+    float* dps = scratch;   // [(TeP+32)][32] d pre-activations of attention'(t): live until the prologue of step t-1
+    float* dq_s = recv;     // [32][132] dq rows of phase B'e (recv is idle between the drains of A'g(t+1) and B'g(t))
     long long* dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
     // profiling aid: CTA 0 stamps every step with its SM clock; at the middle step EVERY CTA also stamps the global timer
     // (rows 0..127 of the same buffer, one row per CTA) so that tools/phase_times.py can show the arrival spread at each barrier
@@ -382,12 +382,15 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     // Stages everything of attention'(t) that depends only on saved forward data: alignment, cumulative alignment
     // (shifted by 15, zero borders), zero borders of the d pre-activation buffer, and s = tanh(keys + q + loc) of this
     // warp's 16 positions.  Runs inside the barrier wait that precedes phase C'(t).
-    float de_keep[16];
-    auto attention_prologue = [&](int t) {
+    // (split in two: the staging half reads HBM and runs inside the wait of barrier 4 -- nothing reads cum_s / a_s after the
+    //  wait of barrier 2 -- so that the wait of barrier 5 holds only the convolution and the tanh)
+    float qf_next = 0.f;
+    auto attention_stage = [&](int t) {
       if (cid >= B) return;
       const int bb = cid;
       const float* al = P.align_tm + ((size_t)t * B + bb) * Te;
       const float* cum_prev = P.cum + ((size_t)t * B + bb) * Te;
+      qf_next = P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane];
       for (int i = tid; i < TeP + 32; i += kTcCompute) {
         const int x = i - 15;
         cum_s[i] = (x >= 0 && x < Te) ? cum_prev[x] : 0.f;
@@ -395,8 +398,10 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       for (int x = tid; x < TeP; x += kTcCompute) a_s[x] = (x < Te) ? al[x] : 0.f;
       for (int i = tid; i < 15 * 32; i += kTcCompute) dps[i] = 0.f;
       for (int i = (15 + tl) * 32 + tid; i < (TeP + 32) * 32; i += kTcCompute) dps[i] = 0.f;
-      const float qf = P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane];
-      ptx::bar_sync(1, kTcCompute);
+    };
+    auto attention_prologue = [&]() {  // needs a barrier among the compute warps after attention_stage
+      if (cid >= B) return;
+      const float qf = qf_next;
       const int t0 = warp * 16;
       if (t0 < tl) {
         float acc[16];
@@ -418,7 +423,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         for (int p = 0; p < 16; ++p) s_s[p * kTcCompute + tid] = tanhf(__uint_as_float(kv[p]) + qf + acc[p]);
       }
     };
-    attention_prologue(T - 1);
+    attention_stage(T - 1);
+    ptx::bar_sync(1, kTcCompute);
+    attention_prologue();
     ptx::bar_sync(1, kTcCompute);
     // Saved forward activations come from HBM (2.4 GB per launch, nothing of it is L2-resident): every phase issues the
     // loads of its saved operands BEFORE the grid-barrier wait that precedes it, so their latency rides in the wait.
@@ -508,7 +515,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 #pragma unroll
             for (int p = 0; p < 16; ++p) {
               const float sv = s_s[p * kTcCompute + tid];
-              const float dpre = (t0 + p < tl) ? de_blk[p] * sw_l * (1.f - sv * sv) : 0.f;
+              const bool ok = t0 + p < tl;
+              const float dpre = ok ? de_blk[p] * sw_l * (1.f - sv * sv) : 0.f;
+              if (ok) dsw_acc = fmaf(de_blk[p], sv, dsw_acc);
               dq_acc += dpre;
               dps[(15 + t0 + p) * 32 + lane] = dpre;
             }
@@ -522,39 +531,30 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
           P.dq[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s;
         }
-        // keep d e for the deferred part
-#pragma unroll
-        for (int p = 0; p < 16; ++p) de_keep[p] = de_blk[p];
       }
       STAMP(1);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
-      // ---- inside the barrier wait: everything of attention' that only feeds later steps / weight gradients ----
+      if (brow) {  // saved operands of phase B'e (d h1 partials of JB2(t+1) are complete since the last barrier of step t+1)
+        const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = P.act1[ai + gi * kCell];
+        pf_cn = P.c1n[(size_t)t * BC + si];
+        pf_cz = P.cz1[(size_t)t * BC + si];
+        pf_mc = (float)zm[2 * BC + si];
+        pf_mh = (float)zm[3 * BC + si];
+        pf_dm = P.dm1_proj[(size_t)t * BC + si];
+        pf_dh = dh1d;
+        if (!last) {
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) pf_dh += __ldcg(P.ph1 + ((size_t)k4 * B + b) * kCell + unit);
+        }
+      }
+      // ---- inside the barrier wait: the part of attention' that feeds the next reverse step (d cum_{t-1}).  What only feeds
+      //      weight gradients (d F, d keys) reads the d pre-activations back from `dps` inside the waits of barriers 2 and 3:
+      //      all of it here took ~3.5 us, three times the barrier's own latency ----
       if (cid < B) {
         const int t0 = warp * 16;
         if (t0 < tl) {
-          float dp[16];
-          uint32_t dk[16];
-          const uint32_t ka = ((uint32_t)(q4 * 32) << 16) + half * 16;
-          ptx::tmem_ld16(tmem_dkeys + ka, dk);
-          ptx::tmem_wait_ld();
-#pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const float sv = s_s[p * kTcCompute + tid];
-            const bool ok = t0 + p < tl;
-            dp[p] = ok ? de_keep[p] * sw_l * (1.f - sv * sv) : 0.f;
-            if (ok) dsw_acc = fmaf(de_keep[p], sv, dsw_acc);
-            dk[p] = __float_as_uint(__uint_as_float(dk[p]) + dp[p]);
-          }
-          ptx::tmem_st16(tmem_dkeys + ka, dk);
-#pragma unroll
-          for (int c = 0; c < 16 + kConvK - 1; ++c) {
-            const float cv = cum_s[t0 + c];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              const int k = c - p;
-              if (k >= 0 && k < kConvK) dF_reg[k] = fmaf(cv, dp[p], dF_reg[k]);
-            }
-          }
           // conv transpose: gradient reaching cum_{t-1} through the location features (partial over this CTA's units)
           float G[16];
 #pragma unroll
@@ -578,28 +578,12 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
               for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), tot, ptx::mapa(eb, dst));
             }
           }
-          ptx::tmem_wait_st();
         }
         if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
         mbar_wait_warp(e_bar, e_parity);
         e_parity ^= 1u;
         for (int x = tid; x < tl; x += kTcCompute)
           dcum_s[x] += ((e_parts2[x] + e_parts2[TeP + x]) + e_parts2[2 * TeP + x]) + e_parts2[3 * TeP + x];
-      }
-      if (brow) {  // saved operands of phase B'e (d h1 partials of JB2(t+1) are complete since the last barrier of step t+1)
-        const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = P.act1[ai + gi * kCell];
-        pf_cn = P.c1n[(size_t)t * BC + si];
-        pf_cz = P.cz1[(size_t)t * BC + si];
-        pf_mc = (float)zm[2 * BC + si];
-        pf_mh = (float)zm[3 * BC + si];
-        pf_dm = P.dm1_proj[(size_t)t * BC + si];
-        pf_dh = dh1d;
-        if (!last) {
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) pf_dh += __ldcg(P.ph1 + ((size_t)k4 * B + b) * kCell + unit);
-        }
       }
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(2);
@@ -636,6 +620,21 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           P.dG1[ai + 2 * kCell] = g.df;
           P.dG1[ai + 3 * kCell] = g.dop;
         }
+        if (cid < B && warp * 16 < tl) {  // d F of attention'(t) (deferred from phase C')
+          const int t0 = warp * 16;
+          float dp[16];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) dp[p] = dps[(15 + t0 + p) * 32 + lane];
+#pragma unroll
+          for (int c = 0; c < 16 + kConvK - 1; ++c) {
+            const float cv = cum_s[t0 + c];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+              const int k = c - p;
+              if (k >= 0 && k < kConvK) dF_reg[k] = fmaf(cv, dp[p], dF_reg[k]);
+            }
+          }
+        }
         grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       }
       STAMP(4);
@@ -652,6 +651,16 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         pf_cz = P.cz0[(size_t)t * BC + si];
         pf_mc = (float)zm[si];
         pf_mh = (float)zm[BC + si];
+      }
+      if (cid < B && warp * 16 < tl) {  // d keys += d pre-activations of attention'(t) (deferred from phase C')
+        uint32_t dk[16];
+        const uint32_t ka = ((uint32_t)(q4 * 32) << 16) + half * 16;
+        ptx::tmem_ld16(tmem_dkeys + ka, dk);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int p = 0; p < 16; ++p) dk[p] = __float_as_uint(__uint_as_float(dk[p]) + dps[(15 + warp * 16 + p) * 32 + lane]);
+        ptx::tmem_st16(tmem_dkeys + ka, dk);
+        ptx::tmem_wait_st();
       }
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(6);
@@ -691,6 +700,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           P.dG0[ai + 2 * kCell] = g.df;
           P.dG0[ai + 3 * kCell] = g.dop;
         }
+        attention_stage(t - 1);
         grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       }
       STAMP(8);
@@ -699,7 +709,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       drain(isctx ? &job_done[2] : &job_done[1], sp, isctx ? P.pctx : nullptr, D, P.ph1, kCell);
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
-      attention_prologue(t - 1);
+      attention_prologue();
       if (cid < B && tid < Dq) pf_dctx = P.dctx[((size_t)(t - 1) * B + cid) * D + crank * Dq + tid];
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(10);
@@ -841,7 +851,9 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   prep_wimg_bwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_b), D);
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_g1, 0, l.ximg_g_end - l.ximg_g1, s));
   bool ok = false;
-  int rc = launch_bwd_tc<2>(P, s, tc_bwd_smem(2, io->Te, D).total, &ok);
+  int rc = launch_bwd_tc<3>(P, s, tc_bwd_smem(3, io->Te, D).total, &ok);  // 3 of a critical job's 4 weight tiles prefetched
+  if (rc) return rc;
+  if (!ok) rc = launch_bwd_tc<2>(P, s, tc_bwd_smem(2, io->Te, D).total, &ok);
   if (rc) return rc;
   MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_bwd_tc: shared memory does not fit for Te=%d", io->Te);
   return MSTTS_OK;
