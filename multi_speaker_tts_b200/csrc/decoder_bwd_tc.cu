@@ -549,42 +549,6 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           for (int k4 = 0; k4 < 4; ++k4) pf_dh += __ldcg(P.ph1 + ((size_t)k4 * B + b) * kCell + unit);
         }
       }
-      // ---- inside the barrier wait: the part of attention' that feeds the next reverse step (d cum_{t-1}).  What only feeds
-      //      weight gradients (d F, d keys) reads the d pre-activations back from `dps` inside the waits of barriers 2 and 3:
-      //      all of it here took ~3.5 us, three times the barrier's own latency ----
-      if (cid < B) {
-        const int t0 = warp * 16;
-        if (t0 < tl) {
-          // conv transpose: gradient reaching cum_{t-1} through the location features (partial over this CTA's units)
-          float G[16];
-#pragma unroll
-          for (int p = 0; p < 16; ++p) G[p] = 0.f;
-#pragma unroll
-          for (int c = 0; c < 16 + kConvK - 1; ++c) {
-            const float v = dps[(t0 + c) * 32 + lane];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              const int k = p + (kConvK - 1) - c;
-              if (k >= 0 && k < kConvK) G[p] = fmaf(v, F_reg[k], G[p]);
-            }
-          }
-          const float tot = warp_sum16(G, lane);
-          if ((lane & 1) == 0) {
-            const int x = t0 + warp_sum16_index(lane);
-            if (x < tl) {
-              const uint32_t ep = ptx::smem_u32(e_parts2) + (uint32_t)((crank * TeP + x) * 4);
-              const uint32_t eb = ptx::smem_u32(e_bar);
-#pragma unroll
-              for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), tot, ptx::mapa(eb, dst));
-            }
-          }
-        }
-        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
-        mbar_wait_warp(e_bar, e_parity);
-        e_parity ^= 1u;
-        for (int x = tid; x < tl; x += kTcCompute)
-          dcum_s[x] += ((e_parts2[x] + e_parts2[TeP + x]) + e_parts2[2 * TeP + x]) + e_parts2[3 * TeP + x];
-      }
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(2);
 
@@ -620,20 +584,37 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           P.dG1[ai + 2 * kCell] = g.df;
           P.dG1[ai + 3 * kCell] = g.dop;
         }
-        if (cid < B && warp * 16 < tl) {  // d F of attention'(t) (deferred from phase C')
+        // ---- deferred halves of attention'(t), spread over the barrier waits so that none holds more than the barrier's own
+        //      ~1.3 us (all of it inside the wait of barrier 1 took ~3.5 us): here the conv transpose that feeds d cum_{t-1};
+        //      the wait of barrier 3 collects it and accumulates d F / d keys from the d pre-activations kept in `dps` ----
+        if (cid < B) {
           const int t0 = warp * 16;
-          float dp[16];
+          if (t0 < tl) {
+            // conv transpose: gradient reaching cum_{t-1} through the location features (partial over this CTA's units)
+            float G[16];
 #pragma unroll
-          for (int p = 0; p < 16; ++p) dp[p] = dps[(15 + t0 + p) * 32 + lane];
+            for (int p = 0; p < 16; ++p) G[p] = 0.f;
 #pragma unroll
-          for (int c = 0; c < 16 + kConvK - 1; ++c) {
-            const float cv = cum_s[t0 + c];
+            for (int c = 0; c < 16 + kConvK - 1; ++c) {
+              const float v = dps[(t0 + c) * 32 + lane];
 #pragma unroll
-            for (int p = 0; p < 16; ++p) {
-              const int k = c - p;
-              if (k >= 0 && k < kConvK) dF_reg[k] = fmaf(cv, dp[p], dF_reg[k]);
+              for (int p = 0; p < 16; ++p) {
+                const int k = p + (kConvK - 1) - c;
+                if (k >= 0 && k < kConvK) G[p] = fmaf(v, F_reg[k], G[p]);
+              }
+            }
+            const float tot = warp_sum16(G, lane);
+            if ((lane & 1) == 0) {
+              const int x = t0 + warp_sum16_index(lane);
+              if (x < tl) {
+                const uint32_t ep = ptx::smem_u32(e_parts2) + (uint32_t)((crank * TeP + x) * 4);
+                const uint32_t eb = ptx::smem_u32(e_bar);
+#pragma unroll
+                for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), tot, ptx::mapa(eb, dst));
+              }
             }
           }
+          if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));  // collected in the wait of barrier 3
         }
         grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       }
@@ -651,6 +632,27 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         pf_cz = P.cz0[(size_t)t * BC + si];
         pf_mc = (float)zm[si];
         pf_mh = (float)zm[BC + si];
+      }
+      if (cid < B) {  // d cum_{t-1}: the cluster's partial conv-transpose sums pushed during the wait of barrier 2
+        mbar_wait_warp(e_bar, e_parity);
+        e_parity ^= 1u;
+        for (int x = tid; x < tl; x += kTcCompute)
+          dcum_s[x] += ((e_parts2[x] + e_parts2[TeP + x]) + e_parts2[2 * TeP + x]) + e_parts2[3 * TeP + x];
+      }
+      if (cid < B && warp * 16 < tl) {  // d F of attention'(t) (deferred from phase C')
+        const int t0 = warp * 16;
+        float dp[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) dp[p] = dps[(15 + t0 + p) * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 16 + kConvK - 1; ++c) {
+          const float cv = cum_s[t0 + c];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const int k = c - p;
+            if (k >= 0 && k < kConvK) dF_reg[k] = fmaf(cv, dp[p], dF_reg[k]);
+          }
+        }
       }
       if (cid < B && warp * 16 < tl) {  // d keys += d pre-activations of attention'(t) (deferred from phase C')
         uint32_t dk[16];

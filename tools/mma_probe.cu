@@ -105,13 +105,16 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(const Params P) {
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  setvbuf(stdout, NULL, _IONBF, 0);
+  const bool only_multi = argc > 1;  // any argument: only the multi-issuer part
   unsigned long long* cyc;
   CK(cudaMalloc(&cyc, 148 * sizeof(unsigned long long)));
   CK(cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   const int iters = 4096;
   const char* names[] = {"SS same acc", "SS 3 accs", "TS (A in TMEM)", "CP 128x256b only", "2 CP + 3 TS (one bf16x3 K-step)"};
   for (int elect : {0, 1}) {
+  if (only_multi) break;
   for (int grid : {128}) {
     for (int mode = 0; mode < 5; ++mode) {
       for (int M : {128, 64}) {
@@ -147,5 +150,15 @@ int main() {
       CK(cudaMemcpy(h, cyc, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
       printf("%d issuing warps, N=%d: %.1f cycles per MMA per warp -> %.1f cycles per MMA aggregate\n", nw, N, (double)h[0] / iters, (double)h[0] / iters / nw);
     }
+  // the decoder's shape (M=64 stacked hi/lo batch rows, N=256 stacked hi/lo gate rows): does a second issuing warp help?
+  for (int nw : {1, 2}) {
+    Params P{64, 256, 0, 0, nw, iters, cyc};
+    mma_kernel<<<128, 128, 128 * 1024>>>(P);
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[148];
+    CK(cudaMemcpy(h, cyc, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    printf("M=64 N=256, %d issuing warps (own accumulators): %.1f cycles per MMA per warp -> %.1f aggregate\n", nw, (double)h[0] / iters,
+           (double)h[0] / iters / nw);
+  }
   return 0;
 }
