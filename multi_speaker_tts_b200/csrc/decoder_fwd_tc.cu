@@ -293,7 +293,18 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     const int unit0 = cid * 32 + crank * kUnitsPerCta;
     const size_t img_chunk = (size_t)(unit0 >> 6) * kXTileBytes + (size_t)((unit0 & 63) >> 3) * 128;
     long long* dbg = (P.dbg && blockIdx.x == 0 && tid == 0) ? P.dbg : nullptr;
-#define STAMP(k) do { if (dbg) dbg[(size_t)t * 32 + (k)] = clock64(); } while (0)
+    // at the middle step EVERY CTA also stamps the global timer (rows 0..127 of the same buffer, one row per CTA) so that
+    // tools/phase_times.py can show the arrival spread at each barrier
+    long long* dbg_all = (P.dbg && tid == 0) ? P.dbg + (size_t)blockIdx.x * 32 : nullptr;
+#define STAMP(k)                                                 \
+  do {                                                           \
+    if (dbg) dbg[(size_t)t * 32 + (k)] = clock64();              \
+    if (dbg_all && t == P.T / 2) {                               \
+      unsigned long long gt;                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));     \
+      dbg_all[(k)] = (long long)gt;                              \
+    }                                                            \
+  } while (0)
 
     // Pulls this CTA's partial accumulator (cell = job & 1) out of TMEM, adds its four hi/lo quadrants and scatters
     // the 128 gate rows to the CTAs that own the units.  X-image rows are ordered so that TMEM lane quarter q holds

@@ -46,6 +46,16 @@ if which == "bwd":
         prev = sel[:, k]
     print("  total/step     %8.0f cycles" % (sel[:, 10] - sel[:, 0]).mean().item())
     sys.exit(0)
+allc = stamps[:128, :16]
+if T // 2 >= 128 and (allc[:, :11] > 0).all():
+    base = allc[:, 0].min()
+    print("middle step, all 128 CTAs, global timer (ns since the first CTA started the step): min / median / max over CTAs")
+    for k in order_f:
+        col = allc[:, k] - base
+        if (col < 0).any():   # attention stamps exist only in the CTAs that own a batch row
+            continue
+        print("  %-14s %8.0f %8.0f %8.0f   slowest CTA %d" % (names_f[k], col.min().item(), col.median().item(), col.max().item(),
+                                                               int(col.argmax())))
 prev = sel[:, 0]
 print("cycles per step (mean over the middle half of the steps), CTA 0:")
 for k in order_f:
