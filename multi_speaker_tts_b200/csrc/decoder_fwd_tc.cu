@@ -55,7 +55,7 @@ __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
     return o;
   };
   s.ring = take(NS * kWTileBytes);
-  s.xbuf = take(2 * 4 * kXTileBytes);
+  s.xbuf = take(4 * kXTileBytes);  // ONE activation slice: the four jobs of a step read it in turn
   s.recv = take(kDecCluster * kTcN * kRecvStride * 4);
   s.keys = take(Te * 32 * 4);
   s.wq = take(kUnitsPerCta * kAtt * 4);
@@ -227,13 +227,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             src = P.ximg_h1 + (size_t)(t & 1) * vec_img + (size_t)(crank * 4) * kXTileBytes;
             need = 3u * t + 2;
           }
-          // the buffer is free once the previous job that read it has completed
-          if (job >= 2) ptx::mbar_wait(&job_done[job - 2], t & 1);
-          else if (t > 0) ptx::mbar_wait(&job_done[job + 2], (t - 1) & 1);
+          // the buffer is free once the previous job has completed (J2 / J3 are deferred work and J0 / J1 wait for a grid
+          // barrier that passes long after their predecessor ended, so one buffer costs nothing and pays for a 4th ring slot)
+          if (job >= 1) ptx::mbar_wait(&job_done[job - 1], t & 1);
+          else if (t > 0) ptx::mbar_wait(&job_done[3], (t - 1) & 1);
           while (ld_volatile_shared(ready_seq) < need) {
           }
           ptx::mbar_arrive_expect_tx(&xfull[job & 1], bytes);
-          ptx::bulk_g2s(xbuf + (size_t)(job & 1) * 4 * kXTileBytes, src, bytes, &xfull[job & 1]);
+          ptx::bulk_g2s(xbuf, src, bytes, &xfull[job & 1]);
         }
       }
     }
@@ -249,7 +250,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           const int nt = job == 0 ? n0 : 4;
           ptx::mbar_wait(&xfull[job & 1], (uint32_t)(job >> 1));  // buffer A: J0, J2, J0, ... ; buffer B: J1, J3, ...
           const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
-          const uint32_t xbase = ptx::smem_u32(xbuf + (size_t)(job & 1) * 4 * kXTileBytes);
+          const uint32_t xbase = ptx::smem_u32(xbuf);
           for (int kt = 0; kt < nt; ++kt, ++i) {
             const int s = i % NS, round = i / NS;
             ptx::mbar_wait(&wfull[s], round & 1);
@@ -759,8 +760,12 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   prep_wimg_fwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_f), D);
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_ctx, 0, l.ximg_end - l.ximg_ctx, s));
   bool ok = false;
-  int rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D).total, &ok);
+  int rc = launch_fwd_tc<4>(P, s, tc_fwd_smem(4, io->Te, D).total, &ok);  // all 4 weight tiles of J1 resident when m0 arrives
   if (rc) return rc;
+  if (!ok) {
+    rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D).total, &ok);
+    if (rc) return rc;
+  }
   if (!ok) {
     rc = launch_fwd_tc<2>(P, s, tc_fwd_smem(2, io->Te, D).total, &ok);
     if (rc) return rc;

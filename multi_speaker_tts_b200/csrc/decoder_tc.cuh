@@ -3,7 +3,7 @@
 // Numerics: every recurrent skinny GEMM  Y[B,rows] = X[B,K] . W[rows,K]^T  runs on the 5th-gen tensor cores
 // with both operands split into bf16 hi + bf16 lo (x = hi + lo to ~16 mantissa bits), fp32 accumulation in
 // TMEM: measured L_inf vs the fp32 oracle ~2e-6 on the mel outputs (plain bf16 would be ~1e-3, i.e. at the
-// parity gate).  One tcgen05.mma costs ~150 cycles to issue whatever its shape (tools/mma_probe.cu), so the
+// parity gate).  A skinny tcgen05.mma is bound by its issue interval (tools/mma_probe.cu: 78-128 cycles), so the
 // hi/lo halves are STACKED into one instruction per K-step: A = [X_hi ; X_lo] (M = 64 rows), B = [W_hi ; W_lo]
 // (N = 256 rows) gives all four partial products in one 64 x 256 accumulator; the epilogue adds the quadrants.
 //

@@ -22,7 +22,8 @@ def _oracle_grads(w, b, T, dtype=torch.float64):
 
 
 @pytest.mark.parametrize("B,Te,L,ragged", [(2, 32, 24, False), (3, 40, 17, True), (8, 50, 9, True), (32, 128, 5, True),
-                                           (36, 24, 4, True)])
+                                           (36, 24, 4, True),
+                                           (3, 20, 1, False), (2, 9, 2, False)])   # shortest loops: T = 2 and T = 3
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
 def test_decoder_gradients(cuda_dev, B, Te, L, ragged, mode):
     if mode == "bf16x3" and B > 32:

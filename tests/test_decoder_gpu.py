@@ -69,7 +69,8 @@ def test_ragged_parity(cuda_dev, mode):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("B,Te,L", [(1, 16, 8), (5, 33, 12), (8, 128, 10), (16, 100, 6), (32, 128, 6), (40, 48, 5),
-                                    (7, 160, 5), (7, 224, 5)])
+                                    (7, 160, 5), (7, 224, 5),
+                                    (3, 20, 1), (2, 9, 2), (1, 1, 3)])   # shortest loops (T = 2, 3) and a one-token text
 def test_shapes_parity(cuda_dev, B, Te, L, mode):
     if mode == "bf16x3" and not _tc_supported(B, Te):
         from multi_speaker_tts_b200._lib import MsttsError
