@@ -170,6 +170,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: library chatter (NCCL prints its version banner to stdout) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     pg = None
@@ -293,7 +297,10 @@ def main():
             out["cpu_baseline"] = {
                 "value": B * Ls / sec, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": "B=%d Te=%d L=%d (%d of 801 decoder steps), 1 train step, %.1f s" % (B, TE, Ls, Ls + 1, sec)}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         torch.distributed.destroy_process_group()
 
