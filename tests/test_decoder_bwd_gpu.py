@@ -56,3 +56,32 @@ def test_decoder_gradients(cuda_dev, B, Te, L, ragged, mode):
         print("%-24s max|ref| %.3e  err %.3e  rel %.2e" % (k, scale, err, rel))
         assert err <= 2e-4 * scale + 1e-7, (k, err, scale)
     print("worst rel err %.2e" % worst)
+
+
+@pytest.mark.parametrize("D", [256, 512])
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_other_memory_widths(cuda_dev, D, mode):
+    """The reference's memory is 768 wide (encoder 512 + speaker embedding 256, MSTTS_SV.py:70-71); the kernels also take
+    256 and 512 (a decoder without the speaker concat): forward outputs and every gradient against the oracle."""
+    from oracle import decoder_oracle as O
+    from multi_speaker_tts_b200.decoder import decoder_forward, decoder_backward, decoder_loss
+    B, Te, L = 5, 40, 7
+    w = S.init_decoder_weights(0, mem_dim=D, bias_scale=0.05)
+    b = S.synthetic_decoder_batch(B, Te, L, seed=D, ragged=True, mem_dim=D)
+    T = L + 1
+    ref_g, ref_dmem, (rll, rsl) = _oracle_grads(w, b, T)
+    with torch.no_grad():
+        rl, rs, ra = O.decoder_forward(w, b['memory'], b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'], b['zone_mask'])
+    wd = {k: v.to(cuda_dev) for k, v in w.items()}
+    bd = {k: v.to(cuda_dev) for k, v in b.items()}
+    lin, stop, align, st = decoder_forward(wd, bd['memory'], bd['text_len'], bd['mel'], bd['mel_len'], bd['prenet_mask'],
+                                           bd['zone_mask'], True, T, mode)
+    assert (lin.cpu() - rl).abs().max() < 1e-3 and (stop.cpu() - rs).abs().max() < 1e-3 and (align.cpu() - ra).abs().max() < 1e-3
+    assert torch.equal(align.cpu().argmax(-1), ra.argmax(-1))
+    loss2, dlin, dstop = decoder_loss(lin, stop, bd['mel'], bd['mel_len'])
+    grads, dmem = decoder_backward(st, wd, dlin, dstop)
+    torch.cuda.synchronize()
+    for k, rg in list(ref_g.items()) + [('d_memory', ref_dmem)]:
+        gg = (dmem if k == 'd_memory' else grads[k]).cpu().double()
+        scale = rg.abs().max().item()
+        assert (gg - rg).abs().max().item() <= 2e-4 * scale + 1e-7, (k, D, mode)
