@@ -142,7 +142,7 @@ int main(int argc, char** argv) {
   }
   }
   for (int nw : {1, 2, 4})
-    for (int N : {32, 128}) {
+    for (int N : {32, 64, 128}) {  // N = 64: the swapped-role shape (A = 128 weight rows, B = 32 batch rows x hi/lo)
       Params P{128, N, 0, 0, nw, iters, cyc};
       mma_kernel<<<128, 128, 128 * 1024>>>(P);
       CK(cudaDeviceSynchronize());
