@@ -107,7 +107,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   const TcSmem L = tc_fwd_smem(NS, Te, D);
 
   uint8_t* ring = smem + L.ring;   // [NS][32 KB] weight tiles
-  uint8_t* xbuf = smem + L.xbuf;   // [2][32 KB]  activation operand of the running jobs (A: J0/J2, B: J1/J3)
+  uint8_t* xbuf = smem + L.xbuf;   // [32 KB]  activation operand of the running job (J0, J1, J2, J3 in turn)
   float* recv = reinterpret_cast<float*>(smem + L.recv);
   float* keys_s = reinterpret_cast<float*>(smem + L.keys);
   float* wq_s = reinterpret_cast<float*>(smem + L.wq);
@@ -248,7 +248,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         const int njobs = (t == P.T - 1) ? 2 : 4;
         for (int job = 0; job < njobs; ++job) {
           const int nt = job == 0 ? n0 : 4;
-          ptx::mbar_wait(&xfull[job & 1], (uint32_t)(job >> 1));  // buffer A: J0, J2, J0, ... ; buffer B: J1, J3, ...
+          ptx::mbar_wait(&xfull[job & 1], (uint32_t)(job >> 1));  // two barriers over the one buffer: even jobs J0, J2, J0, ... ; odd jobs J1, J3, ...
           const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
           const uint32_t xbase = ptx::smem_u32(xbuf);
           for (int kt = 0; kt < nt; ++kt, ++i) {
