@@ -14,8 +14,7 @@ build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) includ
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
 $(OUT): $(OBJS)
-	$(NVCC) -shared -o $@ $(OBJS) -L/usr/local/cuda/lib64 -lcublas \
-	  -Xlinker -rpath=/usr/local/cuda/lib64
+	$(NVCC) -shared -o $@ $(OBJS)
 
 clean:
 	rm -rf build $(OUT)

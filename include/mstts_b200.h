@@ -270,6 +270,22 @@ int mstts_stft_mel(const float* wav, int B, int S, int n_fft, int hop, int win, 
 int mstts_tc_gemm_tiled(const void* A_tiled, const void* B_tiled, int M, int N, int K, float* C, int ldc, void* scratch, void* stream);
 int mstts_tc_gemm_test(const float* A, const float* Bt, int M, int N, int K, float* C, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * General dense product on that kernel (what every product outside the persistent loops goes through: the hoisted decoder
+ * products and weight gradients, Modules.py:239-255,309-321; the WaveGlow reverse pass, WaveGlow/WaveGlow.py:54-74; the mel
+ * up-sampling contraction, WaveGlow/Modules.py:198-208; the encoder / postnet convolutions).  The library links no vendor GEMM.
+ *   C_b[M,N] = op(A_b) op(B_b) + beta C_b,  b in [0, batch)     row-major fp32, any leading dimensions
+ *   op(A) is M x K (A stored K x M when transA), op(B) is K x N (B stored N x K when transB); stride* = elements between
+ *   consecutive batches (strideB = 0 shares B).
+ * A pack kernel splits the operands into bf16 hi + lo tile images (zero padded), the product runs as bf16x3 with fp32
+ * accumulation in TMEM, and few-tile / long-K shapes are split over K with a deterministic second-pass reduction.  Scratch for
+ * the images comes from a stream-ordered pool inside the library (cudaMallocAsync on the caller's stream, retained between
+ * calls); mstts_release_scratch() synchronises the device and returns it to the driver.
+ * ---------------------------------------------------------------------------------------------- */
+int mstts_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, long long strideA, const float* B, int ldb,
+                   long long strideB, float* C, int ldc, long long strideC, float beta, int batch, void* stream);
+int mstts_release_scratch(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import Hyper_Parameters as hp
-from . import Feeder, Modules
+from . import Feeder, Modules, checkpoint
 from .Location_Sensitive_Attention import Location_Sensitive_Attention
 from .Speaker_Embedding import Modules as Speaker_Embedding_Modules
 from .decoder import adam_tf
@@ -155,8 +155,8 @@ class Tacotron2(object):
         return {short: v[name] for short, name in TF_VARIABLE_NAMES.items()}
 
     def Speaker_Embedding_Load(self):
-        path = os.path.join(hp.Speaker_Embedding.Checkpoint_Path, 'CHECKPOINT.pt').replace("\\", "/")
-        if os.path.exists(path):
+        path = checkpoint.latest_checkpoint(hp.Speaker_Embedding.Checkpoint_Path)
+        if path is not None:
             self._load(path, lambda k: k.startswith('speaker_embedding'))
             print('Speaker embedding checkpoint \'{}\' is loaded.'.format(path))
         else:
@@ -166,8 +166,8 @@ class Tacotron2(object):
         if hp.Use_Vocoder.upper() != 'WaveGlow'.upper():
             print('Vocoder \'{}\' is not part of this build; Inference returns mels without waveforms.'.format(hp.Use_Vocoder))
             return
-        path = os.path.join(hp.WaveGlow.Checkpoint_Path, 'CHECKPOINT.pt').replace("\\", "/")
-        if os.path.exists(path):
+        path = checkpoint.latest_checkpoint(hp.WaveGlow.Checkpoint_Path)
+        if path is not None:
             from .WaveGlow import Modules as WaveGlow_Modules
             blob = torch.load(path, map_location='cpu')
             self.waveglow_params = WaveGlow_Modules.WaveGlowParams(blob['raws'], blob['up_kernel'], blob['up_bias'], self.device)
@@ -183,8 +183,9 @@ class Tacotron2(object):
         return blob
 
     def Restore(self):
-        path = os.path.join(hp.Checkpoint_Path, 'CHECKPOINT.pt').replace("\\", "/")
-        if not os.path.exists(path):
+        """MSTTS_SV.py:244-251: tf.train.latest_checkpoint(hp.Checkpoint_Path) -> Saver.restore"""
+        path = checkpoint.latest_checkpoint(hp.Checkpoint_Path)
+        if path is None:
             print('There is no checkpoint.')
             return
         blob = self._load(path, lambda k: not k.startswith(_FROZEN_SCOPES))
@@ -195,12 +196,18 @@ class Tacotron2(object):
         print('Checkpoint \'{}\' is loaded.'.format(path))
 
     def Save(self):
-        """variables keyed by their TF names (SURVEY A-8) + optimizer moments"""
-        os.makedirs(hp.Checkpoint_Path.replace("\\", "/"), exist_ok=True)
-        path = os.path.join(hp.Checkpoint_Path, 'CHECKPOINT.pt').replace("\\", "/")
-        torch.save({'variables': {k: v.detach().cpu() for k, v in self.variables.items()}, 'global_step': self.global_Step,
-                    'flat_m': self.flat_m.cpu(), 'flat_v': self.flat_v.cpu()}, path)
-        return path
+        """MSTTS_SV.py:30-40,287-289: Saver(max_to_keep=5).save(..., 'CHECKPOINT', global_step) -> CHECKPOINT-<step> (+ the
+        `checkpoint` state file); variables keyed by their TF names (SURVEY A-8) + the Adam slots, like tf.train.Saver.
+        Under data parallel the batch-norm moving statistics (updated from per-rank batches) are averaged first so that
+        every rank would write the same file, and rank 0 writes it."""
+        if self.world > 1:
+            for k in sorted(self.variables):
+                if k.endswith(('/moving_mean', '/moving_variance')) and not k.startswith(_FROZEN_SCOPES):
+                    torch.distributed.all_reduce(self.variables[k], group=self.pg)
+                    self.variables[k].div_(self.world)
+        blob = {'variables': {k: v.detach().cpu() for k, v in self.variables.items()}, 'global_step': self.global_Step,
+                'flat_m': self.flat_m.cpu(), 'flat_v': self.flat_v.cpu()}
+        return checkpoint.save(hp.Checkpoint_Path, blob, self.global_Step, max_to_keep=5, process_group=self.pg)
 
     # ---- graph ----------------------------------------------------------------------------------------------------
     def _to_device(self, feed_dict):

@@ -47,15 +47,20 @@ class Decoder_State(namedtuple('Decoder_State', ('time', 'alignment_history'))):
 
 
 _WORKSPACE = {}
+_WORKSPACE_GEN = {}
 
 
 def _workspace(dev, nbytes):
     """One cached decoder workspace per device (3.6 GB at B=32, Te=128, L=800 in bf16x3 mode): the saved activations of
-    the latest forward live in it until its backward ran, so at most one decoder call may be in flight per device."""
+    the latest forward live in it until its backward ran, so at most one decoder call may be in flight per device.  Every
+    training forward stamps the workspace with a new generation; a backward whose stamp is stale raises instead of
+    differentiating through another call's activations.  Returns (workspace, generation)."""
     ws = _WORKSPACE.get(dev)
     if ws is None or ws.numel() < nbytes:
         _WORKSPACE[dev] = ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-    return ws
+    gen = _WORKSPACE_GEN.get(dev, 0) + 1
+    _WORKSPACE_GEN[dev] = gen
+    return ws, gen
 
 
 class _DecoderFunction(torch.autograd.Function):
@@ -65,14 +70,20 @@ class _DecoderFunction(torch.autograd.Function):
         B, Te, D = memory.shape
         m = _lib.MODES[mode]
         nbytes = _lib.lib().mstts_decoder_workspace_bytes(B, Te, mel.shape[1], D, n_steps, m)
+        ws, gen = _workspace(memory.device, nbytes)
         lin, stop, align, st = decoder_forward(w, memory, text_len, mel, mel_len, prenet_mask, zone_mask, True, n_steps,
-                                               mode, workspace=_workspace(memory.device, nbytes))
-        ctx.state, ctx.weights = st, w
+                                               mode, workspace=ws)
+        ctx.state, ctx.weights, ctx.ws_gen, ctx.ws_dev = st, w, gen, memory.device
         ctx.mark_non_differentiable(align)
         return lin, stop, align
 
     @staticmethod
     def backward(ctx, d_linear, d_stop, _d_align):
+        if _WORKSPACE_GEN.get(ctx.ws_dev) != ctx.ws_gen:
+            raise RuntimeError(
+                "Decoder_LSTM: the saved activations of this forward were overwritten by a later training forward on %s "
+                "(generation %d, now %s).  One decoder call may be in flight per device: run backward before the next "
+                "forward (gradient accumulation = one backward per forward)." % (ctx.ws_dev, ctx.ws_gen, _WORKSPACE_GEN.get(ctx.ws_dev)))
         grads, d_memory = decoder_backward(ctx.state, ctx.weights, d_linear.contiguous(), d_stop.contiguous(),
                                            want_d_memory=ctx.needs_input_grad[0])
         return (d_memory, None, None, None, None, None, None, None) + tuple(grads[k] for k in DECODER_KEYS)
@@ -102,6 +113,11 @@ def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False
     B, Te, D = memory.shape
     dev = memory.device
     training = bool(is_training)
+    # the kernels compile the prenet dropout scale and the zoneout keep factor in (csrc/common.cuh kZoneKeep, 1 / 0.5)
+    if hp.Decoder.PreNet.Dropout_Rate != 0.5 or hp.Decoder.LSTM.Zoneout_Rate != 0.1:
+        raise ValueError("Decoder_LSTM: the decoder kernels are built for PreNet.Dropout_Rate = 0.5 and LSTM.Zoneout_Rate = 0.1 "
+                         "(got %r / %r); rebuild csrc/common.cuh with the new rates" %
+                         (hp.Decoder.PreNet.Dropout_Rate, hp.Decoder.LSTM.Zoneout_Rate))
     T = int(sequence_length.max().item()) + 1 if training else hp.Decoder.LSTM.Max_Inference_Length + 1
     if masks is None:
         pm = torch.empty(T, 2, B, 256, device=dev, dtype=torch.uint8)

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from .. import Hyper_Parameters as hp
+from .. import checkpoint
 from ..Feeder import Placeholder
 from ..decoder import adam_tf
 from . import Modules
@@ -166,23 +167,37 @@ class WaveGlow(object):
         return {'Global_Step': self.global_Step, 'Audio': Modules.Glow_Inference(a, m, self.params, sigma, generator=generator)}
 
     def Save(self):
-        os.makedirs(hp.WaveGlow.Checkpoint_Path.replace("\\", "/"), exist_ok=True)
-        path = os.path.join(hp.WaveGlow.Checkpoint_Path, 'CHECKPOINT.pt').replace("\\", "/")
+        """tf.train.Saver(max_to_keep=5).save(..., 'CHECKPOINT', global_step): variables + the Adam slots (the reference's Saver
+        checkpoints the optimizer's m / v with the variables); rank 0 writes, CHECKPOINT-<step>.pt, newest five kept"""
         cpu = lambda d: {k: (cpu(v) if isinstance(v, dict) else [cpu(x) for x in v] if isinstance(v, list) else v.detach().cpu())
                          for k, v in d.items()}
-        torch.save({'raws': [cpu(r) for r in self.params.raws], 'up_kernel': self.params.up_kernel.cpu(),
-                    'up_bias': self.params.up_bias.cpu(), 'global_step': self.global_Step}, path)
-        return path
+        blob = {'raws': [cpu(r) for r in self.params.raws], 'up_kernel': self.params.up_kernel.cpu(),
+                'up_bias': self.params.up_bias.cpu(), 'global_step': self.global_Step,
+                'flat_m': self.flat_m.cpu(), 'flat_v': self.flat_v.cpu()}
+        return checkpoint.save(hp.WaveGlow.Checkpoint_Path, blob, self.global_Step, max_to_keep=5, process_group=self.pg)
 
     def Restore(self):
-        path = os.path.join(hp.WaveGlow.Checkpoint_Path, 'CHECKPOINT.pt').replace("\\", "/")
-        if not os.path.exists(path):
+        path = checkpoint.latest_checkpoint(hp.WaveGlow.Checkpoint_Path)
+        if path is None:
             print('There is no checkpoint.')
             return
         blob = torch.load(path, map_location='cpu')
-        fresh = WaveGlow(device=self.device, process_group=self.pg, feeder=self.feeder, raws=blob['raws'], up_kernel=blob['up_kernel'],
-                         up_bias=blob['up_bias'])
-        self.flat_p.copy_(fresh.flat_p)
+
+        def put(dst, src):  # copy a saved tree into the views of the flat parameter buffer
+            if isinstance(dst, dict):
+                for k in dst:
+                    put(dst[k], src[k])
+            elif isinstance(dst, list):
+                for d, x in zip(dst, src):
+                    put(d, x)
+            else:
+                dst.copy_(src.to(self.device))
+        put(self.params.raws, blob['raws'])
+        self.params.up_kernel.copy_(blob['up_kernel'].to(self.device))
+        self.params.up_bias.copy_(blob['up_bias'].to(self.device))
+        for name in ('flat_m', 'flat_v'):
+            if name in blob and blob[name].numel() == getattr(self, name).numel():
+                getattr(self, name).copy_(blob[name].to(self.device))
         self.global_Step = int(blob.get('global_step', 0))
         print('Checkpoint \'{}\' is loaded.'.format(path))
 

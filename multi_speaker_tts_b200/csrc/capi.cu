@@ -72,6 +72,46 @@ extern "C" int mstts_kernel_ms(int which, float* sum_ms, int* count) {
   return MSTTS_OK;
 }
 
+// ---- stream-ordered scratch (scratch_pool.h) ----
+#include "scratch_pool.h"
+static int scratch_pool_ready(int dev) {
+  static std::once_flag once[64];
+  static cudaError_t err[64];
+  std::call_once(once[dev & 63], [dev] {
+    cudaMemPool_t pool;
+    err[dev & 63] = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (err[dev & 63] == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;  // never hand the memory back between steps
+      err[dev & 63] = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  });
+  if (err[dev & 63] != cudaSuccess) {
+    mstts_set_error("scratch pool: %s", cudaGetErrorString(err[dev & 63]));
+    return MSTTS_E_CUDA;
+  }
+  return MSTTS_OK;
+}
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+  int dev = 0;
+  MSTTS_CUDA(cudaGetDevice(&dev));
+  int rc = scratch_pool_ready(dev);
+  if (rc) return rc;
+  MSTTS_CUDA(cudaMallocAsync(p, bytes < 256 ? 256 : bytes, s));
+  return MSTTS_OK;
+}
+void scratch_free(void* p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+extern "C" int mstts_release_scratch(void) {
+  int dev = 0;
+  MSTTS_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  MSTTS_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  MSTTS_CUDA(cudaDeviceSynchronize());
+  MSTTS_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return MSTTS_OK;
+}
+
 extern "C" int mstts_version(void) { return MSTTS_VERSION; }
 extern "C" const char* mstts_last_error(void) { return g_err; }
 
@@ -94,9 +134,12 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 // keep=0.9, so each byte uses its own 32-bit draw from two hashes of the 4-element group).
 __global__ void fill_mask_kernel(uint8_t* __restrict__ out, size_t n, uint32_t thresh, uint64_t seed) {
   const size_t ngroups = (n + 3) / 4;
+  const uint64_t key = splitmix64(splitmix64(seed) ^ 0xD1B54A32D192ED03ull);
   for (size_t gidx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gidx < ngroups; gidx += (size_t)gridDim.x * blockDim.x) {
-    const uint64_t h0 = splitmix64(seed ^ (gidx * 2 + 0));
-    const uint64_t h1 = splitmix64(seed ^ (gidx * 2 + 1) ^ 0xD1B54A32D192ED03ull);
+    // the seed is hashed into a key BEFORE the counter is mixed in: callers pass consecutive small seeds (step numbers), and
+    // seed ^ counter would make the masks of different steps XOR-permutations of each other
+    const uint64_t h0 = splitmix64(key + gidx * 2 + 0);
+    const uint64_t h1 = splitmix64(key + gidx * 2 + 1);
     const uint32_t r[4] = {(uint32_t)h0, (uint32_t)(h0 >> 32), (uint32_t)h1, (uint32_t)(h1 >> 32)};
     const size_t base = gidx * 4;
     if (base + 3 < n && (((uintptr_t)(out + base)) & 3) == 0) {

@@ -14,6 +14,8 @@
 #include "decoder_gemv.cuh"
 #include "decoder_layout.h"
 #include "gemm.h"
+#include "scratch_pool.h"
+#include "tc_gemm.h"
 
 namespace cg = cooperative_groups;
 
@@ -603,35 +605,33 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   P.barrier = (unsigned*)(ws + l.barrier);
   if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
 
-  // ---- weight gradients: batched GEMMs over all steps ----
-  // [activation]^T [T*B, 4096 gate gradients]: ~1 TFLOP at config 2.  bf16x3 mode runs them as three bf16 tensor-core
-  // GEMMs over hi/lo splits (gemm.h); fp32 mode as pedantic SGEMM.
-  const Bf16Pair sg0 = {(__nv_bfloat16*)(ws + l.sp_g0_hi), (__nv_bfloat16*)(ws + l.sp_g0_lo)};
-  const Bf16Pair sg1 = {(__nv_bfloat16*)(ws + l.sp_g1_hi), (__nv_bfloat16*)(ws + l.sp_g1_lo)};
-  const Bf16Pair sl = {(__nv_bfloat16*)(ws + l.sp_left_hi), (__nv_bfloat16*)(ws + l.sp_left_lo)};
-  // the forward call left the prenet rows of cell0_kernel stacked (hi ; hi ; lo) in sp_w3: block 0 = hi, block 2 = lo
-  const Bf16Pair sw = {(__nv_bfloat16*)(ws + l.sp_w3), (__nv_bfloat16*)(ws + l.sp_w3) + (size_t)2 * kPrenet * kGates};
-  if (tc) {
-    if ((rc = split_bf16_matrix(s, F(l.dG0), TB, kGates, kGates, sg0))) return rc;
-    if ((rc = split_bf16_matrix(s, F(l.dG1), TB, kGates, kGates, sg1))) return rc;
-  }
-  // dW[rows, 4096] = X[T*B, rows]^T dG[T*B, 4096]
-  auto wgrad = [&](const float* X, int rows, const float* dG, Bf16Pair sg, float* dW) -> int {
-    if (!tc) return gemm_rowmajor_ex(s, true, false, rows, kGates, (int)TB, X, rows, dG, kGates, dW, kGates, 0.f);
-    int r2 = split_bf16_matrix(s, X, TB, rows, rows, sl);
+  // ---- weight gradients: products over all steps ----
+  // dW[rows, 4096] = X[T*B, rows]^T dG[T*B, 4096]: ~1 TFLOP at config 2, bf16x3 on the hand-written tcgen05 kernel.  The
+  // gate-gradient operand is packed once per cell into its tile image (4096 image rows, K = T*B) and shared by the
+  // products of that cell; the activation operands take turns in one image buffer.
+  ScratchScope sc(s);
+  void *gimg = nullptr, *ximg = nullptr;
+  const int KbT = (int)((TB + 63) / 64);
+  const int xmax = D > kCell ? D : kCell;
+  if ((rc = sc.get(&gimg, tc_image_bytes(kGates, (int)TB, 256)))) return rc;
+  if ((rc = sc.get(&ximg, tc_image_bytes(xmax, (int)TB, 128)))) return rc;
+  auto wgrad = [&](const float* X, int rows, float* dW) -> int {
+    int r2 = tc_pack_f32(s, X, rows, true, rows, (int)TB, 128, KbT, ximg, 0, 0);
     if (r2) return r2;
-    return gemm_rowmajor_x3(s, true, false, rows, kGates, (int)TB, sl, rows, sg, kGates, dW, kGates, 0.f);
+    return tc_gemm_images(s, ximg, gimg, rows, kGates, (int)TB, dW, kGates, 0.f);
   };
   // cell 1: rows [m0 | h1_prev]
-  if ((rc = wgrad(F(l.m0), kCell, F(l.dG1), sg1, dw->cell1_kernel))) return rc;
-  if ((rc = wgrad(F(l.hz1), kCell, F(l.dG1), sg1, dw->cell1_kernel + (size_t)kCell * kGates))) return rc;
+  if ((rc = tc_pack_f32(s, F(l.dG1), kGates, true, kGates, (int)TB, 256, KbT, gimg, 0, 0))) return rc;
+  if ((rc = wgrad(F(l.m0), kCell, dw->cell1_kernel))) return rc;
+  if ((rc = wgrad(F(l.hz1), kCell, dw->cell1_kernel + (size_t)kCell * kGates))) return rc;
   colsum(s, F(l.dG1), dw->cell1_bias, TB, kGates, F(l.colsum_scratch));
   // cell 0: rows [prenet | ctx | ctx | h0_prev]
-  if ((rc = wgrad(F(l.pre), kPrenet, F(l.dG0), sg0, dw->cell0_kernel))) return rc;
+  if ((rc = tc_pack_f32(s, F(l.dG0), kGates, true, kGates, (int)TB, 256, KbT, gimg, 0, 0))) return rc;
+  if ((rc = wgrad(F(l.pre), kPrenet, dw->cell0_kernel))) return rc;
   float* dK0_ctx = dw->cell0_kernel + (size_t)kPrenet * kGates;
-  if ((rc = wgrad(F(l.ctx), D, F(l.dG0), sg0, dK0_ctx))) return rc;
+  if ((rc = wgrad(F(l.ctx), D, dK0_ctx))) return rc;
   copy_rows_kernel<<<ew_grid((size_t)D * kGates), 256, 0, s>>>(dK0_ctx, dK0_ctx + (size_t)D * kGates, (size_t)D * kGates);
-  if ((rc = wgrad(F(l.hz0), kCell, F(l.dG0), sg0, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates))) return rc;
+  if ((rc = wgrad(F(l.hz0), kCell, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates))) return rc;
   colsum(s, F(l.dG0), dw->cell0_bias, TB, kGates, F(l.colsum_scratch));
   // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
   if ((rc = gemm_rowmajor_ex(s, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
@@ -640,11 +640,7 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
                                            dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
   MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // prenet: d pre = dG0 @ K0[0:256]^T, then back through the two dense+relu+dropout layers
-  if (tc) {  // sw was filled with the prenet rows of cell0_kernel by the forward call (weights unchanged since)
-    if ((rc = gemm_rowmajor_x3(s, false, true, (int)TB, kPrenet, kGates, sg0, kGates, sw, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
-  } else {
-    if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
-  }
+  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
   prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre), F(l.pre), TB * kPrenet);
   if ((rc = gemm_rowmajor_ex(s, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
   colsum(s, F(l.dpre), dw->prenet1_bias, TB, kPrenet, F(l.colsum_scratch));

@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "decoder_layout.h"
 #include "gemm.h"
+#include "scratch_pool.h"
+#include "tc_gemm.h"
 
 struct DecFwdParams;  // decoder_fwd.cu
 int dec_fwd_persistent_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws,
@@ -189,6 +191,25 @@ static int decoder_fwd_free_running(const MsttsDecoderWeights* w, const MsttsDec
   return MSTTS_OK;
 }
 
+// [m1 | ctx_t] . Wp over all steps as ONE product: the two activation blocks are packed side by side along K
+static int dec_projection(cudaStream_t s, const float* m1, const float* ctx, const float* Wp, float* out, int TB, int D) {
+  const int K = kCell + D, NP = kMel + 1, Kb = (K + 63) / 64;
+  if (D % 64 != 0) {  // k-block aligned blocks only; otherwise two accumulating products
+    int rc = gemm_rowmajor(s, TB, NP, kCell, m1, kCell, Wp, NP, out, NP, 0.f);
+    if (rc) return rc;
+    return gemm_rowmajor(s, TB, NP, D, ctx, D, Wp + (size_t)kCell * NP, NP, out, NP, 1.f);
+  }
+  ScratchScope sc(s);
+  void *ai = nullptr, *bi = nullptr;
+  int rc;
+  if ((rc = sc.get(&ai, tc_image_bytes(TB, K, 128)))) return rc;
+  if ((rc = sc.get(&bi, tc_image_bytes(NP, K, 256)))) return rc;
+  if ((rc = tc_pack_f32(s, m1, kCell, false, TB, kCell, 128, Kb, ai, 0, 0))) return rc;
+  if ((rc = tc_pack_f32(s, ctx, D, false, TB, D, 128, Kb, ai, 0, kCell / 64))) return rc;
+  if ((rc = tc_pack_f32(s, Wp, NP, true, NP, K, 256, Kb, bi, 0, 0))) return rc;
+  return tc_gemm_images(s, ai, bi, TB, NP, K, out, NP, 0.f);
+}
+
 extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes,
                                  void* stream_) {
   int rc = check_io(w, io);
@@ -220,17 +241,8 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   rc = gemm_rowmajor(s, (int)TB, kPrenet, kPrenet, F(l.pre_h), kPrenet, w->prenet1_kernel, kPrenet, F(l.pre), kPrenet, 0.f);
   if (rc) return rc;
   prenet_act_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.pre), w->prenet1_bias, io->prenet_mask, 1, B, TB * kPrenet);
-  if (io->mode == MSTTS_MODE_BF16X3) {  // 54 GFLOP at config 2: tensor cores, bf16x3
-    // one bf16 GEMM with the three bf16x3 products folded into K (768): g0pre [TB,4096] is written once instead of being
-    // read-modify-written by three K=256 calls (420 MB each way)
-    __nv_bfloat16* a3 = (__nv_bfloat16*)(ws + l.sp_left_hi);  // [TB, 768] fits the [TB, 1024] split buffer
-    __nv_bfloat16* b3 = (__nv_bfloat16*)(ws + l.sp_w3);       // [768, 4096]
-    if ((rc = split_bf16_stack(s, F(l.pre), TB, kPrenet, kPrenet, a3, false))) return rc;
-    if ((rc = split_bf16_stack(s, w->cell0_kernel, kPrenet, kGates, kGates, b3, true))) return rc;
-    rc = gemm_rowmajor_bf16(s, (int)TB, kGates, 3 * kPrenet, a3, 3 * kPrenet, b3, kGates, F(l.g0pre), kGates, 0.f);
-  } else {
-    rc = gemm_rowmajor(s, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
-  }
+  // prenet rows of cell 0's kernel over all steps (54 GFLOP at config 2)
+  rc = gemm_rowmajor(s, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
   if (rc) return rc;
   // ---- zero initial state (AttentionWrapper.zero_state, Modules.py:112) and the barrier counter ----
   const size_t BC = (size_t)B * kCell * sizeof(float);
@@ -245,10 +257,7 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   rc = io->mode == MSTTS_MODE_BF16X3 ? dec_fwd_tc_entry(w, io, l, ws, s) : dec_fwd_persistent_entry(w, io, l, ws, s);
   if (rc) return rc;
   // ---- hoisted projection: [m1 | ctx] @ Wp + bp over all steps (Modules.py:292-294,309-321) ----
-  rc = gemm_rowmajor(s, (int)TB, kMel + 1, kCell, F(l.m1), kCell, w->proj_kernel, kMel + 1, F(l.proj_tm), kMel + 1, 0.f);
-  if (rc) return rc;
-  rc = gemm_rowmajor(s, (int)TB, kMel + 1, D, F(l.ctx) + (size_t)B * D, D, w->proj_kernel + (size_t)kCell * (kMel + 1),
-                     kMel + 1, F(l.proj_tm), kMel + 1, 1.f);
+  rc = dec_projection(s, F(l.m1), F(l.ctx) + (size_t)B * D, w->proj_kernel, F(l.proj_tm), (int)TB, D);
   if (rc) return rc;
   finish_outputs_kernel<<<ew_grid(TB * (kMel + 1 + Te)), 256, 0, s>>>(F(l.proj_tm), w->proj_bias, F(l.align_tm), io->linear,
                                                                     io->stop, io->align, B, T, Te);

@@ -53,11 +53,6 @@ struct DecLayout {
   size_t ximg_g1, ximg_g0, ximg_g_end;   // [64 k-tiles][8 KB] operand images of dG1_t / dG0_t
   size_t pm0, ph1, ph0, pctx;            // K-quarter partials [4][B][1024] / [4][B][D]
   size_t dbg_b;                          // [T][32] int64 phase stamps of the reverse kernel
-  // bf16 hi/lo copies of the operands of the big hoisted GEMMs (bf16x3 library GEMMs, gemm.h)
-  size_t sp_g0_hi, sp_g0_lo, sp_g1_hi, sp_g1_lo;   // [T*B,4096] dG0 / dG1
-  size_t sp_left_hi, sp_left_lo;                   // [T*B,1024] the activation operand of the current GEMM
-  size_t sp_w_hi, sp_w_lo;                         // [256,4096] prenet rows of cell0_kernel
-  size_t sp_w3;                                    // [768,4096] the same rows stacked (hi;hi;lo) for the one-call forward product
   size_t total;
 };
 
@@ -131,7 +126,6 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dpre_h = take(TB * kPrenet);
   l.colsum_scratch = take((size_t)64 * kGates);
   l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = off;
-  l.sp_g0_hi = l.sp_g0_lo = l.sp_g1_hi = l.sp_g1_lo = l.sp_left_hi = l.sp_left_lo = l.sp_w_hi = l.sp_w_lo = l.sp_w3 = off;
   if (mode == MSTTS_MODE_BF16X3) {
     auto take_bytes = [&](size_t nbytes) {
       size_t o = off;
@@ -147,15 +141,6 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
     l.ph0 = take((size_t)4 * B * kCell);
     l.pctx = take((size_t)4 * B * D);
     l.dbg_b = take_bytes((size_t)T * 32 * 8);
-    l.sp_g0_hi = take_bytes(TB * kGates * 2);
-    l.sp_g0_lo = take_bytes(TB * kGates * 2);
-    l.sp_g1_hi = take_bytes(TB * kGates * 2);
-    l.sp_g1_lo = take_bytes(TB * kGates * 2);
-    l.sp_left_hi = take_bytes(TB * kCell * 2);
-    l.sp_left_lo = take_bytes(TB * kCell * 2);
-    l.sp_w_hi = take_bytes((size_t)kPrenet * kGates * 2);
-    l.sp_w_lo = take_bytes((size_t)kPrenet * kGates * 2);
-    l.sp_w3 = take_bytes((size_t)3 * kPrenet * kGates * 2);
   }
   l.total = off;
   return l;

@@ -1,71 +1,20 @@
-// cuBLAS SGEMM wrapper (library GEMM for the plain, non-recurrent products; full fp32 math so the
-// parity mode stays at fp32 accuracy).  One handle per (thread, device).
-#include <cublas_v2.h>
-
+// Dense products outside the recurrent loops (hoisted prenet / projection / memory-layer products, weight gradients,
+// WaveGlow reverse pass, convolutions).  Row-major in, row-major out.  Every entry point runs on the hand-written tcgen05
+// kernel of tc_gemm.cu (bf16x3: operands split hi + lo, three partial products accumulated in fp32 in TMEM); this
+// library links no vendor GEMM.
 #include "gemm.h"
 
-static cublasHandle_t get_handle(int* rc) {
-  static thread_local cublasHandle_t handles[64] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
-    mstts_set_error("gemm: cudaGetDevice failed");
-    *rc = MSTTS_E_CUDA;
-    return nullptr;
-  }
-  if (!handles[dev]) {
-    cublasStatus_t st = cublasCreate(&handles[dev]);
-    if (st != CUBLAS_STATUS_SUCCESS) {
-      mstts_set_error("gemm: cublasCreate failed (%d)", (int)st);
-      *rc = MSTTS_E_CUDA;
-      handles[dev] = nullptr;
-      return nullptr;
-    }
-    cublasSetMathMode(handles[dev], CUBLAS_PEDANTIC_MATH);
-  }
-  *rc = MSTTS_OK;
-  return handles[dev];
-}
+#include "tc_gemm.h"
 
 int gemm_rowmajor_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
                      const float* B, int ldb, float* C, int ldc, float beta) {
-  int rc;
-  cublasHandle_t h = get_handle(&rc);
-  if (!h) return rc;
-  cublasStatus_t st = cublasSetStream(h, s);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
-    return MSTTS_E_CUDA;
-  }
-  const float alpha = 1.f;
-  // row-major C = op(A) op(B)  <=>  column-major C^T = op(B)^T op(A)^T
-  st = cublasSgemm(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A,
-                   lda, &beta, C, ldc);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSgemm(M=%d,N=%d,K=%d) failed (%d)", M, N, K, (int)st);
-    return MSTTS_E_CUDA;
-  }
-  return MSTTS_OK;
+  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, beta, 1);
 }
 
 int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
                           long long sA, const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta,
                           int batch) {
-  int rc;
-  cublasHandle_t h = get_handle(&rc);
-  if (!h) return rc;
-  cublasStatus_t st = cublasSetStream(h, s);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
-    return MSTTS_E_CUDA;
-  }
-  const float alpha = 1.f;
-  st = cublasSgemmStridedBatched(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha,
-                                 B, ldb, sB, A, lda, sA, &beta, C, ldc, sC, batch);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSgemmStridedBatched(M=%d,N=%d,K=%d,batch=%d) failed (%d)", M, N, K, batch, (int)st);
-    return MSTTS_E_CUDA;
-  }
-  return MSTTS_OK;
+  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, beta, batch);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -153,96 +102,10 @@ int split_bf16_matrix(cudaStream_t s, const float* src, size_t rows, size_t cols
 
 int gemm_rowmajor_x3(cudaStream_t s, bool transA, bool transB, int M, int N, int K, Bf16Pair A, int lda, Bf16Pair B, int ldb,
                      float* C, int ldc, float beta) {
-  int rc;
-  cublasHandle_t h = get_handle(&rc);
-  if (!h) return rc;
-  cublasStatus_t st = cublasSetStream(h, s);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
-    return MSTTS_E_CUDA;
-  }
-  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);  // the handle is pedantic for the fp32 path
-  const float one = 1.f;
-  const cublasOperation_t opB = transB ? CUBLAS_OP_T : CUBLAS_OP_N, opA = transA ? CUBLAS_OP_T : CUBLAS_OP_N;
-  // small terms first, the dominant hi.hi product last
-  const __nv_bfloat16* a_ops[3] = {A.lo, A.hi, A.hi};
-  const __nv_bfloat16* b_ops[3] = {B.hi, B.lo, B.hi};
-  for (int i = 0; i < 3; ++i) {
-    const float bt = i == 0 ? beta : 1.f;
-    st = cublasGemmEx(h, opB, opA, N, M, K, &one, b_ops[i], CUDA_R_16BF, ldb, a_ops[i], CUDA_R_16BF, lda, &bt, C, CUDA_R_32F, ldc,
-                      CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-    if (st != CUBLAS_STATUS_SUCCESS) {
-      cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-      mstts_set_error("gemm: cublasGemmEx bf16 (M=%d,N=%d,K=%d) failed (%d)", M, N, K, (int)st);
-      return MSTTS_E_CUDA;
-    }
-  }
-  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-  return MSTTS_OK;
+  return tc_gemm_hl(s, transA, transB, M, N, K, A.hi, A.lo, lda, 0, B.hi, B.lo, ldb, 0, C, ldc, 0, beta, 1);
 }
 
-int gemm_rowmajor_bf16(cudaStream_t s, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
-                       float* C, int ldc, float beta) {
-  int rc;
-  cublasHandle_t h = get_handle(&rc);
-  if (!h) return rc;
-  cublasStatus_t st = cublasSetStream(h, s);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
-    return MSTTS_E_CUDA;
-  }
-  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);  // the handle is pedantic for the fp32 path
-  const float one = 1.f;
-  st = cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, &one, B, CUDA_R_16BF, ldb, A, CUDA_R_16BF, lda, &beta, C, CUDA_R_32F, ldc,
-                    CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasGemmEx bf16 (M=%d,N=%d,K=%d) failed (%d)", M, N, K, (int)st);
-    return MSTTS_E_CUDA;
-  }
-  return MSTTS_OK;
-}
-
-int gemm_bf16_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B,
-                 int ldb, float* C, int ldc, float beta) {
-  int rc;
-  cublasHandle_t h = get_handle(&rc);
-  if (!h) return rc;
-  cublasStatus_t st = cublasSetStream(h, s);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
-    return MSTTS_E_CUDA;
-  }
-  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
-  const float one = 1.f;
-  st = cublasGemmEx(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &one, B, CUDA_R_16BF, ldb, A,
-                    CUDA_R_16BF, lda, &beta, C, CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasGemmEx bf16 (M=%d,N=%d,K=%d,tA=%d,tB=%d) failed (%d)", M, N, K, (int)transA, (int)transB, (int)st);
-    return MSTTS_E_CUDA;
-  }
-  return MSTTS_OK;
-}
-
-int gemm_bf16_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A, int lda, long long sA,
-                      const __nv_bfloat16* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch) {
-  int rc;
-  cublasHandle_t h = get_handle(&rc);
-  if (!h) return rc;
-  cublasStatus_t st = cublasSetStream(h, s);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasSetStream failed (%d)", (int)st);
-    return MSTTS_E_CUDA;
-  }
-  cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
-  const float one = 1.f;
-  st = cublasGemmStridedBatchedEx(h, transB ? CUBLAS_OP_T : CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &one, B, CUDA_R_16BF, ldb,
-                                  sB, A, CUDA_R_16BF, lda, sA, &beta, C, CUDA_R_32F, ldc, sC, batch, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
-  cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-  if (st != CUBLAS_STATUS_SUCCESS) {
-    mstts_set_error("gemm: cublasGemmStridedBatchedEx bf16 (M=%d,N=%d,K=%d,batch=%d) failed (%d)", M, N, K, batch, (int)st);
-    return MSTTS_E_CUDA;
-  }
-  return MSTTS_OK;
+int gemm_hl_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, Bf16Pair A, int lda, long long sA, Bf16Pair B, int ldb,
+                    long long sB, float* C, int ldc, long long sC, float beta, int batch) {
+  return tc_gemm_hl(s, transA, transB, M, N, K, A.hi, A.lo, lda, sA, B.hi, B.lo, ldb, sB, C, ldc, sC, beta, batch);
 }

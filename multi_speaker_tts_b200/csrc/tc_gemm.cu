@@ -16,28 +16,35 @@
 // Kernel: persistent, one CTA per SM, 320 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
 // thread, M = 128, N = 256, K = 16 per instruction), warps 2-9 = epilogue (two per TMEM lane quarter).  2-stage smem ring
 // (96 KB / stage), two 256-column accumulators in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <mutex>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "tc_gemm.h"
+#include "scratch_pool.h"
 
 constexpr int kGemmStages = 2;
 constexpr uint32_t kGemmATile = 128 * 64 * 2, kGemmBTile = 256 * 64 * 2;                 // one hi or lo tile
 constexpr uint32_t kGemmAChunk = 2 * kGemmATile, kGemmBChunk = 2 * kGemmBTile, kGemmStage = kGemmAChunk + kGemmBChunk;
 constexpr int kGemmThreads = 320;  // producer, MMA, 8 epilogue warps (two per TMEM lane quarter, half the columns each)
 
-// work item i -> (tile, K-block range, role): role 0 = whole tile, 1 = writer (first K half), 2 = finisher (second half)
-struct TcItem {
-  int tile, kb0, kb1, role, split;
-};
 __device__ __forceinline__ TcItem tc_item(const TcGemmParams& P, int i) {
   TcItem it;
-  if (i < P.n_full) {
+  if (P.ksplit > 1) {  // general front-end: (tile, K slice)
+    it.tile = i / P.ksplit; it.split = i - it.tile * P.ksplit; it.role = 0;
+    it.kb0 = (int)((long long)it.split * P.Kb / P.ksplit); it.kb1 = (int)((long long)(it.split + 1) * P.Kb / P.ksplit);
+  } else if (i < P.n_full) {
     it.tile = i; it.kb0 = 0; it.kb1 = P.Kb; it.role = 0; it.split = 0;
   } else {
     const int j = (i - P.n_full) >> 1, h = (i - P.n_full) & 1, kh = P.Kb >> 1;
     it.tile = P.n_full + j; it.split = j;
     it.kb0 = h ? kh : 0; it.kb1 = h ? P.Kb : kh; it.role = 1 + h;
   }
+  const int per = P.Mt * P.Nt;
+  it.b = it.tile / per;
+  const int rem = it.tile - it.b * per;
+  it.mt = rem / P.Nt;
+  it.nt = (rem % P.Nt + it.mt) % P.Nt;  // rotated: every CTA gets a mix of n-tiles
   return it;
 }
 
@@ -67,16 +74,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const int nitems = P.n_full + 2 * P.n_split;
+  const int nitems = P.ksplit > 1 ? P.n_full * P.ksplit : P.n_full + 2 * P.n_split;
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const TcItem w = tc_item(P, item);
-        const int mt = w.tile / P.Nt, nt = (w.tile % P.Nt + mt) % P.Nt;  // rotated: every CTA gets a mix of n-tiles
-        const uint8_t* a = P.A + (size_t)mt * P.Kb * kGemmAChunk;
-        const uint8_t* b = P.B + (size_t)nt * P.Kb * kGemmBChunk;
+        const uint8_t* a = P.A + (size_t)w.b * P.a_bstride + (size_t)w.mt * P.Kb * kGemmAChunk;
+        const uint8_t* b = P.B + (size_t)w.b * P.b_bstride + (size_t)w.nt * P.Kb * kGemmBChunk;
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
           const int s = it % kGemmStages, round = it / kGemmStages;
           if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
     int ti = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ti) {
       const TcItem w = tc_item(P, item);
-      const int mt = w.tile / P.Nt, nt = (w.tile % P.Nt + mt) % P.Nt;
+      const int mt = w.mt, nt = w.nt;
       const int ab = ti & 1, use = ti >> 1;
       ptx::mbar_wait(&acc_full[ab], use & 1);
       ptx::tc_fence_after();
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
           __syncwarp();
           part = P.partial + (size_t)w.split * 256 * 128 + q * 32 + lane;
         }
-        tc_gemm_epilogue<MODE>(P, ta, row, nt, half, part);
+        tc_gemm_epilogue<MODE>(P, ta, row, nt, half, part, w);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
 // ---- epilogues --------------------------------------------------------------------------------------------------
 // MODE 0: plain fp32 store C[row, nt*256 + c]
 template <>
-__device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part) {
+__device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part, const TcItem&) {
 #pragma unroll 1
   for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
     uint32_t v[32];
@@ -190,7 +196,7 @@ __device__ __forceinline__ void tc_gemm_epilogue<0>(const TcGemmParams& P, uint3
 
 // MODE 1 (WN gate): columns [0,128) = tanh pre-activations of channels 128 nt + c, [128,256) = the matching sigmoid ones
 template <>
-__device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part) {
+__device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part, const TcItem&) {
   const bool valid = row < P.M;  // rows are compact: m = n * T + t
 #pragma unroll 1
   for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
@@ -226,7 +232,7 @@ __device__ __forceinline__ void tc_gemm_epilogue<1>(const TcGemmParams& P, uint3
 // 32 columns per iteration; everything the chunk needs from memory (bias, the gated activation's hi/lo chunks or the old skip
 // values) is requested before the TMEM load is waited for, so the three latencies overlap instead of chaining.
 template <>
-__device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part) {
+__device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part, const TcItem&) {
   const int t = row % P.T;
   const bool valid = row < P.M;
   const size_t prow = (size_t)(row / P.T) * P.Tp + 128 + t;  // row of the padded fp32 layout the flow epilogue reads
@@ -288,6 +294,43 @@ __device__ __forceinline__ void tc_gemm_epilogue<2>(const TcGemmParams& P, uint3
         if (!P.first) o = make_float4(o.x + old[j].x, o.y + old[j].y, o.z + old[j].z, o.w + old[j].w);
         sp[j] = o;
       }
+    }
+  }
+}
+
+// MODE 3 (general front-end): C = acc + beta C over the valid M x N window, any leading dimension; or, for a K slice of a
+// split product, a plain store into the slice's slab
+template <>
+__device__ __forceinline__ void tc_gemm_epilogue<3>(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float*,
+                                                    const TcItem& w) {
+  const bool slab = P.ksplit > 1, valid = row < P.M;
+  const int Np = P.Nt * 256;
+  float* base = slab ? P.slabs + ((size_t)(w.split * P.batch + w.b) * P.Mt * 128 + row) * Np + nt * 256
+                     : P.C + (size_t)w.b * P.c_bstride + (size_t)row * P.ldc + nt * 256;
+  const int ncols = slab ? 256 : min(256, P.N - nt * 256);
+  const bool vec = slab || ((P.ldc & 3) == 0 && (P.c_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+  const float beta = slab ? 0.f : P.beta;
+#pragma unroll 1
+  for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(ta + c0, v);
+    ptx::tmem_wait_ld();
+    if (!valid || c0 >= ncols) continue;
+    float* dst = base + c0;
+    if (vec && c0 + 32 <= ncols) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        if (beta != 0.f) {
+          const float4 c = *reinterpret_cast<const float4*>(dst + j);
+          o = make_float4(o.x + beta * c.x, o.y + beta * c.y, o.z + beta * c.z, o.w + beta * c.w);
+        }
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < ncols) dst[j] = __uint_as_float(v[j]) + (beta != 0.f ? beta * dst[j] : 0.f);
     }
   }
 }
@@ -385,4 +428,233 @@ extern "C" int mstts_tc_gemm_tiled(const void* A_tiled, const void* B_tiled, int
                                    void* stream) {
   MSTTS_REQUIRE(A_tiled && B_tiled && C, MSTTS_E_INVALID, "tc_gemm_tiled: null pointer");
   return tc_gemm_plain((cudaStream_t)stream, A_tiled, B_tiled, C, M, N, K, ldc, scratch);
+}
+
+// =====================================================================================================================
+// General row-major front-ends: pack -> tc_gemm_kernel<3> -> (split-K reduce).  These carry every dense product outside
+// the persistent loops (hoisted decoder products and weight gradients, the WaveGlow reverse pass, the mel up-sampling
+// contraction, the encoder / postnet convolutions): the library links no vendor GEMM.
+// =====================================================================================================================
+struct PackSrc {
+  const void* hi;   // fp32 matrix (F32) or bf16 hi part
+  const void* lo;   // bf16 lo part (unused for F32)
+  int ld;
+  long long bstride;  // elements between batches
+  int trans;          // 0: element (r, k) at [r * ld + k];  1: at [k * ld + r]
+};
+
+// One warp packs 256 elements per pass.  Not transposed: 8 rows x 32 k (a lane reads 8 consecutive k of one row, the four
+// lanes of a row 128 contiguous bytes of fp32); transposed: 32 rows x 8 k (a lane reads 8 strided values, the warp 128
+// contiguous bytes per k).  Either way a lane owns one 16-byte chunk of the hi tile and one of the lo tile, and 8 lanes
+// with consecutive rows write one full 128-byte line.
+template <bool F32>
+__global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R, int K, int TR, int Kb, int Kb_total,
+                                                         uint8_t* __restrict__ dst, size_t dst_bstride, int batch, int vec) {
+  const int Rp = (R + TR - 1) / TR * TR, Kp = Kb * 64;
+  const long long per = (long long)Rp * Kp / 256, total = per * batch;
+  const int lane = threadIdx.x & 31;
+  const size_t tile_bytes = (size_t)TR * 128;
+  for (long long wu = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); wu < total;
+       wu += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int b = (int)(wu / per);
+    const long long u = wu - (long long)b * per;
+    int r, k0;
+    if (!S.trans) {
+      const int nrb = Rp >> 3;
+      r = (int)(u % nrb) * 8 + (lane & 7);
+      k0 = (int)(u / nrb) * 32 + (lane >> 3) * 8;
+    } else {
+      const int nrb = Rp >> 5;
+      r = (int)(u % nrb) * 32 + lane;
+      k0 = (int)(u / nrb) * 8;
+    }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    if (F32) {
+      const float* src = reinterpret_cast<const float*>(S.hi) + (long long)b * S.bstride;
+      float x[8];
+      if (!S.trans) {
+        const float* p = src + (size_t)r * S.ld + k0;
+        if (vec && r < R && k0 + 8 <= K) {
+          const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+          x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (r < R && k0 + j < K) ? p[j] : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (r < R && k0 + j < K) ? src[(size_t)(k0 + j) * S.ld + r] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = __float2bfloat16_rn(x[j]);
+        lo[j] = __float2bfloat16_rn(x[j] - __bfloat162float(hi[j]));
+      }
+    } else {
+      const __nv_bfloat16* sh = reinterpret_cast<const __nv_bfloat16*>(S.hi) + (long long)b * S.bstride;
+      const __nv_bfloat16* sl = reinterpret_cast<const __nv_bfloat16*>(S.lo) + (long long)b * S.bstride;
+      const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+      if (!S.trans) {
+        const size_t o = (size_t)r * S.ld + k0;
+        if (vec && r < R && k0 + 8 <= K) {
+          *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(sh + o);
+          *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(sl + o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool ok = r < R && k0 + j < K;
+            hi[j] = ok ? sh[o + j] : z;
+            lo[j] = ok ? sl[o + j] : z;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = r < R && k0 + j < K;
+          const size_t o = (size_t)(k0 + j) * S.ld + r;
+          hi[j] = ok ? sh[o] : z;
+          lo[j] = ok ? sl[o] : z;
+        }
+      }
+    }
+    uint8_t* d = dst + (size_t)b * dst_bstride + ((size_t)(r / TR) * Kb_total + (k0 >> 6)) * 2 * tile_bytes + (size_t)((r % TR) >> 3) * 1024 +
+                 (size_t)((k0 & 63) >> 3) * 128 + (size_t)(r & 7) * 16;
+    *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(d + tile_bytes) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// C_b[m, n] = beta C_b[m, n] + sum_s slab[s][b][m][n]   (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ slabs, int S, int batch, int M, int N, int Mp, int Np,
+                                                            float* __restrict__ C, int ldc, size_t c_bstride, float beta) {
+  const size_t total = (size_t)batch * M * N, slab = (size_t)batch * Mp * Np;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const size_t bm = i / N;
+    const int m = (int)(bm % M), b = (int)(bm / M);
+    const float* p = slabs + ((size_t)b * Mp + m) * Np + n;
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += p[(size_t)s * slab];
+    float* c = C + (size_t)b * c_bstride + (size_t)m * ldc + n;
+    *c = beta != 0.f ? acc + beta * *c : acc;
+  }
+}
+
+// K slices per tile: few-tile products with a long K (weight gradients over all decoder steps) would leave most SMs idle,
+// and a tile count just above a multiple of the SM count wastes most of the last round.  Cost model in k-block times
+// (12 MMAs, ~1 us): rounds x (slice length + pipeline fill) + the reduce pass.
+static int choose_ksplit(int ntiles, int Kb) {
+  int best = 1;
+  double best_cost = 1e30;
+  const int smax = Kb / 2 < 148 ? Kb / 2 : 148;
+  for (int S = 1; S <= (smax < 1 ? 1 : smax); ++S) {
+    const long long rounds = ((long long)ntiles * S + 147) / 148;
+    double cost = (double)rounds * ((double)Kb / S + 2.0);
+    if (S > 1) cost += 3.0 + 0.03 * S * ntiles;
+    if (cost < best_cost * 0.97) {  // prefer fewer slices unless the gain is real
+      best_cost = cost;
+      best = S;
+    }
+  }
+  return best;
+}
+
+static inline bool pack_vec_ok(const PackSrc& P, bool f32) {
+  const size_t al = f32 ? 4 : 8;  // elements per 16 bytes
+  return !P.trans && P.ld % al == 0 && P.bstride % (long long)al == 0 && ((uintptr_t)P.hi & 15) == 0 && (f32 || ((uintptr_t)P.lo & 15) == 0);
+}
+
+// pack `nb` matrices of R rows x K into images of Kb_total k-blocks, starting at tile row rt0 / k-block kb0 of each image
+template <bool F32>
+static int pack_launch(cudaStream_t s, const PackSrc& P, int R, int K, int TR, int Kb_total, uint8_t* img, size_t img_bstride, int nb, int rt0,
+                       int kb0) {
+  if (R <= 0 || K <= 0 || nb <= 0) return MSTTS_OK;
+  const int Kb = (K + 63) / 64;
+  const long long wu = (long long)((R + TR - 1) / TR * TR) * Kb * 64 / 256 * nb;
+  long long g = (wu + 7) / 8;
+  if (g > 148 * 16) g = 148 * 16;
+  // the kernel addresses chunks relative to an image whose k-block count is Kb_total: shift the base to (rt0, kb0)
+  uint8_t* base = img + ((size_t)rt0 * Kb_total + kb0) * 2 * (size_t)TR * 128;
+  pack_image_kernel<F32><<<(int)g, 256, 0, s>>>(P, R, K, TR, Kb, Kb_total, base, img_bstride, nb, pack_vec_ok(P, F32) ? 1 : 0);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0) {
+  MSTTS_REQUIRE(src && img && (TR == 128 || TR == 256) && kb0 + (K + 63) / 64 <= Kb_total, MSTTS_E_INVALID,
+                "tc_pack_f32: R=%d K=%d TR=%d kb0=%d Kb=%d", R, K, TR, kb0, Kb_total);
+  const PackSrc P{src, nullptr, ld, 0, trans ? 1 : 0};
+  return pack_launch<true>(s, P, R, K, TR, Kb_total, (uint8_t*)img, 0, 1, rt0, kb0);
+}
+
+// the product over packed images: C_b = A_b . B_b^T (+ beta C_b), Kb k-blocks
+static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, const uint8_t* bi, size_t b_bstride, int M, int N, int Kb,
+                         float* C, int ldc, long long sC, float beta, int batch) {
+  const int Mt = (M + 127) / 128, Nt = (N + 255) / 256;
+  const int ntiles = batch * Mt * Nt;
+  const int ksplit = choose_ksplit(ntiles, Kb);
+  ScratchScope scope(s);
+  float* slabs = nullptr;
+  int rc;
+  if (ksplit > 1 && (rc = scope.get((void**)&slabs, (size_t)ksplit * batch * Mt * 128 * Nt * 256 * sizeof(float)))) return rc;
+  TcGemmParams P;
+  memset(&P, 0, sizeof(P));
+  P.A = ai; P.B = bi; P.C = C; P.M = M; P.N = N; P.Mt = Mt; P.Nt = Nt; P.Kb = Kb; P.ldc = ldc;
+  P.batch = batch; P.ksplit = ksplit; P.a_bstride = a_bstride; P.b_bstride = b_bstride; P.c_bstride = (size_t)sC; P.beta = beta;
+  P.slabs = slabs; P.n_full = ntiles;
+  const size_t smem = tc_gemm_smem();
+  MSTTS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long nitems = (long long)ntiles * ksplit;
+  tc_gemm_kernel<3><<<(int)(nitems < 148 ? nitems : 148), kGemmThreads, smem, s>>>(P);
+  MSTTS_CUDA(cudaGetLastError());
+  if (ksplit > 1) {
+    size_t g = ((size_t)batch * M * N + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    splitk_reduce_kernel<<<(int)g, 256, 0, s>>>(slabs, ksplit, batch, M, N, Mt * 128, Nt * 256, C, ldc, (size_t)sC, beta);
+    MSTTS_CUDA(cudaGetLastError());
+  }
+  return MSTTS_OK;
+}
+
+int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta) {
+  if (M <= 0 || N <= 0) return MSTTS_OK;
+  MSTTS_REQUIRE(A_img && B_img && C && K >= 1, MSTTS_E_INVALID, "tc_gemm_images: null operand or K=%d", K);
+  return launch_images(s, (const uint8_t*)A_img, 0, (const uint8_t*)B_img, 0, M, N, (K + 63) / 64, C, ldc, 0, beta, 1);
+}
+
+template <bool F32>
+static int tc_gemm_general(cudaStream_t s, PackSrc A, PackSrc B, int M, int N, int K, float* C, int ldc, long long sC, float beta, int batch) {
+  if (M <= 0 || N <= 0 || batch <= 0) return MSTTS_OK;
+  MSTTS_REQUIRE(K >= 1 && A.hi && B.hi && C && (F32 || (A.lo && B.lo)), MSTTS_E_INVALID, "tc_gemm: M=%d N=%d K=%d batch=%d or null operand",
+                M, N, K, batch);
+  const int Mt = (M + 127) / 128, Nt = (N + 255) / 256, Kb = (K + 63) / 64;
+  const bool shareB = batch > 1 && B.bstride == 0;
+  const size_t a_img = (size_t)Mt * Kb * kGemmAChunk, b_img = (size_t)Nt * Kb * kGemmBChunk;
+  ScratchScope scope(s);
+  uint8_t *ai = nullptr, *bi = nullptr;
+  int rc;
+  if ((rc = scope.get((void**)&ai, a_img * batch))) return rc;
+  if ((rc = scope.get((void**)&bi, b_img * (shareB ? 1 : batch)))) return rc;
+  if ((rc = pack_launch<F32>(s, A, M, K, 128, Kb, ai, a_img, batch, 0, 0))) return rc;
+  if ((rc = pack_launch<F32>(s, B, N, K, 256, Kb, bi, b_img, shareB ? 1 : batch, 0, 0))) return rc;
+  return launch_images(s, ai, a_img, bi, shareB ? 0 : b_img, M, N, Kb, C, ldc, sC, beta, batch);
+}
+
+int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
+                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch) {
+  // image rows of the B operand are output columns: element (n, k) = B[k][n] unless B is given transposed
+  const PackSrc a{A, nullptr, lda, sA, transA ? 1 : 0}, b{B, nullptr, ldb, sB, transB ? 0 : 1};
+  return tc_gemm_general<true>(s, a, b, M, N, K, C, ldc, sC, beta, batch);
+}
+
+int tc_gemm_hl(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
+               int lda, long long sA, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, long long sB, float* C, int ldc,
+               long long sC, float beta, int batch) {
+  const PackSrc a{A_hi, A_lo, lda, sA, transA ? 1 : 0}, b{B_hi, B_lo, ldb, sB, transB ? 0 : 1};
+  return tc_gemm_general<false>(s, a, b, M, N, K, C, ldc, sC, beta, batch);
+}
+
+extern "C" int mstts_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, long long strideA, const float* B,
+                              int ldb, long long strideB, float* C, int ldc, long long strideC, float beta, int batch, void* stream) {
+  return tc_gemm_f32((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, beta, batch);
 }

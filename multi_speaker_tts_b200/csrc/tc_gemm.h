@@ -18,12 +18,27 @@ struct TcGemmParams {
   int n_full, n_split;
   float* partial;     // [n_split][256 cols][128 rows]
   unsigned* flags;    // [n_split], zeroed before the launch; the 8 writer warps each add 1
+  // general front-end (MODE 3, tc_gemm_f32 / tc_gemm_hl): `batch` independent products with byte strides between the operand
+  // images and an element stride between the outputs; N valid output columns (the last n-tile may be partial); C = acc +
+  // beta * C.  ksplit > 1: work item = (tile, K slice); slice s of batch b stores its fp32 accumulator to the slab
+  // slabs[(s * batch + b)][Mt * 128][Nt * 256] and a second kernel sums the slabs in a fixed order (deterministic split-K).
+  int batch, N, ksplit;
+  size_t a_bstride, b_bstride, c_bstride;
+  float beta;
+  float* slabs;
 };
 // scratch bytes a caller must provide for the split-K tail (partials + flags)
 constexpr size_t kTcGemmScratchBytes = (size_t)74 * 256 * 128 * 4 + 1024;
 
+// work item -> (tile, K-block range, role): role 0 = whole tile (or one K slice of a ksplit product), 1 = writer (first K
+// half of a tail tile), 2 = finisher (second half)
+struct TcItem {
+  int tile, kb0, kb1, role, split;
+  int b, mt, nt;  // batch index, m-tile, n-tile
+};
 template <int MODE>
-__device__ __forceinline__ void tc_gemm_epilogue(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part);
+__device__ __forceinline__ void tc_gemm_epilogue(const TcGemmParams& P, uint32_t ta, int row, int nt, int half, const float* part,
+                                                 const TcItem& w);
 
 // WaveGlow WN layer, fused epilogues (tc_gemm.cu):
 //   gate : A = im2col image [3 taps x 512 | mel 640] (K = 2176, hi and lo tiles), B columns permuted so that n-tile j
@@ -84,3 +99,24 @@ __device__ __forceinline__ void wn_store_hl(uint8_t* img, int m, int Kb, int k, 
 #endif
 
 int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, float* C, int M, int N, int K, int ldc, void* scratch);
+
+// ---- general row-major front-ends (every dense product outside the recurrent loops; no library GEMM anywhere) ----
+// C_b[M,N] = op(A_b) op(B_b) + beta C_b for b in [0, batch), all row-major; op(A) is M x K (A stored K x M when transA),
+// op(B) is K x N (B stored N x K when transB); sA / sB / sC are element strides between batches (sB = 0 shares B).
+// The operands are packed into the tensor core's tile images (hi + lo bf16, zero padded to 128 / 256 rows and 64-wide
+// k-blocks) by a pack kernel, multiplied as bf16x3 by tc_gemm_kernel<3>, and (for few-tile / long-K shapes) summed over
+// K slices by a deterministic reduce kernel.  Scratch comes from the library's stream-ordered pool (scratch_pool.h).
+int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
+                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch);
+// building blocks for call sites that share a packed operand between products or assemble one from several matrices:
+// an image holds ceil(R / TR) tile rows (TR = 128 for the A side, 256 for the B side) x Kb k-blocks of [hi | lo] tiles
+static inline size_t tc_image_bytes(int R, int K, int TR) { return (size_t)((R + TR - 1) / TR) * ((K + 63) / 64) * 2 * (size_t)TR * 128; }
+// pack R rows x K (element (r, k) at src[r * ld + k], or src[k * ld + r] when trans) at tile row rt0 / k-block kb0 of an
+// image with Kb_total k-blocks; rows up to the next multiple of TR and k up to the next multiple of 64 are zero filled
+int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0);
+// C[M,N] = A_img . B_img^T + beta C  (K = the images' k extent)
+int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta);
+// same with operands already split into bf16 hi + lo row-major matrices (hi and lo share the leading dimension / strides)
+int tc_gemm_hl(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
+               int lda, long long sA, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, long long sB, float* C, int ldc,
+               long long sC, float beta, int batch);

@@ -553,6 +553,19 @@ static WgSave wg_save_layout(int N, int T, size_t base) {
 
 static inline int flow_c(int f) { return 8 - 2 * (f / 4); }
 
+// Products over the K-stacked operands of the saved-activation path, on the hand-written kernel (the pack step reads the hi
+// and lo blocks of the stacked rows; the third block is a leftover of the folded-K library form and is ignored):
+//   activation rows  [hi (K) | lo (K) | hi (K)]            leading dimension 3K
+//   row-stacked W    [W_hi (K rows) ; W_hi ; W_lo] x N     (forward products)
+//   column-stacked W rows [hi (N) | hi (N) | lo (N)]       (transposed products, stored N_out x 3K)
+static int gemm_stacked(cudaStream_t s, int M, int N, int K, const __nv_bfloat16* A3, const __nv_bfloat16* B3, float* C, int ldc, float beta) {
+  return tc_gemm_hl(s, false, false, M, N, K, A3, A3 + K, 3 * K, 0, B3, B3 + (size_t)2 * K * N, N, 0, C, ldc, 0, beta, 1);
+}
+// C[M, N] (+)= A . W^T with A activation-stacked (width K) and W column-stacked [N][3K]
+static int gemm_stacked_nt(cudaStream_t s, int M, int N, int K, const __nv_bfloat16* A3, const __nv_bfloat16* Wc, float* C, int ldc, float beta) {
+  return tc_gemm_hl(s, false, true, M, N, K, A3, A3 + K, 3 * K, 0, Wc, Wc + 2 * K, 3 * K, 0, C, ldc, 0, beta, 1);
+}
+
 // Runs all 12 flows.  direction 0: training direction x -> z with sums[0] = sum(log_s), sums[1] = sum(z^2);
 // direction 1: synthesis z -> x (early_noise[2]: the two [N,T,2] noise tensors injected before flows 7 and 3 are run,
 // i.e. after undoing flows 8 and 4; inv_w then holds the INVERSE 1x1 kernels).
@@ -711,23 +724,17 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
       const __nv_bfloat16* Wtap = wq + wo;
       const __nv_bfloat16* Wc = wq + wo + (size_t)3 * K3 * 2 * kWnCh;
       // conditioning first (beta = 0), then the three taps accumulate: 4 GEMMs with K = 1920 / 1536
-      if ((rc = gemm_rowmajor_bf16(s, M, 2 * kWnCh, 3 * kWnMel, BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel, 3 * kWnMel, Wc, 2 * kWnCh, a_out,
-                                   2 * kWnCh, 0.f)))
-        return rc;
+      if ((rc = gemm_stacked(s, M, 2 * kWnCh, kWnMel, BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel, Wc, a_out, 2 * kWnCh, 0.f))) return rc;
       for (int k = 0; k < 3; ++k) {
         const long long shift = (long long)(kWgPad + (k - 1) * d) * K3;
-        if ((rc = gemm_rowmajor_bf16(s, M, 2 * kWnCh, K3, H3(f, i) + shift, K3, Wtap + (size_t)k * K3 * 2 * kWnCh, 2 * kWnCh, a_out,
-                                     2 * kWnCh, 1.f)))
-          return rc;
+        if ((rc = gemm_stacked(s, M, 2 * kWnCh, kWnCh, H3(f, i) + shift, Wtap + (size_t)k * K3 * 2 * kWnCh, a_out, 2 * kWnCh, 1.f))) return rc;
       }
       wo += (size_t)3 * K3 * 2 * kWnCh + (size_t)3 * kWnMel * 2 * kWnCh;
       gate_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(APRE(f, i), w->in_b[f][i], w->cond_b[f][i], FP(l.g), G3(f, i), N, T);
       const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
       // res/skip output: the scratch pre-activation buffer when the pre-activations are saved elsewhere, else in place
       float* rsbuf = save ? FP(l.rs) : FP(l.a);
-      if ((rc = gemm_rowmajor_bf16(s, M, rout, K3, G3(f, i) + (size_t)kWgPad * K3, K3, wq + wo, rout, rsbuf + (size_t)kWgPad * rout, rout,
-                                   0.f)))
-        return rc;
+      if ((rc = gemm_stacked(s, M, rout, kWnCh, G3(f, i) + (size_t)kWgPad * K3, wq + wo, rsbuf + (size_t)kWgPad * rout, rout, 0.f))) return rc;
       wo += (size_t)K3 * rout;
       resskip_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(rsbuf, w->res_b[f][i], FP(l.g), H3(f, i < kWnLayers - 1 ? i + 1 : i), SKIP(f), N,
                                                            T, i == 0, i == kWnLayers - 1);
@@ -1193,10 +1200,7 @@ static void colsum_valid(cudaStream_t s, const float* in, int ld, int C, float* 
 
 // dW = A_hi^T B_hi + A_lo^T B_hi + A_hi^T B_lo over `rows` rows of two stacked operands (block widths ka / nb)
 static int wgrad_x3(cudaStream_t s, int ka, int nb, int rows, const __nv_bfloat16* A3, int lda, const __nv_bfloat16* B3, int ldb, float* C) {
-  int rc;
-  if ((rc = gemm_bf16_ex(s, true, false, ka, nb, rows, A3, lda, B3, ldb, C, nb, 0.f))) return rc;
-  if ((rc = gemm_bf16_ex(s, true, false, ka, nb, rows, A3 + ka, lda, B3, ldb, C, nb, 1.f))) return rc;
-  return gemm_bf16_ex(s, true, false, ka, nb, rows, A3, lda, B3 + nb, ldb, C, nb, 1.f);
+  return tc_gemm_hl(s, true, false, ka, nb, rows, A3, A3 + ka, lda, 0, B3, B3 + nb, ldb, 0, C, nb, 0, 0.f, 1);
 }
 
 extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const MsttsWaveGlowGrads* dwt, const float* z, int N, int T,
@@ -1299,9 +1303,7 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
       wn_bwd_kernel<<<(R + 31) / 32, dim3(32, 32), 0, s>>>(w->res_v[f][i], w->res_g[f][i], FP(b.dw_eff), kWnCh, R, dwt->res_g[f][i],
                                                           dwt->res_v[f][i]);
       // d g = d rs W_res^T
-      if ((rc = gemm_bf16_ex(s, false, true, Mr, kWnCh, 3 * R, drs3 + (size_t)kWgPad * 3 * R, 3 * R, Wr_c, 3 * R,
-                             FP(b.dg) + (size_t)kWgPad * kWnCh, kWnCh, 0.f)))
-        return rc;
+      if ((rc = gemm_stacked_nt(s, Mr, kWnCh, R, drs3 + (size_t)kWgPad * 3 * R, Wr_c, FP(b.dg) + (size_t)kWgPad * kWnCh, kWnCh, 0.f))) return rc;
       gate_bwd_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(APRE(f, i), w->in_b[f][i], w->cond_b[f][i], FP(b.dg), dh_in, FP(b.da), BF(b.da3),
                                                             N, T);
       colsum_valid(s, FP(b.da), 2 * kWnCh, 2 * kWnCh, dwt->in_b[f][i], dwt->cond_b[f][i], FP(b.part), N, T);
@@ -1311,7 +1313,7 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
       wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->cond_v[f][i], w->cond_g[f][i], FP(b.dw_eff), kWnMel, 2 * kWnCh,
                                                                   dwt->cond_g[f][i], dwt->cond_v[f][i]);
       if (d_mel_nt640)
-        if ((rc = gemm_bf16_ex(s, false, true, Mr, kWnMel, A3, da3p, A3, Wc_c, A3, FP(b.dmel) + (size_t)kWgPad * kWnMel, kWnMel, 1.f))) return rc;
+        if ((rc = gemm_stacked_nt(s, Mr, kWnMel, 2 * kWnCh, da3p, Wc_c, FP(b.dmel) + (size_t)kWgPad * kWnMel, kWnMel, 1.f))) return rc;
       // dilated conv: d W_in[k] = h(t + (k-1) d)^T d a(t) ; d h(u) = sum_k d a(u - (k-1) d) W_in[k]^T
       for (int k = 0; k < 3; ++k) {
         const long long sh = (long long)(kWgPad + (k - 1) * d) * K3;
@@ -1322,8 +1324,8 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
       const int nxt = cur ^ 1;
       for (int k = 0; k < 3; ++k) {
         const long long sh = (long long)(kWgPad - (k - 1) * d) * A3;
-        if ((rc = gemm_bf16_ex(s, false, true, Mr, kWnCh, A3, BF(b.da3) + sh, A3, Wtap_c + (size_t)k * kWnCh * A3, A3,
-                               FP(b.dh[nxt]) + (size_t)kWgPad * kWnCh, kWnCh, k == 0 ? 0.f : 1.f)))
+        if ((rc = gemm_stacked_nt(s, Mr, kWnCh, 2 * kWnCh, BF(b.da3) + sh, Wtap_c + (size_t)k * kWnCh * A3, FP(b.dh[nxt]) + (size_t)kWgPad * kWnCh,
+                                  kWnCh, k == 0 ? 0.f : 1.f)))
           return rc;
       }
       cur = nxt;

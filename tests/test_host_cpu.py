@@ -60,3 +60,21 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_library_links_no_vendor_gemm():
+    """Every dense product runs on the hand-written tcgen05 kernel: the shared library must not depend on cuBLAS / cuBLASLt /
+    cuDNN / cuFFT (checked on the ELF's DT_NEEDED entries, no GPU required)."""
+    import subprocess
+    from multi_speaker_tts_b200 import _lib
+    out = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("readelf not available")
+    needed = re.findall(r"NEEDED.*\[(.*?)\]", out.stdout)
+    assert needed, out.stdout
+    for n in needed:
+        assert not re.search(r"cublas|cudnn|cufft|cutlass|nvjet", n, flags=re.I), needed
+    src = os.path.join(ROOT, "multi_speaker_tts_b200", "csrc")
+    for f in os.listdir(src):
+        txt = open(os.path.join(src, f)).read()
+        assert "cublas_v2.h" not in txt and "cublasLt" not in txt and "cudnn.h" not in txt, f
