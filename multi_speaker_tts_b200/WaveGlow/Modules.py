@@ -70,7 +70,7 @@ class WaveGlowParams(object):
         for r in self.raws:
             W = r['inv_w']
             c = W.shape[0]
-            det = torch.linalg.det(W.double() * 1e3)
+            det = torch.linalg.det((W * 1e3).double())   # scaled in fp32, then cast (Inv1x1.py:25)
             out.append(((torch.log(det + 1e-6)).float() - math.log(1e3) * c) * float(n_positions))
         return out
 
@@ -220,7 +220,7 @@ def Glow_Train_Backward(audio_Tensor, mel_Tensor, params, sigma=1.0, grads=None,
     for r, gr in zip(params.raws, grads):
         W = r['inv_w'].double()
         c = W.shape[0]
-        det3 = torch.linalg.det(W * 1e3)
+        det3 = torch.linalg.det((r['inv_w'] * 1e3).double())   # scaled in fp32, then cast (Inv1x1.py:25)
         log_dets.append(((torch.log(det3 + 1e-6)).float() - math.log(1e3) * c) * float(N * T))
         gr['inv_w'].add_((-(float(N * T) / n) * (det3 / (det3 + 1e-6)) * torch.linalg.inv(W).t()).float())
     losses = Glow_Loss(z, sums[0], log_dets, sums[1], sigma)

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mstts_b200.h"
@@ -49,6 +50,20 @@ constexpr int kDecGrid = 128;
 constexpr int kDecCluster = 4;
 constexpr int kDecThreads = 256;
 constexpr int kUnitsPerCta = kCell / kDecGrid;  // 8
+
+// launch attribute shared by the four persistent decoder launchers (grid barrier inside): cudaLaunchAttributeCooperative,
+// valid together with the compile-time cluster dimensions.  MSTTS_NO_COOP=1 in the environment drops it (A/B measurements).
+static inline void dec_cooperative_attr(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr) {
+  static const bool off = [] {
+    const char* e = getenv("MSTTS_NO_COOP");
+    return e && e[0] == '1';
+  }();
+  if (off) return;
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
 
 // ---- device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -725,6 +725,10 @@ static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t sm
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  // cooperative launch: the runtime gang-schedules the whole grid (all 32 clusters resident before any CTA starts), so the
+  // grid barrier cannot deadlock behind a concurrent kernel that holds SMs (an NCCL kernel on another stream, MPS)
+  cudaLaunchAttribute coop_attr[1];
+  dec_cooperative_attr(&cfg, coop_attr);
   int nclusters = 0;
   MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_tc_kernel<NS>, &cfg));
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,

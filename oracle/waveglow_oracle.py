@@ -73,7 +73,7 @@ def inv1x1(x, W, reverse=False):
     if reverse:
         return x @ torch.linalg.inv(W)
     c = W.shape[0]
-    det = torch.linalg.det(W.double() * 1e3)
+    det = torch.linalg.det((W * 1e3).double())   # Inv1x1.py:25: the scaling happens in the kernel's dtype, then the cast
     logdet = (torch.log(det + 1e-6)).float() - math.log(1e3) * c
     logdet = logdet * float(x.shape[0] * x.shape[1])  # tf.shape(inputs)[0:3] of the [N,1,T,c] tensor = N*1*T
     return x @ W, logdet

@@ -3,10 +3,13 @@ against the domain's size-independent properties.
 
 The oracle finishes these sizes in seconds (decoder forward 801 steps x 32 rows: ~5 s on the GPU box's host cores;
 WaveGlow N=8 x 16000: ~10 s; STFT 64 x 10 s: ~1 s), so the comparison is direct, not sampled.  Gates as in the
-small-shape tests (north_star): outputs L_inf < 1e-3, stop decision bit-exact, alignment argmax bit-exact.  At
-25 632 (row, step) pairs the oracle itself holds a handful of attention rows whose two largest entries differ by less
-than fp32 rounding (measured: 10 pairs below 1e-6, 90 below 1e-5): the argmax gate is exact everywhere the oracle's own
-top-2 margin exceeds 1e-5, and the near-tie positions are counted and bounded instead."""
+small-shape tests (north_star): outputs L_inf < 1e-3, stop decision bit-exact, alignment argmax bit-exact.
+
+The bit-exact reference is the oracle run in fp64 (its own rounding cannot decide a comparison).  At 25 632 (row, step)
+pairs a handful of attention rows hold two largest entries closer than fp32 rounding; the fp32 run of the SAME oracle code
+shows which ones (where fp32 and fp64 oracles disagree, "the reference in fp32" is itself undecided).  Gate: the CUDA argmax /
+stop decision must equal the fp64 oracle at EVERY position where the two oracle precisions agree, and the total number of
+positions where CUDA differs from the fp64 oracle is printed and hard-bounded by a constant (expected 0)."""
 import numpy as np
 import pytest
 import torch
@@ -15,6 +18,7 @@ from multi_speaker_tts_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+MAX_FLIPS = 3     # hard bound on decisions that differ from the fp64 oracle over all 25 632 positions (expected: 0)
 B, TE, L = 32, 128, 800
 
 
@@ -44,24 +48,30 @@ def test_decoder_config2_forward_vs_oracle(cuda_dev, ragged):
     with torch.no_grad():
         rl, rs, ra = O.decoder_forward(w, b['memory'], b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'],
                                        b['zone_mask'])
-    top2 = ra.topk(2, -1).values
-    clear = (top2[..., 0] - top2[..., 1]) > 1e-5          # oracle margin above its own fp32 rounding noise
-    stop_clear = rs.abs() > 1e-5
+        w64 = {k: v.double() for k, v in w.items()}
+        rl64, rs64, ra64 = O.decoder_forward(w64, b['memory'].double(), b['text_len'], b['mel'].double(), b['mel_len'],
+                                             b['prenet_mask'], b['zone_mask'])
+    arg64, stop64 = ra64.argmax(-1), rs64 >= 0
+    agree = ra.argmax(-1) == arg64                        # positions the oracle decides the same way in fp32 and fp64
+    stop_agree = (rs >= 0) == stop64
+    print("oracle fp32 vs fp64: argmax undecided at %d of %d positions, stop at %d" %
+          (int((~agree).sum()), agree.numel(), int((~stop_agree).sum())))
+    assert int((~agree).sum()) <= MAX_FLIPS and int((~stop_agree).sum()) <= MAX_FLIPS, "the oracle itself is unstable"
     for mode in ("bf16x3", "fp32"):
         _, _, lin, stop, align, _ = _gpu_forward(w, b, cuda_dev, mode)
         gl, gs, ga = lin.cpu(), stop.cpu(), align.cpu()
         assert gl.shape == rl.shape == (B, L + 1, 80) and ga.shape == ra.shape == (B, L + 1, TE)
         assert torch.isfinite(gl).all() and torch.isfinite(gs).all() and torch.isfinite(ga).all()
-        e = [(gl - rl).abs().max().item(), (gs - rs).abs().max().item(), (ga - ra).abs().max().item()]
-        same = ga.argmax(-1) == ra.argmax(-1)
-        near_tie_flips = int((~same & ~clear).sum())
-        print("%s ragged=%s: Linf linear %.3e stop %.3e align %.3e; argmax flips at oracle near-ties: %d of %d near-ties"
-              % (mode, ragged, e[0], e[1], e[2], near_tie_flips, int((~clear).sum())))
+        e = [(gl - rl64).abs().max().item(), (gs - rs64).abs().max().item(), (ga - ra64).abs().max().item()]
+        same = ga.argmax(-1) == arg64
+        stop_same = (gs >= 0) == stop64
+        flips, stop_flips = int((~same).sum()), int((~stop_same).sum())
+        print("%s ragged=%s: Linf vs fp64 oracle linear %.3e stop %.3e align %.3e; argmax flips %d, stop flips %d (of %d)"
+              % (mode, ragged, e[0], e[1], e[2], flips, stop_flips, same.numel()))
         assert max(e) < TOL
-        assert bool(same[clear].all()), "alignment argmax differs where the oracle's margin is > 1e-5"
-        assert near_tie_flips <= int((~clear).sum())
-        assert torch.equal((gs >= 0)[stop_clear], (rs >= 0)[stop_clear]), "stop decision differs"
-        assert int(((gs >= 0) != (rs >= 0)).sum()) <= int((~stop_clear).sum())
+        assert bool(same[agree].all()), "alignment argmax differs from the fp64 oracle where the fp32 oracle agrees with it"
+        assert bool(stop_same[stop_agree].all()), "stop decision differs from the fp64 oracle where the fp32 oracle agrees with it"
+        assert flips <= MAX_FLIPS and stop_flips <= MAX_FLIPS, (flips, stop_flips)
         # properties: rows sum to 1, exactly 0 beyond text_len
         assert (ga.sum(-1) - 1).abs().max() < 1e-5
         beyond = torch.arange(TE)[None, None, :] >= b['text_len'][:, None, None]
