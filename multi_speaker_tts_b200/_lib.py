@@ -93,7 +93,7 @@ EXPORTS = {
     "mstts_tc_gemm_tiled": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, _fp, _fp]),
     "mstts_tc_gemm_test": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),
     "mstts_gemm_f32": (C.c_int, [C.c_int] * 5 + [_fp, C.c_int, C.c_longlong, _fp, C.c_int, C.c_longlong, _fp, C.c_int, C.c_longlong,
-                                 C.c_float, C.c_int, _fp]),
+                                 C.c_float, C.c_int, C.c_int, _fp]),
     "mstts_release_scratch": (C.c_int, []),
     "mstts_conv1d_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "mstts_conv1d_fwd": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_size_t, _fp]),

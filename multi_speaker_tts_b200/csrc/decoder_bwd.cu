@@ -644,7 +644,7 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
                                            dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
   MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // prenet: d pre = dG0 @ K0[0:256]^T, then back through the two dense+relu+dropout layers
-  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_fast(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
   prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre), F(l.pre), TB * kPrenet);
   if ((rc = gemm_rowmajor_ex(s, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
   colsum(s, F(l.dpre), dw->prenet1_bias, TB, kPrenet, F(l.colsum_scratch));

@@ -1,5 +1,7 @@
 // Dense products that sit outside the recurrent loops (hoisted prenet / projection / weight-gradient products).
-// Row-major fp32 in, row-major fp32 out; computed as bf16x3 on the hand-written tcgen05 kernel (tc_gemm.h).
+// Row-major fp32 in, row-major fp32 out, on the hand-written tcgen05 kernel (tc_gemm.h).  gemm_rowmajor* keep fp32-SGEMM
+// accuracy (3-way bf16 split, six partial products: the narrow layers whose gradients are tiny against their terms);
+// gemm_rowmajor_fast / _batched_fast are bf16x3 (2-way split, three products) for the large products.
 #pragma once
 #include "common.cuh"
 
@@ -13,6 +15,11 @@ static inline int gemm_rowmajor(cudaStream_t s, int M, int N, int K, const float
   return gemm_rowmajor_ex(s, false, false, M, N, K, A, lda, B, ldb, C, ldc, beta);
 }
 
+
+int gemm_rowmajor_fast(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                       float* C, int ldc, float beta);
+int gemm_rowmajor_batched_fast(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA,
+                               const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch);
 
 // batched: for i in [0,batch): C_i = op(A_i) op(B_i) + beta C_i with element strides sA/sB/sC between batches
 int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,

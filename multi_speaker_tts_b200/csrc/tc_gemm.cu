@@ -449,11 +449,13 @@ struct PackSrc {
 // with consecutive rows write one full 128-byte line.
 template <bool F32>
 __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R, int K, int TR, int Kb, int Kb_total,
-                                                         uint8_t* __restrict__ dst, size_t dst_bstride, int batch, int vec) {
+                                                         uint8_t* __restrict__ dst, size_t dst_bstride, int batch, int vec,
+                                                         int precise, int b_side) {
   const int Rp = (R + TR - 1) / TR * TR, Kp = Kb * 64;
   const long long per = (long long)Rp * Kp / 256, total = per * batch;
   const int lane = threadIdx.x & 31;
   const size_t tile_bytes = (size_t)TR * 128;
+  const int Kb_img = Kb_total * (precise ? 4 : 1);  // k-blocks per tile row of the image
   for (long long wu = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); wu < total;
        wu += (long long)gridDim.x * (blockDim.x >> 5)) {
     const int b = (int)(wu / per);
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
       r = (int)(u % nrb) * 32 + lane;
       k0 = (int)(u / nrb) * 8;
     }
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    __align__(16) __nv_bfloat16 hi[8], lo[8], lo2[8];
     if (F32) {
       const float* src = reinterpret_cast<const float*>(S.hi) + (long long)b * S.bstride;
       float x[8];
@@ -488,7 +490,9 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         hi[j] = __float2bfloat16_rn(x[j]);
-        lo[j] = __float2bfloat16_rn(x[j] - __bfloat162float(hi[j]));
+        const float r1 = x[j] - __bfloat162float(hi[j]);
+        lo[j] = __float2bfloat16_rn(r1);
+        lo2[j] = __float2bfloat16_rn(r1 - __bfloat162float(lo[j]));
       }
     } else {
       const __nv_bfloat16* sh = reinterpret_cast<const __nv_bfloat16*>(S.hi) + (long long)b * S.bstride;
@@ -517,10 +521,24 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
         }
       }
     }
-    uint8_t* d = dst + (size_t)b * dst_bstride + ((size_t)(r / TR) * Kb_total + (k0 >> 6)) * 2 * tile_bytes + (size_t)((r % TR) >> 3) * 1024 +
+    uint8_t* d = dst + (size_t)b * dst_bstride + ((size_t)(r / TR) * Kb_img + (k0 >> 6)) * 2 * tile_bytes + (size_t)((r % TR) >> 3) * 1024 +
                  (size_t)((k0 & 63) >> 3) * 128 + (size_t)(r & 7) * 16;
-    *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(d + tile_bytes) = *reinterpret_cast<const uint4*>(lo);
+    const uint4 h4 = *reinterpret_cast<const uint4*>(hi), m4 = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(d) = h4;
+    *reinterpret_cast<uint4*>(d + tile_bytes) = m4;
+    if (F32 && precise) {
+      // segments 1-3 of the 3-way split (x = h + m + l, 24 mantissa bits), Kb_total k-blocks apart:
+      //   seg 0: (h, m) x (h, m) -> hh + mh + hm     seg 1: (m, 0) x (m, 0) -> mm
+      //   seg 2: A (h, 0) x B (l, 0) -> hl           seg 3: A (l, 0) x B (h, 0) -> lh
+      const uint4 l4 = *reinterpret_cast<const uint4*>(lo2), z4 = make_uint4(0u, 0u, 0u, 0u);
+      const size_t seg = (size_t)Kb_total * 2 * tile_bytes;
+      *reinterpret_cast<uint4*>(d + seg) = m4;
+      *reinterpret_cast<uint4*>(d + seg + tile_bytes) = z4;
+      *reinterpret_cast<uint4*>(d + 2 * seg) = b_side ? l4 : h4;
+      *reinterpret_cast<uint4*>(d + 2 * seg + tile_bytes) = z4;
+      *reinterpret_cast<uint4*>(d + 3 * seg) = b_side ? h4 : l4;
+      *reinterpret_cast<uint4*>(d + 3 * seg + tile_bytes) = z4;
+    }
   }
 }
 
@@ -564,30 +582,34 @@ static inline bool pack_vec_ok(const PackSrc& P, bool f32) {
   return !P.trans && P.ld % al == 0 && P.bstride % (long long)al == 0 && ((uintptr_t)P.hi & 15) == 0 && (f32 || ((uintptr_t)P.lo & 15) == 0);
 }
 
-// pack `nb` matrices of R rows x K into images of Kb_total k-blocks, starting at tile row rt0 / k-block kb0 of each image
+// pack `nb` matrices of R rows x K into images of Kb_total source k-blocks (x 4 segments when precise), starting at tile
+// row rt0 / k-block kb0 of each image
 template <bool F32>
 static int pack_launch(cudaStream_t s, const PackSrc& P, int R, int K, int TR, int Kb_total, uint8_t* img, size_t img_bstride, int nb, int rt0,
-                       int kb0) {
+                       int kb0, bool precise, bool b_side) {
   if (R <= 0 || K <= 0 || nb <= 0) return MSTTS_OK;
   const int Kb = (K + 63) / 64;
   const long long wu = (long long)((R + TR - 1) / TR * TR) * Kb * 64 / 256 * nb;
   long long g = (wu + 7) / 8;
   if (g > 148 * 16) g = 148 * 16;
-  // the kernel addresses chunks relative to an image whose k-block count is Kb_total: shift the base to (rt0, kb0)
-  uint8_t* base = img + ((size_t)rt0 * Kb_total + kb0) * 2 * (size_t)TR * 128;
-  pack_image_kernel<F32><<<(int)g, 256, 0, s>>>(P, R, K, TR, Kb, Kb_total, base, img_bstride, nb, pack_vec_ok(P, F32) ? 1 : 0);
+  // the kernel addresses chunks relative to an image whose tile rows hold Kb_img k-blocks: shift the base to (rt0, kb0)
+  const int Kb_img = Kb_total * (precise ? 4 : 1);
+  uint8_t* base = img + ((size_t)rt0 * Kb_img + kb0) * 2 * (size_t)TR * 128;
+  pack_image_kernel<F32><<<(int)g, 256, 0, s>>>(P, R, K, TR, Kb, Kb_total, base, img_bstride, nb, pack_vec_ok(P, F32) ? 1 : 0, precise ? 1 : 0,
+                                                b_side ? 1 : 0);
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }
 
-int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0) {
+int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0,
+                bool precise) {
   MSTTS_REQUIRE(src && img && (TR == 128 || TR == 256) && kb0 + (K + 63) / 64 <= Kb_total, MSTTS_E_INVALID,
                 "tc_pack_f32: R=%d K=%d TR=%d kb0=%d Kb=%d", R, K, TR, kb0, Kb_total);
   const PackSrc P{src, nullptr, ld, 0, trans ? 1 : 0};
-  return pack_launch<true>(s, P, R, K, TR, Kb_total, (uint8_t*)img, 0, 1, rt0, kb0);
+  return pack_launch<true>(s, P, R, K, TR, Kb_total, (uint8_t*)img, 0, 1, rt0, kb0, precise, TR == 256);
 }
 
-// the product over packed images: C_b = A_b . B_b^T (+ beta C_b), Kb k-blocks
+// the product over packed images: C_b = A_b . B_b^T (+ beta C_b), Kb image k-blocks
 static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, const uint8_t* bi, size_t b_bstride, int M, int N, int Kb,
                          float* C, int ldc, long long sC, float beta, int batch) {
   const int Mt = (M + 127) / 128, Nt = (N + 255) / 256;
@@ -616,45 +638,48 @@ static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, co
   return MSTTS_OK;
 }
 
-int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta) {
+int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta, bool precise) {
   if (M <= 0 || N <= 0) return MSTTS_OK;
   MSTTS_REQUIRE(A_img && B_img && C && K >= 1, MSTTS_E_INVALID, "tc_gemm_images: null operand or K=%d", K);
-  return launch_images(s, (const uint8_t*)A_img, 0, (const uint8_t*)B_img, 0, M, N, (K + 63) / 64, C, ldc, 0, beta, 1);
+  return launch_images(s, (const uint8_t*)A_img, 0, (const uint8_t*)B_img, 0, M, N, (K + 63) / 64 * (precise ? 4 : 1), C, ldc, 0, beta, 1);
 }
 
 template <bool F32>
-static int tc_gemm_general(cudaStream_t s, PackSrc A, PackSrc B, int M, int N, int K, float* C, int ldc, long long sC, float beta, int batch) {
+static int tc_gemm_general(cudaStream_t s, PackSrc A, PackSrc B, int M, int N, int K, float* C, int ldc, long long sC, float beta, int batch,
+                           bool precise) {
   if (M <= 0 || N <= 0 || batch <= 0) return MSTTS_OK;
   MSTTS_REQUIRE(K >= 1 && A.hi && B.hi && C && (F32 || (A.lo && B.lo)), MSTTS_E_INVALID, "tc_gemm: M=%d N=%d K=%d batch=%d or null operand",
                 M, N, K, batch);
-  const int Mt = (M + 127) / 128, Nt = (N + 255) / 256, Kb = (K + 63) / 64;
+  const int Mt = (M + 127) / 128, Nt = (N + 255) / 256, Kb = (K + 63) / 64, segs = precise ? 4 : 1;
   const bool shareB = batch > 1 && B.bstride == 0;
-  const size_t a_img = (size_t)Mt * Kb * kGemmAChunk, b_img = (size_t)Nt * Kb * kGemmBChunk;
+  const size_t a_img = (size_t)Mt * Kb * segs * kGemmAChunk, b_img = (size_t)Nt * Kb * segs * kGemmBChunk;
   ScratchScope scope(s);
   uint8_t *ai = nullptr, *bi = nullptr;
   int rc;
   if ((rc = scope.get((void**)&ai, a_img * batch))) return rc;
   if ((rc = scope.get((void**)&bi, b_img * (shareB ? 1 : batch)))) return rc;
-  if ((rc = pack_launch<F32>(s, A, M, K, 128, Kb, ai, a_img, batch, 0, 0))) return rc;
-  if ((rc = pack_launch<F32>(s, B, N, K, 256, Kb, bi, b_img, shareB ? 1 : batch, 0, 0))) return rc;
-  return launch_images(s, ai, a_img, bi, shareB ? 0 : b_img, M, N, Kb, C, ldc, sC, beta, batch);
+  if ((rc = pack_launch<F32>(s, A, M, K, 128, Kb, ai, a_img, batch, 0, 0, precise, false))) return rc;
+  if ((rc = pack_launch<F32>(s, B, N, K, 256, Kb, bi, b_img, shareB ? 1 : batch, 0, 0, precise, true))) return rc;
+  return launch_images(s, ai, a_img, bi, shareB ? 0 : b_img, M, N, Kb * segs, C, ldc, sC, beta, batch);
 }
 
 int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
-                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch) {
+                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, bool precise) {
   // image rows of the B operand are output columns: element (n, k) = B[k][n] unless B is given transposed
   const PackSrc a{A, nullptr, lda, sA, transA ? 1 : 0}, b{B, nullptr, ldb, sB, transB ? 0 : 1};
-  return tc_gemm_general<true>(s, a, b, M, N, K, C, ldc, sC, beta, batch);
+  return tc_gemm_general<true>(s, a, b, M, N, K, C, ldc, sC, beta, batch, precise);
 }
 
 int tc_gemm_hl(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                int lda, long long sA, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, long long sB, float* C, int ldc,
                long long sC, float beta, int batch) {
   const PackSrc a{A_hi, A_lo, lda, sA, transA ? 1 : 0}, b{B_hi, B_lo, ldb, sB, transB ? 0 : 1};
-  return tc_gemm_general<false>(s, a, b, M, N, K, C, ldc, sC, beta, batch);
+  return tc_gemm_general<false>(s, a, b, M, N, K, C, ldc, sC, beta, batch, false);
 }
 
 extern "C" int mstts_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, long long strideA, const float* B,
-                              int ldb, long long strideB, float* C, int ldc, long long strideC, float beta, int batch, void* stream) {
-  return tc_gemm_f32((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, beta, batch);
+                              int ldb, long long strideB, float* C, int ldc, long long strideC, float beta, int batch, int precise,
+                              void* stream) {
+  return tc_gemm_f32((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, beta, batch,
+                     precise != 0);
 }

@@ -106,16 +106,23 @@ int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, floa
 // The operands are packed into the tensor core's tile images (hi + lo bf16, zero padded to 128 / 256 rows and 64-wide
 // k-blocks) by a pack kernel, multiplied as bf16x3 by tc_gemm_kernel<3>, and (for few-tile / long-K shapes) summed over
 // K slices by a deterministic reduce kernel.  Scratch comes from the library's stream-ordered pool (scratch_pool.h).
+// precise: the fp32 operands are split THREE ways (h + m + l, 24 mantissa bits) and six partial products are accumulated
+// (hh + hm + mh + mm + hl + lh, as four K segments of the same kernel): fp32-SGEMM accuracy at 4x the tensor work -- for the
+// products whose fp32 result is small against the magnitude of its terms (weight gradients of the narrow layers).
 int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
-                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch);
+                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, bool precise);
 // building blocks for call sites that share a packed operand between products or assemble one from several matrices:
 // an image holds ceil(R / TR) tile rows (TR = 128 for the A side, 256 for the B side) x Kb k-blocks of [hi | lo] tiles
-static inline size_t tc_image_bytes(int R, int K, int TR) { return (size_t)((R + TR - 1) / TR) * ((K + 63) / 64) * 2 * (size_t)TR * 128; }
+static inline size_t tc_image_bytes(int R, int K, int TR, bool precise = false) {
+  return (size_t)((R + TR - 1) / TR) * ((K + 63) / 64) * (precise ? 4 : 1) * 2 * (size_t)TR * 128;
+}
 // pack R rows x K (element (r, k) at src[r * ld + k], or src[k * ld + r] when trans) at tile row rt0 / k-block kb0 of an
 // image with Kb_total k-blocks; rows up to the next multiple of TR and k up to the next multiple of 64 are zero filled
-int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0);
+int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0,
+                bool precise = false);
 // C[M,N] = A_img . B_img^T + beta C  (K = the images' k extent)
-int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta);
+int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta,
+                   bool precise = false);
 // same with operands already split into bf16 hi + lo row-major matrices (hi and lo share the leading dimension / strides)
 int tc_gemm_hl(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                int lda, long long sA, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, long long sB, float* C, int ldc,

@@ -25,7 +25,7 @@ def test_tacotron2_save_restore_next_step_identical(cuda_dev, tmp_path):
         assert os.path.basename(path) == 'CHECKPOINT-2.pt'          # Saver.save(..., global_step = Global_Step + 1)
         ra = a.Run_Train_Step(feeds[2])
         # a fresh model with a different seed picks the checkpoint up and must reproduce step 3 bit for bit
-        b = M.Tacotron2(is_Training=True, device=cuda_dev, seed=99, feeder=Feeder.Feeder(is_Training=True, synthetic=True, synthetic_shape=shape))
+        b = M.Tacotron2(is_Training=True, device=cuda_dev, seed=99, feeder=a.feeder)   # feed dicts are keyed by the feeder's placeholders
         b.seed = a.seed                                              # the dropout / zoneout stream is keyed by (seed, step)
         b.Restore()
         assert b.global_Step == 2
@@ -55,7 +55,7 @@ def test_waveglow_save_restore_keeps_adam_slots(cuda_dev, tmp_path):
         path = a.Save()
         assert os.path.basename(path) == 'CHECKPOINT-2.pt'
         ra = a.Run_Train_Step(feeds[2])
-        b = WG.WaveGlow(device=cuda_dev, seed=77, feeder=WG.Feeder(seed=5, batch_size=1, signal_length=2048))
+        b = WG.WaveGlow(device=cuda_dev, seed=77, feeder=a.feeder)
         b.Restore()
         assert b.global_Step == 2 and float(b.flat_v.abs().sum()) > 0.0   # the moments came back, not zeros
         rb = b.Run_Train_Step(feeds[2])

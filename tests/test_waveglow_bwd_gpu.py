@@ -64,8 +64,8 @@ def test_gradients_match_autograd(cuda_dev, N, S, Tm, seed):
 
 
 def test_forward_values_unchanged_by_saving(cuda_dev):
-    """the training forward (activations kept for the reverse pass; library GEMMs over row-major stacked operands) and Glow_Train
-    (hand-written tcgen05 GEMMs over tiled operands) compute the same bf16x3 products in a different summation order"""
+    """the training forward (activations kept for the reverse pass; row-major stacked operands packed per product) and Glow_Train
+    (fused-epilogue tcgen05 GEMMs over tiled operands) compute the same bf16x3 products in a different summation order"""
     from oracle import waveglow_oracle as W
     from multi_speaker_tts_b200.WaveGlow import Modules as M
     raws, upk, upb = W.init_waveglow(2, end_scale=0.02, g_mode="unit", inv_mode="orthogonal")
@@ -77,7 +77,7 @@ def test_forward_values_unchanged_by_saving(cuda_dev):
     assert (z0 - z1).abs().max().item() < 1e-4
     l0 = M.Glow_Loss(z0, ls0, ld0, ss0)
     for x, y in zip(l0, losses):
-        assert abs(float(x) - float(y)) <= 1e-6 * max(1.0, abs(float(y)))
+        assert abs(float(x) - float(y)) <= 5e-6 * max(1.0, abs(float(y)))   # fp32 summation-order noise of a 0.13-sized mean
 
 
 def test_trainer_step_clip_and_adam(cuda_dev, capsys):
