@@ -287,7 +287,14 @@ class Tacotron2(object):
             else:
                 self._grad_views[k].copy_(g)
         if self.world > 1:
+            ev = getattr(self, 'allreduce_events', None)
+            if ev is not None:  # bench: per-rank wait + wire time of the collective (CUDA events, no synchronisation)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             torch.distributed.all_reduce(self.flat_g, group=self.pg)  # the single gradient all-reduce of the step
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
         step = self.global_Step
         lr = self.learning_rate(step)
         t = step + 1

@@ -79,7 +79,14 @@ class DecoderTrainer(object):
         loss2, dlin, dstop = decoder_loss(lin, stop, mel, mel_len, hp.Train.Use_L1_Loss)
         _, self.d_memory = decoder_backward(st, self.w, dlin, dstop, grad_out=self.g)
         if self.world > 1:
+            ev = getattr(self, 'allreduce_events', None)
+            if ev is not None:  # bench: per-rank wait + wire time of the collective (CUDA events, no synchronisation)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             torch.distributed.all_reduce(self.flat_g, group=self.pg)  # the single gradient all-reduce
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
         self.global_step += 1
         t = self.global_step
         a = hp.Train.ADAM

@@ -21,7 +21,11 @@ def _check_line(stdout, n_gpus):
     assert d["metric"] == "decoder mel-frames/s (train step)" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "sample" in d["config"] and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "sample" in d["cpu_baseline"] and d["vs_baseline"] is None
+    # both arms print the same config dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(n_gpus)
     return d
 
 
@@ -30,7 +34,7 @@ def test_reference_arm_single_process():
     assert r.returncode == 0, r.stderr[-2000:]
     d = _check_line(r.stdout, 1)
     import re
-    L = int(re.search(r" L=(\d+) ", d["config"]["sample"]).group(1))
+    L = int(re.search(r" L=(\d+) ", d["cpu_baseline"]["sample"]).group(1))
     assert 24 <= L <= 200                           # a 2 s budget selects a short sample, never the full 800 frames
 
 
