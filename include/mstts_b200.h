@@ -278,8 +278,9 @@ int mstts_tc_gemm_test(const float* A, const float* Bt, int M, int N, int K, flo
  *   op(A) is M x K (A stored K x M when transA), op(B) is K x N (B stored N x K when transB); stride* = elements between
  *   consecutive batches (strideB = 0 shares B).
  * A pack kernel splits the operands into bf16 hi + lo tile images (zero padded), the product runs as bf16x3 with fp32
- * accumulation in TMEM (precise = 0: relative error ~1e-5 of sum |a||b|), or, with precise = 1, as a 3-way split with six
- * partial products (fp32-SGEMM accuracy, 4x the tensor work: the narrow layers and their weight gradients), and few-tile / long-K shapes are split over K with a deterministic second-pass reduction.  Scratch for
+ * accumulation in TMEM.  precise = 0: one accumulation chain over K (the TMEM accumulator truncates: ~1e-5 of max at K ~ 10^3);
+ * 1: chains of <= 512 K-elements summed in double; 2: 3-way operand split, six partial products, chains of <= 256
+ * (fp32-SGEMM accuracy at 4x the tensor work: the weight gradients of the narrow layers), and few-tile / long-K shapes are split over K with a deterministic second-pass reduction.  Scratch for
  * the images comes from a stream-ordered pool inside the library (cudaMallocAsync on the caller's stream, retained between
  * calls); mstts_release_scratch() synchronises the device and returns it to the driver.
  * ---------------------------------------------------------------------------------------------- */

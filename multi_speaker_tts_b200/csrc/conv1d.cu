@@ -73,7 +73,7 @@ extern "C" int mstts_conv1d_fwd(const float* x, const float* kernel, const float
   conv_pad_kernel<<<cv_grid((size_t)B * T * Cin / 4), 256, 0, s>>>(x, B, T, Cin, p, xp);
   if (bias) conv_bias_fill_kernel<<<cv_grid((size_t)B * T * Cout), 256, 0, s>>>(bias, (size_t)B * T, Cout, y);
   MSTTS_CUDA(cudaGetLastError());
-  return gemm_rowmajor_batched_fast(s, false, false, T, Cout, k * Cin, xp, Cin, (long long)Tp * Cin, kernel, Cout, 0, y, Cout, (long long)T * Cout,
+  return gemm_rowmajor_batched(s, false, false, T, Cout, k * Cin, xp, Cin, (long long)Tp * Cin, kernel, Cout, 0, y, Cout, (long long)T * Cout,
                                bias ? 1.f : 0.f, B);
 }
 
@@ -96,12 +96,12 @@ extern "C" int mstts_conv1d_bwd(const float* x, const float* kernel, const float
   if (dx) {
     // dx[b, t, ci] = sum_j sum_co dyp[b, t + j, co] W[k-1-j][ci][co]
     conv_flip_w_kernel<<<cv_grid((size_t)k * Cin * Cout), 256, 0, s>>>(kernel, k, Cin, Cout, wf);
-    if ((rc = gemm_rowmajor_batched_fast(s, false, true, T, Cin, k * Cout, dyp, Cout, (long long)Tp * Cout, wf, k * Cout, 0, dx, Cin,
+    if ((rc = gemm_rowmajor_batched(s, false, true, T, Cin, k * Cout, dyp, Cout, (long long)Tp * Cout, wf, k * Cout, 0, dx, Cin,
                                     (long long)T * Cin, 0.f, B)))
       return rc;
   }
   MSTTS_CUDA(cudaGetLastError());
   // dW[(tap, ci), co] = sum over flat padded rows r in [0, B Tp - 2p): xp_flat[r + tap][ci] dyp_flat[r + p][co]
   const int R = B * Tp - 2 * p;
-  return gemm_rowmajor_fast(s, true, false, k * Cin, Cout, R, xp, Cin, dyp + (size_t)p * Cout, Cout, dkernel, Cout, 0.f);
+  return gemm_rowmajor_ex(s, true, false, k * Cin, Cout, R, xp, Cin, dyp + (size_t)p * Cout, Cout, dkernel, Cout, 0.f);
 }

@@ -202,12 +202,12 @@ static int dec_projection(cudaStream_t s, const float* m1, const float* ctx, con
   ScratchScope sc(s);
   void *ai = nullptr, *bi = nullptr;
   int rc;
-  if ((rc = sc.get(&ai, tc_image_bytes(TB, K, 128, true)))) return rc;
-  if ((rc = sc.get(&bi, tc_image_bytes(NP, K, 256, true)))) return rc;
-  if ((rc = tc_pack_f32(s, m1, kCell, false, TB, kCell, 128, Kb, ai, 0, 0, true))) return rc;
-  if ((rc = tc_pack_f32(s, ctx, D, false, TB, D, 128, Kb, ai, 0, kCell / 64, true))) return rc;
-  if ((rc = tc_pack_f32(s, Wp, NP, true, NP, K, 256, Kb, bi, 0, 0, true))) return rc;
-  return tc_gemm_images(s, ai, bi, TB, NP, K, out, NP, 0.f, true);
+  if ((rc = sc.get(&ai, tc_image_bytes(TB, K, 128)))) return rc;
+  if ((rc = sc.get(&bi, tc_image_bytes(NP, K, 256)))) return rc;
+  if ((rc = tc_pack_f32(s, m1, kCell, false, TB, kCell, 128, Kb, ai, 0, 0))) return rc;
+  if ((rc = tc_pack_f32(s, ctx, D, false, TB, D, 128, Kb, ai, 0, kCell / 64))) return rc;
+  if ((rc = tc_pack_f32(s, Wp, NP, true, NP, K, 256, Kb, bi, 0, 0))) return rc;
+  return tc_gemm_images(s, ai, bi, TB, NP, K, out, NP, 0.f);
 }
 
 extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes,
@@ -242,7 +242,7 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   if (rc) return rc;
   prenet_act_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.pre), w->prenet1_bias, io->prenet_mask, 1, B, TB * kPrenet);
   // prenet rows of cell 0's kernel over all steps (54 GFLOP at config 2)
-  rc = gemm_rowmajor_fast(s, false, false, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
+  rc = gemm_rowmajor_ex(s, false, false, (int)TB, kGates, kPrenet, F(l.pre), kPrenet, w->cell0_kernel, kGates, F(l.g0pre), kGates, 0.f);
   if (rc) return rc;
   // ---- zero initial state (AttentionWrapper.zero_state, Modules.py:112) and the barrier counter ----
   const size_t BC = (size_t)B * kCell * sizeof(float);

@@ -6,25 +6,20 @@
 
 #include "tc_gemm.h"
 
-int gemm_rowmajor_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
-                     const float* B, int ldb, float* C, int ldc, float beta) {
-  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, beta, 1, true);
+int gemm_rowmajor_p(cudaStream_t s, int prec, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B,
+                    int ldb, float* C, int ldc, float beta) {
+  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, beta, 1, prec);
 }
 
-int gemm_rowmajor_fast(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                       float* C, int ldc, float beta) {
-  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, beta, 1, false);
+int gemm_rowmajor_ex(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
+                     const float* B, int ldb, float* C, int ldc, float beta) {
+  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, 0, B, ldb, 0, C, ldc, 0, beta, 1, TC_FAST);
 }
 
 int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,
                           long long sA, const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta,
                           int batch) {
-  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, beta, batch, true);
-}
-
-int gemm_rowmajor_batched_fast(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA,
-                               const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch) {
-  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, beta, batch, false);
+  return tc_gemm_f32(s, transA, transB, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, beta, batch, TC_FAST);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

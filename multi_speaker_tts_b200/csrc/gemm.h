@@ -1,9 +1,10 @@
 // Dense products that sit outside the recurrent loops (hoisted prenet / projection / weight-gradient products).
-// Row-major fp32 in, row-major fp32 out, on the hand-written tcgen05 kernel (tc_gemm.h).  gemm_rowmajor* keep fp32-SGEMM
-// accuracy (3-way bf16 split, six partial products: the narrow layers whose gradients are tiny against their terms);
-// gemm_rowmajor_fast / _batched_fast are bf16x3 (2-way split, three products) for the large products.
+// Row-major fp32 in, row-major fp32 out, on the hand-written tcgen05 kernel (tc_gemm.h): bf16x3 (operands split hi + lo, three
+// partial products, fp32 accumulation in TMEM).  gemm_rowmajor_p takes a precision level (tc_gemm.h: TC_FAST / TC_CHAINED /
+// TC_PRECISE) for the products whose result is small against its terms (weight gradients of the narrow layers).
 #pragma once
 #include "common.cuh"
+#include "tc_gemm.h"
 
 // C[M,N] = op(A) * op(B) + beta * C, all row-major with leading dimensions lda/ldb/ldc.
 // op(A) is M x K (A stored K x M when transA), op(B) is K x N (B stored N x K when transB).
@@ -16,10 +17,8 @@ static inline int gemm_rowmajor(cudaStream_t s, int M, int N, int K, const float
 }
 
 
-int gemm_rowmajor_fast(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                       float* C, int ldc, float beta);
-int gemm_rowmajor_batched_fast(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA,
-                               const float* B, int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch);
+int gemm_rowmajor_p(cudaStream_t s, int prec, bool transA, bool transB, int M, int N, int K, const float* A, int lda, const float* B,
+                    int ldb, float* C, int ldc, float beta);
 
 // batched: for i in [0,batch): C_i = op(A_i) op(B_i) + beta C_i with element strides sA/sB/sC between batches
 int gemm_rowmajor_batched(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda,

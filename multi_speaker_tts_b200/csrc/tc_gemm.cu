@@ -551,21 +551,27 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     const size_t bm = i / N;
     const int m = (int)(bm % M), b = (int)(bm / M);
     const float* p = slabs + ((size_t)b * Mp + m) * Np + n;
-    float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += p[(size_t)s * slab];
+    double acc = 0.0;  // the slices are short tensor-core accumulation chains; their sum is exact to fp32
+    for (int s = 0; s < S; ++s) acc += (double)p[(size_t)s * slab];
     float* c = C + (size_t)b * c_bstride + (size_t)m * ldc + n;
-    *c = beta != 0.f ? acc + beta * *c : acc;
+    *c = beta != 0.f ? (float)(acc + (double)beta * (double)*c) : (float)acc;
   }
 }
 
 // K slices per tile: few-tile products with a long K (weight gradients over all decoder steps) would leave most SMs idle,
 // and a tile count just above a multiple of the SM count wastes most of the last round.  Cost model in k-block times
 // (12 MMAs, ~1 us): rounds x (slice length + pipeline fill) + the reduce pass.
-static int choose_ksplit(int ntiles, int Kb) {
-  int best = 1;
+static int choose_ksplit(int ntiles, int Kb, int kb_max) {
+  // kb_max > 0 bounds the length of one tensor-core accumulation chain (k-blocks per slice): the fp32 accumulator in TMEM
+  // truncates, so the error of a product grows linearly with the chain length (measured: 2.3e-5 of max at K = 3000, ten
+  // times an fp32 SGEMM); short slices summed in double by the reduce kernel bring it back to fp32-SGEMM level
+  const int s_min = kb_max > 0 ? (Kb + kb_max - 1) / kb_max : 1;
+  int s_hi = Kb / 2 < 148 ? Kb / 2 : 148;
+  if (s_hi < s_min) s_hi = s_min;
+  if (s_hi < 1) s_hi = 1;
+  int best = s_min;
   double best_cost = 1e30;
-  const int smax = Kb / 2 < 148 ? Kb / 2 : 148;
-  for (int S = 1; S <= (smax < 1 ? 1 : smax); ++S) {
+  for (int S = s_min; S <= s_hi; ++S) {
     const long long rounds = ((long long)ntiles * S + 147) / 148;
     double cost = (double)rounds * ((double)Kb / S + 2.0);
     if (S > 1) cost += 3.0 + 0.03 * S * ntiles;
@@ -611,10 +617,10 @@ int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int
 
 // the product over packed images: C_b = A_b . B_b^T (+ beta C_b), Kb image k-blocks
 static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, const uint8_t* bi, size_t b_bstride, int M, int N, int Kb,
-                         float* C, int ldc, long long sC, float beta, int batch) {
+                         float* C, int ldc, long long sC, float beta, int batch, int prec) {
   const int Mt = (M + 127) / 128, Nt = (N + 255) / 256;
   const int ntiles = batch * Mt * Nt;
-  const int ksplit = choose_ksplit(ntiles, Kb);
+  const int ksplit = choose_ksplit(ntiles, Kb, prec == TC_PRECISE ? 4 : (prec == TC_CHAINED ? 8 : 0));
   ScratchScope scope(s);
   float* slabs = nullptr;
   int rc;
@@ -638,15 +644,17 @@ static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, co
   return MSTTS_OK;
 }
 
-int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta, bool precise) {
+int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta, int prec) {
   if (M <= 0 || N <= 0) return MSTTS_OK;
   MSTTS_REQUIRE(A_img && B_img && C && K >= 1, MSTTS_E_INVALID, "tc_gemm_images: null operand or K=%d", K);
-  return launch_images(s, (const uint8_t*)A_img, 0, (const uint8_t*)B_img, 0, M, N, (K + 63) / 64 * (precise ? 4 : 1), C, ldc, 0, beta, 1);
+  return launch_images(s, (const uint8_t*)A_img, 0, (const uint8_t*)B_img, 0, M, N, (K + 63) / 64 * (prec == TC_PRECISE ? 4 : 1), C, ldc, 0,
+                       beta, 1, prec);
 }
 
 template <bool F32>
 static int tc_gemm_general(cudaStream_t s, PackSrc A, PackSrc B, int M, int N, int K, float* C, int ldc, long long sC, float beta, int batch,
-                           bool precise) {
+                           int prec) {
+  const bool precise = F32 && prec == TC_PRECISE;
   if (M <= 0 || N <= 0 || batch <= 0) return MSTTS_OK;
   MSTTS_REQUIRE(K >= 1 && A.hi && B.hi && C && (F32 || (A.lo && B.lo)), MSTTS_E_INVALID, "tc_gemm: M=%d N=%d K=%d batch=%d or null operand",
                 M, N, K, batch);
@@ -660,26 +668,27 @@ static int tc_gemm_general(cudaStream_t s, PackSrc A, PackSrc B, int M, int N, i
   if ((rc = scope.get((void**)&bi, b_img * (shareB ? 1 : batch)))) return rc;
   if ((rc = pack_launch<F32>(s, A, M, K, 128, Kb, ai, a_img, batch, 0, 0, precise, false))) return rc;
   if ((rc = pack_launch<F32>(s, B, N, K, 256, Kb, bi, b_img, shareB ? 1 : batch, 0, 0, precise, true))) return rc;
-  return launch_images(s, ai, a_img, bi, shareB ? 0 : b_img, M, N, Kb * segs, C, ldc, sC, beta, batch);
+  return launch_images(s, ai, a_img, bi, shareB ? 0 : b_img, M, N, Kb * segs, C, ldc, sC, beta, batch, prec);
 }
 
 int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
-                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, bool precise) {
+                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, int prec) {
   // image rows of the B operand are output columns: element (n, k) = B[k][n] unless B is given transposed
   const PackSrc a{A, nullptr, lda, sA, transA ? 1 : 0}, b{B, nullptr, ldb, sB, transB ? 0 : 1};
-  return tc_gemm_general<true>(s, a, b, M, N, K, C, ldc, sC, beta, batch, precise);
+  return tc_gemm_general<true>(s, a, b, M, N, K, C, ldc, sC, beta, batch, prec);
 }
 
 int tc_gemm_hl(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                int lda, long long sA, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, long long sB, float* C, int ldc,
                long long sC, float beta, int batch) {
   const PackSrc a{A_hi, A_lo, lda, sA, transA ? 1 : 0}, b{B_hi, B_lo, ldb, sB, transB ? 0 : 1};
-  return tc_gemm_general<false>(s, a, b, M, N, K, C, ldc, sC, beta, batch, false);
+  return tc_gemm_general<false>(s, a, b, M, N, K, C, ldc, sC, beta, batch, TC_FAST);
 }
 
 extern "C" int mstts_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, long long strideA, const float* B,
                               int ldb, long long strideB, float* C, int ldc, long long strideC, float beta, int batch, int precise,
                               void* stream) {
+  MSTTS_REQUIRE(precise >= 0 && precise <= 2, MSTTS_E_INVALID, "gemm_f32: precision level %d (0 fast, 1 chained, 2 precise)", precise);
   return tc_gemm_f32((cudaStream_t)stream, transA != 0, transB != 0, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, beta, batch,
-                     precise != 0);
+                     precise);
 }

@@ -106,11 +106,16 @@ int tc_gemm_plain(cudaStream_t s, const void* A_tiled, const void* B_tiled, floa
 // The operands are packed into the tensor core's tile images (hi + lo bf16, zero padded to 128 / 256 rows and 64-wide
 // k-blocks) by a pack kernel, multiplied as bf16x3 by tc_gemm_kernel<3>, and (for few-tile / long-K shapes) summed over
 // K slices by a deterministic reduce kernel.  Scratch comes from the library's stream-ordered pool (scratch_pool.h).
-// precise: the fp32 operands are split THREE ways (h + m + l, 24 mantissa bits) and six partial products are accumulated
-// (hh + hm + mh + mm + hl + lh, as four K segments of the same kernel): fp32-SGEMM accuracy at 4x the tensor work -- for the
-// products whose fp32 result is small against the magnitude of its terms (weight gradients of the narrow layers).
+// Precision levels.  The fp32 accumulator of the tensor core truncates, so the error of one accumulation chain grows linearly
+// with its length; the operand split bounds the error per product.
+//   TC_FAST    bf16x3 (operands split hi + lo, three products), one chain over the whole K: ~1e-5 of max at K ~ 10^3
+//   TC_CHAINED bf16x3, chains of <= 8 k-blocks (K = 512) summed in double by the reduce kernel
+//   TC_PRECISE operands split THREE ways (h + m + l, 24 mantissa bits), six partial products (hh + hm + mh + mm + hl + lh, as
+//              four K segments of the same kernel), chains of <= 4 k-blocks: fp32-SGEMM accuracy at 4x the tensor work -- for
+//              the products whose fp32 result is small against the magnitude of its terms (weight gradients of narrow layers)
+enum { TC_FAST = 0, TC_CHAINED = 1, TC_PRECISE = 2 };
 int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
-                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, bool precise);
+                int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, int prec);
 // building blocks for call sites that share a packed operand between products or assemble one from several matrices:
 // an image holds ceil(R / TR) tile rows (TR = 128 for the A side, 256 for the B side) x Kb k-blocks of [hi | lo] tiles
 static inline size_t tc_image_bytes(int R, int K, int TR, bool precise = false) {
@@ -122,7 +127,7 @@ int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int
                 bool precise = false);
 // C[M,N] = A_img . B_img^T + beta C  (K = the images' k extent)
 int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta,
-                   bool precise = false);
+                   int prec = TC_FAST);
 // same with operands already split into bf16 hi + lo row-major matrices (hi and lo share the leading dimension / strides)
 int tc_gemm_hl(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo,
                int lda, long long sA, const __nv_bfloat16* B_hi, const __nv_bfloat16* B_lo, int ldb, long long sB, float* C, int ldc,

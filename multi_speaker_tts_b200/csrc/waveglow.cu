@@ -1268,7 +1268,7 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
     coupling_bwd_kernel<<<148 * 2, 256, 0, s>>>(SKIP(f), w->end_w[f], w->end_b[f], YBUF(f), dxcur, -1.f / n_el, FP(b.dy), FP(b.dopad),
                                                FP(b.dskip), N, T, c);
     // end conv: dWe = skip^T do, dbe = colsum(do)   (fp32 library GEMM: 512 x c output)
-    if ((rc = gemm_rowmajor_ex(s, true, false, kWnCh, c, (int)rows_p, SKIP(f), kWnCh, FP(b.dopad), 8, dwt->end_w[f], c, 0.f))) return rc;
+    if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, kWnCh, c, (int)rows_p, SKIP(f), kWnCh, FP(b.dopad), 8, dwt->end_w[f], c, 0.f))) return rc;
     colsum_valid(s, FP(b.dopad), 8, c, dwt->end_b[f], nullptr, FP(b.part), N, T);
     int cur = 0;
     // per-layer offsets inside the flow's stacked weight image

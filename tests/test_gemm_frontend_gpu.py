@@ -29,7 +29,7 @@ def _run(lib, _lib, tA, tB, M, N, K, A, lda, sA, B, ldb, sB, Cm, ldc, sC, beta, 
     (1, 1, 300, 130, 70, 1.0),       # both transposed, nothing aligned, beta = 1
     (0, 0, 1, 1, 1, 0.0),            # degenerate
 ])
-@pytest.mark.parametrize("precise", [0, 1])
+@pytest.mark.parametrize("precise", [0, 1, 2])
 def test_gemm_f32_matches_fp64(cuda_dev, tA, tB, M, N, K, beta, precise):
     from multi_speaker_tts_b200 import _lib
     lib = _lib.lib()
@@ -44,11 +44,12 @@ def test_gemm_f32_matches_fp64(cuda_dev, tA, tB, M, N, K, beta, precise):
     ref = opA @ opB + beta * C0.double()
     assert torch.isfinite(out).all()
     err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
-    # bf16x3: ~16 mantissa bits per operand; precise (3-way split, six products): fp32-SGEMM accuracy -- compare with the
-    # error of the fp32 product itself
+    # level 0: bf16x3, one accumulation chain (the truncating TMEM accumulator adds ~K * 1e-8); level 1: chains <= 512;
+    # level 2 (3-way split, six products, chains <= 256, double reduce): fp32-SGEMM accuracy -- compared with the error of
+    # the fp32 product itself
     sgemm_err = ((A.t() if tA else A) @ (B.t() if tB else B) + beta * C0 - ref).abs().max().item() / ref.abs().max().item()
     print("M=%d N=%d K=%d precise=%d: rel err %.2e (fp32 matmul: %.2e)" % (M, N, K, precise, err, sgemm_err))
-    assert err < (max(3e-6, 4 * sgemm_err) if precise else 5e-5), err
+    assert err < {0: 5e-5, 1: 1.5e-5, 2: max(1e-6, 2 * sgemm_err)}[precise], err
 
 
 def test_gemm_f32_is_deterministic_with_split_k(cuda_dev):
