@@ -16,6 +16,7 @@
 // Kernel: persistent, one CTA per SM, 320 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
 // thread, M = 128, N = 256, K = 16 per instruction), warps 2-9 = epilogue (two per TMEM lane quarter).  2-stage smem ring
 // (96 KB / stage), two 256-column accumulators in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -671,8 +672,35 @@ static int tc_gemm_general(cudaStream_t s, PackSrc A, PackSrc B, int M, int N, i
   return launch_images(s, ai, a_img, bi, shareB ? 0 : b_img, M, N, Kb * segs, C, ldc, sC, beta, batch, prec);
 }
 
+// Debug aid (tools/grad_probe.py): MSTTS_GEMM_FORCE=<level> overrides the precision level of every fp32 front-end call, or
+// only of the calls whose running index (since process start) is listed in MSTTS_GEMM_FORCE_SITES="3,7,..."; MSTTS_GEMM_TRACE=1
+// prints index and shape of each call.  Read per call; unset in production.
+static int gemm_site_prec(int prec, bool tA, bool tB, int M, int N, int K, int batch) {
+  static std::atomic<int> ctr{0};
+  const char* force = getenv("MSTTS_GEMM_FORCE");
+  const char* trace = getenv("MSTTS_GEMM_TRACE");
+  if (!force && !trace) return prec;
+  const int id = ctr++;
+  int out = prec;
+  if (force) {
+    const char* sites = getenv("MSTTS_GEMM_FORCE_SITES");
+    bool hit = sites == nullptr;
+    for (const char* p = sites; p && *p;) {
+      char* e;
+      const long v = strtol(p, &e, 10);
+      if (e == p) break;
+      if (v == id) hit = true;
+      p = *e ? e + 1 : e;
+    }
+    if (hit) out = atoi(force);
+  }
+  if (trace) fprintf(stderr, "[mstts gemm %d] tA=%d tB=%d M=%d N=%d K=%d batch=%d prec %d -> %d\n", id, (int)tA, (int)tB, M, N, K, batch, prec, out);
+  return out;
+}
+
 int tc_gemm_f32(cudaStream_t s, bool transA, bool transB, int M, int N, int K, const float* A, int lda, long long sA, const float* B,
                 int ldb, long long sB, float* C, int ldc, long long sC, float beta, int batch, int prec) {
+  prec = gemm_site_prec(prec, transA, transB, M, N, K, batch);
   // image rows of the B operand are output columns: element (n, k) = B[k][n] unless B is given transposed
   const PackSrc a{A, nullptr, lda, sA, transA ? 1 : 0}, b{B, nullptr, ldb, sB, transB ? 0 : 1};
   return tc_gemm_general<true>(s, a, b, M, N, K, C, ldc, sC, beta, batch, prec);
