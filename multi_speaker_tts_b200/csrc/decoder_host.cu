@@ -130,6 +130,7 @@ extern "C" size_t mstts_decoder_ws_offset(const char* name, int B, int Te, int L
   REGION(values) REGION(keys) REGION(g0pre) REGION(act0) REGION(act1) REGION(c0n) REGION(c1n) REGION(cz0) REGION(hz0)
   REGION(cz1) REGION(hz1) REGION(m0) REGION(m1) REGION(ctx) REGION(cum) REGION(align_tm) REGION(qf) REGION(dG0) REGION(dG1)
   REGION(dctx) REGION(dq) REGION(dbg) REGION(dbg_b) REGION(wimg_f) REGION(total)
+  REGION(frames) REGION(pre_h) REGION(pre) REGION(dpre) REGION(dpre_h) REGION(dproj_tm) REGION(dm1_proj) REGION(proj_tm)
 #undef REGION
   return (size_t)-1;
 }

@@ -85,16 +85,18 @@ def test_decoder_config2_gradients(cuda_dev):
     from oracle import decoder_oracle as O
     from multi_speaker_tts_b200.decoder import decoder_backward, decoder_loss
     w, b = _decoder_inputs(True)
-    res = {}
+    res, upstream = {}, None
     for mode in ("bf16x3", "fp32"):
         wd, bd, lin, stop, align, st = _gpu_forward(w, b, cuda_dev, mode)
         loss2, dlin, dstop = decoder_loss(lin, stop, bd['mel'], bd['mel_len'])
-        grads, dmem = decoder_backward(st, wd, dlin, dstop)
+        if upstream is None:
+            upstream = (dlin, dstop)     # both reverse passes differentiate the same upstream gradient (see the L1 note below)
+        grads, dmem = decoder_backward(st, wd, upstream[0].to(cuda_dev), upstream[1].to(cuda_dev))
         torch.cuda.synchronize()
-        res[mode] = ({k: v.cpu() for k, v in grads.items()}, dmem.cpu(), loss2.cpu())
+        res[mode] = ({k: v.cpu() for k, v in grads.items()}, dmem.cpu(), loss2.cpu(), upstream[0].cpu(), upstream[1].cpu())
         del st, grads, dmem
         torch.cuda.empty_cache()
-    (ga, ma, la), (gb, mb, lb) = res["bf16x3"], res["fp32"]
+    (ga, ma, la, dlin_a, dstop_a), (gb, mb, lb, _, _) = res["bf16x3"], res["fp32"]
     assert (la - lb).abs().max() < 1e-5 * max(1.0, lb.abs().max().item())
     worst = 0.0
     for k in list(gb) + ['d_memory']:
@@ -110,8 +112,20 @@ def test_decoder_config2_gradients(cuda_dev):
     mem = b['memory'].clone().requires_grad_(True)
     lin, stop, al = O.decoder_forward(wr, mem, b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'], b['zone_mask'])
     ll, sl = O.decoder_loss(lin, stop, b['mel'], b['mel_len'])
-    (ll + sl).backward()
     assert abs(ll.item() - la[0].item()) < 1e-5 * max(1, abs(ll.item())) and abs(sl.item() - la[1].item()) < 1e-5
+    # The L1 term makes the loss gradient discontinuous: d|x|/dx = sign(lin - mel) flips wherever the CUDA forward (L_inf 5e-6
+    # from the oracle) lands on the other side of a mel value.  Over 2 M elements that is a handful of positions, each moving
+    # d_linear by 2/n -- enough to move the cancellation-heavy prenet gradients by 3e-3 (measured), so the two stages are
+    # gated separately: (1) the loss kernel's d_linear / d_stop equal the oracle's autograd except at near-ties, which are
+    # counted and bounded; (2) the reverse pass is compared with the oracle's backward of THE SAME upstream gradient.
+    dlin_ref, dstop_ref = torch.autograd.grad(ll + sl, [lin, stop], retain_graph=True)
+    tie = (lin.detach()[:, :-1] - b['mel']).abs() < 2e-5
+    differs = (dlin_a - dlin_ref).abs() > 1e-9
+    n_flip = int(differs.sum())
+    print("d_linear: %d of %d elements differ from the oracle's autograd (L1 sign at near-ties)" % (n_flip, differs.numel()))
+    assert n_flip <= 32 and bool(tie[differs[:, :-1]].all()) and not bool(differs[:, -1].any())
+    assert (dstop_a - dstop_ref).abs().max() <= 1e-4 * dstop_ref.abs().max()
+    torch.autograd.backward([lin, stop], [dlin_a, dstop_a])
     worst, bad = 0.0, []
     for k in list(gb) + ['d_memory']:
         ref = mem.grad if k == 'd_memory' else wr[k].grad

@@ -34,6 +34,46 @@ def child(path, mode):
     loss2, dlin, dstop = decoder_loss(lin, stop, bd['mel'], bd['mel_len'])
     grads, dmem = decoder_backward(st, wd, dlin, dstop)
     torch.cuda.synchronize()
+    if os.environ.get("PROBE_CHAIN"):
+        # re-derive the prenet gradient chain from the workspace's own dG0 in fp64 (torch on the GPU as the checker)
+        from multi_speaker_tts_b200 import _lib
+        lib = _lib.lib()
+        Bn, Te, D = bd['memory'].shape
+        m = _lib.MODES[mode]
+
+        def reg(name, cols):
+            off = lib.mstts_decoder_ws_offset(name.encode(), Bn, Te, bd['mel'].shape[1], D, T, m)
+            return st.ws[off:off + T * Bn * cols * 4].view(torch.float32).view(T * Bn, cols)
+        dG0, pre, pre_h, frames, dpre, dpre_h = (reg(n, c) for n, c in (("dG0", 4096), ("pre", 256), ("pre_h", 256), ("frames", 80),
+                                                                         ("dpre", 256), ("dpre_h", 256)))
+        K0, W1 = wd['cell_0/kernel'].double(), wd['prenet_1/kernel'].double()
+        r_dpre = (dG0.double() @ K0[:256].t()) * 2 * (pre > 0)
+        r_dpre_h = (r_dpre @ W1.t()) * 2 * (pre_h > 0)
+
+        def cmp(tag, x, r):
+            e = (x.double() - r).abs()
+            rows = e.max(dim=1).values if e.dim() == 2 and e.shape[0] == T * Bn else None
+            msg = "%-10s max|ref| %.3e err %.3e" % (tag, r.abs().max().item(), e.max().item())
+            if rows is not None:
+                bad = (rows > 1e-3 * r.abs().max()).nonzero().flatten()
+                msg += " bad rows %d %s" % (bad.numel(), bad[:8].tolist())
+            print(msg)
+        dproj, dm1p, proj_tm, m1, ctx = (reg(n, c) for n, c in (("dproj_tm", 81), ("dm1_proj", 1024), ("proj_tm", 81), ("m1", 1024), ("ctx", D)))
+        Wp = wd['projection/kernel'].double()
+        cmp("dm1_proj", dm1p, dproj.double() @ Wp[:1024].t())
+        off = lib.mstts_decoder_ws_offset(b"ctx", Bn, Te, bd['mel'].shape[1], D, T, m)
+        ctx1 = st.ws[off + Bn * D * 4: off + (T + 1) * Bn * D * 4].view(torch.float32).view(T * Bn, D)
+        cmp("proj_tm", proj_tm, m1.double() @ Wp[:1024] + ctx1.double() @ Wp[1024:])
+        # upstream gradient as the loss kernel produced it vs torch
+        lin64, stop64 = lin.double(), stop.double()
+        cmp("dpre", dpre, r_dpre)
+        cmp("dpre_h", dpre_h, r_dpre_h)
+        cmp("dW1", grads['prenet_1/kernel'], pre_h.double().t() @ r_dpre)
+        cmp("db1", grads['prenet_1/bias'], r_dpre.sum(0))
+        cmp("dW0", grads['prenet_0/kernel'], frames.double().t() @ r_dpre_h)
+        cmp("db0", grads['prenet_0/bias'], r_dpre_h.sum(0))
+        cmp("dK0pre", grads['cell_0/kernel'][:256], pre.double().t() @ dG0.double())
+        cmp("db_c0", grads['cell_0/bias'], dG0.double().sum(0))
     out = []
     for k, r in ref.items():
         x = dmem.cpu() if k == 'd_memory' else grads[k].cpu()
@@ -46,6 +86,7 @@ def main():
     ap.add_argument("--child", default=None)
     ap.add_argument("--mode", default="bf16x3")
     ap.add_argument("--sites", default="")
+    ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     if args.child:
         return child(args.child, args.mode)
@@ -67,12 +108,13 @@ def main():
         print("%-28s %s" % (tag, r.stdout.strip() or r.stderr[-400:]))
         return r
 
-    r = run("as built", {"MSTTS_GEMM_TRACE": "1"})
+    r = run("as built", {"MSTTS_GEMM_TRACE": "1", "PROBE_CHAIN": "1"})
     calls = [l for l in r.stderr.splitlines() if l.startswith("[mstts gemm")]
     print("\n".join(calls))
-    run("all precise", {"MSTTS_GEMM_FORCE": "2"})
-    run("all chained", {"MSTTS_GEMM_FORCE": "1"})
-    sites = [int(x) for x in args.sites.split(",") if x] or list(range(len(calls)))
+    if not args.quick:
+        run("all precise", {"MSTTS_GEMM_FORCE": "2"})
+        run("all chained", {"MSTTS_GEMM_FORCE": "1"})
+    sites = [int(x) for x in args.sites.split(",") if x]
     for i in sites:
         run("site %d precise" % i, {"MSTTS_GEMM_FORCE": "2", "MSTTS_GEMM_FORCE_SITES": str(i)})
 
