@@ -578,8 +578,8 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   // ---- upstream gradient through the hoisted projection ----
   gather_dproj_kernel<<<ew_grid(TB * NP), 256, 0, s>>>(g->d_linear, g->d_stop, F(l.dproj_tm), B, T);
   // dWp = [m1 | ctx]^T dproj ; dbp = colsum(dproj)
-  if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return rc;
-  if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
+  if ((rc = gemm_rowmajor_ex(s, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
                              dw->proj_kernel + (size_t)kCell * NP, NP, 0.f))) return rc;
   colsum(s, F(l.dproj_tm), dw->proj_bias, TB, NP, F(l.colsum_scratch));
   // d m1 (projection part) and d ctx (projection part)
@@ -609,6 +609,9 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   P.barrier = (unsigned*)(ws + l.barrier);
   if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
 
+  // Precision: every product below is bf16x3 (TC_FAST).  The 3-way-split level (TC_PRECISE) was measured on the full-size
+  // gradients (tools/grad_probe.py) and changes nothing: the agreement with the oracle is limited by the ReLU / L1 decisions
+  // of the forward pass, not by the products (tests/test_full_size_gpu.py pins those).
   // ---- weight gradients: products over all steps ----
   // dW[rows, 4096] = X[T*B, rows]^T dG[T*B, 4096]: ~1 TFLOP at config 2, bf16x3 on the hand-written tcgen05 kernel.  The
   // gate-gradient operand is packed once per cell into its tile image (4096 image rows, K = T*B) and shared by the
@@ -638,25 +641,25 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
   if ((rc = wgrad(F(l.hz0), kCell, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates))) return rc;
   colsum(s, F(l.dG0), dw->cell0_bias, TB, kGates, F(l.colsum_scratch));
   // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
-  if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
   colsum(s, F(l.dq), F(l.dfb), TB, kAtt, F(l.colsum_scratch));
   location_grads_kernel<<<1, 1024, 0, s>>>(F(l.dF), F(l.dfb), w->loc_conv_kernel, w->loc_conv_bias, w->loc_dense_kernel,
                                            dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
   MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, s));
   // prenet: d pre = dG0 @ K0[0:256]^T, then back through the two dense+relu+dropout layers
-  if ((rc = gemm_rowmajor_p(s, TC_CHAINED, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
   prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre), F(l.pre), TB * kPrenet);
-  if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
   colsum(s, F(l.dpre), dw->prenet1_bias, TB, kPrenet, F(l.colsum_scratch));
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kPrenet, F(l.dpre), kPrenet, w->prenet1_kernel, kPrenet, F(l.dpre_h), kPrenet, 0.f))) return rc;
   prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre_h), F(l.pre_h), TB * kPrenet);
-  if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, kMel, kPrenet, (int)TB, F(l.frames), kMel, F(l.dpre_h), kPrenet, dw->prenet0_kernel, kPrenet, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, kMel, kPrenet, (int)TB, F(l.frames), kMel, F(l.dpre_h), kPrenet, dw->prenet0_kernel, kPrenet, 0.f))) return rc;
   colsum(s, F(l.dpre_h), dw->prenet0_bias, TB, kPrenet, F(l.colsum_scratch));
   // memory side: dvalues[b] = A_b^T dctx_b (over steps) + dkeys[b] @ Wm^T ; dWm = values^T dkeys
   if ((rc = gemm_rowmajor_batched(s, true, false, Te, D, T, F(l.align_tm), B * Te, Te, F(l.dctx), B * D, D, F(l.dvalues), D,
                                   (long long)Te * D, 0.f, B))) return rc;
   if ((rc = gemm_rowmajor_ex(s, false, true, B * Te, D, kAtt, F(l.dkeys), kAtt, w->memory_kernel, kAtt, F(l.dvalues), D, 1.f))) return rc;
-  if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, D, kAtt, B * Te, F(l.values), D, F(l.dkeys), kAtt, dw->memory_kernel, kAtt, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, D, kAtt, B * Te, F(l.values), D, F(l.dkeys), kAtt, dw->memory_kernel, kAtt, 0.f))) return rc;
   if (g->d_memory)
     mask_dmemory_kernel<<<ew_grid((size_t)B * Te * D), 256, 0, s>>>(F(l.dvalues), io->text_len, g->d_memory, B, Te, D);
   MSTTS_CUDA(cudaGetLastError());

@@ -78,10 +78,49 @@ def test_decoder_config2_forward_vs_oracle(cuda_dev, ragged):
         assert (ga[beyond.expand_as(ga)] == 0).all()
 
 
+def _ws_region(st, name, cols, mode):
+    """[T*B, cols] view of a named region of the decoder workspace (mstts_decoder_ws_offset)"""
+    from multi_speaker_tts_b200 import _lib
+    Bn, Te, Ln, Dn, T = st.shape
+    off = _lib.lib().mstts_decoder_ws_offset(name.encode(), Bn, Te, Ln, Dn, T, _lib.MODES[mode])
+    assert off != 2 ** 64 - 1, name
+    return st.ws[off:off + T * Bn * cols * 4].view(torch.float32).view(T, Bn, cols)
+
+
+class _PinnedPrenet(object):
+    """The oracle's prenet (Modules.py:239-255) with the ReLU decisions taken from the CUDA forward.  A ReLU's derivative is
+    discontinuous at 0: any two correct fp32 implementations disagree on the sign of a few of the 13 M pre-activations
+    (|z| below their rounding noise), and ONE such element moves the cancellation-heavy prenet weight gradients by 1e-3 of
+    their max (measured on the oracle alone: 5e-7 relative noise on z -> 3.6e-3 on d prenet_0/kernel).  So the decisions
+    are pinned, and the disagreements are counted and must all be near-ties."""
+
+    def __init__(self, pos_h, pos_p):
+        self.pos = (pos_h, pos_p)   # [T, B, 256] bool: CUDA forward's (output > 0) of the two layers
+        self.t = 0
+        self.flips = 0
+        self.worst = 0.0
+
+    def __call__(self, x, w, m0, m1):
+        h = x
+        for layer, m in enumerate((m0, m1)):
+            z = h @ w['prenet_%d/kernel' % layer] + w['prenet_%d/bias' % layer]
+            kept = m > 0
+            cuda_pos = self.pos[layer][self.t].to(z.device)
+            dis = kept & ((z > 0) != cuda_pos)
+            if bool(dis.any()):
+                self.flips += int(dis.sum())
+                self.worst = max(self.worst, float(z.detach()[dis].abs().max()))
+            gate = torch.where(kept, cuda_pos, z > 0).to(z.dtype)
+            h = (z * gate / 0.5) * m
+        self.t += 1
+        return h
+
+
 def test_decoder_config2_gradients(cuda_dev):
     """Full-size reverse pass: the tcgen05 (bf16x3) and the fp32 SIMT kernels are independent implementations and must
     agree on every gradient tensor within 2e-4 of its max; the fp32 oracle (torch.autograd over 801 steps, itself
-    carrying fp32 rounding) within 1e-3 of max."""
+    carrying fp32 rounding) within 1e-3 of max.  The two non-smooth points of the graph (L1 sign, prenet ReLU) are pinned
+    to the CUDA forward's decisions and their disagreements counted (see _PinnedPrenet and the L1 note below)."""
     from oracle import decoder_oracle as O
     from multi_speaker_tts_b200.decoder import decoder_backward, decoder_loss
     w, b = _decoder_inputs(True)
@@ -94,6 +133,8 @@ def test_decoder_config2_gradients(cuda_dev):
         grads, dmem = decoder_backward(st, wd, upstream[0].to(cuda_dev), upstream[1].to(cuda_dev))
         torch.cuda.synchronize()
         res[mode] = ({k: v.cpu() for k, v in grads.items()}, dmem.cpu(), loss2.cpu(), upstream[0].cpu(), upstream[1].cpu())
+        if mode == "bf16x3":
+            relu_pos = ((_ws_region(st, "pre_h", 256, mode) > 0).cpu(), (_ws_region(st, "pre", 256, mode) > 0).cpu())
         del st, grads, dmem
         torch.cuda.empty_cache()
     (ga, ma, la, dlin_a, dstop_a), (gb, mb, lb, _, _) = res["bf16x3"], res["fp32"]
@@ -110,7 +151,15 @@ def test_decoder_config2_gradients(cuda_dev):
     # the oracle's own gradients (fp32 autograd)
     wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
     mem = b['memory'].clone().requires_grad_(True)
-    lin, stop, al = O.decoder_forward(wr, mem, b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'], b['zone_mask'])
+    pinned, plain_prenet = _PinnedPrenet(*relu_pos), O.prenet
+    O.prenet = pinned
+    try:
+        lin, stop, al = O.decoder_forward(wr, mem, b['text_len'], b['mel'], b['mel_len'], b['prenet_mask'], b['zone_mask'])
+    finally:
+        O.prenet = plain_prenet
+    print("prenet ReLU decisions: %d of %d differ between the CUDA forward and the fp32 oracle, largest |z| among them %.2e"
+          % (pinned.flips, 2 * relu_pos[0].numel(), pinned.worst))
+    assert pinned.flips <= 2000 and pinned.worst < 1e-4
     ll, sl = O.decoder_loss(lin, stop, b['mel'], b['mel_len'])
     assert abs(ll.item() - la[0].item()) < 1e-5 * max(1, abs(ll.item())) and abs(sl.item() - la[1].item()) < 1e-5
     # The L1 term makes the loss gradient discontinuous: d|x|/dx = sign(lin - mel) flips wherever the CUDA forward (L_inf 5e-6
