@@ -105,7 +105,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
     l.ximg_h0 = take_bytes((size_t)2 * (kCell / 64) * 8192);
     l.ximg_h1 = take_bytes((size_t)2 * (kCell / 64) * 8192);
     l.ximg_end = off;
-    l.dbg = take_bytes((size_t)T * 32 * 8);
+    l.dbg = take_bytes((size_t)(T > kDecGrid ? T : kDecGrid) * 32 * 8);  // also [128 CTAs][32] stamps of the middle step
   }
   l.bwd_begin = off;
   l.W0rT = take((size_t)kGates * (D + kCell));
@@ -140,7 +140,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
     l.ph1 = take((size_t)4 * B * kCell);
     l.ph0 = take((size_t)4 * B * kCell);
     l.pctx = take((size_t)4 * B * D);
-    l.dbg_b = take_bytes((size_t)T * 32 * 8);
+    l.dbg_b = take_bytes((size_t)(T > kDecGrid ? T : kDecGrid) * 32 * 8);  // also [128 CTAs][32] stamps of the middle step
   }
   l.total = off;
   return l;
