@@ -90,8 +90,9 @@ class _DecoderFunction(torch.autograd.Function):
 
 
 def decoder_mode(B, Te, D):
-    """tensor-core (bf16x3) loop where its tiling applies, the fp32 SIMT loop otherwise (both meet the 1e-3 gate)"""
-    return "bf16x3" if (B <= 32 and Te <= 128 and D in (256, 512, 768)) else "fp32"
+    """tensor-core (bf16x3) loop where its tiling applies -- any batch size (rows beyond 32 run as further chunks of the
+    same kernels), texts up to 128 positions -- the fp32 SIMT loop otherwise (both meet the 1e-3 gate)"""
+    return "bf16x3" if (Te <= 128 and D in (256, 512, 768)) else "fp32"
 
 
 def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False, variables=None, masks=None, mode=None,

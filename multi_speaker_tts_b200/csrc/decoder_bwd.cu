@@ -554,6 +554,66 @@ static inline int ew_grid(size_t n) {
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const MsttsDecoderGrads* g,
+                           const MsttsDecoderWeightGrads* dw, void* ws_, size_t ws_bytes, cudaStream_t s);
+
+// B > 32 in bf16x3 mode: the row chunks of the forward call (DecChunkPlan), weight gradients summed over the chunks
+static int decoder_bwd_chunked(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const MsttsDecoderGrads* g,
+                               const MsttsDecoderWeightGrads* dw, void* ws_, size_t ws_bytes, cudaStream_t s) {
+  const int B = io->B, Te = io->Te, L = io->L, D = io->D, T = io->n_steps;
+  const DecChunkPlan p = dec_chunk_plan(B, Te, L, D, T, io->mode);
+  MSTTS_REQUIRE(ws_bytes >= p.total, MSTTS_E_WORKSPACE, "decoder_bwd: workspace %zu < %zu", ws_bytes, p.total);
+  char* ws = (char*)ws_;
+  const size_t n[17] = {(size_t)kMel * kPrenet, kPrenet, (size_t)kPrenet * kPrenet, kPrenet, (size_t)(kPrenet + 2 * D + kCell) * kGates, kGates,
+                        (size_t)2 * kCell * kGates, kGates, (size_t)D * kAtt, (size_t)kCell * kAtt, (size_t)kConvK * kConvC, kConvC,
+                        (size_t)kConvC * kAtt, kAtt, kAtt, (size_t)(kCell + D) * (kMel + 1), kMel + 1};
+  static_assert(sizeof(MsttsDecoderWeightGrads) == 17 * sizeof(float*), "weight-gradient struct has 17 tensors");
+  MsttsDecoderWeightGrads tmp;
+  {
+    float** tp = reinterpret_cast<float**>(&tmp);
+    float* base = (float*)(ws + p.dw_off);
+    size_t off = 0;
+    for (int i = 0; i < 17; ++i) {
+      tp[i] = base + off;
+      off += (n[i] + 63) / 64 * 64;
+    }
+  }
+  for (int c = 0; c < p.nchunks; ++c) {
+    const int b0 = c * p.bc, bc = (B - b0 < p.bc) ? B - b0 : p.bc;
+    MsttsDecoderIO sub = *io;
+    sub.B = bc;
+    sub.memory = io->memory + (size_t)b0 * Te * D;
+    sub.text_len = io->text_len + b0;
+    sub.mel = io->mel + (size_t)b0 * L * kMel;
+    sub.mel_len = io->mel_len + b0;
+    sub.prenet_mask = (const uint8_t*)(ws + p.pm_off + (size_t)c * p.pm_bytes);  // gathered by the forward call
+    sub.zone_mask = (const uint8_t*)(ws + p.zm_off + (size_t)c * p.zm_bytes);
+    sub.linear = io->linear + (size_t)b0 * T * kMel;
+    sub.stop = io->stop + (size_t)b0 * T;
+    sub.align = io->align + (size_t)b0 * T * Te;
+    MsttsDecoderGrads gs;
+    gs.d_linear = g->d_linear + (size_t)b0 * T * kMel;
+    gs.d_stop = g->d_stop + (size_t)b0 * T;
+    gs.d_memory = g->d_memory ? g->d_memory + (size_t)b0 * Te * D : nullptr;
+    int rc = decoder_bwd_one(w, &sub, &gs, c == 0 ? dw : &tmp, ws + (size_t)c * p.chunk_ws, p.chunk_ws, s);
+    if (rc) return rc;
+    if (c > 0) {
+      float* const* dst = reinterpret_cast<float* const*>(dw);
+      float* const* src = reinterpret_cast<float* const*>(&tmp);
+      for (int i = 0; i < 17; ++i) {
+        size_t gsz = (n[i] + 255) / 256;
+        add_inplace_kernel<<<(int)(gsz < 148 * 8 ? gsz : 148 * 8), 256, 0, s>>>(dst[i], src[i], n[i]);
+      }
+    }
+  }
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
 extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const MsttsDecoderGrads* g,
                                  const MsttsDecoderWeightGrads* dw, void* ws_, size_t ws_bytes, void* stream_) {
   MSTTS_REQUIRE(w && io && g && dw && ws_, MSTTS_E_INVALID, "decoder_bwd: null argument");
@@ -565,7 +625,12 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
     for (size_t i = 0; i < sizeof(MsttsDecoderWeightGrads) / sizeof(float*); ++i)
       MSTTS_REQUIRE(gp[i], MSTTS_E_INVALID, "decoder_bwd: null weight-gradient pointer #%zu", i);
   }
-  cudaStream_t s = (cudaStream_t)stream_;
+  if (dec_is_chunked(io->B, io->mode)) return decoder_bwd_chunked(w, io, g, dw, ws_, ws_bytes, (cudaStream_t)stream_);
+  return decoder_bwd_one(w, io, g, dw, ws_, ws_bytes, (cudaStream_t)stream_);
+}
+
+static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const MsttsDecoderGrads* g,
+                           const MsttsDecoderWeightGrads* dw, void* ws_, size_t ws_bytes, cudaStream_t s) {
   const int B = io->B, Te = io->Te, L = io->L, D = io->D, T = io->n_steps;
   const DecLayout l = dec_layout(B, Te, L, D, T, io->mode);
   MSTTS_REQUIRE(ws_bytes >= l.total, MSTTS_E_WORKSPACE, "decoder_bwd: workspace %zu < %zu", ws_bytes, l.total);

@@ -118,6 +118,7 @@ static inline int ew_grid(size_t n) {
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int n_steps, int mode) {
   if (B <= 0 || Te <= 0 || D <= 0 || n_steps <= 0) return 0;
+  if (dec_is_chunked(B, mode)) return dec_chunk_plan(B, Te, L, D, n_steps, mode).total;
   return dec_layout(B, Te, L, D, n_steps, mode).total;
 }
 
@@ -125,6 +126,7 @@ extern "C" size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int
 // activations and the phase time stamps without knowing the layout
 extern "C" size_t mstts_decoder_ws_offset(const char* name, int B, int Te, int L, int D, int n_steps, int mode) {
   if (!name || B <= 0 || Te <= 0 || D <= 0 || n_steps <= 0) return (size_t)-1;
+  if (dec_is_chunked(B, mode)) return (size_t)-1;  // several chunk workspaces: no single region
   const DecLayout l = dec_layout(B, Te, L, D, n_steps, mode);
 #define REGION(x) if (!strcmp(name, #x)) return l.x;
   REGION(values) REGION(keys) REGION(g0pre) REGION(act0) REGION(act1) REGION(c0n) REGION(c1n) REGION(cz0) REGION(hz0)
@@ -211,12 +213,68 @@ static int dec_projection(cudaStream_t s, const float* m1, const float* ctx, con
   return tc_gemm_images(s, ai, bi, TB, NP, K, out, NP, 0.f);
 }
 
+// rows [b0, b0 + bc) of a time-major byte tensor [outer][B][inner] -> contiguous [outer][bc][inner]
+__global__ void gather_batch_rows_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t outer, int B, int b0, int bc,
+                                         int inner16) {
+  const size_t n = outer * bc * inner16;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t c = i % inner16, ob = i / inner16;
+    const size_t o = ob / bc, b = ob % bc;
+    d4[i] = s4[(o * B + b0 + b) * inner16 + c];
+  }
+}
+
+static int decoder_fwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes, cudaStream_t s);
+
+// B > 32 in bf16x3 mode: balanced row chunks through the one-tile path (decoder_layout.h: DecChunkPlan)
+static int decoder_fwd_chunked(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes, cudaStream_t s) {
+  const int B = io->B, Te = io->Te, L = io->L, D = io->D, T = io->n_steps;
+  const DecChunkPlan p = dec_chunk_plan(B, Te, L, D, T, io->mode);
+  MSTTS_REQUIRE(ws_ && ws_bytes >= p.total, MSTTS_E_WORKSPACE, "decoder: workspace %zu < %zu", ws_bytes, p.total);
+  MSTTS_REQUIRE(((uintptr_t)ws_ & 255) == 0, MSTTS_E_INVALID, "decoder: workspace must be 256-byte aligned");
+  MSTTS_REQUIRE(((uintptr_t)io->prenet_mask & 15) == 0 && ((uintptr_t)io->zone_mask & 15) == 0, MSTTS_E_INVALID,
+                "decoder: masks must be 16-byte aligned");
+  char* ws = (char*)ws_;
+  for (int c = 0; c < p.nchunks; ++c) {
+    const int b0 = c * p.bc, bc = (B - b0 < p.bc) ? B - b0 : p.bc;
+    uint8_t* pm = (uint8_t*)(ws + p.pm_off + (size_t)c * p.pm_bytes);
+    uint8_t* zm = (uint8_t*)(ws + p.zm_off + (size_t)c * p.zm_bytes);
+    gather_batch_rows_kernel<<<ew_grid((size_t)T * 2 * bc * kPrenet / 16), 256, 0, s>>>(io->prenet_mask, pm, (size_t)T * 2, B, b0, bc, kPrenet / 16);
+    gather_batch_rows_kernel<<<ew_grid((size_t)T * 4 * bc * kCell / 16), 256, 0, s>>>(io->zone_mask, zm, (size_t)T * 4, B, b0, bc, kCell / 16);
+    MsttsDecoderIO sub = *io;
+    sub.B = bc;
+    sub.memory = io->memory + (size_t)b0 * Te * D;
+    sub.text_len = io->text_len + b0;
+    sub.mel = io->mel + (size_t)b0 * L * kMel;
+    sub.mel_len = io->mel_len + b0;
+    sub.prenet_mask = pm;
+    sub.zone_mask = zm;
+    sub.linear = io->linear + (size_t)b0 * T * kMel;
+    sub.stop = io->stop + (size_t)b0 * T;
+    sub.align = io->align + (size_t)b0 * T * Te;
+    int rc = decoder_fwd_one(w, &sub, ws + (size_t)c * p.chunk_ws, p.chunk_ws, s);
+    if (rc) return rc;
+  }
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
 extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes,
                                  void* stream_) {
   int rc = check_io(w, io);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream_;
   if (!io->is_training) return decoder_fwd_free_running(w, io, ws_, ws_bytes, s);
+  MSTTS_REQUIRE(io->mel && io->mel_len && io->zone_mask, MSTTS_E_INVALID, "decoder: training needs mel/mel_len/zone_mask");
+  MSTTS_REQUIRE(io->n_steps <= io->L + 1, MSTTS_E_INVALID, "decoder: n_steps=%d > L+1=%d", io->n_steps, io->L + 1);
+  if (dec_is_chunked(io->B, io->mode)) return decoder_fwd_chunked(w, io, ws_, ws_bytes, s);
+  return decoder_fwd_one(w, io, ws_, ws_bytes, s);
+}
+
+static int decoder_fwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes, cudaStream_t s) {
+  int rc;
   MSTTS_REQUIRE(io->mel && io->mel_len && io->zone_mask, MSTTS_E_INVALID, "decoder: training needs mel/mel_len/zone_mask");
   MSTTS_REQUIRE(io->n_steps <= io->L + 1, MSTTS_E_INVALID, "decoder: n_steps=%d > L+1=%d", io->n_steps, io->L + 1);
   const int B = io->B, Te = io->Te, L = io->L, D = io->D, T = io->n_steps;

@@ -145,3 +145,45 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.total = off;
   return l;
 }
+
+// ---- batches beyond one tensor-core tile (bf16x3 mode, B > 32) ----------------------------------------------------
+// The persistent tcgen05 loops handle up to 32 batch rows (one M = 64 operand tile of hi + lo rows).  Decoder rows are
+// independent, so a larger batch runs as ceil(B / 32) balanced row chunks, each with its own workspace (the saved
+// activations of every chunk must survive until the reverse pass) and its own contiguous copy of the dropout / zoneout
+// masks (time-major with the batch inside); the weight gradients of the chunks are summed.
+struct DecChunkPlan {
+  int nchunks, bc;          // chunks of bc rows (the last one may be smaller)
+  size_t chunk_ws;          // bytes per chunk workspace (layout of bc rows)
+  size_t pm_off, zm_off;    // per-chunk mask copies: [nchunks][T,2,bc,256] / [nchunks][T,2,2,bc,1024]
+  size_t pm_bytes, zm_bytes;
+  size_t dw_off;            // scratch weight gradients of chunks >= 1 (summed into the caller's)
+  size_t dw_floats;
+  size_t total;
+};
+static inline bool dec_is_chunked(int B, int mode) { return mode == MSTTS_MODE_BF16X3 && B > 32; }
+static inline size_t dec_weight_floats(int D) {  // every tensor padded to 64 floats (256-byte aligned slices)
+  const size_t n[17] = {(size_t)kMel * kPrenet, kPrenet, (size_t)kPrenet * kPrenet, kPrenet, (size_t)(kPrenet + 2 * D + kCell) * kGates, kGates,
+                        (size_t)2 * kCell * kGates, kGates, (size_t)D * kAtt, (size_t)kCell * kAtt, (size_t)kConvK * kConvC, kConvC,
+                        (size_t)kConvC * kAtt, kAtt, kAtt, (size_t)(kCell + D) * (kMel + 1), kMel + 1};
+  size_t tot = 0;
+  for (int i = 0; i < 17; ++i) tot += (n[i] + 63) / 64 * 64;
+  return tot;
+}
+static inline DecChunkPlan dec_chunk_plan(int B, int Te, int L, int D, int T, int mode) {
+  DecChunkPlan p;
+  p.nchunks = (B + 31) / 32;
+  p.bc = (B + p.nchunks - 1) / p.nchunks;
+  p.chunk_ws = align_up(dec_layout(p.bc, Te, L, D, T, mode).total, 1024);
+  size_t off = p.chunk_ws * p.nchunks;
+  p.pm_bytes = align_up((size_t)T * 2 * p.bc * kPrenet, 256);
+  p.zm_bytes = align_up((size_t)T * 4 * p.bc * kCell, 256);
+  p.pm_off = off;
+  off += p.pm_bytes * p.nchunks;
+  p.zm_off = off;
+  off += p.zm_bytes * p.nchunks;
+  p.dw_off = off;
+  p.dw_floats = dec_weight_floats(D);
+  off += p.dw_floats * sizeof(float);
+  p.total = off;
+  return p;
+}
