@@ -355,7 +355,12 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    launches = count_launches(step_resident) if rank == 0 else None  # one extra untimed step under the CUPTI profiler
+    # one extra untimed step on EVERY rank (it contains the all-reduce); rank 0 runs it under the CUPTI profiler
+    launches = None
+    if rank == 0:
+        launches = count_launches(step_resident)
+    else:
+        step_resident()
     step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
