@@ -616,6 +616,14 @@ int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int
   return pack_launch<true>(s, P, R, K, TR, Kb_total, (uint8_t*)img, 0, 1, rt0, kb0, precise, TR == 256);
 }
 
+int tc_pack_hl(cudaStream_t s, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img,
+               int rt0, int kb0) {
+  MSTTS_REQUIRE(hi && lo && img && (TR == 128 || TR == 256) && kb0 + (K + 63) / 64 <= Kb_total, MSTTS_E_INVALID,
+                "tc_pack_hl: R=%d K=%d TR=%d kb0=%d Kb=%d", R, K, TR, kb0, Kb_total);
+  const PackSrc P{hi, lo, ld, 0, trans ? 1 : 0};
+  return pack_launch<false>(s, P, R, K, TR, Kb_total, (uint8_t*)img, 0, 1, rt0, kb0, false, TR == 256);
+}
+
 // the product over packed images: C_b = A_b . B_b^T (+ beta C_b), Kb image k-blocks
 static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, const uint8_t* bi, size_t b_bstride, int M, int N, int Kb,
                          float* C, int ldc, long long sC, float beta, int batch, int prec) {

@@ -125,6 +125,9 @@ static inline size_t tc_image_bytes(int R, int K, int TR, bool precise = false) 
 // image with Kb_total k-blocks; rows up to the next multiple of TR and k up to the next multiple of 64 are zero filled
 int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0,
                 bool precise = false);
+// same from a matrix already split into bf16 hi + lo parts (hi and lo share the leading dimension)
+int tc_pack_hl(cudaStream_t s, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img,
+               int rt0, int kb0);
 // C[M,N] = A_img . B_img^T + beta C  (K = the images' k extent)
 int tc_gemm_images(cudaStream_t s, const void* A_img, const void* B_img, int M, int N, int K, float* C, int ldc, float beta,
                    int prec = TC_FAST);

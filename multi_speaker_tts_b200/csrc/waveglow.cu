@@ -19,6 +19,7 @@
 // clamped at 8 in forward only + sum(log_s) in double, or the inverse transform followed by the inverse 1x1), mel upsampling.
 #include "common.cuh"
 #include "gemm.h"
+#include "scratch_pool.h"
 #include "tc_gemm.h"
 
 constexpr int kWnCh = 512, kWnLayers = 8, kWnMel = 640, kWgPad = 128, kWgFlows = 12;
@@ -677,6 +678,14 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   if (direction == 0) MSTTS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
 
   const int M = (int)(rows_p - 2 * kWgPad);  // GEMM rows: everything except the outermost pads
+  ScratchScope wg_scope(s);
+  void *a1img = nullptr, *b1img = nullptr;
+  if (!use_tc) {
+    if ((rc = wg_scope.get(&a1img, tc_image_bytes(M, kWnK1, 128)))) return rc;
+    if ((rc = wg_scope.get(&b1img, tc_image_bytes(2 * kWnCh, kWnK1, 256)))) return rc;
+    const __nv_bfloat16* m3 = BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel;
+    if ((rc = tc_pack_hl(s, m3, m3 + kWnMel, 3 * kWnMel, false, M, kWnMel, 128, kWnK1 / 64, a1img, 0, 24))) return rc;
+  }
   const float* xcur = audio_in;              // [N,T,c] of the current flow
   float* xbuf[2] = {FP(l.xa), FP(l.xb)};
   int xsel = 0;
@@ -723,12 +732,17 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
       float* a_out = APRE(f, i) + (size_t)kWgPad * 2 * kWnCh;
       const __nv_bfloat16* Wtap = wq + wo;
       const __nv_bfloat16* Wc = wq + wo + (size_t)3 * K3 * 2 * kWnCh;
-      // conditioning first (beta = 0), then the three taps accumulate: 4 GEMMs with K = 1920 / 1536
-      if ((rc = gemm_stacked(s, M, 2 * kWnCh, kWnMel, BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel, Wc, a_out, 2 * kWnCh, 0.f))) return rc;
+      // ONE product per gate pre-activation: the operand image [3 taps x 512 | mel 640] (K = 2176) is assembled from the three
+      // row-shifted views of the layer input; its conditioning k-blocks were packed once before the flow loop and stay in place
       for (int k = 0; k < 3; ++k) {
         const long long shift = (long long)(kWgPad + (k - 1) * d) * K3;
-        if ((rc = gemm_stacked(s, M, 2 * kWnCh, kWnCh, H3(f, i) + shift, Wtap + (size_t)k * K3 * 2 * kWnCh, a_out, 2 * kWnCh, 1.f))) return rc;
+        const __nv_bfloat16* hk = H3(f, i) + shift;
+        if ((rc = tc_pack_hl(s, hk, hk + kWnCh, K3, false, M, kWnCh, 128, kWnK1 / 64, a1img, 0, 8 * k))) return rc;
+        const __nv_bfloat16* wk = Wtap + (size_t)k * K3 * 2 * kWnCh;
+        if ((rc = tc_pack_hl(s, wk, wk + (size_t)2 * kWnCh * 2 * kWnCh, 2 * kWnCh, true, 2 * kWnCh, kWnCh, 256, kWnK1 / 64, b1img, 0, 8 * k))) return rc;
       }
+      if ((rc = tc_pack_hl(s, Wc, Wc + (size_t)2 * kWnMel * 2 * kWnCh, 2 * kWnCh, true, 2 * kWnCh, kWnMel, 256, kWnK1 / 64, b1img, 0, 24))) return rc;
+      if ((rc = tc_gemm_images(s, a1img, b1img, M, 2 * kWnCh, kWnK1, a_out, 2 * kWnCh, 0.f))) return rc;
       wo += (size_t)3 * K3 * 2 * kWnCh + (size_t)3 * kWnMel * 2 * kWnCh;
       gate_kernel<<<ew_grid(rows * kWnCh / 4), 256, 0, s>>>(APRE(f, i), w->in_b[f][i], w->cond_b[f][i], FP(l.g), G3(f, i), N, T);
       const int rout = i < kWnLayers - 1 ? 2 * kWnCh : kWnCh;
@@ -1198,6 +1212,40 @@ static void colsum_valid(cudaStream_t s, const float* in, int ld, int C, float* 
   if (out2) sum_partials_kernel<<<(C + 127) / 128, 128, 0, s>>>(part, kWgPartSlices, C, out2, 0);
 }
 
+// P [Mr rows = padded rows 128 .. rows_p - 129][3 x 512 | 640]: d h(u) = sum_k P_k(u - (k-1) d) (rows outside the utterance
+// contribute nothing: their d a is zero), d mel(u) += P_cond(u).  One thread = 4 channels of one valid position.
+__global__ void shift_add_kernel(const float* __restrict__ P, float* __restrict__ dh, float* __restrict__ dmel, int N, int T, int d) {
+  const int Tp = T + 2 * kWgPad;
+  constexpr int W4 = kWnK1 / 4, H4 = kWnCh / 4;  // float4 columns of a P row / of the d h part
+  const size_t n = (size_t)N * T * (H4 + kWnMel / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % (H4 + kWnMel / 4));
+    const size_t nt = i / (H4 + kWnMel / 4);
+    const int t = (int)(nt % T), u = (int)(nt / T);
+    const size_t prow = (size_t)u * Tp + kWgPad + t;   // padded row; P row = prow - kWgPad
+    const float4* Pr = reinterpret_cast<const float4*>(P);
+    if (c4 < H4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int ts = t - (k - 1) * d;
+        if (ts >= 0 && ts < T) {
+          const float4 v = Pr[((size_t)u * Tp + ts) * W4 + k * H4 + c4];  // P row of padded row (u Tp + 128 + ts)
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      reinterpret_cast<float4*>(dh)[prow * H4 + c4] = acc;
+    } else if (dmel) {
+      const int m4 = c4 - H4;
+      const float4 v = Pr[(prow - kWgPad) * W4 + 3 * H4 + m4];
+      float4* o = reinterpret_cast<float4*>(dmel) + prow * (kWnMel / 4) + m4;
+      float4 c = *o;
+      c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+      *o = c;
+    }
+  }
+}
+
 // dW = A_hi^T B_hi + A_lo^T B_hi + A_hi^T B_lo over `rows` rows of two stacked operands (block widths ka / nb)
 static int wgrad_x3(cudaStream_t s, int ka, int nb, int rows, const __nv_bfloat16* A3, int lda, const __nv_bfloat16* B3, int ldb, float* C) {
   return tc_gemm_hl(s, true, false, ka, nb, rows, A3, A3 + ka, lda, 0, B3, B3 + nb, ldb, 0, C, nb, 0, 0.f, 1);
@@ -1256,6 +1304,23 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
   MSTTS_CUDA(cudaMemsetAsync(ws + b.dopad, 0, rows_p * 8 * 4, s));
   MSTTS_CUDA(cudaMemsetAsync(ws + b.dskip, 0, rows_p * kWnCh * 4, s));
 
+  // operand images and product buffers of the merged per-layer products (stream-ordered scratch, one set per call)
+  ScratchScope wg_scope(s);
+  const int KbR = (Mr + 63) / 64;
+  void *wimgA = nullptr, *daT = nullptr, *daA = nullptr, *wimgB = nullptr;
+  float *dw_all = nullptr, *Pbuf = nullptr;
+  if ((rc = wg_scope.get(&wimgA, tc_image_bytes(kWnK1, Mr, 128)))) return rc;     // [3 taps x 512 | mel 640] rows, K = positions
+  if ((rc = wg_scope.get(&daT, tc_image_bytes(2 * kWnCh, Mr, 256)))) return rc;   // d a^T
+  if ((rc = wg_scope.get(&daA, tc_image_bytes(Mr, 2 * kWnCh, 128)))) return rc;   // d a
+  if ((rc = wg_scope.get(&wimgB, tc_image_bytes(9 * 256, 2 * kWnCh, 256)))) return rc;  // 3 x 512 tap rows + 640 cond rows (padded to 768)
+  if ((rc = wg_scope.get((void**)&dw_all, (size_t)kWnK1 * 2 * kWnCh * sizeof(float)))) return rc;
+  if ((rc = wg_scope.get((void**)&Pbuf, (size_t)Mr * kWnK1 * sizeof(float)))) return rc;
+  MSTTS_CUDA(cudaMemsetAsync(wimgB, 0, tc_image_bytes(9 * 256, 2 * kWnCh, 256), s));  // the 128 pad rows of the last n-tile stay zero
+  {
+    const __nv_bfloat16* m3 = BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel;
+    if ((rc = tc_pack_hl(s, m3, m3 + kWnMel, 3 * kWnMel, true, kWnMel, Mr, 128, KbR, wimgA, 12, 0))) return rc;
+  }
+
   float* dz = FP(l.xa);  // forward scratch, free now
   dz_kernel<<<ew_grid(rows * 8), 256, 0, s>>>(z, 1.f / (sigma * sigma * n_el), rows * 8, dz);
   float* dxcur = FP(b.dx2);
@@ -1308,26 +1373,31 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
                                                             N, T);
       colsum_valid(s, FP(b.da), 2 * kWnCh, 2 * kWnCh, dwt->in_b[f][i], dwt->cond_b[f][i], FP(b.part), N, T);
       const __nv_bfloat16* da3p = BF(b.da3) + (size_t)kWgPad * A3;
-      // conditioning conv: d W_cond = mel^T d a ; d mel += d a W_cond^T
-      if ((rc = wgrad_x3(s, kWnMel, 2 * kWnCh, Mr, BF(l.mel3) + (size_t)kWgPad * 3 * kWnMel, 3 * kWnMel, da3p, A3, FP(b.dw_eff)))) return rc;
-      wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->cond_v[f][i], w->cond_g[f][i], FP(b.dw_eff), kWnMel, 2 * kWnCh,
-                                                                  dwt->cond_g[f][i], dwt->cond_v[f][i]);
-      if (d_mel_nt640)
-        if ((rc = gemm_stacked_nt(s, Mr, kWnMel, 2 * kWnCh, da3p, Wc_c, FP(b.dmel) + (size_t)kWgPad * kWnMel, kWnMel, 1.f))) return rc;
-      // dilated conv: d W_in[k] = h(t + (k-1) d)^T d a(t) ; d h(u) = sum_k d a(u - (k-1) d) W_in[k]^T
+      // ---- weight gradients of the dilated conv and the conditioning conv: ONE product ----
+      //   dW[(tap k, ci) | mel m][co] = sum over rows  [h(t + (k-1) d) | mel(t)]^T  d a(t)        (M = 2176, N = 1024, K = rows)
+      // operand rows: three transposed row-shifted views of the layer input + the transposed conditioning (packed once per
+      // call); the d a operand is packed once and shared
       for (int k = 0; k < 3; ++k) {
-        const long long sh = (long long)(kWgPad + (k - 1) * d) * K3;
-        if ((rc = wgrad_x3(s, kWnCh, 2 * kWnCh, Mr, H3(f, i) + sh, K3, da3p, A3, FP(b.dw_eff) + (size_t)k * kWnCh * 2 * kWnCh))) return rc;
+        const __nv_bfloat16* hk = H3(f, i) + (long long)(kWgPad + (k - 1) * d) * K3;
+        if ((rc = tc_pack_hl(s, hk, hk + kWnCh, K3, true, kWnCh, Mr, 128, KbR, wimgA, 4 * k, 0))) return rc;
       }
-      wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->in_v[f][i], w->in_g[f][i], FP(b.dw_eff), 3 * kWnCh, 2 * kWnCh,
+      if ((rc = tc_pack_hl(s, da3p, da3p + 2 * kWnCh, A3, true, 2 * kWnCh, Mr, 256, KbR, daT, 0, 0))) return rc;
+      if ((rc = tc_gemm_images(s, wimgA, daT, kWnK1, 2 * kWnCh, Mr, dw_all, 2 * kWnCh, 0.f))) return rc;
+      wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->cond_v[f][i], w->cond_g[f][i], dw_all + (size_t)3 * kWnCh * 2 * kWnCh, kWnMel,
+                                                                  2 * kWnCh, dwt->cond_g[f][i], dwt->cond_v[f][i]);
+      wn_bwd_kernel<<<(2 * kWnCh + 31) / 32, dim3(32, 32), 0, s>>>(w->in_v[f][i], w->in_g[f][i], dw_all, 3 * kWnCh, 2 * kWnCh,
                                                                   dwt->in_g[f][i], dwt->in_v[f][i]);
-      const int nxt = cur ^ 1;
+      // ---- activation-side products: ONE product P = d a . [W_in[0]^T | W_in[1]^T | W_in[2]^T | W_cond^T]  (N = 2176, K = 1024),
+      //      then d h(u) = sum_k P_k(u - (k-1) d)  and  d mel += P_cond  in one pass ----
+      if ((rc = tc_pack_hl(s, da3p, da3p + 2 * kWnCh, A3, false, Mr, 2 * kWnCh, 128, 2 * kWnCh / 64, daA, 0, 0))) return rc;
       for (int k = 0; k < 3; ++k) {
-        const long long sh = (long long)(kWgPad - (k - 1) * d) * A3;
-        if ((rc = gemm_stacked_nt(s, Mr, kWnCh, 2 * kWnCh, BF(b.da3) + sh, Wtap_c + (size_t)k * kWnCh * A3, FP(b.dh[nxt]) + (size_t)kWgPad * kWnCh,
-                                  kWnCh, k == 0 ? 0.f : 1.f)))
-          return rc;
+        const __nv_bfloat16* wk = Wtap_c + (size_t)k * kWnCh * A3;
+        if ((rc = tc_pack_hl(s, wk, wk + 2 * 2 * kWnCh, A3, false, kWnCh, 2 * kWnCh, 256, 2 * kWnCh / 64, wimgB, 2 * k, 0))) return rc;
       }
+      if ((rc = tc_pack_hl(s, Wc_c, Wc_c + 2 * 2 * kWnCh, A3, false, kWnMel, 2 * kWnCh, 256, 2 * kWnCh / 64, wimgB, 6, 0))) return rc;
+      if ((rc = tc_gemm_images(s, daA, wimgB, Mr, kWnK1, 2 * kWnCh, Pbuf, kWnK1, 0.f))) return rc;
+      const int nxt = cur ^ 1;
+      shift_add_kernel<<<ew_grid(rows * (kWnK1 / 4)), 256, 0, s>>>(Pbuf, FP(b.dh[nxt]), d_mel_nt640 ? FP(b.dmel) : nullptr, N, T, d);
       cur = nxt;
     }
     // ---- start conv (weight-normed 1x1, c/2 -> 512) ----
