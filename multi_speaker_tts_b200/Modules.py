@@ -134,8 +134,10 @@ def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False
         lin, stop, align = _DecoderFunction.apply(memory, text_len, inputs, sequence_length, pm, zm, T, mode,
                                                   *[w[k] for k in DECODER_KEYS])
     else:
+        # free-running decode: the tcgen05 loop (projection + prenet inside the kernel) for up to 32 rows, else the SIMT kernel
+        mode = mode or ("bf16x3" if (B <= 32 and Te <= 128 and D in (256, 512, 768)) else "fp32")
         with torch.no_grad():
-            lin, stop, align, _ = decoder_forward(w, memory, text_len, None, None, pm, None, False, T, "fp32")
+            lin, stop, align, _ = decoder_forward(w, memory, text_len, None, None, pm, None, False, T, mode)
     return (Decoder_Output(linear=lin, stop=stop.unsqueeze(-1)),
             Decoder_State(time=lin.shape[1], alignment_history=Alignment_History(align)))
 

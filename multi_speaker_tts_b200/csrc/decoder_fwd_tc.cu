@@ -38,14 +38,23 @@ struct DecFwdTcParams {
   float *act0, *act1, *c0n, *c1n, *cz0, *hz0, *cz1, *hz1, *m0, *m1, *ctx, *cum, *align_tm, *qpart, *qf;
   unsigned* barrier;
   long long* dbg;  // [T][32] phase time stamps of CTA 0 (may be null)
+  // free-running decode (Modules.py:212-237): projection + prenet inside the loop, stop-token exit
+  int infer;
+  const float *Wp, *bp, *P0, *pb0, *P1, *pb1;
+  const uint8_t* prenet_mask;  // [T,2,B,256]
+  uint8_t* ximg_pre;           // [2 parities][4 tiles][8 KB] prenet output of the coming step
+  float* proj_tm;              // [T,B,81] bias-free projection (finish_outputs adds the bias)
+  int* steps_done;
 };
 
 struct TcSmem {
   // byte offsets into dynamic shared memory
-  uint32_t ring, xbuf, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, total;
+  uint32_t ring, xbuf, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, inf, total;
 };
+// free-running extras (floats): x_s [256] | pred [8][96] | pparts [4][96] | frame_s [96] | h1_s [256] | p2red [256] | pre_s [64]
+constexpr uint32_t kTcInferFloats = 256 + 8 * 96 + 4 * 96 + 96 + 256 + 256 + 64;
 
-__host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
+__host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D, int infer = 0) {
   const int TeP = (Te + 31) & ~31;
   TcSmem s;
   uint32_t off = 0;
@@ -70,6 +79,7 @@ __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D) {
   s.ctx_s = take((D / kDecCluster) * 4);
   s.bred = take(16 * 4);
   s.bars = take(256);
+  s.inf = take(infer ? kTcInferFloats * 4 : 0);
   s.total = off;
   return s;
 }
@@ -102,9 +112,10 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   const int cid = blockIdx.x / kDecCluster;
   const int TeP = (Te + 31) & ~31;
   const int n0 = P.n0;
-  const int tps = n0 + 12;  // weight tiles per step
-  const int total_tiles = tps * (P.T - 1) + n0 + 4;
-  const TcSmem L = tc_fwd_smem(NS, Te, D);
+  const int infer = P.infer;
+  const int tps = n0 + 12 + infer;  // weight tiles per step (free-running: + the prenet rows of cell 0's kernel)
+  const int total_tiles = tps * (P.T - 1) + n0 + infer + 4;
+  const TcSmem L = tc_fwd_smem(NS, Te, D, infer);
 
   uint8_t* ring = smem + L.ring;   // [NS][32 KB] weight tiles
   uint8_t* xbuf = smem + L.xbuf;   // [32 KB]  activation operand of the running job (J0, J1, J2, J3 in turn)
@@ -127,8 +138,17 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   uint64_t* job_done = xfull + 2;      // [4]
   uint64_t* rs_bar = job_done + 4;     // K-split reduction pushes (st.async complete_tx)
   uint64_t* e_bar = rs_bar + 1;        // partial-energy all-gather
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_bar + 1);
+  uint64_t* pp_bar = e_bar + 1;        // free-running: projection partials all-gather
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pp_bar + 1);
   unsigned* ready_seq = tmem_slot + 1;
+  unsigned* exit_flag = ready_seq + 1;  // free-running: every row has emitted its stop token -> producers / MMA issuer leave
+  float* x_s = reinterpret_cast<float*>(smem + L.inf);  // free-running scratch (see kTcInferFloats)
+  float* pred = x_s + 256;
+  float* pparts = pred + 8 * 96;
+  float* frame_s = pparts + 4 * 96;
+  float* h1_s = frame_s + 96;
+  float* p2red = h1_s + 256;
+  float* pre_s = p2red + 256;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -140,7 +160,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     for (int j = 0; j < 4; ++j) ptx::mbar_init(&job_done[j], 1);
     ptx::mbar_init(rs_bar, 1);
     ptx::mbar_init(e_bar, 1);
+    ptx::mbar_init(pp_bar, 1);
     *ready_seq = 0;
+    *exit_flag = 0;
     ptx::fence_mbar_init();
   }
   if (warp == kTcMmaWarp) ptx::tmem_alloc(tmem_slot, 512);
@@ -197,6 +219,19 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       const uint8_t* wsrc = P.wimg + (size_t)blockIdx.x * tps * kWTileBytes;
       for (int i = warp - 8; i < total_tiles; i += 2) {
         const int s = i % NS, round = i / NS;
+        if (infer) {
+          // free-running: whether step i / tps runs at all is known only after the barrier that ends the previous step, and
+          // a tile issued for a step that never runs would land in the shared memory of an exiting CTA -> no prefetch across steps
+          const unsigned need = 3u * (unsigned)(i / tps);
+          bool stop = false;
+          while (ld_volatile_shared(ready_seq) < need) {
+            if (ld_volatile_shared(exit_flag)) {
+              stop = true;
+              break;
+            }
+          }
+          if (stop) break;
+        }
         if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
         ptx::mbar_arrive_expect_tx(&wfull[s], kWTileBytes);
         ptx::bulk_g2s(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s]);
@@ -231,13 +266,27 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           // barrier that passes long after their predecessor ended, so one buffer costs nothing and pays for a 4th ring slot)
           if (job >= 1) ptx::mbar_wait(&job_done[job - 1], t & 1);
           else if (t > 0) ptx::mbar_wait(&job_done[3], (t - 1) & 1);
+          bool stop = false;
           while (ld_volatile_shared(ready_seq) < need) {
+            if (infer && ld_volatile_shared(exit_flag)) {
+              stop = true;
+              break;
+            }
           }
-          ptx::mbar_arrive_expect_tx(&xfull[job & 1], bytes);
-          ptx::bulk_g2s(xbuf, src, bytes, &xfull[job & 1]);
+          if (stop) goto act_done;
+          if (job == 0 && infer) {  // + the K-slice of prenet(frame_{t-1}) behind the context tiles
+            ptx::mbar_arrive_expect_tx(&xfull[0], bytes + kXTileBytes);
+            ptx::bulk_g2s(xbuf, src, bytes, &xfull[0]);
+            ptx::bulk_g2s(xbuf + bytes, P.ximg_pre + (size_t)(t & 1) * (kPrenet / kTcKT) * kXTileBytes + (size_t)crank * kXTileBytes, kXTileBytes,
+                          &xfull[0]);
+          } else {
+            ptx::mbar_arrive_expect_tx(&xfull[job & 1], bytes);
+            ptx::bulk_g2s(xbuf, src, bytes, &xfull[job & 1]);
+          }
         }
       }
     }
+  act_done:
     __syncwarp();
   } else if (warp == kTcMmaWarp) {
     // =========================== MMA issuer ===========================
@@ -247,8 +296,20 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       for (int t = 0; t < P.T; ++t) {
         const int njobs = (t == P.T - 1) ? 2 : 4;
         for (int job = 0; job < njobs; ++job) {
-          const int nt = job == 0 ? n0 : 4;
-          ptx::mbar_wait(&xfull[job & 1], (uint32_t)(job >> 1));  // two barriers over the one buffer: even jobs J0, J2, J0, ... ; odd jobs J1, J3, ...
+          const int nt = job == 0 ? n0 + infer : 4;
+          // two barriers over the one buffer: even jobs J0, J2, J0, ... ; odd jobs J1, J3, ...
+          if (!infer) {
+            ptx::mbar_wait(&xfull[job & 1], (uint32_t)(job >> 1));
+          } else {
+            bool stop = false;
+            while (!ptx::mbar_try_wait(&xfull[job & 1], (uint32_t)(job >> 1))) {
+              if (ld_volatile_shared(exit_flag)) {
+                stop = true;
+                break;
+              }
+            }
+            if (stop) goto mma_done;
+          }
           const uint32_t d = tmem + ((job & 1) ? (16u << 16) : 0u);
           const uint32_t xbase = ptx::smem_u32(xbuf);
           for (int kt = 0; kt < nt; ++kt, ++i) {
@@ -271,6 +332,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         }
       }
     }
+  mma_done:
     __syncwarp();
   } else {
     // =========================== compute warps ===========================
@@ -280,7 +342,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     const size_t BC = (size_t)B * kCell, BG = (size_t)B * kGates;
     const uint32_t recv_addr = ptx::smem_u32(recv);
     const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quarter / accumulator column half of this warp
-    uint32_t rs_parity = 0, e_parity = 0;
+    uint32_t rs_parity = 0, e_parity = 0, pp_parity = 0;
+    int fin_row = 0;  // free-running: warp 0, lane b: row b has emitted stop >= 0
     float c0 = 0.f, h0 = 0.f, c1 = 0.f, h1 = 0.f;  // zoned state of this (batch, unit), AttentionWrapper.zero_state
     const float bias0[4] = {P.b0[unit], P.b0[kCell + unit], P.b0[2 * kCell + unit], P.b0[3 * kCell + unit]};
     const float bias1[4] = {P.b1[unit], P.b1[kCell + unit], P.b1[2 * kCell + unit], P.b1[3 * kCell + unit]};
@@ -372,7 +435,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     location_features();
 
     for (int t = 0; t < P.T; ++t) {
-      const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
+      const uint8_t* zm = P.training ? P.zone_mask + (size_t)t * 4 * BC : nullptr;  // inference: mask = 1, the (1 - r) factor stays
       const int par = t & 1;
       STAMP(0);
       // ================= phase A: LSTM cell 0 =================
@@ -380,11 +443,18 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         float add[4] = {0.f, 0.f, 0.f, 0.f};
         float mc = 1.f, mh = 1.f;
         if (brow) {
-          const float* gp = P.g0pre + (size_t)t * BG + (size_t)b * kGates + unit;
+          if (!infer) {
+            const float* gp = P.g0pre + (size_t)t * BG + (size_t)b * kGates + unit;
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) add[gi] = gp[gi * kCell] + bias0[gi];
-          mc = (float)zm[(size_t)b * kCell + unit];
-          mh = (float)zm[BC + (size_t)b * kCell + unit];
+            for (int gi = 0; gi < 4; ++gi) add[gi] = gp[gi * kCell] + bias0[gi];
+          } else {  // the prenet rows of cell 0's kernel are part of job J0
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) add[gi] = bias0[gi];
+          }
+          if (zm) {
+            mc = (float)zm[(size_t)b * kCell + unit];
+            mh = (float)zm[BC + (size_t)b * kCell + unit];
+          }
         }
         reduce_scatter(0, t);
         STAMP(2);
@@ -418,7 +488,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         }
         STAMP(3);
         grid_arrive_compute(P.barrier, bar_target, gridDim.x);
-        if (brow) {  // activations saved for the reverse pass: nobody waits for these inside the loop
+        if (brow && !infer) {  // activations saved for the reverse pass: nobody waits for these inside the loop
           const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
           P.act0[ai] = r.ig;
           P.act0[ai + kCell] = r.jg;
@@ -436,7 +506,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       // ================= phase B: LSTM cell 1 (+ partial query projection) =================
       {
         float mc = 1.f, mh = 1.f;
-        if (brow) {
+        if (brow && zm) {
           mc = (float)zm[2 * BC + (size_t)b * kCell + unit];
           mh = (float)zm[3 * BC + (size_t)b * kCell + unit];
         }
@@ -489,8 +559,10 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           }
         }
         STAMP(7);
+        // free-running: the projection of phase C reads every unit of m1_t from global memory -> store it before the barrier
+        if (infer && brow) P.m1[(size_t)t * BC + (size_t)b * kCell + unit] = r.m;
         grid_arrive_compute(P.barrier, bar_target, gridDim.x);
-        if (brow) {
+        if (brow && !infer) {
           const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
           P.act1[ai] = r.ig;
           P.act1[ai + kCell] = r.jg;
@@ -638,6 +710,78 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
                          ximg_row_offset(bb, hl);
           *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(o);
         }
+        if (infer) {
+          // ---- free running (Modules.py:212-237,309-321): frame_t = [m1_t | ctx_t] . Wp + bp, K split over the cluster;
+          //      then prenet(frame_t) = the decoder input of step t + 1 (dropout stays on, Modules.py:252) ----
+          x_s[tid] = __ldcg(P.m1 + ((size_t)t * B + bb) * kCell + crank * 256 + tid);
+          if (tid == 0) ptx::mbar_arrive_expect_tx(pp_bar, kDecCluster * (kMel + 1) * 4);
+          ptx::bar_sync(1, kTcCompute);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+          for (int r = warp; r < 256 + Dq; r += 8) {
+            const int grow = r < 256 ? crank * 256 + r : kCell + crank * Dq + (r - 256);
+            const float* wr = P.Wp + (size_t)grow * (kMel + 1);
+            const float xv = r < 256 ? x_s[r] : ctx_s[r - 256];
+            a0 = fmaf(xv, __ldg(wr + lane), a0);
+            a1 = fmaf(xv, __ldg(wr + 32 + lane), a1);
+            if (lane < kMel + 1 - 64) a2 = fmaf(xv, __ldg(wr + 64 + lane), a2);
+          }
+          pred[warp * 96 + lane] = a0;
+          pred[warp * 96 + 32 + lane] = a1;
+          pred[warp * 96 + 64 + lane] = a2;
+          ptx::bar_sync(1, kTcCompute);
+          if (tid < kMel + 1) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sacc += pred[w * 96 + tid];
+            const uint32_t pa = ptx::smem_u32(pparts) + (uint32_t)((crank * 96 + tid) * 4);
+            const uint32_t pb = ptx::smem_u32(pp_bar);
+#pragma unroll
+            for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(pa, dst), sacc, ptx::mapa(pb, dst));
+          }
+          mbar_wait_warp(pp_bar, pp_parity);
+          pp_parity ^= 1u;
+          if (tid < kMel + 1) {
+            const float sacc = ((pparts[tid] + pparts[96 + tid]) + pparts[192 + tid]) + pparts[288 + tid];
+            if (crank == 0) P.proj_tm[((size_t)t * B + bb) * (kMel + 1) + tid] = sacc;  // bias-free; read by every CTA after the barrier
+            frame_s[tid] = sacc + P.bp[tid];
+          }
+          ptx::bar_sync(1, kTcCompute);
+          if (t + 1 < P.T) {
+            const uint8_t* pm = P.prenet_mask + (size_t)(t + 1) * 2 * B * kPrenet;
+            {  // layer 0: every CTA of the cluster computes all 256 outputs (80 x 256)
+              float sacc = P.pb0[tid];
+              for (int k = 0; k < kMel; ++k) sacc = fmaf(frame_s[k], __ldg(P.P0 + k * kPrenet + tid), sacc);
+              h1_s[tid] = (fmaxf(sacc, 0.f) / 0.5f) * (float)pm[(size_t)bb * kPrenet + tid];
+            }
+            ptx::bar_sync(1, kTcCompute);
+            {  // layer 1: CTA r computes outputs 64 r .. 64 r + 63 = its K-slice of the next step's job J0
+              const int j = crank * 64 + (tid & 63), kq = tid >> 6;
+              float sacc = 0.f;
+              for (int k = kq * 64; k < kq * 64 + 64; ++k) sacc = fmaf(h1_s[k], __ldg(P.P1 + k * kPrenet + j), sacc);
+              p2red[kq * 64 + (tid & 63)] = sacc;
+            }
+            ptx::bar_sync(1, kTcCompute);
+            if (tid < 64) {
+              const int j = crank * 64 + tid;
+              const float sacc = ((p2red[tid] + p2red[64 + tid]) + p2red[128 + tid]) + p2red[192 + tid] + P.pb1[j];
+              pre_s[tid] = (fmaxf(sacc, 0.f) / 0.5f) * (float)pm[((size_t)B + bb) * kPrenet + j];
+            }
+            ptx::bar_sync(1, kTcCompute);
+            if (tid < 16) {  // 16-byte rows of the pre image: (hi|lo, 8-value chunk)
+              const int hl = tid >> 3, ch = tid & 7;
+              __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(pre_s[ch * 8 + jj], hi, lo);
+                o[jj] = hl ? lo : hi;
+              }
+              uint8_t* img = P.ximg_pre + (size_t)((t + 1) & 1) * (kPrenet / kTcKT) * kXTileBytes + (size_t)crank * kXTileBytes +
+                             (size_t)ch * 128 + ximg_row_offset(bb, hl);
+              *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(o);
+            }
+          }
+        }
       }
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
@@ -653,7 +797,39 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         }
         location_features();
       }
-      grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 3);
+      if (!infer) {
+        grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 3);
+      } else {
+        // wait WITHOUT publishing the event: whether a next step exists is decided first.  finished |= stop >= 0
+        // (Modules.py:216-219, OR-ed at :409); every CTA evaluates the same data => uniform exit.  The step cap
+        // (time >= Max_Inference_Length) is the loop bound T = cap + 1.
+        if ((tid & 31) == 0 && tid < 128) {
+          while (ld_acquire_gpu(P.barrier) < bar_target) {
+          }
+        }
+        ptx::bar_sync(1, kTcCompute);
+        if (warp == 0) {
+          if (lane < B) {
+            const float st = __ldcg(P.proj_tm + ((size_t)t * B + lane) * (kMel + 1) + kMel) + P.bp[kMel];
+            if (st >= 0.f) fin_row = 1;
+          }
+          const int all = __all_sync(0xffffffffu, lane < B ? fin_row : 1);
+          if (lane == 0) {
+            if (blockIdx.x == 0) *P.steps_done = t + 1;
+            if (all) st_volatile_shared(exit_flag, 1u);
+            else st_volatile_shared(ready_seq, 3u * t + 3);
+          }
+        }
+        ptx::bar_sync(1, kTcCompute);
+        if (ld_volatile_shared(exit_flag)) {
+          // the deferred jobs J2 / J3 of this step were issued already: let them finish before the accumulators go away
+          if (t < P.T - 1) {
+            mbar_wait_warp(&job_done[2], t & 1);
+            mbar_wait_warp(&job_done[3], t & 1);
+          }
+          break;
+        }
+      }
       STAMP(10);
     }
 #undef STAMP
@@ -670,8 +846,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 // ---- weight image: bf16 hi/lo tiles in stream order for every CTA ----------------------------------------
 // tile rows i = rr*32 + g*8 + u  <->  gate column g*1024 + 32c + 8rr + u ; k runs over this CTA's K-slice
 __global__ void prep_wimg_fwd_kernel(const float* __restrict__ K0, const float* __restrict__ K1, uint8_t* __restrict__ wimg,
-                                     int D) {
-  const int n0 = D / 256, tps = n0 + 12, Dq = D / kDecCluster;
+                                     int D, int infer) {
+  const int n0 = D / 256, tps = n0 + 12 + infer, Dq = D / kDecCluster;
   const size_t total = (size_t)kDecGrid * tps * 8 * 128;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(idx & 127);
@@ -687,8 +863,12 @@ __global__ void prep_wimg_fwd_kernel(const float* __restrict__ K0, const float* 
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         v[j] = K0[(size_t)(kPrenet + k + j) * kGates + col] + K0[(size_t)(kPrenet + D + k + j) * kGates + col];
+    } else if (infer && q == n0) {  // free-running: prenet rows of cell 0's kernel, K-slice r (64 of the 256 rows)
+      const int k = r * kTcKT + kc * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = K0[(size_t)(k + j) * kGates + col];
     } else {
-      const int jq = (q - n0) >> 2, kt = (q - n0) & 3;
+      const int jq = (q - n0 - infer) >> 2, kt = (q - n0 - infer) & 3;
       const int k = r * 256 + kt * kTcKT + kc * 8;
       const float* src = jq == 0 ? K1 + (size_t)k * kGates
                                  : (jq == 1 ? K0 + (size_t)(kPrenet + 2 * D + k) * kGates : K1 + (size_t)(kCell + k) * kGates);
@@ -701,6 +881,32 @@ __global__ void prep_wimg_fwd_kernel(const float* __restrict__ K0, const float* 
     uint8_t* tile = wimg + tq * kWTileBytes + (size_t)(i >> 3) * 1024 + (size_t)kc * 128 + (size_t)(i & 7) * 16;
     *reinterpret_cast<uint4*>(tile) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(tile + kWTileBytes / 2) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// free-running decode: prenet of the all-zero first frame for batch row blockIdx.x -> parity-0 operand image of job J0
+__global__ void prenet_zero_frame_kernel(const float* __restrict__ pb0, const float* __restrict__ P1, const float* __restrict__ pb1,
+                                         const uint8_t* __restrict__ mask, int B, uint8_t* __restrict__ ximg_pre) {
+  __shared__ float h1[kPrenet], pre[kPrenet];
+  const int b = blockIdx.x, j = threadIdx.x;
+  h1[j] = (fmaxf(pb0[j], 0.f) / 0.5f) * (float)mask[(size_t)b * kPrenet + j];
+  __syncthreads();
+  float sacc = pb1[j];
+  for (int k = 0; k < kPrenet; ++k) sacc = fmaf(h1[k], P1[k * kPrenet + j], sacc);
+  pre[j] = (fmaxf(sacc, 0.f) / 0.5f) * (float)mask[((size_t)B + b) * kPrenet + j];
+  __syncthreads();
+  if (j < 64) {  // (hi|lo, 8-value chunk): 2 x 32 chunks of 16 bytes
+    const int hl = j >> 5, ch = j & 31;
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(pre[ch * 8 + jj], hi, lo);
+      o[jj] = hl ? lo : hi;
+    }
+    const int k = ch * 8;
+    uint8_t* img = ximg_pre + (size_t)(k >> 6) * kXTileBytes + (size_t)((k & 63) >> 3) * 128 + ximg_row_offset(b, hl);
+    *reinterpret_cast<uint4*>(img) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -761,17 +967,26 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   P.barrier = (unsigned*)(ws + l.barrier);
   P.dbg = (long long*)(ws + l.dbg);
   // weight image (weights change every optimiser step) and zeroed activation images (initial state = 0)
-  prep_wimg_fwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_f), D);
+  const int infer = io->is_training ? 0 : 1;
+  prep_wimg_fwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_f), D, infer);
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_ctx, 0, l.ximg_end - l.ximg_ctx, s));
+  if (infer) {
+    P.infer = 1;
+    P.Wp = w->proj_kernel; P.bp = w->proj_bias; P.P0 = w->prenet0_kernel; P.pb0 = w->prenet0_bias;
+    P.P1 = w->prenet1_kernel; P.pb1 = w->prenet1_bias; P.prenet_mask = io->prenet_mask;
+    P.ximg_pre = (uint8_t*)(ws + l.ximg_pre); P.proj_tm = F(l.proj_tm); P.steps_done = io->steps_done;
+    // decoder input of step 0 = prenet(zero frame) (Modules.py:178-185), straight into the operand image
+    prenet_zero_frame_kernel<<<io->B, kPrenet, 0, s>>>(w->prenet0_bias, w->prenet1_kernel, w->prenet1_bias, io->prenet_mask, io->B, P.ximg_pre);
+  }
   bool ok = false;
-  int rc = launch_fwd_tc<4>(P, s, tc_fwd_smem(4, io->Te, D).total, &ok);  // all 4 weight tiles of J1 resident when m0 arrives
+  int rc = launch_fwd_tc<4>(P, s, tc_fwd_smem(4, io->Te, D, infer).total, &ok);  // all 4 weight tiles of J1 resident when m0 arrives
   if (rc) return rc;
   if (!ok) {
-    rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D).total, &ok);
+    rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D, infer).total, &ok);
     if (rc) return rc;
   }
   if (!ok) {
-    rc = launch_fwd_tc<2>(P, s, tc_fwd_smem(2, io->Te, D).total, &ok);
+    rc = launch_fwd_tc<2>(P, s, tc_fwd_smem(2, io->Te, D, infer).total, &ok);
     if (rc) return rc;
   }
   MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_fwd_tc: shared memory does not fit for Te=%d", io->Te);

@@ -159,9 +159,11 @@ static int check_io(const MsttsDecoderWeights* w, const MsttsDecoderIO* io) {
 // n_steps = step cap + 1 (Max_Inference_Length + 1); outputs beyond *steps_done are zero.
 static int decoder_fwd_free_running(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, void* ws_, size_t ws_bytes,
                                     cudaStream_t s) {
-  MSTTS_REQUIRE(io->mode == MSTTS_MODE_FP32, MSTTS_E_UNSUPPORTED,
-                "decoder: free-running mode runs on the fp32 kernel only (mode=%d)", io->mode);
   MSTTS_REQUIRE(io->steps_done, MSTTS_E_INVALID, "decoder: free-running mode needs steps_done");
+  const bool tc = io->mode == MSTTS_MODE_BF16X3;  // tcgen05 loop with the projection + prenet inside (decoder_fwd_tc.cu)
+  MSTTS_REQUIRE(!tc || (io->B <= 32 && io->Te <= 128 && io->D % 256 == 0 && io->D <= 768), MSTTS_E_UNSUPPORTED,
+                "decoder: free-running bf16x3 mode needs B<=32, Te<=128, D in {256,512,768} (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te,
+                io->D);
   const int B = io->B, Te = io->Te, D = io->D, T = io->n_steps;
   const DecLayout l = dec_layout(B, Te, io->L, D, T, io->mode);
   MSTTS_REQUIRE(ws_ && ws_bytes >= l.total, MSTTS_E_WORKSPACE, "decoder: workspace %zu < %zu", ws_bytes, l.total);
@@ -186,7 +188,7 @@ static int decoder_fwd_free_running(const MsttsDecoderWeights* w, const MsttsDec
   MSTTS_CUDA(cudaMemsetAsync(ws + l.proj_tm, 0, TB * (kMel + 1) * sizeof(float), s));
   MSTTS_CUDA(cudaMemsetAsync(ws + l.align_tm, 0, TB * Te * sizeof(float), s));
   MSTTS_CUDA(cudaMemsetAsync(io->steps_done, 0, sizeof(int), s));
-  rc = dec_fwd_persistent_entry(w, io, l, ws, s);
+  rc = tc ? dec_fwd_tc_entry(w, io, l, ws, s) : dec_fwd_persistent_entry(w, io, l, ws, s);
   if (rc) return rc;
   finish_outputs_kernel<<<ew_grid(TB * (kMel + 1 + Te)), 256, 0, s>>>(F(l.proj_tm), w->proj_bias, F(l.align_tm), io->linear,
                                                                     io->stop, io->align, B, T, Te);

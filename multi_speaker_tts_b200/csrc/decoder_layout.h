@@ -29,7 +29,7 @@ struct DecLayout {
   size_t barrier;             // 64 B of counters
   // ---- bf16x3 (tcgen05) mode only: operand images in the tensor-core shared-memory layout (decoder_tc.cuh) ----
   size_t wimg_f;              // [128 CTAs][D/256+12 tiles][32 KB] forward weight stream (hi|lo bf16)
-  size_t ximg_ctx, ximg_m0, ximg_h0, ximg_h1, ximg_end;  // [2 parities][K/64 tiles][8 KB] activation images
+  size_t ximg_ctx, ximg_m0, ximg_h0, ximg_h1, ximg_pre, ximg_end;  // [2 parities][K/64 tiles][8 KB] activation images (pre: free-running decode)
   size_t dbg;                 // [T][32] int64 clock64 stamps of CTA 0 at the phase boundaries (profiling aid)
   // ---- reverse pass scratch ----
   size_t bwd_begin;
@@ -92,18 +92,19 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.qf = take(TB * kAtt);
   l.proj_tm = take(TB * (kMel + 1));
   l.barrier = take(16);
-  l.wimg_f = l.ximg_ctx = l.ximg_m0 = l.ximg_h0 = l.ximg_h1 = l.ximg_end = l.dbg = off;
+  l.wimg_f = l.ximg_ctx = l.ximg_m0 = l.ximg_h0 = l.ximg_h1 = l.ximg_pre = l.ximg_end = l.dbg = off;
   if (mode == MSTTS_MODE_BF16X3) {
     auto take_bytes = [&](size_t nbytes) {
       size_t o = off;
       off += align_up(nbytes, 1024);
       return o;
     };
-    l.wimg_f = take_bytes((size_t)kDecGrid * (D / 256 + 12) * 32768);
+    l.wimg_f = take_bytes((size_t)kDecGrid * (D / 256 + 13) * 32768);  // + the prenet-row tile of the free-running decode
     l.ximg_ctx = take_bytes((size_t)2 * (D / 64) * 8192);
     l.ximg_m0 = take_bytes((size_t)2 * (kCell / 64) * 8192);
     l.ximg_h0 = take_bytes((size_t)2 * (kCell / 64) * 8192);
     l.ximg_h1 = take_bytes((size_t)2 * (kCell / 64) * 8192);
+    l.ximg_pre = take_bytes((size_t)2 * (kPrenet / 64) * 8192);
     l.ximg_end = off;
     l.dbg = take_bytes((size_t)(T > kDecGrid ? T : kDecGrid) * 32 * 8);  // also [128 CTAs][32] stamps of the middle step
   }

@@ -44,14 +44,15 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
     ``is_training=False`` is the free-running decode of Modules.py:212-237 (``mel`` / ``mel_len`` / ``zone_mask`` are
     ignored and may be None): ``n_steps`` is the step cap + 1 (default Max_Inference_Length + 1 = 1001), the loop
     stops once every row has emitted ``stop >= 0`` and the outputs are cut to the executed steps (one host sync).
-    It always runs on the fp32 kernel.
+    ``mode="bf16x3"`` runs it on the tcgen05 loop (projection + prenet inside the kernel; B <= 32, Te <= 128), ``"fp32"`` on
+    the SIMT kernel.
     """
     _require_cuda(memory, text_len, prenet_mask)
     lib = _lib.lib()
     B, Te, D = memory.shape
     dev = memory.device
     if not is_training:
-        mel, mel_len, zone_mask, mode = None, None, None, "fp32"
+        mel, mel_len, zone_mask = None, None, None
         if n_steps is None:
             n_steps = 1001
     else:

@@ -10,7 +10,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _run(B, Te, cap, seed, dev, stop_bias=None):
+MODES = ["fp32", "bf16x3"]
+
+
+def _run(B, Te, cap, seed, dev, stop_bias=None, mode="fp32"):
     from oracle import decoder_oracle as O
     from multi_speaker_tts_b200.decoder import decoder_forward
     w = S.init_decoder_weights(0, bias_scale=0.05)
@@ -22,7 +25,7 @@ def _run(B, Te, cap, seed, dev, stop_bias=None):
     wd = {k: v.to(dev) for k, v in w.items()}
     bd = {k: v.to(dev) for k, v in b.items()}
     lin, stop, align, _ = decoder_forward(wd, bd['memory'], bd['text_len'], None, None, bd['prenet_mask'], None,
-                                          is_training=False, n_steps=cap + 1)
+                                          is_training=False, n_steps=cap + 1, mode=mode)
     return ref, (lin.cpu(), stop.cpu(), align.cpu())
 
 
@@ -35,23 +38,26 @@ def _check(ref, got):
     assert torch.equal(got[2].argmax(-1), ref[2].argmax(-1)), "alignment argmax differs"
 
 
-def test_stops_on_stop_token(cuda_dev):
-    ref, got = _run(2, 32, 30, 1, cuda_dev)
+@pytest.mark.parametrize("mode", MODES)
+def test_stops_on_stop_token(cuda_dev, mode):
+    ref, got = _run(2, 32, 30, 1, cuda_dev, mode=mode)
     assert ref[0].shape[1] < 31  # the oracle stopped before the cap
     _check(ref, got)
 
 
-@pytest.mark.parametrize("B,Te,cap,seed", [(5, 33, 40, 4), (4, 64, 30, 5)])
-def test_runs_to_step_cap(cuda_dev, B, Te, cap, seed):
-    ref, got = _run(B, Te, cap, seed, cuda_dev)
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,Te,cap,seed", [(5, 33, 40, 4), (4, 64, 30, 5), (32, 128, 12, 6), (1, 7, 9, 8)])
+def test_runs_to_step_cap(cuda_dev, B, Te, cap, seed, mode):
+    ref, got = _run(B, Te, cap, seed, cuda_dev, mode=mode)
     assert ref[0].shape[1] == cap + 1
     _check(ref, got)
 
 
-def test_delayed_stop(cuda_dev):
+@pytest.mark.parametrize("mode", MODES)
+def test_delayed_stop(cuda_dev, mode):
     """rows finish at different steps (0 and 5) and the finished row keeps computing (impute_finished=False,
     Modules.py:116) until the last one emits stop >= 0"""
-    ref, got = _run(2, 40, 60, 3, cuda_dev, stop_bias=-0.05)
+    ref, got = _run(2, 40, 60, 3, cuda_dev, stop_bias=-0.05, mode=mode)
     assert ref[0].shape[1] == 6
     _check(ref, got)
 
@@ -62,10 +68,10 @@ def test_large_batch_rows_wrap_clusters(cuda_dev):
     _check(ref, got)
 
 
-def test_bf16x3_free_running_uses_fp32_kernel(cuda_dev):
-    from multi_speaker_tts_b200.decoder import decoder_forward
-    w = {k: v.to(cuda_dev) for k, v in S.init_decoder_weights(0).items()}
-    b = {k: v.to(cuda_dev) for k, v in S.synthetic_decoder_batch(2, 16, 4, seed=3).items()}
-    lin, stop, align, _ = decoder_forward(w, b['memory'], b['text_len'], None, None, b['prenet_mask'], None,
-                                          is_training=False, n_steps=5, mode="bf16x3")
-    assert 1 <= lin.shape[1] <= 5 and torch.isfinite(lin).all()
+def test_bf16x3_free_running_refuses_shapes_beyond_its_tiling(cuda_dev):
+    """B > 32 or Te > 128: explicit refusal (the caller picks mode fp32), never a silent fallback"""
+    from multi_speaker_tts_b200._lib import MsttsError
+    with pytest.raises(MsttsError):
+        _run(36, 24, 6, 9, cuda_dev, mode="bf16x3")
+    with pytest.raises(MsttsError):
+        _run(2, 160, 6, 9, cuda_dev, mode="bf16x3")
