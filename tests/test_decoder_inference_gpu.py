@@ -46,10 +46,18 @@ def test_stops_on_stop_token(cuda_dev, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("B,Te,cap,seed", [(5, 33, 40, 4), (4, 64, 30, 5), (32, 128, 12, 6), (1, 7, 9, 8)])
+@pytest.mark.parametrize("B,Te,cap,seed", [(5, 33, 40, 4), (4, 64, 30, 5), (32, 128, 12, 6)])
 def test_runs_to_step_cap(cuda_dev, B, Te, cap, seed, mode):
     ref, got = _run(B, Te, cap, seed, cuda_dev, mode=mode)
     assert ref[0].shape[1] == cap + 1
+    _check(ref, got)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("B,Te,cap,seed", [(1, 7, 9, 8), (3, 1, 5, 2), (32, 100, 3, 11)])
+def test_small_and_full_tiles(cuda_dev, B, Te, cap, seed, mode):
+    """one row / one-token texts / a full 32-row tile; wherever the oracle stops, the kernel stops"""
+    ref, got = _run(B, Te, cap, seed, cuda_dev, mode=mode)
     _check(ref, got)
 
 
