@@ -101,7 +101,8 @@ __device__ __forceinline__ CellOut cell_forward(const float (&g)[4], float cp, f
   return r;
 }
 
-template <int NS>
+// INFER = 1: free-running decode (a compile-time switch: the training instantiation carries none of its branches)
+template <int NS, int INFER>
 __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads, 1)
     decoder_fwd_tc_kernel(const DecFwdTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -112,7 +113,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   const int cid = blockIdx.x / kDecCluster;
   const int TeP = (Te + 31) & ~31;
   const int n0 = P.n0;
-  const int infer = P.infer;
+  constexpr int infer = INFER;
   const int tps = n0 + 12 + infer;  // weight tiles per step (free-running: + the prenet rows of cell 0's kernel)
   const int total_tiles = tps * (P.T - 1) + n0 + infer + 4;
   const TcSmem L = tc_fwd_smem(NS, Te, D, infer);
@@ -913,7 +914,7 @@ __global__ void prenet_zero_frame_kernel(const float* __restrict__ pb0, const fl
 // ======================================== host side ================================================
 bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 128 && D % 256 == 0 && D <= 768; }
 
-template <int NS>
+template <int NS, int INFER>
 static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t smem, bool* ok) {
   int dev = 0;
   MSTTS_CUDA(cudaGetDevice(&dev));
@@ -924,7 +925,7 @@ static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t sm
     return MSTTS_OK;
   }
   *ok = true;
-  MSTTS_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSTTS_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<NS, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(kDecGrid);
@@ -936,12 +937,12 @@ static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t sm
   cudaLaunchAttribute coop_attr[1];
   dec_cooperative_attr(&cfg, coop_attr);
   int nclusters = 0;
-  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_tc_kernel<NS>, &cfg));
+  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_tc_kernel<NS, INFER>, &cfg));
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
                 "decoder_fwd_tc: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
                 kDecGrid / kDecCluster);
   mstts_timer_start(0, stream);
-  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<NS>, P));
+  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<NS, INFER>, P));
   mstts_timer_stop(0, stream);
   return MSTTS_OK;
 }
@@ -979,16 +980,17 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
     prenet_zero_frame_kernel<<<io->B, kPrenet, 0, s>>>(w->prenet0_bias, w->prenet1_kernel, w->prenet1_bias, io->prenet_mask, io->B, P.ximg_pre);
   }
   bool ok = false;
-  int rc = launch_fwd_tc<4>(P, s, tc_fwd_smem(4, io->Te, D, infer).total, &ok);  // all 4 weight tiles of J1 resident when m0 arrives
-  if (rc) return rc;
-  if (!ok) {
-    rc = launch_fwd_tc<3>(P, s, tc_fwd_smem(3, io->Te, D, infer).total, &ok);
-    if (rc) return rc;
+  int rc;
+#define MSTTS_TRY_NS(NS_)                                                                                                   \
+  if (!ok) {                                                                                                                 \
+    rc = infer ? launch_fwd_tc<NS_, 1>(P, s, tc_fwd_smem(NS_, io->Te, D, 1).total, &ok)                                      \
+               : launch_fwd_tc<NS_, 0>(P, s, tc_fwd_smem(NS_, io->Te, D, 0).total, &ok);                                     \
+    if (rc) return rc;                                                                                                       \
   }
-  if (!ok) {
-    rc = launch_fwd_tc<2>(P, s, tc_fwd_smem(2, io->Te, D, infer).total, &ok);
-    if (rc) return rc;
-  }
+  MSTTS_TRY_NS(4)  // all 4 weight tiles of J1 resident when m0 arrives
+  MSTTS_TRY_NS(3)
+  MSTTS_TRY_NS(2)
+#undef MSTTS_TRY_NS
   MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_fwd_tc: shared memory does not fit for Te=%d", io->Te);
   return MSTTS_OK;
 }

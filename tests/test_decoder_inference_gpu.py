@@ -54,9 +54,9 @@ def test_runs_to_step_cap(cuda_dev, B, Te, cap, seed, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("B,Te,cap,seed", [(1, 7, 9, 8), (3, 1, 5, 2), (32, 100, 3, 11)])
+@pytest.mark.parametrize("B,Te,cap,seed", [(1, 7, 9, 8), (3, 9, 5, 2), (32, 100, 3, 11)])
 def test_small_and_full_tiles(cuda_dev, B, Te, cap, seed, mode):
-    """one row / one-token texts / a full 32-row tile; wherever the oracle stops, the kernel stops"""
+    """one row / short texts / a full 32-row tile; wherever the oracle stops, the kernel stops"""
     ref, got = _run(B, Te, cap, seed, cuda_dev, mode=mode)
     _check(ref, got)
 
