@@ -625,7 +625,7 @@ extern "C" int mstts_decoder_bwd(const MsttsDecoderWeights* w, const MsttsDecode
     for (size_t i = 0; i < sizeof(MsttsDecoderWeightGrads) / sizeof(float*); ++i)
       MSTTS_REQUIRE(gp[i], MSTTS_E_INVALID, "decoder_bwd: null weight-gradient pointer #%zu", i);
   }
-  if (dec_is_chunked(io->B, io->mode)) return decoder_bwd_chunked(w, io, g, dw, ws_, ws_bytes, (cudaStream_t)stream_);
+  if (dec_is_chunked(io->B, io->Te, io->mode)) return decoder_bwd_chunked(w, io, g, dw, ws_, ws_bytes, (cudaStream_t)stream_);
   return decoder_bwd_one(w, io, g, dw, ws_, ws_bytes, (cudaStream_t)stream_);
 }
 

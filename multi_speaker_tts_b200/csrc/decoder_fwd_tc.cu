@@ -49,7 +49,7 @@ struct DecFwdTcParams {
 
 struct TcSmem {
   // byte offsets into dynamic shared memory
-  uint32_t ring, xbuf, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, inf, total;
+  uint32_t ring, xbuf, recv, keys, wq, xs, m_s, qred, qf_s, cum_s, e_loc, e_parts, a_s, ctx_s, bred, bars, inf, pre2, total;
 };
 // free-running extras (floats): x_s [256] | pred [8][96] | pparts [4][96] | frame_s [96] | h1_s [256] | p2red [256] | pre_s [64]
 constexpr uint32_t kTcInferFloats = 256 + 8 * 96 + 4 * 96 + 96 + 256 + 256 + 64;
@@ -80,6 +80,7 @@ __host__ __device__ inline TcSmem tc_fwd_smem(int NS, int Te, int D, int infer =
   s.bred = take(16 * 4);
   s.bars = take(256);
   s.inf = take(infer ? kTcInferFloats * 4 : 0);
+  s.pre2 = take(Te > 128 ? 8 * 16 * 32 * 4 : 0);  // TE2: location features of each warp's second 16-position block
   s.total = off;
   return s;
 }
@@ -102,15 +103,23 @@ __device__ __forceinline__ CellOut cell_forward(const float (&g)[4], float cp, f
 }
 
 // INFER = 1: free-running decode (a compile-time switch: the training instantiation carries none of its branches)
-template <int NS, int INFER>
+// TE2 = 1: texts of 129 .. 256 positions.  A CTA cannot hold its D/4 x Te slice of the attention values any more (TMEM has
+// 256 free columns x 128 lanes), so TWO clusters serve a batch row (B <= 16): both compute the energies and the softmax over
+// all positions -- redundantly and bit-identically, no exchange between them -- and each forms the context for half of the
+// dims of its CTAs (values slice: 2 position blocks x D/8 dims).  Training only (the free-running projection needs the whole
+// context inside one cluster).
+template <int NS, int INFER, int TE2>
 __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads, 1)
     decoder_fwd_tc_kernel(const DecFwdTcParams P) {
+  static_assert(!(INFER && TE2), "free-running decode runs on one cluster per row");
   extern __shared__ __align__(1024) uint8_t smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int B = P.B, Te = P.Te, D = P.D, Dq = D / kDecCluster, Dh = Dq / 2;
   const int crank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kDecCluster;
+  const int arow = TE2 ? (cid & 15) : cid;   // batch row this cluster's attention phase serves
+  const int dsel = TE2 ? (cid >> 4) : 0;      // TE2: which half of the CTA's context dims
   const int TeP = (Te + 31) & ~31;
   const int n0 = P.n0;
   constexpr int infer = INFER;
@@ -150,6 +159,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   float* h1_s = frame_s + 96;
   float* p2red = h1_s + 256;
   float* pre_s = p2red + 256;
+  float* pre2_s = reinterpret_cast<float*>(smem + L.pre2);
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -188,19 +198,22 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     fb_l = P.fb[crank * 32 + lane];
     for (int i = tid; i < TeP + 32; i += kTcCompute) cum_s[i] = 0.f;
     for (int i = tid; i < TeP; i += kTcCompute) a_s[i] = 0.f;
-    if (cid < B) {
-      const float* kg = P.keys + (size_t)cid * Te * kAtt;
+    if (arow < B) {
+      const float* kg = P.keys + (size_t)arow * Te * kAtt;
       for (int i = tid; i < Te * 32; i += kTcCompute) keys_s[i] = kg[(size_t)(i >> 5) * kAtt + crank * 32 + (i & 31)];
-      // values slice -> TMEM, lane = context dim (two blocks of Dq/2 dims), column = text position
+      // values slice -> TMEM, lane = context dim, column = text position.  Two blocks (warps 0-3 / 4-7):
+      //   TE2 = 0: block = half of the CTA's Dq dims, all TeP positions (columns blk * TeP ..)
+      //   TE2 = 1: block = 128-position half, the Dq/2 dims selected by dsel (columns blk * 128 ..)
       const int q = warp & 3, blk = warp >> 2, dloc = q * 32 + lane;
       if (q * 32 < Dh) {
-        const float* vg = P.values + (size_t)cid * Te * D + crank * Dq + blk * Dh + dloc;
-        for (int c0 = 0; c0 < TeP; c0 += 32) {
+        const float* vg = P.values + (size_t)arow * Te * D + crank * Dq + (TE2 ? dsel : blk) * Dh + dloc;
+        const int x0 = TE2 ? blk * 128 : 0, ncol = TE2 ? 128 : TeP;
+        for (int c0 = 0; c0 < ncol; c0 += 32) {
           uint32_t v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            v[j] = (dloc < Dh && c0 + j < Te) ? __float_as_uint(vg[(size_t)(c0 + j) * D]) : 0u;
-          ptx::tmem_st32(tmem_val + ((uint32_t)(q * 32) << 16) + blk * TeP + c0, v);
+            v[j] = (dloc < Dh && x0 + c0 + j < Te) ? __float_as_uint(vg[(size_t)(x0 + c0 + j) * D]) : 0u;
+          ptx::tmem_st32(tmem_val + ((uint32_t)(q * 32) << 16) + blk * ncol + c0, v);
         }
         ptx::tmem_wait_st();
       }
@@ -352,7 +365,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 #pragma unroll
     for (int u = 0; u < kUnitsPerCta; ++u) wq_r[u] = wq_s[u * kAtt + (tid & 127)];
     unsigned bar_target = 0;
-    const int tl = (cid < B) ? min(P.text_len[cid], Te) : 0;
+    const int tl = (arow < B) ? min(P.text_len[arow], Te) : 0;
     const size_t vec_img = (size_t)(kCell / kTcKT) * kXTileBytes, ctx_img = (size_t)(D / kTcKT) * kXTileBytes;
     // byte offset of this CTA's 8-unit chunk inside a [32 x 1024] activation image, for batch row r: + (r/8)*1024 + (r%8)*16
     const int unit0 = cid * 32 + crank * kUnitsPerCta;
@@ -412,11 +425,12 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 
     // keys + location features of the NEXT attention step: depends only on the cumulative alignment, so it runs
     // inside the barrier wait that follows the softmax (Location_Sensitive_Attention.py:48-61,82)
+    // one 16-position block per warp (positions 16 w ..); TE2: a second block (128 + 16 w ..) whose values wait in shared
+    // memory (pre2_s [warp][16][32]) instead of registers
     float pre_e[16];
-    auto location_features = [&]() {
-      const int t0 = warp * 16;  // Te <= 128: one 16-position block per warp
+    auto location_block = [&](int t0, float (&out)[16]) {
 #pragma unroll
-      for (int p = 0; p < 16; ++p) pre_e[p] = 0.f;
+      for (int p = 0; p < 16; ++p) out[p] = 0.f;
       if (t0 < tl) {
 #pragma unroll
         for (int c = 0; c < 16 + kConvK - 1; ++c) {
@@ -424,13 +438,22 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 #pragma unroll
           for (int p = 0; p < 16; ++p) {
             const int k = c - p;
-            if (k >= 0 && k < kConvK) pre_e[p] = fmaf(cv, F_reg[k], pre_e[p]);
+            if (k >= 0 && k < kConvK) out[p] = fmaf(cv, F_reg[k], out[p]);
           }
         }
 #pragma unroll
         for (int p = 0; p < 16; ++p)
-          if (t0 + p < tl) pre_e[p] += keys_s[(t0 + p) * 32 + lane];
+          if (t0 + p < tl) out[p] += keys_s[(t0 + p) * 32 + lane];
       }
+    };
+    auto location_features = [&]() {
+      if (TE2) {
+        float tmp[16];
+        location_block(128 + warp * 16, tmp);
+#pragma unroll
+        for (int p = 0; p < 16; ++p) pre2_s[(warp * 16 + p) * 32 + lane] = tmp[p];
+      }
+      location_block(warp * 16, pre_e);
     };
     ptx::bar_sync(1, kTcCompute);
     location_features();
@@ -580,8 +603,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 
       // ================= phase C: location-sensitive attention, batch row = cluster index ==========
       float ctx_keep = 0.f;
-      if (cid < B) {
-        const int bb = cid;
+      if (arow < B) {
+        const int bb = arow;
         {  // q slice = sum of the 128 per-CTA partials (fixed order)
           float pq[kDecGrid / 8];
 #pragma unroll
@@ -596,14 +619,18 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         float qf = fb_l;
 #pragma unroll
         for (int w = 0; w < 8; ++w) qf += qred[w * 32 + lane];
-        if (warp == 0) P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane] = qf;
+        if (warp == 0 && dsel == 0) P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane] = qf;
         STAMP(14);
-        {
-          const int t0 = warp * 16;
+#pragma unroll
+        for (int blk = 0; blk < (TE2 ? 2 : 1); ++blk) {
+          const int t0 = blk * 128 + warp * 16;
           if (t0 < tl) {
             float v[16];
 #pragma unroll
-            for (int p = 0; p < 16; ++p) v[p] = (t0 + p < tl) ? sw_l * tanhf(pre_e[p] + qf) : 0.f;
+            for (int p = 0; p < 16; ++p) {
+              const float pe = blk ? pre2_s[(warp * 16 + p) * 32 + lane] : pre_e[p];
+              v[p] = (t0 + p < tl) ? sw_l * tanhf(pe + qf) : 0.f;
+            }
             // sum over the 32 lanes (attention units) of 16 independent values: halve the value count at every
             // butterfly step (31 shuffles instead of 80, all independent within a level)
 #pragma unroll
@@ -650,10 +677,11 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         STAMP(12);
         // masked softmax over positions < tl (score_mask_value = -inf => exactly 0 beyond tl); Te <= 128: every
         // warp redundantly reduces all positions (4 per lane), no block-level exchange
-        float ev[4];
+        constexpr int NJ = TE2 ? 8 : 4;  // positions per lane
+        float ev[NJ];
         float lmax = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           const int x = lane + 32 * j;
           ev[j] = -INFINITY;
           if (x < tl) ev[j] = ((e_parts[x] + e_parts[TeP + x]) + e_parts[2 * TeP + x]) + e_parts[3 * TeP + x];
@@ -662,7 +690,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         lmax = warp_max(lmax);
         float lsum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           ev[j] = (lane + 32 * j < tl) ? expf(ev[j] - lmax) : 0.f;
           lsum += ev[j];
         }
@@ -670,7 +698,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         lsum = warp_sum(lsum);
         if (warp == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NJ; ++j) {
             const int x = lane + 32 * j;
             if (x < Te) {
               const float a = ev[j] / lsum;
@@ -685,21 +713,31 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         if (q4 * 32 < Dh) {
           const int dloc = q4 * 32 + lane;
           float s = 0.f;
-          const uint32_t va = tmem_val + ((uint32_t)(q4 * 32) << 16) + half * TeP;
-          for (int c0 = 0; c0 < tl; c0 += 32) {
+          // TE2 = 0: block `half` = half of the dims over all positions; TE2 = 1: block `half` = positions 128 half .. of dims dsel
+          const int xb = TE2 ? half * 128 : 0, xe = TE2 ? min(tl, xb + 128) : tl;
+          const uint32_t va = tmem_val + ((uint32_t)(q4 * 32) << 16) + half * (TE2 ? 128 : TeP);
+          for (int c0 = 0; xb + c0 < xe; c0 += 32) {
             uint32_t v[32];
             ptx::tmem_ld32(va + c0, v);
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s = fmaf(a_s[c0 + j], __uint_as_float(v[j]), s);
+            for (int j = 0; j < 32; ++j) s = fmaf(a_s[xb + c0 + j], __uint_as_float(v[j]), s);
           }
-          if (dloc < Dh) ctx_s[half * Dh + dloc] = s;
+          if (dloc < Dh) ctx_s[half * Dh + dloc] = s;   // TE2: the two position-half partial sums of dim dloc
           ctx_keep = s;
         }
         ptx::bar_sync(1, kTcCompute);
-        if (tid < Dq / 4) {  // 16-byte rows of the ctx image: (hi|lo, 8-dim chunk)
-          const int hl = tid / (Dq / 8), ch = tid % (Dq / 8);
-          const int k = crank * Dq + ch * 8;
+        if (TE2) {  // combine the two position halves (fixed order); ctx_s[0 .. Dh) = this CTA's context dims
+          float tot = 0.f;
+          if (tid < Dh) tot = ctx_s[tid] + ctx_s[Dh + tid];
+          ptx::bar_sync(1, kTcCompute);
+          if (tid < Dh) ctx_s[tid] = tot;
+          ptx::bar_sync(1, kTcCompute);
+        }
+        constexpr int kImgDiv = TE2 ? 8 : 4;  // dims of this CTA in the image: Dq (TE2: Dq / 2)
+        if (tid < Dq / kImgDiv) {  // 16-byte rows of the ctx image: (hi|lo, 8-dim chunk)
+          const int hl = tid / (Dq / (2 * kImgDiv)), ch = tid % (Dq / (2 * kImgDiv));
+          const int k = crank * Dq + dsel * Dh + ch * 8;
           __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -786,11 +824,15 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       }
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
-      if (cid < B) {  // saved outputs + next step's location features ride in the barrier wait
-        const int bb = cid;
-        if (q4 * 32 < Dh && q4 * 32 + lane < Dh)
-          P.ctx[((size_t)(t + 1) * B + bb) * D + crank * Dq + half * Dh + q4 * 32 + lane] = ctx_keep;
-        if (crank == 0) {
+      if (arow < B) {  // saved outputs + next step's location features ride in the barrier wait
+        const int bb = arow;
+        if (!TE2) {
+          if (q4 * 32 < Dh && q4 * 32 + lane < Dh)
+            P.ctx[((size_t)(t + 1) * B + bb) * D + crank * Dq + half * Dh + q4 * 32 + lane] = ctx_keep;
+        } else if (tid < Dh) {
+          P.ctx[((size_t)(t + 1) * B + bb) * D + crank * Dq + dsel * Dh + tid] = ctx_s[tid];
+        }
+        if (crank == 0 && dsel == 0) {
           for (int x = tid; x < Te; x += kTcCompute) {
             P.align_tm[((size_t)t * B + bb) * Te + x] = a_s[x];
             P.cum[((size_t)(t + 1) * B + bb) * Te + x] = cum_s[15 + x];
@@ -912,9 +954,13 @@ __global__ void prenet_zero_frame_kernel(const float* __restrict__ pb0, const fl
 }
 
 // ======================================== host side ================================================
-bool dec_tc_supported(int B, int Te, int D) { return B >= 1 && B <= kTcN && Te <= 128 && D % 256 == 0 && D <= 768; }
+// one launch: 32 rows of texts up to 128 positions, or 16 rows of texts up to 256 (two clusters per row); larger batches run
+// as row chunks (decoder_layout.h: DecChunkPlan)
+bool dec_tc_supported(int B, int Te, int D) {
+  return B >= 1 && Te >= 1 && Te <= 256 && B <= (Te > 128 ? kTcN / 2 : kTcN) && D % 256 == 0 && D <= 768;
+}
 
-template <int NS, int INFER>
+template <int NS, int INFER, int TE2>
 static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t smem, bool* ok) {
   int dev = 0;
   MSTTS_CUDA(cudaGetDevice(&dev));
@@ -925,7 +971,7 @@ static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t sm
     return MSTTS_OK;
   }
   *ok = true;
-  MSTTS_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<NS, INFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSTTS_CUDA(cudaFuncSetAttribute(decoder_fwd_tc_kernel<NS, INFER, TE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(kDecGrid);
@@ -937,12 +983,12 @@ static int launch_fwd_tc(const DecFwdTcParams& P, cudaStream_t stream, size_t sm
   cudaLaunchAttribute coop_attr[1];
   dec_cooperative_attr(&cfg, coop_attr);
   int nclusters = 0;
-  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_tc_kernel<NS, INFER>, &cfg));
+  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_fwd_tc_kernel<NS, INFER, TE2>, &cfg));
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
                 "decoder_fwd_tc: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
                 kDecGrid / kDecCluster);
   mstts_timer_start(0, stream);
-  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<NS, INFER>, P));
+  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_fwd_tc_kernel<NS, INFER, TE2>, P));
   mstts_timer_stop(0, stream);
   return MSTTS_OK;
 }
@@ -951,7 +997,8 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   auto F = [&](size_t off) { return (float*)(ws + off); };
   const int D = io->D;
   MSTTS_REQUIRE(dec_tc_supported(io->B, io->Te, D), MSTTS_E_UNSUPPORTED,
-                "decoder bf16x3 mode needs B<=32, Te<=128, D in {256,512,768} (got B=%d Te=%d D=%d); use mode fp32", io->B, io->Te, D);
+                "decoder bf16x3 mode needs Te<=256, D in {256,512,768} and B<=32 (16 for Te>128) per chunk (got B=%d Te=%d D=%d); use mode fp32",
+                io->B, io->Te, D);
   DecFwdTcParams P;
   memset(&P, 0, sizeof(P));
   P.B = io->B; P.Te = io->Te; P.T = io->n_steps; P.D = D; P.training = io->is_training; P.n0 = D / 256;
@@ -983,8 +1030,9 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   int rc;
 #define MSTTS_TRY_NS(NS_)                                                                                                   \
   if (!ok) {                                                                                                                 \
-    rc = infer ? launch_fwd_tc<NS_, 1>(P, s, tc_fwd_smem(NS_, io->Te, D, 1).total, &ok)                                      \
-               : launch_fwd_tc<NS_, 0>(P, s, tc_fwd_smem(NS_, io->Te, D, 0).total, &ok);                                     \
+    rc = infer ? launch_fwd_tc<NS_, 1, 0>(P, s, tc_fwd_smem(NS_, io->Te, D, 1).total, &ok)                                   \
+               : (io->Te > 128 ? launch_fwd_tc<NS_, 0, 1>(P, s, tc_fwd_smem(NS_, io->Te, D, 0).total, &ok)                   \
+                               : launch_fwd_tc<NS_, 0, 0>(P, s, tc_fwd_smem(NS_, io->Te, D, 0).total, &ok));                 \
     if (rc) return rc;                                                                                                       \
   }
   MSTTS_TRY_NS(4)  // all 4 weight tiles of J1 resident when m0 arrives

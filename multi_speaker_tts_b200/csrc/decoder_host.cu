@@ -118,7 +118,7 @@ static inline int ew_grid(size_t n) {
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int n_steps, int mode) {
   if (B <= 0 || Te <= 0 || D <= 0 || n_steps <= 0) return 0;
-  if (dec_is_chunked(B, mode)) return dec_chunk_plan(B, Te, L, D, n_steps, mode).total;
+  if (dec_is_chunked(B, Te, mode)) return dec_chunk_plan(B, Te, L, D, n_steps, mode).total;
   return dec_layout(B, Te, L, D, n_steps, mode).total;
 }
 
@@ -126,7 +126,7 @@ extern "C" size_t mstts_decoder_workspace_bytes(int B, int Te, int L, int D, int
 // activations and the phase time stamps without knowing the layout
 extern "C" size_t mstts_decoder_ws_offset(const char* name, int B, int Te, int L, int D, int n_steps, int mode) {
   if (!name || B <= 0 || Te <= 0 || D <= 0 || n_steps <= 0) return (size_t)-1;
-  if (dec_is_chunked(B, mode)) return (size_t)-1;  // several chunk workspaces: no single region
+  if (dec_is_chunked(B, Te, mode)) return (size_t)-1;  // several chunk workspaces: no single region
   const DecLayout l = dec_layout(B, Te, L, D, n_steps, mode);
 #define REGION(x) if (!strcmp(name, #x)) return l.x;
   REGION(values) REGION(keys) REGION(g0pre) REGION(act0) REGION(act1) REGION(c0n) REGION(c1n) REGION(cz0) REGION(hz0)
@@ -271,7 +271,7 @@ extern "C" int mstts_decoder_fwd(const MsttsDecoderWeights* w, const MsttsDecode
   if (!io->is_training) return decoder_fwd_free_running(w, io, ws_, ws_bytes, s);
   MSTTS_REQUIRE(io->mel && io->mel_len && io->zone_mask, MSTTS_E_INVALID, "decoder: training needs mel/mel_len/zone_mask");
   MSTTS_REQUIRE(io->n_steps <= io->L + 1, MSTTS_E_INVALID, "decoder: n_steps=%d > L+1=%d", io->n_steps, io->L + 1);
-  if (dec_is_chunked(io->B, io->mode)) return decoder_fwd_chunked(w, io, ws_, ws_bytes, s);
+  if (dec_is_chunked(io->B, io->Te, io->mode)) return decoder_fwd_chunked(w, io, ws_, ws_bytes, s);
   return decoder_fwd_one(w, io, ws_, ws_bytes, s);
 }
 

@@ -148,8 +148,8 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
 }
 
 // ---- batches beyond one tensor-core tile (bf16x3 mode, B > 32) ----------------------------------------------------
-// The persistent tcgen05 loops handle up to 32 batch rows (one M = 64 operand tile of hi + lo rows).  Decoder rows are
-// independent, so a larger batch runs as ceil(B / 32) balanced row chunks, each with its own workspace (the saved
+// The persistent tcgen05 loops handle up to 32 batch rows (one M = 64 operand tile of hi + lo rows; 16 rows for texts of
+// 129 .. 256 positions, where two clusters serve a row).  Decoder rows are independent, so a larger batch runs as balanced row chunks, each with its own workspace (the saved
 // activations of every chunk must survive until the reverse pass) and its own contiguous copy of the dropout / zoneout
 // masks (time-major with the batch inside); the weight gradients of the chunks are summed.
 struct DecChunkPlan {
@@ -161,7 +161,9 @@ struct DecChunkPlan {
   size_t dw_floats;
   size_t total;
 };
-static inline bool dec_is_chunked(int B, int mode) { return mode == MSTTS_MODE_BF16X3 && B > 32; }
+// rows one launch of the tcgen05 loops takes: 32, or 16 for texts beyond 128 positions (two clusters serve a row there)
+static inline int dec_chunk_cap(int Te) { return Te > 128 ? 16 : 32; }
+static inline bool dec_is_chunked(int B, int Te, int mode) { return mode == MSTTS_MODE_BF16X3 && B > dec_chunk_cap(Te); }
 static inline size_t dec_weight_floats(int D) {  // every tensor padded to 64 floats (256-byte aligned slices)
   const size_t n[17] = {(size_t)kMel * kPrenet, kPrenet, (size_t)kPrenet * kPrenet, kPrenet, (size_t)(kPrenet + 2 * D + kCell) * kGates, kGates,
                         (size_t)2 * kCell * kGates, kGates, (size_t)D * kAtt, (size_t)kCell * kAtt, (size_t)kConvK * kConvC, kConvC,
@@ -172,7 +174,8 @@ static inline size_t dec_weight_floats(int D) {  // every tensor padded to 64 fl
 }
 static inline DecChunkPlan dec_chunk_plan(int B, int Te, int L, int D, int T, int mode) {
   DecChunkPlan p;
-  p.nchunks = (B + 31) / 32;
+  const int cap = dec_chunk_cap(Te);
+  p.nchunks = (B + cap - 1) / cap;
   p.bc = (B + p.nchunks - 1) / p.nchunks;
   p.chunk_ws = align_up(dec_layout(p.bc, Te, L, D, T, mode).total, 1024);
   size_t off = p.chunk_ws * p.nchunks;
