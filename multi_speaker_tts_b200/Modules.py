@@ -90,9 +90,10 @@ class _DecoderFunction(torch.autograd.Function):
 
 
 def decoder_mode(B, Te, D):
-    """tensor-core (bf16x3) loop where its tiling applies -- any batch size (rows beyond 32 run as further chunks of the
-    same kernels), texts up to 128 positions -- the fp32 SIMT loop otherwise (both meet the 1e-3 gate)"""
-    return "bf16x3" if (Te <= 128 and D in (256, 512, 768)) else "fp32"
+    """tensor-core (bf16x3) loop where its tiling applies -- any batch size (rows beyond one launch's 32, or 16 for texts
+    of 129 .. 256 positions, run as further chunks of the same kernels), texts up to 256 positions -- the fp32 SIMT loop
+    otherwise (both meet the 1e-3 gate)"""
+    return "bf16x3" if (Te <= 256 and D in (256, 512, 768)) else "fp32"
 
 
 def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False, variables=None, masks=None, mode=None,

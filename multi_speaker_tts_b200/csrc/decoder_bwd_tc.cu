@@ -38,6 +38,10 @@ struct DecBwdTcParams {
   float *dctx, *dG0, *dG1, *dq, *dkeys, *dF, *dsw;
   unsigned* barrier;
   long long* dbg;
+  // texts of 129 .. 256 positions (TE2): two clusters per batch row, each owning 128 positions
+  float* dq2;        // [T,B,128] d q partial of the upper position half (summed into dq after the loop)
+  float* ldot_part;  // [2][16]   per-half sum_x a[x] (d a[x] + d cum[x]) of the running step
+  float* halo_part;  // [16 rows][2 halves][4 CTAs][16] conv-transpose sums reaching the OTHER half's 15 border positions
 };
 
 struct TcBwdSmem {
@@ -80,20 +84,29 @@ __host__ __device__ inline TcBwdSmem tc_bwd_smem(int NS, int Te, int D) {
   return s;
 }
 
-template <int NS>
+// TE2 = 1: texts of 129 .. 256 positions (B <= 16).  The values / keys / d-keys of a batch row no longer fit one cluster's
+// TMEM, so TWO clusters serve a row, each owning 128 text positions (cluster c: row c & 15, positions 128 (c >> 4) ..).
+// Three quantities cross the position halves: the softmax' inner product sum_x a (d a + d cum) (one float per row and step:
+// exchanged through global memory around ONE extra grid barrier per step), d q (two partial buffers, summed by the
+// consumer) and the 15 border positions of the location-conv transpose (exchanged through global memory one phase later).
+template <int NS, int TE2>
 __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads, 1)
     decoder_bwd_tc_kernel(const DecBwdTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int B = P.B, Te = P.Te, D = P.D, Dq = D / kDecCluster, T = P.T;
+  const int B = P.B, Teg = P.Te, D = P.D, Dq = D / kDecCluster, T = P.T;
   const int crank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kDecCluster;
-  const int TeP = (Te + 31) & ~31;
+  const int arow = TE2 ? (cid & 15) : cid;       // batch row of this cluster's attention' phase
+  const int ph = TE2 ? (cid >> 4) : 0;            // TE2: position half
+  const int x0 = 128 * ph;                        // first text position of this cluster
+  const int Te = TE2 ? max(0, min(128, Teg - x0)) : Teg;  // positions of this cluster inside the padded text
+  const int TeP = TE2 ? 128 : ((Teg + 31) & ~31);
   const int tile = cid & 7, kq = cid >> 3;         // output tile / K-quarter of this cluster
   const int kslice = kq * 4 + crank;               // gate columns 256*kslice .. +255
   const bool isctx = tile < P.nct;                 // JA1 exists for this cluster
-  const TcBwdSmem L = tc_bwd_smem(NS, Te, D);
+  const TcBwdSmem L = tc_bwd_smem(NS, TE2 ? 128 : Teg, D);
 
   uint8_t* ring = smem + L.ring;
   uint8_t* xbuf = smem + L.xbuf;  // dG1_t slice from barrier 2 until JB2(t) has read it, then dG0_t slice (JA jobs)
@@ -165,11 +178,11 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     for (int k = 0; k < kConvK; ++k) F_reg[k] = P.F[k * kAtt + crank * 32 + lane];
     sw_l = P.sw[crank * 32 + lane];
     for (int i = tid; i < TeP; i += kTcCompute) dcum_s[i] = 0.f;
-    if (cid < B) {
+    if (arow < B) {
       const int q = warp & 3, hf = warp >> 2;
       {  // values: lane = text position x = 32q + lane, columns = this CTA's context dims; warps 0-3 / 4-7 take half each
         const int x = q * 32 + lane;
-        const float* vg = P.values + ((size_t)cid * Te + x) * D + crank * Dq;
+        const float* vg = P.values + ((size_t)arow * Teg + x0 + x) * D + crank * Dq;
         for (int d0 = hf * (Dq / 2); d0 < (hf + 1) * (Dq / 2); d0 += 32) {
           uint32_t v[32];
 #pragma unroll
@@ -182,7 +195,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
           const int x = warp * 16 + p;
-          v[p] = (x < Te) ? __float_as_uint(P.keys[((size_t)cid * Te + x) * kAtt + crank * 32 + lane]) : 0u;
+          v[p] = (x < Te) ? __float_as_uint(P.keys[((size_t)arow * Teg + x0 + x) * kAtt + crank * 32 + lane]) : 0u;
           z[p] = 0u;
         }
         ptx::tmem_st16(tmem_keys + ((uint32_t)(q * 32) << 16) + hf * 16, v);
@@ -221,14 +234,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         const unsigned sidx = (unsigned)(T - 1 - t);
         // dG1_t slice (the buffer's previous readers: JA1 / JA2 of step t+1, long finished)
         if (sidx > 0) ptx::mbar_wait(&job_done[3], (sidx - 1) & 1);
-        while (ld_volatile_shared(ready_seq) < 5u * sidx + 2) {
+        while (ld_volatile_shared(ready_seq) < (5u + TE2) * sidx + 2 + TE2) {  // TE2: one more barrier per step, inside phase C'
         }
         ptx::mbar_arrive_expect_tx(&xfull[1], 4 * kXTileBytes);
         ptx::bulk_g2s(xbuf, P.ximg_g1 + (size_t)kslice * 4 * kXTileBytes, 4 * kXTileBytes, &xfull[1]);
         if (t == 0) break;
         // dG0_t slice (previous readers: JB1 / JB2 of this step; JB2 ends ~3 us before barrier 4 passes)
         ptx::mbar_wait(&job_done[1], sidx & 1);
-        while (ld_volatile_shared(ready_seq) < 5u * sidx + 4) {
+        while (ld_volatile_shared(ready_seq) < (5u + TE2) * sidx + 4 + TE2) {
         }
         ptx::mbar_arrive_expect_tx(&xfull[0], 4 * kXTileBytes);
         ptx::bulk_g2s(xbuf, P.ximg_g0 + (size_t)kslice * 4 * kXTileBytes, 4 * kXTileBytes, &xfull[0]);
@@ -281,7 +294,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     uint32_t rs_parity = 0, e_parity = 0;
     unsigned bar_target = 0, ev = 0;
     float dc0 = 0.f, dh0d = 0.f, dc1 = 0.f, dh1d = 0.f;  // carries: d c (zoned) and the direct zoneout path of d h
-    const int tl = (cid < B) ? min(P.text_len[cid], Te) : 0;
+    const int tlg = (arow < B) ? min(P.text_len[arow], Teg) : 0;   // valid positions of the row
+    const int tl = TE2 ? max(0, min(128, tlg - x0)) : tlg;          // ... of this cluster's positions
+    const bool halo = TE2 && tlg > 128;                              // both halves hold valid positions
     const uint32_t recv_addr = ptx::smem_u32(recv);
     float* dps = scratch;   // [(TeP+32)][32] d pre-activations of attention'(t): live until the prologue of step t-1
     float* dq_s = recv;     // [32][132] dq rows of phase B'e (recv is idle between the drains of A'g(t+1) and B'g(t))
@@ -385,22 +400,29 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     // (split in two: the staging half reads HBM and runs inside the wait of barrier 4 -- nothing reads cum_s / a_s after the
     //  wait of barrier 2 -- so that the wait of barrier 5 holds only the convolution and the tanh)
     float qf_next = 0.f;
-    auto attention_stage = [&](int t) {
-      if (cid >= B) return;
-      const int bb = cid;
-      const float* al = P.align_tm + ((size_t)t * B + bb) * Te;
-      const float* cum_prev = P.cum + ((size_t)t * B + bb) * Te;
+    auto attention_stage = [&](int t, bool with_halo) {
+      if (arow >= B) return;
+      if (with_halo && halo && tid < 15) {
+        // d cum_t: conv-transpose sums that the other position half's d pre-activations of step t + 1 send into this half's
+        // 15 border positions (written by the peer cluster during its barrier-2 wait, two grid barriers ago)
+        const float* hp = P.halo_part + (size_t)((arow * 2 + (1 - ph)) * kDecCluster) * 16 + tid;
+        const float add = ((__ldcg(hp) + __ldcg(hp + 16)) + __ldcg(hp + 32)) + __ldcg(hp + 48);
+        dcum_s[ph == 0 ? 113 + tid : tid] += add;
+      }
+      const int bb = arow;
+      const float* al = P.align_tm + ((size_t)t * B + bb) * Teg + x0;
+      const float* cum_prev = P.cum + ((size_t)t * B + bb) * Teg;
       qf_next = P.qf[((size_t)t * B + bb) * kAtt + crank * 32 + lane];
       for (int i = tid; i < TeP + 32; i += kTcCompute) {
-        const int x = i - 15;
-        cum_s[i] = (x >= 0 && x < Te) ? cum_prev[x] : 0.f;
+        const int x = x0 + i - 15;   // the 15-position borders reach into the other half (TE2)
+        cum_s[i] = (x >= 0 && x < Teg) ? cum_prev[x] : 0.f;
       }
       for (int x = tid; x < TeP; x += kTcCompute) a_s[x] = (x < Te) ? al[x] : 0.f;
       for (int i = tid; i < 15 * 32; i += kTcCompute) dps[i] = 0.f;
       for (int i = (15 + tl) * 32 + tid; i < (TeP + 32) * 32; i += kTcCompute) dps[i] = 0.f;
     };
     auto attention_prologue = [&]() {  // needs a barrier among the compute warps after attention_stage
-      if (cid >= B) return;
+      if (arow >= B) return;
       const float qf = qf_next;
       const int t0 = warp * 16;
       if (t0 < tl) {
@@ -423,7 +445,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         for (int p = 0; p < 16; ++p) s_s[p * kTcCompute + tid] = tanhf(__uint_as_float(kv[p]) + qf + acc[p]);
       }
     };
-    attention_stage(T - 1);
+    attention_stage(T - 1, false);
     ptx::bar_sync(1, kTcCompute);
     attention_prologue();
     ptx::bar_sync(1, kTcCompute);
@@ -431,7 +453,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     // loads of its saved operands BEFORE the grid-barrier wait that precedes it, so their latency rides in the wait.
     float pf_act[4] = {0.f, 0.f, 0.f, 0.f}, pf_cn = 0.f, pf_cz = 0.f, pf_mc = 0.f, pf_mh = 0.f, pf_dm = 0.f, pf_dh = 0.f;
     float pf_dctx = 0.f;
-    if (cid < B && tid < Dq) pf_dctx = P.dctx[((size_t)(T - 1) * B + cid) * D + crank * Dq + tid];
+    if (arow < B && tid < Dq) pf_dctx = P.dctx[((size_t)(T - 1) * B + arow) * D + crank * Dq + tid];
 
     for (int t = T - 1; t >= 0; --t) {
       const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
@@ -441,8 +463,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       // ================= phase C': attention backward, batch row = cluster index =================
       // (alignment, cumulative alignment and tanh(keys + q + loc) of this step were staged by attention_prologue(t)
       //  inside the previous barrier wait: they depend only on saved forward data)
-      if (cid < B) {
-        const int bb = cid;
+      float dav[4] = {0.f, 0.f, 0.f, 0.f}, ldot = 0.f;
+      if (arow < B) {
+        const int bb = arow;
         if (tid < Dq) {  // total gradient w.r.t. ctx_t: projection part + the 4 K-quarter partials of JA1(t+1)
           const size_t gi = ((size_t)t * B + bb) * D + crank * Dq + tid;
           float v = pf_dctx;
@@ -482,19 +505,29 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         e_parity ^= 1u;
         // softmax backward (every warp reduces all positions redundantly: Te <= 128 -> 4 per lane); this warp's
         // 16 positions of d e stay in registers (position t0 + p comes from lane (t0 + p) & 31, slot (t0 + p) >> 5)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = lane + 32 * j;
+          dav[j] = 0.f;
+          if (x < tl) {
+            dav[j] = (((e_parts1[x] + e_parts1[TeP + x]) + e_parts1[2 * TeP + x]) + e_parts1[3 * TeP + x]) + dcum_s[x];
+            ldot = fmaf(a_s[x], dav[j], ldot);
+          }
+        }
+        ldot = warp_sum(ldot);
+        // TE2: the inner product runs over BOTH position halves of the row: publish this half's part (every warp of every CTA
+        // of the cluster holds the same value), meet the other cluster at a grid barrier, add the two parts in a fixed order
+        if (TE2 && crank == 0 && tid == 0) P.ldot_part[ph * 16 + bb] = ldot;
+      }
+      if (TE2) {
+        grid_arrive_compute(P.barrier, bar_target, gridDim.x);
+        grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
+      }
+      if (arow < B) {
+        const int bb = arow;
+        if (TE2) ldot = __ldcg(P.ldot_part + bb) + __ldcg(P.ldot_part + 16 + bb);
         float de_blk[16];
         {
-          float dav[4], ldot = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int x = lane + 32 * j;
-            dav[j] = 0.f;
-            if (x < tl) {
-              dav[j] = (((e_parts1[x] + e_parts1[TeP + x]) + e_parts1[2 * TeP + x]) + e_parts1[3 * TeP + x]) + dcum_s[x];
-              ldot = fmaf(a_s[x], dav[j], ldot);
-            }
-          }
-          ldot = warp_sum(ldot);
           float dev[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -529,7 +562,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           float s = 0.f;
 #pragma unroll
           for (int w = 0; w < 8; ++w) s += qred[w * 32 + tid];
-          P.dq[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s;
+          (ph ? P.dq2 : P.dq)[((size_t)t * B + bb) * kAtt + crank * 32 + tid] = s;
         }
       }
       STAMP(1);
@@ -554,8 +587,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 
       // ================= phase B'e: cell-1 gate backward for this CTA's 8 units =================
       {
-        for (int i = tid; i < B * (kAtt / 4); i += kTcCompute)  // rows padded to 132 floats: conflict-free float4 reads
-          reinterpret_cast<float4*>(dq_s)[(i >> 5) * 33 + (i & 31)] = __ldcg(reinterpret_cast<const float4*>(P.dq + (size_t)t * B * kAtt) + i);
+        for (int i = tid; i < B * (kAtt / 4); i += kTcCompute) {  // rows padded to 132 floats: conflict-free float4 reads
+          float4 v4 = __ldcg(reinterpret_cast<const float4*>(P.dq + (size_t)t * B * kAtt) + i);
+          if (TE2) {  // + the upper position half's part
+            const float4 u4 = __ldcg(reinterpret_cast<const float4*>(P.dq2 + (size_t)t * B * kAtt) + i);
+            v4 = make_float4(v4.x + u4.x, v4.y + u4.y, v4.z + u4.z, v4.w + u4.w);
+          }
+          reinterpret_cast<float4*>(dq_s)[(i >> 5) * 33 + (i & 31)] = v4;
+        }
         ptx::bar_sync(1, kTcCompute);
         CellGradTc g = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (brow) {
@@ -587,7 +626,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         // ---- deferred halves of attention'(t), spread over the barrier waits so that none holds more than the barrier's own
         //      ~1.3 us (all of it inside the wait of barrier 1 took ~3.5 us): here the conv transpose that feeds d cum_{t-1};
         //      the wait of barrier 3 collects it and accumulates d F / d keys from the d pre-activations kept in `dps` ----
-        if (cid < B) {
+        if (arow < B) {
           const int t0 = warp * 16;
           if (t0 < tl) {
             // conv transpose: gradient reaching cum_{t-1} through the location features (partial over this CTA's units)
@@ -615,6 +654,29 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             }
           }
           if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));  // collected in the wait of barrier 3
+          if (halo && warp == 7) {
+            // the same transpose for the 15 border positions of the OTHER half (|x - x'| <= 15 reaches across): partial over
+            // this CTA's 32 units; the peer cluster adds the four CTA parts to its d cum before its next phase C'
+            float H[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) H[j] = 0.f;
+            if (ph == 0) {  // positions 128 + j  <-  own positions 113 + j + d, tap 30 - d
+#pragma unroll
+              for (int j = 0; j < 15; ++j)
+#pragma unroll
+                for (int d = 0; d < 15 - j; ++d) H[j] = fmaf(dps[(15 + 113 + j + d) * 32 + lane], F_reg[30 - d], H[j]);
+            } else {        // positions 113 + j (own -15 + j)  <-  own positions x' <= j, tap j - x'
+#pragma unroll
+              for (int j = 0; j < 15; ++j)
+#pragma unroll
+                for (int xs2 = 0; xs2 <= j; ++xs2) H[j] = fmaf(dps[(15 + xs2) * 32 + lane], F_reg[j - xs2], H[j]);
+            }
+            const float tot = warp_sum16(H, lane);
+            if ((lane & 1) == 0) {
+              const int j = warp_sum16_index(lane);
+              if (j < 15) P.halo_part[(size_t)((arow * 2 + ph) * kDecCluster + crank) * 16 + j] = tot;
+            }
+          }
         }
         grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       }
@@ -633,13 +695,13 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         pf_mc = (float)zm[si];
         pf_mh = (float)zm[BC + si];
       }
-      if (cid < B) {  // d cum_{t-1}: the cluster's partial conv-transpose sums pushed during the wait of barrier 2
+      if (arow < B) {  // d cum_{t-1}: the cluster's partial conv-transpose sums pushed during the wait of barrier 2
         mbar_wait_warp(e_bar, e_parity);
         e_parity ^= 1u;
         for (int x = tid; x < tl; x += kTcCompute)
           dcum_s[x] += ((e_parts2[x] + e_parts2[TeP + x]) + e_parts2[2 * TeP + x]) + e_parts2[3 * TeP + x];
       }
-      if (cid < B && warp * 16 < tl) {  // d F of attention'(t) (deferred from phase C')
+      if (arow < B && warp * 16 < tl) {  // d F of attention'(t) (deferred from phase C')
         const int t0 = warp * 16;
         float dp[16];
 #pragma unroll
@@ -654,7 +716,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           }
         }
       }
-      if (cid < B && warp * 16 < tl) {  // d keys += d pre-activations of attention'(t) (deferred from phase C')
+      if (arow < B && warp * 16 < tl) {  // d keys += d pre-activations of attention'(t) (deferred from phase C')
         uint32_t dk[16];
         const uint32_t ka = ((uint32_t)(q4 * 32) << 16) + half * 16;
         ptx::tmem_ld16(tmem_dkeys + ka, dk);
@@ -702,7 +764,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           P.dG0[ai + 2 * kCell] = g.df;
           P.dG0[ai + 3 * kCell] = g.dop;
         }
-        attention_stage(t - 1);
+        attention_stage(t - 1, true);
         grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       }
       STAMP(8);
@@ -712,7 +774,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
       attention_prologue();
-      if (cid < B && tid < Dq) pf_dctx = P.dctx[((size_t)(t - 1) * B + cid) * D + crank * Dq + tid];
+      if (arow < B && tid < Dq) pf_dctx = P.dctx[((size_t)(t - 1) * B + arow) * D + crank * Dq + tid];
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(10);
     }
@@ -720,14 +782,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
 
     // ---- flush the per-CTA accumulators ----
     ptx::bar_sync(1, kTcCompute);
-    if (cid < B) {  // d keys: TMEM -> global
+    if (arow < B) {  // d keys: TMEM -> global
       uint32_t dk[16];
       ptx::tmem_ld16(tmem_dkeys + ((uint32_t)(q4 * 32) << 16) + half * 16, dk);
       ptx::tmem_wait_ld();
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int x = warp * 16 + p;
-        if (x < Te) P.dkeys[((size_t)cid * Te + x) * kAtt + crank * 32 + lane] = __uint_as_float(dk[p]);
+        if (x < Te) P.dkeys[((size_t)arow * Teg + x0 + x) * kAtt + crank * 32 + lane] = __uint_as_float(dk[p]);
       }
     }
     // d F / d w: cross-warp reduction in shared memory (recv is free now), then one atomic per (tap, unit) per CTA
@@ -798,10 +860,19 @@ __global__ void prep_wimg_bwd_kernel(const float* __restrict__ K0, const float* 
   }
 }
 
+__global__ void add_dq2_kernel(float* __restrict__ dq, const float* __restrict__ dq2, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<float4*>(dq)[i];
+    const float4 b = reinterpret_cast<const float4*>(dq2)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dq)[i] = a;
+  }
+}
+
 // ======================================== host side ================================================
 bool dec_tc_supported(int B, int Te, int D);  // decoder_fwd_tc.cu
 
-template <int NS>
+template <int NS, int TE2>
 static int launch_bwd_tc(const DecBwdTcParams& P, cudaStream_t stream, size_t smem, bool* ok) {
   int dev = 0;
   MSTTS_CUDA(cudaGetDevice(&dev));
@@ -812,7 +883,7 @@ static int launch_bwd_tc(const DecBwdTcParams& P, cudaStream_t stream, size_t sm
     return MSTTS_OK;
   }
   *ok = true;
-  MSTTS_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSTTS_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel<NS, TE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(kDecGrid);
@@ -824,12 +895,12 @@ static int launch_bwd_tc(const DecBwdTcParams& P, cudaStream_t stream, size_t sm
   cudaLaunchAttribute coop_attr[1];
   dec_cooperative_attr(&cfg, coop_attr);
   int nclusters = 0;
-  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_bwd_tc_kernel<NS>, &cfg));
+  MSTTS_CUDA(cudaOccupancyMaxActiveClusters(&nclusters, decoder_bwd_tc_kernel<NS, TE2>, &cfg));
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
                 "decoder_bwd_tc: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
                 kDecGrid / kDecCluster);
   mstts_timer_start(1, stream);
-  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_bwd_tc_kernel<NS>, P));
+  MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_bwd_tc_kernel<NS, TE2>, P));
   mstts_timer_stop(1, stream);
   return MSTTS_OK;
 }
@@ -857,9 +928,23 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   prep_wimg_bwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_b), D);
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_g1, 0, l.ximg_g_end - l.ximg_g1, s));
   bool ok = false;
-  int rc = launch_bwd_tc<3>(P, s, tc_bwd_smem(3, io->Te, D).total, &ok);  // 3 of a critical job's 4 weight tiles prefetched
+  int rc;
+  if (io->Te > 128) {  // two clusters per row, 128 positions each: the shared-memory layout of a 128-position text
+    P.dq2 = F(l.dq2); P.ldot_part = F(l.xexch); P.halo_part = F(l.xexch) + 32;
+    rc = launch_bwd_tc<3, 1>(P, s, tc_bwd_smem(3, 128, D).total, &ok);
+    if (rc) return rc;
+    if (!ok) rc = launch_bwd_tc<2, 1>(P, s, tc_bwd_smem(2, 128, D).total, &ok);
+    if (rc) return rc;
+    MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_bwd_tc: shared memory does not fit for Te=%d", io->Te);
+    // d q = lower-half part + upper-half part (the weight-gradient product of the query layer reads the sum)
+    const size_t n = (size_t)io->n_steps * B * kAtt;
+    add_dq2_kernel<<<(int)((n / 4 + 255) / 256 < 148 * 8 ? (n / 4 + 255) / 256 : 148 * 8), 256, 0, s>>>(P.dq, P.dq2, n / 4);
+    MSTTS_CUDA(cudaGetLastError());
+    return MSTTS_OK;
+  }
+  rc = launch_bwd_tc<3, 0>(P, s, tc_bwd_smem(3, io->Te, D).total, &ok);  // 3 of a critical job's 4 weight tiles prefetched
   if (rc) return rc;
-  if (!ok) rc = launch_bwd_tc<2>(P, s, tc_bwd_smem(2, io->Te, D).total, &ok);
+  if (!ok) rc = launch_bwd_tc<2, 0>(P, s, tc_bwd_smem(2, io->Te, D).total, &ok);
   if (rc) return rc;
   MSTTS_REQUIRE(ok, MSTTS_E_UNSUPPORTED, "decoder_bwd_tc: shared memory does not fit for Te=%d", io->Te);
   return MSTTS_OK;

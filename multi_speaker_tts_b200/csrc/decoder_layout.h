@@ -53,6 +53,7 @@ struct DecLayout {
   size_t ximg_g1, ximg_g0, ximg_g_end;   // [64 k-tiles][8 KB] operand images of dG1_t / dG0_t
   size_t pm0, ph1, ph0, pctx;            // K-quarter partials [4][B][1024] / [4][B][D]
   size_t dbg_b;                          // [T][32] int64 phase stamps of the reverse kernel
+  size_t dq2, xexch;                     // texts > 128 positions: upper-half d q [T,B,128]; [2][16] inner products + [16][2][4][16] border sums
   size_t total;
 };
 
@@ -126,7 +127,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dpre = take(TB * kPrenet);
   l.dpre_h = take(TB * kPrenet);
   l.colsum_scratch = take((size_t)64 * kGates);
-  l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = off;
+  l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = l.dq2 = l.xexch = off;
   if (mode == MSTTS_MODE_BF16X3) {
     auto take_bytes = [&](size_t nbytes) {
       size_t o = off;
@@ -142,6 +143,10 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
     l.ph0 = take((size_t)4 * B * kCell);
     l.pctx = take((size_t)4 * B * D);
     l.dbg_b = take_bytes((size_t)(T > kDecGrid ? T : kDecGrid) * 32 * 8);  // also [128 CTAs][32] stamps of the middle step
+    if (Te > 128) {
+      l.dq2 = take(TB * kAtt);
+      l.xexch = take(32 + 16 * 2 * kDecCluster * 16);
+    }
   }
   l.total = off;
   return l;

@@ -23,6 +23,8 @@ def _oracle_grads(w, b, T, dtype=torch.float64):
 
 @pytest.mark.parametrize("B,Te,L,ragged", [(2, 32, 24, False), (3, 40, 17, True), (8, 50, 9, True), (32, 128, 5, True),
                                            (36, 24, 4, True), (40, 128, 5, True), (64, 60, 3, True), (65, 16, 2, True),
+                                           (7, 160, 5, True), (16, 256, 6, True), (5, 224, 9, True), (3, 129, 4, True), (9, 140, 4, False),
+                                           (40, 160, 3, True), (20, 256, 4, True),
                                            (3, 20, 1, False), (2, 9, 2, False)])   # shortest loops: T = 2 and T = 3
 @pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
 def test_decoder_gradients(cuda_dev, B, Te, L, ragged, mode):

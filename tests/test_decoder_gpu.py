@@ -16,8 +16,9 @@ MODES = ["fp32", "bf16x3"]
 
 
 def _tc_supported(B, Te, D=768):
-    # B > 32 runs as balanced row chunks of <= 32 rows through the same tcgen05 loops (csrc/decoder_layout.h: DecChunkPlan)
-    return Te <= 128 and D % 256 == 0
+    # texts up to 256 positions (two clusters per row beyond 128); batches beyond one launch's rows run as balanced row chunks
+    # through the same tcgen05 loops (csrc/decoder_layout.h: DecChunkPlan)
+    return Te <= 256 and D % 256 == 0
 
 
 def _run_both(B, Te, L, ragged, dev, seed=1234, bias_scale=0.05, mode="fp32"):
@@ -70,7 +71,7 @@ def test_ragged_parity(cuda_dev, mode):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("B,Te,L", [(1, 16, 8), (5, 33, 12), (8, 128, 10), (16, 100, 6), (32, 128, 6), (40, 48, 5), (64, 128, 4), (70, 30, 3),
-                                    (7, 160, 5), (7, 224, 5),
+                                    (7, 160, 5), (7, 224, 5), (16, 256, 6), (3, 129, 4), (20, 200, 4), (40, 160, 3), (5, 300, 4),
                                     (3, 20, 1), (2, 9, 2), (1, 1, 3)])   # shortest loops (T = 2, 3) and a one-token text
 def test_shapes_parity(cuda_dev, B, Te, L, mode):
     if mode == "bf16x3" and not _tc_supported(B, Te):
