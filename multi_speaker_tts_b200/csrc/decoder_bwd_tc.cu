@@ -42,6 +42,8 @@ struct DecBwdTcParams {
   float* dq2;        // [T,B,128] d q partial of the upper position half (summed into dq after the loop)
   float* ldot_part;  // [2][16]   per-half sum_x a[x] (d a[x] + d cum[x]) of the running step
   float* halo_part;  // [16 rows][2 halves][4 CTAs][16] conv-transpose sums reaching the OTHER half's 15 border positions
+  const float* dctx_in;  // projection part of d ctx.  One cluster per row: the same array as dctx (read, then overwritten with the
+                         // total by the same CTA).  TE2: a copy -- the other cluster of the row may still be reading it
 };
 
 struct TcBwdSmem {
@@ -453,7 +455,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     // loads of its saved operands BEFORE the grid-barrier wait that precedes it, so their latency rides in the wait.
     float pf_act[4] = {0.f, 0.f, 0.f, 0.f}, pf_cn = 0.f, pf_cz = 0.f, pf_mc = 0.f, pf_mh = 0.f, pf_dm = 0.f, pf_dh = 0.f;
     float pf_dctx = 0.f;
-    if (arow < B && tid < Dq) pf_dctx = P.dctx[((size_t)(T - 1) * B + arow) * D + crank * Dq + tid];
+    if (arow < B && tid < Dq) pf_dctx = P.dctx_in[((size_t)(T - 1) * B + arow) * D + crank * Dq + tid];
 
     for (int t = T - 1; t >= 0; --t) {
       const uint8_t* zm = P.zone_mask + (size_t)t * 4 * BC;
@@ -472,7 +474,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           if (!last) {
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) v += __ldcg(P.pctx + ((size_t)k4 * B + bb) * D + crank * Dq + tid);
-            P.dctx[gi] = v;
+            if (ph == 0) P.dctx[gi] = v;
           }
           dctx_s[tid] = v;
         }
@@ -774,7 +776,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       STAMP(9);
       grid_arrive_compute(P.barrier, bar_target, gridDim.x);
       attention_prologue();
-      if (arow < B && tid < Dq) pf_dctx = P.dctx[((size_t)(t - 1) * B + arow) * D + crank * Dq + tid];
+      if (arow < B && tid < Dq) pf_dctx = P.dctx_in[((size_t)(t - 1) * B + arow) * D + crank * Dq + tid];
       grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
       STAMP(10);
     }
@@ -923,6 +925,7 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   P.qf = F(l.qf); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.dm1_proj = F(l.dm1_proj);
   P.dctx = F(l.dctx); P.dG0 = F(l.dG0); P.dG1 = F(l.dG1); P.dq = F(l.dq); P.dkeys = F(l.dkeys);
   P.dF = F(l.dF); P.dsw = F(l.dsw);
+  P.dctx_in = P.dctx;
   P.barrier = (unsigned*)(ws + l.barrier);
   P.dbg = (long long*)(ws + l.dbg_b);
   prep_wimg_bwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_b), D);
@@ -931,6 +934,8 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   int rc;
   if (io->Te > 128) {  // two clusters per row, 128 positions each: the shared-memory layout of a 128-position text
     P.dq2 = F(l.dq2); P.ldot_part = F(l.xexch); P.halo_part = F(l.xexch) + 32;
+    P.dctx_in = F(l.dctx_in);
+    MSTTS_CUDA(cudaMemcpyAsync(ws + l.dctx_in, ws + l.dctx, (size_t)io->n_steps * B * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
     rc = launch_bwd_tc<3, 1>(P, s, tc_bwd_smem(3, 128, D).total, &ok);
     if (rc) return rc;
     if (!ok) rc = launch_bwd_tc<2, 1>(P, s, tc_bwd_smem(2, 128, D).total, &ok);

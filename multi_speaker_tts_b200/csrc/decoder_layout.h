@@ -53,7 +53,7 @@ struct DecLayout {
   size_t ximg_g1, ximg_g0, ximg_g_end;   // [64 k-tiles][8 KB] operand images of dG1_t / dG0_t
   size_t pm0, ph1, ph0, pctx;            // K-quarter partials [4][B][1024] / [4][B][D]
   size_t dbg_b;                          // [T][32] int64 phase stamps of the reverse kernel
-  size_t dq2, xexch;                     // texts > 128 positions: upper-half d q [T,B,128]; [2][16] inner products + [16][2][4][16] border sums
+  size_t dq2, xexch, dctx_in;            // texts > 128 positions: (dctx_in [T,B,D]: copy of the projection part of d ctx) upper-half d q [T,B,128]; [2][16] inner products + [16][2][4][16] border sums
   size_t total;
 };
 
@@ -127,7 +127,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dpre = take(TB * kPrenet);
   l.dpre_h = take(TB * kPrenet);
   l.colsum_scratch = take((size_t)64 * kGates);
-  l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = l.dq2 = l.xexch = off;
+  l.wimg_b = l.ximg_g1 = l.ximg_g0 = l.ximg_g_end = l.pm0 = l.ph1 = l.ph0 = l.pctx = l.dbg_b = l.dq2 = l.xexch = l.dctx_in = off;
   if (mode == MSTTS_MODE_BF16X3) {
     auto take_bytes = [&](size_t nbytes) {
       size_t o = off;
@@ -146,6 +146,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
     if (Te > 128) {
       l.dq2 = take(TB * kAtt);
       l.xexch = take(32 + 16 * 2 * kDecCluster * 16);
+      l.dctx_in = take(TB * D);
     }
   }
   l.total = off;
