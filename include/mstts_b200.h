@@ -31,7 +31,7 @@ enum {
   MSTTS_OK = 0,
   MSTTS_E_INVALID = -1,     /* bad argument (null pointer, size out of range) */
   MSTTS_E_WORKSPACE = -2,   /* workspace too small */
-  MSTTS_E_CUDA = -3,        /* a CUDA runtime / cuBLAS call failed */
+  MSTTS_E_CUDA = -3,        /* a CUDA runtime call failed */
   MSTTS_E_UNSUPPORTED = -4, /* configuration not implemented (e.g. conv stride != 1) */
   MSTTS_E_DEVICE = -5       /* device is not sm_100 or cannot co-schedule the persistent grid */
 };
@@ -174,8 +174,9 @@ size_t mstts_waveglow_workspace_bytes(int N, int T);
 int mstts_waveglow_flows(const MsttsWaveGlowWeights* w, const float* audio_in, const float* mel_nt640, int N, int T,
                          int direction, const float* const* early_noise, float* out, double* sums, void* ws,
                          size_t ws_bytes, void* stream);
-/* A/B switch for measurements: 1 = run the WN contractions of mstts_waveglow_flows as library (cuBLAS) bf16 GEMMs with separate
- * gate / residual-skip kernels instead of the hand-written tcgen05 GEMMs with fused epilogues (default 0). */
+/* A/B switch for measurements: 1 = run the WN contractions of mstts_waveglow_flows through the row-major front-end of the
+ * hand-written GEMM with separate gate / residual-skip kernels (the path the training forward uses) instead of the fused-epilogue
+ * path over tile images (default 0).  Both are the same tcgen05 kernel; no vendor library is involved in either. */
 int mstts_waveglow_set_path(int library_gemm);
 
 /* Training (WaveGlow/WaveGlow.py:48-70): forward in the training direction that keeps every layer's operands in the workspace,

@@ -6,7 +6,8 @@ C ABI (``decoder.py`` -> ``libmstts_b200.so``), as one ``torch.autograd.Function
 reverse-time kernel.  There is no CPU path: non-CUDA tensors raise.
 
 ``Encoder_Embedding / Encoder_Conv / Encoder_BiLSTM / Decoder_Conv`` are the callers either side of the decoder (SURVEY
-8f rank 1).  First pass, as the survey prescribes: library ops (cuDNN convolutions, cuBLAS) composed with the
+8f rank 1): the convolutions on the hand-written tcgen05 GEMM (csrc/conv1d.cu), the zoneout-LSTM sequences and the fused
+activation + batch norm + dropout as library kernels of this repository, embedding / losses as torch ops, composed with the
 reference's exact semantics (TF batch-norm statistics over padding, dropout/zoneout conventions, sequence-length
 handling of stack_bidirectional_dynamic_rnn), with explicit variable dicts instead of TF variable scopes.
 """

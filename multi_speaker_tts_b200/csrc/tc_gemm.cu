@@ -10,8 +10,8 @@
 //   element (r, k) of a tile at byte (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2  =>  LBO = 128 (K), SBO = 1024 (M/N)
 // so one pipeline stage is two contiguous bulk async copies (96 KB, no tensor map, no swizzle) feeding 12 MMAs, and the
 // producers of the activations write their outputs directly in this layout (8 consecutive rows x 16 B = one 128-byte line).
-// Compared with folding the three products into K ([hi|lo|hi] x [hi;hi;lo], the library-GEMM form used elsewhere in this
-// repository) this moves a third less operand data per FLOP and the producers write two copies of every value instead of three.
+// Compared with folding the three products into K ([hi|lo|hi] x [hi;hi;lo], the form a plain bf16 GEMM
+// would need) this moves a third less operand data per FLOP and the producers write two copies of every value instead of three.
 //
 // Kernel: persistent, one CTA per SM, 320 threads.  warp 0 = copy producer, warp 1 = TMEM owner + MMA issuer (one elected
 // thread, M = 128, N = 256, K = 16 per instruction), warps 2-9 = epilogue (two per TMEM lane quarter).  2-stage smem ring

@@ -12,9 +12,11 @@
 //     conditioning) applies bias + tanh * sigmoid in its epilogue and writes the operand of the res/skip GEMM, whose epilogue
 //     adds the residual onto the GATED activation (reference quirk B-6), writes the next layer's taps and accumulates the skip.
 //     wn_apply_tiled_kernel / mel_tiled_kernel / flow_pre_tiled_kernel produce the tile images.
-//   * training forward that keeps every layer's operands + the reverse pass (second half of this file): library bf16 GEMMs over
-//     row-major stacked operands in a time-padded layout [N][T+2P][C] (P = 128 zero rows per utterance side, so the dilated conv
-//     is three GEMMs over row-shifted views), with gate_kernel / resskip_kernel and their backward counterparts.
+//   * training forward that keeps every layer's operands + the reverse pass (second half of this file): the same tcgen05 kernel
+//     through its row-major front-end (tc_gemm.h: tc_pack_hl / tc_gemm_images / tc_gemm_hl) over row-major hi/lo operands in a
+//     time-padded layout [N][T+2P][C] (P = 128 zero rows per utterance side, so a tap of the dilated conv is a row-shifted view),
+//     the per-layer products merged so that every operand is packed once; gate_kernel / resskip_kernel and their backward
+//     counterparts around them.
 // Shared: wn_scale (weight norm g*v/sqrt(max(sum v^2,1e-5))), flow_post_kernel (512->c end conv + affine transform with log_s
 // clamped at 8 in forward only + sum(log_s) in double, or the inverse transform followed by the inverse 1x1), mel upsampling.
 #include "common.cuh"
@@ -99,7 +101,7 @@ __device__ __forceinline__ void store_x3(__nv_bfloat16* row, int C, int c, float
 
 // ---- ConvTranspose1d 80->80, k=1024, stride 256, VALID (WaveGlow/Modules.py:198-208) ----
 // out[n, p, co] = bias[co] + sum_{t: 0 <= p-256t < 1024} sum_ci mel[n,t,ci] * K[p-256t, co, ci]
-// Step 1 (library SGEMM, fp32): C[n*Tm+t][k*80+co] = sum_ci mel[n,t,ci] K[k,co,ci]   ([N*Tm,80] x [81920,80]^T)
+// Step 1 (the hand-written GEMM, gemm.h): C[n*Tm+t][k*80+co] = sum_ci mel[n,t,ci] K[k,co,ci]   ([N*Tm,80] x [81920,80]^T)
 // Step 2 (this kernel): overlap-add of the <= 4 frames that reach output position p, + bias
 __global__ void upsample_overlap_add_kernel(const float* __restrict__ C, const float* __restrict__ bias, float* __restrict__ out, int N,
                                             int Tm, int Lkeep) {
@@ -1332,7 +1334,7 @@ extern "C" int mstts_waveglow_train_bwd(const MsttsWaveGlowWeights* w, const Mst
     const __nv_bfloat16* wqc = BF(b.wqc) + (size_t)f * kWgFlowW * 3;
     coupling_bwd_kernel<<<148 * 2, 256, 0, s>>>(SKIP(f), w->end_w[f], w->end_b[f], YBUF(f), dxcur, -1.f / n_el, FP(b.dy), FP(b.dopad),
                                                FP(b.dskip), N, T, c);
-    // end conv: dWe = skip^T do, dbe = colsum(do)   (fp32 library GEMM: 512 x c output)
+    // end conv: dWe = skip^T do, dbe = colsum(do)   (512 x c output over all positions: the 3-way-split precision level)
     if ((rc = gemm_rowmajor_p(s, TC_PRECISE, true, false, kWnCh, c, (int)rows_p, SKIP(f), kWnCh, FP(b.dopad), 8, dwt->end_w[f], c, 0.f))) return rc;
     colsum_valid(s, FP(b.dopad), 8, c, dwt->end_b[f], nullptr, FP(b.part), N, T);
     int cur = 0;
