@@ -554,6 +554,44 @@ static inline int ew_grid(size_t n) {
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+// ---- products beside the reverse loop (see the weight-gradient section of decoder_bwd_one) ----
+constexpr int kDecIdleSMs = 20;  // 148 SMs - the 128 the persistent loop holds
+struct DecSideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+static int dec_side_stream(DecSideStream** out) {
+  static thread_local DecSideStream table[64];
+  static thread_local bool made[64] = {false};
+  int dev = 0;
+  MSTTS_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (!made[dev]) {
+    MSTTS_CUDA(cudaStreamCreateWithFlags(&table[dev].stream, cudaStreamNonBlocking));
+    MSTTS_CUDA(cudaEventCreateWithFlags(&table[dev].fork, cudaEventDisableTiming));
+    MSTTS_CUDA(cudaEventCreateWithFlags(&table[dev].join, cudaEventDisableTiming));
+    made[dev] = true;
+  }
+  *out = &table[dev];
+  return MSTTS_OK;
+}
+// MSTTS_NO_OVERLAP=1 in the environment runs every weight-gradient product after the loop (A/B measurements)
+static bool dec_overlap_enabled() {
+  static const bool off = [] {
+    const char* e = getenv("MSTTS_NO_OVERLAP");
+    return e && e[0] == '1';
+  }();
+  return !off;
+}
+// one warp; lane 0 polls the loop's barrier counter (monotonic) until it reaches `target`
+__global__ void wait_counter_kernel(const unsigned* __restrict__ counter, unsigned target) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(counter) < target) __nanosleep(200);
+    __threadfence();
+  }
+  __syncwarp();
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
@@ -672,38 +710,80 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   P.dctx = F(l.dctx); P.dG0 = F(l.dG0); P.dG1 = F(l.dG1); P.dq = F(l.dq); P.dkeys = F(l.dkeys);
   P.dF = F(l.dF); P.dsw = F(l.dsw); P.dcum = F(l.dcum);
   P.barrier = (unsigned*)(ws + l.barrier);
-  if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
-
-  // Precision: every product below is bf16x3 (TC_FAST).  The 3-way-split level (TC_PRECISE) was measured on the full-size
-  // gradients (tools/grad_probe.py) and changes nothing: the agreement with the oracle is limited by the ReLU / L1 decisions
-  // of the forward pass, not by the products (tests/test_full_size_gpu.py pins those).
-  // ---- weight gradients: products over all steps ----
-  // dW[rows, 4096] = X[T*B, rows]^T dG[T*B, 4096]: ~1 TFLOP at config 2, bf16x3 on the hand-written tcgen05 kernel.  The
-  // gate-gradient operand is packed once per cell into its tile image (4096 image rows, K = T*B) and shared by the
-  // products of that cell; the activation operands take turns in one image buffer.
-  ScratchScope sc(s);
-  void *gimg = nullptr, *ximg = nullptr;
+  // ---- weight gradients of the two cells: dW[rows, 4096] = X[T*B, rows]^T dG[T*B, 4096] ----
+  // ~1 TFLOP at config 2, bf16x3 on the hand-written tcgen05 kernel (every product here is TC_FAST: the higher precision levels
+  // were measured on the full-size gradients, tools/grad_probe.py, and change nothing -- the agreement with the oracle is
+  // limited by the ReLU / L1 decisions of the forward pass, tests/test_full_size_gpu.py).  The contraction runs over time, and
+  // the reverse loop finishes its steps from the last one down, so the products are cut into time chunks: chunk c (the rows of
+  // steps [t_lo, t_hi)) is packed and accumulated ON A SIDE STREAM, ON THE 20 SMs THE PERSISTENT LOOP LEAVES IDLE, as soon as
+  // the loop's barrier counter shows that step t_lo is done (a one-thread kernel polls it); only the last chunk runs after
+  // the loop, on the whole device.  Every side launch is capped at 20 SMs' worth of CTAs (TcGridCap): the loop's cooperative
+  // launch can always become resident, whatever the order in which the two streams start.
   const int KbT = (int)((TB + 63) / 64);
   const int xmax = D > kCell ? D : kCell;
-  if ((rc = sc.get(&gimg, tc_image_bytes(kGates, (int)TB, 256)))) return rc;
-  if ((rc = sc.get(&ximg, tc_image_bytes(xmax, (int)TB, 128)))) return rc;
-  auto wgrad = [&](const float* X, int rows, float* dW) -> int {
-    int r2 = tc_pack_f32(s, X, rows, true, rows, (int)TB, 128, KbT, ximg, 0, 0);
-    if (r2) return r2;
-    return tc_gemm_images(s, ximg, gimg, rows, kGates, (int)TB, dW, kGates, 0.f);
-  };
-  // cell 1: rows [m0 | h1_prev]
-  if ((rc = tc_pack_f32(s, F(l.dG1), kGates, true, kGates, (int)TB, 256, KbT, gimg, 0, 0))) return rc;
-  if ((rc = wgrad(F(l.m0), kCell, dw->cell1_kernel))) return rc;
-  if ((rc = wgrad(F(l.hz1), kCell, dw->cell1_kernel + (size_t)kCell * kGates))) return rc;
-  colsum(s, F(l.dG1), dw->cell1_bias, TB, kGates, F(l.colsum_scratch));
-  // cell 0: rows [prenet | ctx | ctx | h0_prev]
-  if ((rc = tc_pack_f32(s, F(l.dG0), kGates, true, kGates, (int)TB, 256, KbT, gimg, 0, 0))) return rc;
-  if ((rc = wgrad(F(l.pre), kPrenet, dw->cell0_kernel))) return rc;
   float* dK0_ctx = dw->cell0_kernel + (size_t)kPrenet * kGates;
-  if ((rc = wgrad(F(l.ctx), D, dK0_ctx))) return rc;
+  // rows [r0, r0 + nr) of the time-major operands -> both cells' products, accumulated when acc
+  auto wgrad_rows = [&](cudaStream_t st, void* gimg, void* ximg, size_t r0, int nr, bool acc) -> int {
+    const int kb = (nr + 63) / 64;
+    const float beta = acc ? 1.f : 0.f;
+    int r2;
+    auto one = [&](const float* X, int rows, float* dW) -> int {
+      int r3 = tc_pack_f32(st, X + r0 * rows, rows, true, rows, nr, 128, kb, ximg, 0, 0);
+      if (r3) return r3;
+      return tc_gemm_images(st, ximg, gimg, rows, kGates, nr, dW, kGates, beta);
+    };
+    // cell 1: rows [m0 | h1_prev]
+    if ((r2 = tc_pack_f32(st, F(l.dG1) + r0 * kGates, kGates, true, kGates, nr, 256, kb, gimg, 0, 0))) return r2;
+    if ((r2 = one(F(l.m0), kCell, dw->cell1_kernel))) return r2;
+    if ((r2 = one(F(l.hz1), kCell, dw->cell1_kernel + (size_t)kCell * kGates))) return r2;
+    // cell 0: rows [prenet | ctx | (ctx again: copied at the end) | h0_prev]
+    if ((r2 = tc_pack_f32(st, F(l.dG0) + r0 * kGates, kGates, true, kGates, nr, 256, kb, gimg, 0, 0))) return r2;
+    if ((r2 = one(F(l.pre), kPrenet, dw->cell0_kernel))) return r2;
+    if ((r2 = one(F(l.ctx), D, dK0_ctx))) return r2;
+    return one(F(l.hz0), kCell, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates);
+  };
+  // time chunks: NCH - 1 of them beside the loop (highest steps first), the last one (lowest steps, incl. step 0) after it
+  const int bars_per_step = (tc && Te > 128) ? 6 : 5;   // grid barriers of one reverse step (decoder_bwd_tc.cu)
+  const int NCH = (tc && T >= 64 && dec_overlap_enabled()) ? 8 : 1;
+  const int t_split = NCH > 1 ? T / NCH : T;             // the after-loop chunk covers steps [0, t_split)
+  DecSideStream* side = nullptr;
+  if (NCH > 1) {
+    if ((rc = dec_side_stream(&side))) return rc;
+    MSTTS_CUDA(cudaEventRecord(side->fork, s));           // the barrier counter is zeroed, the saved activations are complete
+    MSTTS_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
+  if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
+  if (NCH > 1) {
+    TcGridCap cap(kDecIdleSMs);
+    ScratchScope ssc(side->stream);
+    void *gimg_s = nullptr, *ximg_s = nullptr;
+    const int max_steps = (T - t_split + NCH - 2) / (NCH - 1);
+    if ((rc = ssc.get(&gimg_s, tc_image_bytes(kGates, max_steps * B, 256)))) return rc;
+    if ((rc = ssc.get(&ximg_s, tc_image_bytes(xmax, max_steps * B, 128)))) return rc;
+    int t_hi = T;
+    for (int c = 0; c < NCH - 1; ++c) {
+      const int t_lo = t_split + (int)((long long)(T - t_split) * (NCH - 2 - c) / (NCH - 1));
+      // every CTA adds 1 per grid barrier; step t is complete (its dG rows written and released) once the last barrier of that
+      // step has been passed: bars_per_step * (T - t) barriers since the start of the loop
+      const unsigned target = (unsigned)kDecGrid * (unsigned)bars_per_step * (unsigned)(T - t_lo);
+      wait_counter_kernel<<<1, 32, 0, side->stream>>>((const unsigned*)(ws + l.barrier), target);
+      if ((rc = wgrad_rows(side->stream, gimg_s, ximg_s, (size_t)t_lo * B, (t_hi - t_lo) * B, c > 0))) return rc;
+      t_hi = t_lo;
+    }
+    MSTTS_CUDA(cudaEventRecord(side->join, side->stream));
+    MSTTS_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  }
+  {
+    ScratchScope sc(s);
+    void *gimg = nullptr, *ximg = nullptr;
+    const int nr = t_split * B;
+    if ((rc = sc.get(&gimg, tc_image_bytes(kGates, nr, 256)))) return rc;
+    if ((rc = sc.get(&ximg, tc_image_bytes(xmax, nr, 128)))) return rc;
+    if ((rc = wgrad_rows(s, gimg, ximg, 0, nr, NCH > 1))) return rc;
+  }
+  (void)KbT;
   copy_rows_kernel<<<ew_grid((size_t)D * kGates), 256, 0, s>>>(dK0_ctx, dK0_ctx + (size_t)D * kGates, (size_t)D * kGates);
-  if ((rc = wgrad(F(l.hz0), kCell, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates))) return rc;
+  colsum(s, F(l.dG1), dw->cell1_bias, TB, kGates, F(l.colsum_scratch));
   colsum(s, F(l.dG0), dw->cell0_bias, TB, kGates, F(l.colsum_scratch));
   // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
   if ((rc = gemm_rowmajor_ex(s, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;

@@ -562,18 +562,24 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // K slices per tile: few-tile products with a long K (weight gradients over all decoder steps) would leave most SMs idle,
 // and a tile count just above a multiple of the SM count wastes most of the last round.  Cost model in k-block times
 // (12 MMAs, ~1 us): rounds x (slice length + pipeline fill) + the reduce pass.
+static thread_local int g_grid_cap = 0;  // 0 = the whole device
+TcGridCap::TcGridCap(int ctas) : prev(g_grid_cap) { g_grid_cap = ctas; }
+TcGridCap::~TcGridCap() { g_grid_cap = prev; }
+static inline int gemm_ctas() { return g_grid_cap > 0 && g_grid_cap < 148 ? g_grid_cap : 148; }
+
 static int choose_ksplit(int ntiles, int Kb, int kb_max) {
+  const int ncta = gemm_ctas();
   // kb_max > 0 bounds the length of one tensor-core accumulation chain (k-blocks per slice): the fp32 accumulator in TMEM
   // truncates, so the error of a product grows linearly with the chain length (measured: 2.3e-5 of max at K = 3000, ten
   // times an fp32 SGEMM); short slices summed in double by the reduce kernel bring it back to fp32-SGEMM level
   const int s_min = kb_max > 0 ? (Kb + kb_max - 1) / kb_max : 1;
-  int s_hi = Kb / 2 < 148 ? Kb / 2 : 148;
+  int s_hi = Kb / 2 < ncta ? Kb / 2 : ncta;
   if (s_hi < s_min) s_hi = s_min;
   if (s_hi < 1) s_hi = 1;
   int best = s_min;
   double best_cost = 1e30;
   for (int S = s_min; S <= s_hi; ++S) {
-    const long long rounds = ((long long)ntiles * S + 147) / 148;
+    const long long rounds = ((long long)ntiles * S + ncta - 1) / ncta;
     double cost = (double)rounds * ((double)Kb / S + 2.0);
     if (S > 1) cost += 3.0 + 0.03 * S * ntiles;
     if (cost < best_cost * 0.97) {  // prefer fewer slices unless the gain is real
@@ -598,7 +604,8 @@ static int pack_launch(cudaStream_t s, const PackSrc& P, int R, int K, int TR, i
   const int Kb = (K + 63) / 64;
   const long long wu = (long long)((R + TR - 1) / TR * TR) * Kb * 64 / 256 * nb;
   long long g = (wu + 7) / 8;
-  if (g > 148 * 16) g = 148 * 16;
+  const long long gmax = g_grid_cap > 0 ? (long long)gemm_ctas() * 6 : 148 * 16;
+  if (g > gmax) g = gmax;
   // the kernel addresses chunks relative to an image whose tile rows hold Kb_img k-blocks: shift the base to (rt0, kb0)
   const int Kb_img = Kb_total * (precise ? 4 : 1);
   uint8_t* base = img + ((size_t)rt0 * Kb_img + kb0) * 2 * (size_t)TR * 128;
@@ -642,11 +649,12 @@ static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, co
   const size_t smem = tc_gemm_smem();
   MSTTS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nitems = (long long)ntiles * ksplit;
-  tc_gemm_kernel<3><<<(int)(nitems < 148 ? nitems : 148), kGemmThreads, smem, s>>>(P);
+  tc_gemm_kernel<3><<<(int)(nitems < gemm_ctas() ? nitems : gemm_ctas()), kGemmThreads, smem, s>>>(P);
   MSTTS_CUDA(cudaGetLastError());
   if (ksplit > 1) {
     size_t g = ((size_t)batch * M * N + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
+    const size_t gmax = g_grid_cap > 0 ? (size_t)gemm_ctas() * 6 : 148 * 8;
+    if (g > gmax) g = gmax;
     splitk_reduce_kernel<<<(int)g, 256, 0, s>>>(slabs, ksplit, batch, M, N, Mt * 128, Nt * 256, C, ldc, (size_t)sC, beta);
     MSTTS_CUDA(cudaGetLastError());
   }

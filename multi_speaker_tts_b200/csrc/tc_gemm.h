@@ -125,6 +125,14 @@ static inline size_t tc_image_bytes(int R, int K, int TR, bool precise = false) 
 // image with Kb_total k-blocks; rows up to the next multiple of TR and k up to the next multiple of 64 are zero filled
 int tc_pack_f32(cudaStream_t s, const float* src, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img, int rt0, int kb0,
                 bool precise = false);
+// While alive, caps the grid of every launch this thread issues through the front-end (pack, product, reduce) at `ctas` SMs'
+// worth of CTAs: products that run on a side stream BESIDE a persistent loop, on the SMs the loop leaves idle, must never
+// hold more SMs than that or the loop's cooperative launch could not become resident.
+struct TcGridCap {
+  int prev;
+  explicit TcGridCap(int ctas);
+  ~TcGridCap();
+};
 // same from a matrix already split into bf16 hi + lo parts (hi and lo share the leading dimension)
 int tc_pack_hl(cudaStream_t s, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int ld, bool trans, int R, int K, int TR, int Kb_total, void* img,
                int rt0, int kb0);
