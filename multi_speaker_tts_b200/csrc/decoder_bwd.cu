@@ -583,10 +583,16 @@ static bool dec_overlap_enabled() {
   }();
   return !off;
 }
+static int dec_env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (!e || !*e) return dflt;
+  const int v = atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
 // one warp; lane 0 polls the loop's barrier counter (monotonic) until it reaches `target`
-__global__ void wait_counter_kernel(const unsigned* __restrict__ counter, unsigned target) {
+__global__ void wait_counter_kernel(const unsigned* __restrict__ counter, unsigned target, unsigned sleep_ns) {
   if (threadIdx.x == 0) {
-    while (ld_acquire_gpu(counter) < target) __nanosleep(200);
+    while (ld_acquire_gpu(counter) < target) __nanosleep(sleep_ns);
     __threadfence();
   }
   __syncwarp();
@@ -744,7 +750,7 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   };
   // time chunks: NCH - 1 of them beside the loop (highest steps first), the last one (lowest steps, incl. step 0) after it
   const int bars_per_step = (tc && Te > 128) ? 6 : 5;   // grid barriers of one reverse step (decoder_bwd_tc.cu)
-  const int NCH = (tc && T >= 64 && dec_overlap_enabled()) ? 8 : 1;
+  const int NCH = (tc && T >= 64 && dec_overlap_enabled()) ? dec_env_int("MSTTS_OVERLAP_CHUNKS", 8, 2, 64) : 1;
   const int t_split = NCH > 1 ? T / NCH : T;             // the after-loop chunk covers steps [0, t_split)
   DecSideStream* side = nullptr;
   if (NCH > 1) {
@@ -754,7 +760,7 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   }
   if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
   if (NCH > 1) {
-    TcGridCap cap(kDecIdleSMs);
+    TcGridCap cap(dec_env_int("MSTTS_OVERLAP_SMS", kDecIdleSMs, 1, kDecIdleSMs));
     ScratchScope ssc(side->stream);
     void *gimg_s = nullptr, *ximg_s = nullptr;
     const int max_steps = (T - t_split + NCH - 2) / (NCH - 1);
@@ -766,7 +772,8 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
       // every CTA adds 1 per grid barrier; step t is complete (its dG rows written and released) once the last barrier of that
       // step has been passed: bars_per_step * (T - t) barriers since the start of the loop
       const unsigned target = (unsigned)kDecGrid * (unsigned)bars_per_step * (unsigned)(T - t_lo);
-      wait_counter_kernel<<<1, 32, 0, side->stream>>>((const unsigned*)(ws + l.barrier), target);
+      wait_counter_kernel<<<1, 32, 0, side->stream>>>((const unsigned*)(ws + l.barrier), target,
+                                                      (unsigned)dec_env_int("MSTTS_OVERLAP_POLL_NS", 200, 20, 100000));
       if ((rc = wgrad_rows(side->stream, gimg_s, ximg_s, (size_t)t_lo * B, (t_hi - t_lo) * B, c > 0))) return rc;
       t_hi = t_lo;
     }

@@ -604,7 +604,12 @@ static int pack_launch(cudaStream_t s, const PackSrc& P, int R, int K, int TR, i
   const int Kb = (K + 63) / 64;
   const long long wu = (long long)((R + TR - 1) / TR * TR) * Kb * 64 / 256 * nb;
   long long g = (wu + 7) / 8;
-  const long long gmax = g_grid_cap > 0 ? (long long)gemm_ctas() * 6 : 148 * 16;
+  static const int pack_mult = [] {
+    const char* e = getenv("MSTTS_OVERLAP_PACK_MULT");
+    const int v = e && *e ? atoi(e) : 6;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  const long long gmax = g_grid_cap > 0 ? (long long)gemm_ctas() * pack_mult : 148 * 16;
   if (g > gmax) g = gmax;
   // the kernel addresses chunks relative to an image whose tile rows hold Kb_img k-blocks: shift the base to (rt0, kb0)
   const int Kb_img = Kb_total * (precise ? 4 : 1);
