@@ -485,17 +485,16 @@ __global__ void colsum_partial_kernel(const float* __restrict__ in, float* __res
     part[(size_t)blockIdx.y * C + c] = tot;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C, int accumulate) {
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float tot = 0.f;
   for (int j = 0; j < kColsumSlices; ++j) tot += part[(size_t)j * C + c];
-  out[c] = accumulate ? out[c] + tot : tot;
+  out[c] = tot;
 }
-// out[c] (+)= sum over R rows; `scratch` [kColsumSlices][C] must not be shared between streams
-static void colsum(cudaStream_t s, const float* in, float* out, size_t R, int C, float* scratch, bool accumulate = false) {
+static void colsum(cudaStream_t s, const float* in, float* out, size_t R, int C, float* scratch) {
   colsum_partial_kernel<<<dim3((C + 31) / 32, kColsumSlices), dim3(32, 8), 0, s>>>(in, scratch, R, C);
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, out, C, accumulate ? 1 : 0);
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, out, C);
 }
 
 // prenet backward through relu + dropout: dz = 2 * dy * [y > 0]   (y = relu(z) * 2 * mask)
@@ -687,18 +686,11 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
 
   // ---- upstream gradient through the hoisted projection ----
   gather_dproj_kernel<<<ew_grid(TB * NP), 256, 0, s>>>(g->d_linear, g->d_stop, F(l.dproj_tm), B, T);
-  // dWp = [m1 | ctx]^T dproj ; dbp = colsum(dproj): nothing downstream in this call reads them, so with the overlap on they
-  // run beside the reverse loop as well (below)
-  auto proj_wgrads = [&](cudaStream_t st, float* cs_scratch) -> int {
-    int r2;
-    if ((r2 = gemm_rowmajor_ex(st, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return r2;
-    if ((r2 = gemm_rowmajor_ex(st, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
-                               dw->proj_kernel + (size_t)kCell * NP, NP, 0.f))) return r2;
-    colsum(st, F(l.dproj_tm), dw->proj_bias, TB, NP, cs_scratch);
-    return MSTTS_OK;
-  };
-  const bool overlap = (io->mode == MSTTS_MODE_BF16X3) && T >= 64 && dec_overlap_enabled();
-  if (!overlap && (rc = proj_wgrads(s, F(l.colsum_scratch)))) return rc;
+  // dWp = [m1 | ctx]^T dproj ; dbp = colsum(dproj)
+  if ((rc = gemm_rowmajor_ex(s, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
+                             dw->proj_kernel + (size_t)kCell * NP, NP, 0.f))) return rc;
+  colsum(s, F(l.dproj_tm), dw->proj_bias, TB, NP, F(l.colsum_scratch));
   // d m1 (projection part) and d ctx (projection part)
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kCell, NP, F(l.dproj_tm), NP, w->proj_kernel, NP, F(l.dm1_proj), kCell, 0.f))) return rc;
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, D, NP, F(l.dproj_tm), NP, w->proj_kernel + (size_t)kCell * NP, NP,
@@ -737,7 +729,7 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   const int xmax = D > kCell ? D : kCell;
   float* dK0_ctx = dw->cell0_kernel + (size_t)kPrenet * kGates;
   // rows [r0, r0 + nr) of the time-major operands -> both cells' products, accumulated when acc
-  auto wgrad_rows = [&](cudaStream_t st, void* gimg, void* ximg, float* cs_scratch, size_t r0, int nr, bool acc) -> int {
+  auto wgrad_rows = [&](cudaStream_t st, void* gimg, void* ximg, size_t r0, int nr, bool acc) -> int {
     const int kb = (nr + 63) / 64;
     const float beta = acc ? 1.f : 0.f;
     int r2;
@@ -754,29 +746,11 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
     if ((r2 = tc_pack_f32(st, F(l.dG0) + r0 * kGates, kGates, true, kGates, nr, 256, kb, gimg, 0, 0))) return r2;
     if ((r2 = one(F(l.pre), kPrenet, dw->cell0_kernel))) return r2;
     if ((r2 = one(F(l.ctx), D, dK0_ctx))) return r2;
-    if ((r2 = one(F(l.hz0), kCell, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates))) return r2;
-    // bias gradients of the cells
-    colsum(st, F(l.dG1) + r0 * kGates, dw->cell1_bias, (size_t)nr, kGates, cs_scratch, acc);
-    colsum(st, F(l.dG0) + r0 * kGates, dw->cell0_bias, (size_t)nr, kGates, cs_scratch, acc);
-    // prenet (row-wise in time, so it rides in the same chunks): d pre = dG0 @ K0[0:256]^T, then back through the two
-    // dense + relu + dropout layers; kernel / bias gradients accumulate over the chunks
-    float *dpre = F(l.dpre) + r0 * kPrenet, *dpre_h = F(l.dpre_h) + r0 * kPrenet;
-    const float *pre = F(l.pre) + r0 * kPrenet, *pre_h = F(l.pre_h) + r0 * kPrenet;
-    if ((r2 = gemm_rowmajor_ex(st, false, true, nr, kPrenet, kGates, F(l.dG0) + r0 * kGates, kGates, w->cell0_kernel, kGates, dpre, kPrenet, 0.f)))
-      return r2;
-    prenet_act_bwd_kernel<<<ew_grid((size_t)nr * kPrenet), 256, 0, st>>>(dpre, pre, (size_t)nr * kPrenet);
-    if ((r2 = gemm_rowmajor_ex(st, true, false, kPrenet, kPrenet, nr, pre_h, kPrenet, dpre, kPrenet, dw->prenet1_kernel, kPrenet, beta))) return r2;
-    colsum(st, dpre, dw->prenet1_bias, (size_t)nr, kPrenet, cs_scratch, acc);
-    if ((r2 = gemm_rowmajor_ex(st, false, true, nr, kPrenet, kPrenet, dpre, kPrenet, w->prenet1_kernel, kPrenet, dpre_h, kPrenet, 0.f))) return r2;
-    prenet_act_bwd_kernel<<<ew_grid((size_t)nr * kPrenet), 256, 0, st>>>(dpre_h, pre_h, (size_t)nr * kPrenet);
-    if ((r2 = gemm_rowmajor_ex(st, true, false, kMel, kPrenet, nr, F(l.frames) + r0 * kMel, kMel, dpre_h, kPrenet, dw->prenet0_kernel, kPrenet, beta)))
-      return r2;
-    colsum(st, dpre_h, dw->prenet0_bias, (size_t)nr, kPrenet, cs_scratch, acc);
-    return MSTTS_OK;
+    return one(F(l.hz0), kCell, dw->cell0_kernel + (size_t)(kPrenet + 2 * D) * kGates);
   };
   // time chunks: NCH - 1 of them beside the loop (highest steps first), the last one (lowest steps, incl. step 0) after it
   const int bars_per_step = (tc && Te > 128) ? 6 : 5;   // grid barriers of one reverse step (decoder_bwd_tc.cu)
-  const int NCH = overlap ? dec_env_int("MSTTS_OVERLAP_CHUNKS", 8, 2, 64) : 1;
+  const int NCH = (tc && T >= 64 && dec_overlap_enabled()) ? dec_env_int("MSTTS_OVERLAP_CHUNKS", 8, 2, 64) : 1;
   const int t_split = NCH > 1 ? T / NCH : T;             // the after-loop chunk covers steps [0, t_split)
   DecSideStream* side = nullptr;
   if (NCH > 1) {
@@ -788,12 +762,10 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   if (NCH > 1) {
     TcGridCap cap(dec_env_int("MSTTS_OVERLAP_SMS", kDecIdleSMs, 1, kDecIdleSMs));
     ScratchScope ssc(side->stream);
-    void *gimg_s = nullptr, *ximg_s = nullptr, *cs_s = nullptr;
+    void *gimg_s = nullptr, *ximg_s = nullptr;
     const int max_steps = (T - t_split + NCH - 2) / (NCH - 1);
     if ((rc = ssc.get(&gimg_s, tc_image_bytes(kGates, max_steps * B, 256)))) return rc;
     if ((rc = ssc.get(&ximg_s, tc_image_bytes(xmax, max_steps * B, 128)))) return rc;
-    if ((rc = ssc.get(&cs_s, (size_t)kColsumSlices * kGates * sizeof(float)))) return rc;
-    if ((rc = proj_wgrads(side->stream, (float*)cs_s))) return rc;
     int t_hi = T;
     for (int c = 0; c < NCH - 1; ++c) {
       const int t_lo = t_split + (int)((long long)(T - t_split) * (NCH - 2 - c) / (NCH - 1));
@@ -802,7 +774,7 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
       const unsigned target = (unsigned)kDecGrid * (unsigned)bars_per_step * (unsigned)(T - t_lo);
       wait_counter_kernel<<<1, 32, 0, side->stream>>>((const unsigned*)(ws + l.barrier), target,
                                                       (unsigned)dec_env_int("MSTTS_OVERLAP_POLL_NS", 200, 20, 100000));
-      if ((rc = wgrad_rows(side->stream, gimg_s, ximg_s, (float*)cs_s, (size_t)t_lo * B, (t_hi - t_lo) * B, c > 0))) return rc;
+      if ((rc = wgrad_rows(side->stream, gimg_s, ximg_s, (size_t)t_lo * B, (t_hi - t_lo) * B, c > 0))) return rc;
       t_hi = t_lo;
     }
     MSTTS_CUDA(cudaEventRecord(side->join, side->stream));
@@ -814,16 +786,27 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
     const int nr = t_split * B;
     if ((rc = sc.get(&gimg, tc_image_bytes(kGates, nr, 256)))) return rc;
     if ((rc = sc.get(&ximg, tc_image_bytes(xmax, nr, 128)))) return rc;
-    if ((rc = wgrad_rows(s, gimg, ximg, F(l.colsum_scratch), 0, nr, NCH > 1))) return rc;
+    if ((rc = wgrad_rows(s, gimg, ximg, 0, nr, NCH > 1))) return rc;
   }
   (void)KbT;
   copy_rows_kernel<<<ew_grid((size_t)D * kGates), 256, 0, s>>>(dK0_ctx, dK0_ctx + (size_t)D * kGates, (size_t)D * kGates);
+  colsum(s, F(l.dG1), dw->cell1_bias, TB, kGates, F(l.colsum_scratch));
+  colsum(s, F(l.dG0), dw->cell0_bias, TB, kGates, F(l.colsum_scratch));
   // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
   if ((rc = gemm_rowmajor_ex(s, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
   colsum(s, F(l.dq), F(l.dfb), TB, kAtt, F(l.colsum_scratch));
   location_grads_kernel<<<1, 1024, 0, s>>>(F(l.dF), F(l.dfb), w->loc_conv_kernel, w->loc_conv_bias, w->loc_dense_kernel,
                                            dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
   MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  // prenet: d pre = dG0 @ K0[0:256]^T, then back through the two dense+relu+dropout layers
+  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
+  prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre), F(l.pre), TB * kPrenet);
+  if ((rc = gemm_rowmajor_ex(s, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
+  colsum(s, F(l.dpre), dw->prenet1_bias, TB, kPrenet, F(l.colsum_scratch));
+  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kPrenet, F(l.dpre), kPrenet, w->prenet1_kernel, kPrenet, F(l.dpre_h), kPrenet, 0.f))) return rc;
+  prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre_h), F(l.pre_h), TB * kPrenet);
+  if ((rc = gemm_rowmajor_ex(s, true, false, kMel, kPrenet, (int)TB, F(l.frames), kMel, F(l.dpre_h), kPrenet, dw->prenet0_kernel, kPrenet, 0.f))) return rc;
+  colsum(s, F(l.dpre_h), dw->prenet0_bias, TB, kPrenet, F(l.colsum_scratch));
   // memory side: dvalues[b] = A_b^T dctx_b (over steps) + dkeys[b] @ Wm^T ; dWm = values^T dkeys
   if ((rc = gemm_rowmajor_batched(s, true, false, Te, D, T, F(l.align_tm), B * Te, Te, F(l.dctx), B * D, D, F(l.dvalues), D,
                                   (long long)Te * D, 0.f, B))) return rc;
