@@ -372,6 +372,17 @@ def main():
     set_profiling(False)
     ar = [a.elapsed_time(b) for a, b in tr.allreduce_events]
     tr.allreduce_events = None
+    # the same step with the weight-gradient products AFTER the reverse loop instead of beside it (MSTTS_NO_OVERLAP=1): shows what
+    # the overlap buys and what the contention costs the loop kernel (short run, not part of `value`)
+    os.environ["MSTTS_NO_OVERLAP"] = "1"
+    step_resident()
+    set_profiling(True)
+    ms_no, _, _ = time_region(step_resident, min(args.steps, 5), barrier)
+    f2, n2 = kernel_ms(0)
+    b2, m2 = kernel_ms(1)
+    set_profiling(False)
+    del os.environ["MSTTS_NO_OVERLAP"]
+    no_overlap = {"step_ms": ms_no / min(args.steps, 5), "fwd_loop_ms": f2 / max(n2, 1), "bwd_loop_ms": b2 / max(m2, 1)}
     # end-to-end arm (host buffers, copies inside the timed region)
     step_e2e()
     ms_e2e, wall_e2e, last = time_region(step_e2e, args.steps, barrier)
@@ -430,7 +441,10 @@ def main():
             "clocks": sampler.summary(),
             "roofline": dominant, "roofline_other": other,
             "kernel_share": {"fwd_loop_ms": fwd_avg, "bwd_loop_ms": bwd_avg, "step_ms": ms / args.steps,
-                             "outside_loops_ms": ms / args.steps - fwd_avg - bwd_avg},
+                             "outside_loops_ms": ms / args.steps - fwd_avg - bwd_avg,
+                             "note": "the weight-gradient products of finished time chunks run BESIDE the reverse loop on the 20 SMs it "
+                                     "leaves idle; the loop's duration (and roofline.frac) includes that contention",
+                             "without_overlap": no_overlap},
             "ms_per_step_per_rank": per_rank_ms, "allreduce_ms_per_rank": ar_rank,
             "allreduce_bytes": int(tr.flat_g.numel()) * 4 if world > 1 else 0,
             "loss": [float(x) for x in last.tolist()],

@@ -576,12 +576,9 @@ static int dec_side_stream(DecSideStream** out) {
   return MSTTS_OK;
 }
 // MSTTS_NO_OVERLAP=1 in the environment runs every weight-gradient product after the loop (A/B measurements)
-static bool dec_overlap_enabled() {
-  static const bool off = [] {
-    const char* e = getenv("MSTTS_NO_OVERLAP");
-    return e && e[0] == '1';
-  }();
-  return !off;
+static bool dec_overlap_enabled() {  // read per call: bench.py times both settings in one process
+  const char* e = getenv("MSTTS_NO_OVERLAP");
+  return !(e && e[0] == '1');
 }
 static int dec_env_int(const char* name, int dflt, int lo, int hi) {
   const char* e = getenv(name);
