@@ -226,7 +226,8 @@ class Tacotron2(object):
         """MSTTS_SV.py:45-98.  v: name -> tensor (leaves for autograd in training)."""
         training = feed['Is_Training']
         masks = masks or {}
-        with torch.no_grad():  # frozen (MSTTS_SV.py:183-190)
+        branch = Modules.side_stream(feed['Token'].device, 'speaker')
+        with branch, torch.no_grad():  # frozen (MSTTS_SV.py:183-190); independent of the encoder: runs beside it
             e = Speaker_Embedding_Modules.Restructure(feed['Speaker_Embedding_Mel'], self.variables)
             lengths = torch.full((e.shape[0],), hp.Speaker_Embedding.Inference.Mel_Frame, device=e.device)
             e = Speaker_Embedding_Modules.Stack_LSTM(e, lengths, training, self.variables)
@@ -234,6 +235,7 @@ class Tacotron2(object):
         x = Modules.Encoder_Embedding(feed['Token'], v)
         x = Modules.Encoder_Conv(x, training, v, masks.get('encoder_conv'))
         x = Modules.Encoder_BiLSTM(x, feed['Token_Length'], training, v, masks.get('encoder_bilstm'))
+        e = branch.join(e)
         memory = torch.cat([x, e[:, None, :].expand(-1, x.shape[1], -1)], dim=-1).contiguous()
         dv = self._decoder_variables(v)
         att = Location_Sensitive_Attention(

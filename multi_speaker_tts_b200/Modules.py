@@ -299,6 +299,103 @@ def Encoder_Conv(inputs, is_training=False, variables=None, masks=None):
     return x
 
 
+def _gemm(tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, beta=0.0, precise=0):
+    """C[M,N] = op(A) op(B) + beta C on the hand-written tcgen05 kernel (mstts_gemm_f32: bf16x3, fp32 accumulation)"""
+    import ctypes as C
+    with torch.cuda.device(A.device):
+        rc = _lib.lib().mstts_gemm_f32(int(tA), int(tB), M, N, K, _lib.ptr(A), lda, 0, _lib.ptr(Bm), ldb, 0, _lib.ptr(Cm), ldc, 0,
+                                       float(beta), 1, int(precise), C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream))
+    _lib.check(rc, "mstts_gemm_f32")
+
+
+class _DenseFunction(torch.autograd.Function):
+    """y[M,N] = x[M,K] w[K,N] (+ bias) and its gradients as three products on the library's own GEMM: the input rows of the
+    zoneout-LSTM kernels applied to all steps at once, and tf.layers.dense of the speaker-embedding net"""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        x, w = x.contiguous(), w.contiguous()
+        M, K = x.shape
+        N = w.shape[1]
+        if bias is not None:
+            y = bias.detach().reshape(1, N).expand(M, N).contiguous()
+            _gemm(0, 0, M, N, K, x, K, w, N, y, N, beta=1.0)
+        else:
+            y = torch.empty(M, N, device=x.device)
+            _gemm(0, 0, M, N, K, x, K, w, N, y, N)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = w.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _gemm(0, 1, M, K, N, dy, N, w, N, dx, K)           # dy w^T  (w stored [K, N] = the N x K operand, transposed)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            _gemm(1, 0, K, N, M, x, K, dy, N, dw, N)           # x^T dy
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=0)
+        return dx, dw, db
+
+
+def dense(x, w, bias=None):
+    """x[..., K] w[K, N] + bias on CUDA fp32 tensors through the library's GEMM; anything else through torch"""
+    if not (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32):
+        y = x @ w
+        return y if bias is None else y + bias
+    lead = x.shape[:-1]
+    y = _DenseFunction.apply(x.reshape(-1, x.shape[-1]), w, bias)
+    return y.reshape(*lead, w.shape[1])
+
+
+_SIDE_STREAM = {}
+
+
+class side_stream(object):
+    """``with side_stream(device, name):`` runs the block on one cached side stream per (device, name), ordered after everything already
+    queued on the current stream; ``join(*tensors)`` makes the current stream wait for it and hands the tensors over.  Branches
+    of the graph that do not depend on each other (the two directions of the encoder BiLSTM, the frozen speaker-embedding
+    net beside the encoder) run concurrently this way -- each is a few-CTA recurrence that leaves most SMs idle.  autograd
+    replays every node on the stream its forward ran on, so the reverse passes overlap as well."""
+
+    def __init__(self, device, name='branch'):
+        self.dev = torch.device(device)
+        self.on = self.dev.type == 'cuda'
+        if self.on:
+            key = (self.dev.index if self.dev.index is not None else torch.cuda.current_device(), name)
+            if key not in _SIDE_STREAM:
+                _SIDE_STREAM[key] = torch.cuda.Stream(device=self.dev)
+            self.side = _SIDE_STREAM[key]
+            self.cur = torch.cuda.current_stream(self.dev)
+            self.ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(self.cur)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.on:
+            self.cur.wait_stream(self.side)
+            for t in tensors:
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(self.cur)
+        return tensors[0] if len(tensors) == 1 else tensors
+
+
 def _reverse_sequence(x, lengths):
     """tf.reverse_sequence over axis 1: the first lengths[b] entries of row b are reversed, the rest stay"""
     T = x.shape[1]
@@ -345,7 +442,8 @@ class _ZlstmFunction(torch.autograd.Function):
                                             B, T, H, reverse, keep, _lib.ptr(dxk),
                                             C.c_void_p(torch.cuda.current_stream(dout.device).cuda_stream))
         _lib.check(rc, "mstts_zlstm_bwd")
-        dkh = hp_.reshape(B * T, H).t() @ dxk.reshape(B * T, 4 * H)
+        dkh = torch.empty(H, 4 * H, device=dout.device)
+        _gemm(1, 0, H, 4 * H, B * T, hp_, H, dxk, 4 * H, dkh, 4 * H)  # h_prev^T d xk
         dres = None
         if has_res:
             live = torch.arange(T, device=dout.device)[None, :] < lengths[:, None]
@@ -364,7 +462,7 @@ def zoneout_lstm_sequence(inputs, lengths, kernel, bias, is_training, zoneout_ra
     H = kernel.shape[1] // 4
     if inputs.is_cuda and inputs.dtype == torch.float32 and H == 256:
         keep = 1.0 - zoneout_rate
-        xk = inputs @ kernel[:In] + bias
+        xk = dense(inputs, kernel[:In], bias)
         m8 = None
         if is_training:
             if masks is None:
@@ -413,12 +511,15 @@ def Encoder_BiLSTM(inputs, lengths, is_training=False, variables=None, masks=Non
         mf = mb = None
         if masks is not None:
             mf, mb = masks[n]
+        branch = side_stream(x.device, 'bilstm_bw')
+        with branch:  # the reverse direction runs beside the forward one
+            bw, _ = zoneout_lstm_sequence(x, lengths, variables[p + '/bw/zoneout_lstm_cell/kernel'],
+                                          variables[p + '/bw/zoneout_lstm_cell/bias'], is_training,
+                                          hp.Encoder.BiLSTM.Zoneout_Rate, mb, reverse=True)
         fw, _ = zoneout_lstm_sequence(x, lengths, variables[p + '/fw/zoneout_lstm_cell/kernel'],
                                       variables[p + '/fw/zoneout_lstm_cell/bias'], is_training,
                                       hp.Encoder.BiLSTM.Zoneout_Rate, mf)
-        bw, _ = zoneout_lstm_sequence(x, lengths, variables[p + '/bw/zoneout_lstm_cell/kernel'],
-                                      variables[p + '/bw/zoneout_lstm_cell/bias'], is_training,
-                                      hp.Encoder.BiLSTM.Zoneout_Rate, mb, reverse=True)
+        bw = branch.join(bw)
         x = torch.cat([fw, bw], dim=-1)
     return x
 

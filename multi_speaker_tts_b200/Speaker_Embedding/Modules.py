@@ -1,14 +1,14 @@
 """Speaker-embedding forward (Speaker_Embedding/Modules.py:6-37,127-137): frozen producer of the 256-d conditioning
-vector.  Library ops; reuses ``Modules.zoneout_lstm_sequence``."""
+vector.  Reuses ``Modules.zoneout_lstm_sequence`` / ``Modules.dense`` (the library's own kernels)."""
 import torch
 
 from .. import Hyper_Parameters as hp
-from ..Modules import zoneout_lstm_sequence
+from ..Modules import dense, zoneout_lstm_sequence
 
 
 def Restructure(inputs, variables):
     """dense 80 -> Embedding_Size so the first residual connection type-checks (:6-10)"""
-    return inputs @ variables['speaker_embedding/dense/kernel'] + variables['speaker_embedding/dense/bias']
+    return dense(inputs, variables['speaker_embedding/dense/kernel'], variables['speaker_embedding/dense/bias'])
 
 
 def Stack_LSTM(inputs, lengths, is_training=False, variables=None):

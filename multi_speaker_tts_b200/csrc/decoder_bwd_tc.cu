@@ -42,6 +42,8 @@ struct DecBwdTcParams {
   float* dq2;        // [T,B,128] d q partial of the upper position half (summed into dq after the loop)
   float* ldot_part;  // [2][16]   per-half sum_x a[x] (d a[x] + d cum[x]) of the running step
   float* halo_part;  // [16 rows][2 halves][4 CTAs][16] conv-transpose sums reaching the OTHER half's 15 border positions
+  int l2_stream;         // saved activations are loaded, gate gradients stored with the evict-first hint (MSTTS_LOOP_STREAM=0: off)
+  int w_evict_last;      // weight tiles are loaded with the L2 evict_last hint (experiment: MSTTS_LOOP_L2=1)
   const float* dctx_in;  // projection part of d ctx.  One cluster per row: the same array as dctx (read, then overwritten with the
                          // total by the same CTA).  TE2: a copy -- the other cluster of the row may still be reading it
 };
@@ -214,6 +216,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
     // =========================== weight-tile producers (even / odd tiles) ===========================
     if (lane == 0) {
       const uint8_t* wsrc = P.wimg + (size_t)blockIdx.x * 16 * kWTileBytes;
+      const uint64_t wpol = P.w_evict_last ? ptx::l2_policy_evict_last() : 0ull;
       int i = 0;
       for (int t = T - 1; t >= 0; --t) {
         for (int job = 0; job < 4; ++job) {
@@ -223,7 +226,10 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             const int s = i % NS, round = i / NS;
             if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
             ptx::mbar_arrive_expect_tx(&wfull[s], kWTileBytes);
-            ptx::bulk_g2s(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(job * 4 + kt) * kWTileBytes, kWTileBytes, &wfull[s]);
+            if (P.w_evict_last)
+              ptx::bulk_g2s_hint(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(job * 4 + kt) * kWTileBytes, kWTileBytes, &wfull[s], wpol);
+            else
+              ptx::bulk_g2s(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(job * 4 + kt) * kWTileBytes, kWTileBytes, &wfull[s]);
           }
         }
       }
@@ -572,9 +578,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       if (brow) {  // saved operands of phase B'e (d h1 partials of JB2(t+1) are complete since the last barrier of step t+1)
         const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = P.act1[ai + gi * kCell];
-        pf_cn = P.c1n[(size_t)t * BC + si];
-        pf_cz = P.cz1[(size_t)t * BC + si];
+        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = ld_stream(P.act1 + ai + gi * kCell, P.l2_stream);
+        pf_cn = ld_stream(P.c1n + (size_t)t * BC + si, P.l2_stream);
+        pf_cz = ld_stream(P.cz1 + (size_t)t * BC + si, P.l2_stream);
         pf_mc = (float)zm[2 * BC + si];
         pf_mh = (float)zm[3 * BC + si];
         pf_dm = P.dm1_proj[(size_t)t * BC + si];
@@ -620,10 +626,10 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         grid_arrive_compute(P.barrier, bar_target, gridDim.x);
         if (brow) {
           const size_t ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          P.dG1[ai] = g.di;
-          P.dG1[ai + kCell] = g.dj;
-          P.dG1[ai + 2 * kCell] = g.df;
-          P.dG1[ai + 3 * kCell] = g.dop;
+          st_stream(P.dG1 + ai, g.di, P.l2_stream);
+          st_stream(P.dG1 + ai + kCell, g.dj, P.l2_stream);
+          st_stream(P.dG1 + ai + 2 * kCell, g.df, P.l2_stream);
+          st_stream(P.dG1 + ai + 3 * kCell, g.dop, P.l2_stream);
         }
         // ---- deferred halves of attention'(t), spread over the barrier waits so that none holds more than the barrier's own
         //      ~1.3 us (all of it inside the wait of barrier 1 took ~3.5 us): here the conv transpose that feeds d cum_{t-1};
@@ -691,9 +697,9 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       if (brow) {  // saved operands of phase A'e
         const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = P.act0[ai + gi * kCell];
-        pf_cn = P.c0n[(size_t)t * BC + si];
-        pf_cz = P.cz0[(size_t)t * BC + si];
+        for (int gi = 0; gi < 4; ++gi) pf_act[gi] = ld_stream(P.act0 + ai + gi * kCell, P.l2_stream);
+        pf_cn = ld_stream(P.c0n + (size_t)t * BC + si, P.l2_stream);
+        pf_cz = ld_stream(P.cz0 + (size_t)t * BC + si, P.l2_stream);
         pf_mc = (float)zm[si];
         pf_mh = (float)zm[BC + si];
       }
@@ -751,20 +757,20 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         if (t == 0) {  // nothing upstream of step 0 needs d ctx_{-1} / d h_{-1}
           if (brow) {
             const size_t ai = (size_t)b * kGates + unit;
-            P.dG0[ai] = g.di;
-            P.dG0[ai + kCell] = g.dj;
-            P.dG0[ai + 2 * kCell] = g.df;
-            P.dG0[ai + 3 * kCell] = g.dop;
+            st_stream(P.dG0 + ai, g.di, P.l2_stream);
+            st_stream(P.dG0 + ai + kCell, g.dj, P.l2_stream);
+            st_stream(P.dG0 + ai + 2 * kCell, g.df, P.l2_stream);
+            st_stream(P.dG0 + ai + 3 * kCell, g.dop, P.l2_stream);
           }
           break;
         }
         grid_arrive_compute(P.barrier, bar_target, gridDim.x);
         if (brow) {
           const size_t ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          P.dG0[ai] = g.di;
-          P.dG0[ai + kCell] = g.dj;
-          P.dG0[ai + 2 * kCell] = g.df;
-          P.dG0[ai + 3 * kCell] = g.dop;
+          st_stream(P.dG0 + ai, g.di, P.l2_stream);
+          st_stream(P.dG0 + ai + kCell, g.dj, P.l2_stream);
+          st_stream(P.dG0 + ai + 2 * kCell, g.df, P.l2_stream);
+          st_stream(P.dG0 + ai + 3 * kCell, g.dop, P.l2_stream);
         }
         attention_stage(t - 1, true);
         grid_wait_compute(P.barrier, bar_target, ready_seq, ++ev);
@@ -952,6 +958,12 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   P.dctx = F(l.dctx); P.dG0 = F(l.dG0); P.dG1 = F(l.dG1); P.dq = F(l.dq); P.dkeys = F(l.dkeys);
   P.dF = F(l.dF); P.dsw = F(l.dsw);
   P.dctx_in = P.dctx;
+  {
+    const char* e = getenv("MSTTS_LOOP_L2");
+    P.w_evict_last = e ? atoi(e) : 0;
+    e = getenv("MSTTS_LOOP_STREAM");
+    P.l2_stream = e ? atoi(e) : 1;
+  }
   P.barrier = (unsigned*)(ws + l.barrier);
   P.dbg = (long long*)(ws + l.dbg_b);
   prep_wimg_bwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_b), D);

@@ -45,6 +45,8 @@ struct DecFwdTcParams {
   uint8_t* ximg_pre;           // [2 parities][4 tiles][8 KB] prenet output of the coming step
   float* proj_tm;              // [T,B,81] bias-free projection (finish_outputs adds the bias)
   int* steps_done;
+  int l2_stream;     // saved activations are stored / g0pre loaded with the evict-first hint (MSTTS_LOOP_STREAM=0: off)
+  int w_evict_last;  // weight tiles loaded with the L2 evict_last hint (MSTTS_LOOP_L2=1)
 };
 
 struct TcSmem {
@@ -248,7 +250,11 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         }
         if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
         ptx::mbar_arrive_expect_tx(&wfull[s], kWTileBytes);
-        ptx::bulk_g2s(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s]);
+        if (P.w_evict_last)
+          ptx::bulk_g2s_hint(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s],
+                             ptx::l2_policy_evict_last());
+        else
+          ptx::bulk_g2s(ring + (size_t)s * kWTileBytes, wsrc + (size_t)(i % tps) * kWTileBytes, kWTileBytes, &wfull[s]);
       }
     }
     __syncwarp();
@@ -470,7 +476,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           if (!infer) {
             const float* gp = P.g0pre + (size_t)t * BG + (size_t)b * kGates + unit;
 #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) add[gi] = gp[gi * kCell] + bias0[gi];
+            for (int gi = 0; gi < 4; ++gi) add[gi] = ld_stream(gp + gi * kCell, P.l2_stream) + bias0[gi];
           } else {  // the prenet rows of cell 0's kernel are part of job J0
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) add[gi] = bias0[gi];
@@ -514,14 +520,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         grid_arrive_compute(P.barrier, bar_target, gridDim.x);
         if (brow && !infer) {  // activations saved for the reverse pass: nobody waits for these inside the loop
           const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          P.act0[ai] = r.ig;
-          P.act0[ai + kCell] = r.jg;
-          P.act0[ai + 2 * kCell] = r.fg;
-          P.act0[ai + 3 * kCell] = r.og;
-          P.c0n[(size_t)t * BC + si] = r.c;
-          P.cz0[(size_t)(t + 1) * BC + si] = r.cz;
-          P.hz0[(size_t)(t + 1) * BC + si] = r.hz;
-          P.m0[(size_t)t * BC + si] = r.m;
+          st_stream(P.act0 + ai, r.ig, P.l2_stream);
+          st_stream(P.act0 + ai + kCell, r.jg, P.l2_stream);
+          st_stream(P.act0 + ai + 2 * kCell, r.fg, P.l2_stream);
+          st_stream(P.act0 + ai + 3 * kCell, r.og, P.l2_stream);
+          st_stream(P.c0n + (size_t)t * BC + si, r.c, P.l2_stream);
+          st_stream(P.cz0 + (size_t)(t + 1) * BC + si, r.cz, P.l2_stream);
+          st_stream(P.hz0 + (size_t)(t + 1) * BC + si, r.hz, P.l2_stream);
+          st_stream(P.m0 + (size_t)t * BC + si, r.m, P.l2_stream);
         }
         grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 1);
       }
@@ -588,14 +594,14 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         grid_arrive_compute(P.barrier, bar_target, gridDim.x);
         if (brow && !infer) {
           const size_t si = (size_t)b * kCell + unit, ai = (size_t)t * BG + (size_t)b * kGates + unit;
-          P.act1[ai] = r.ig;
-          P.act1[ai + kCell] = r.jg;
-          P.act1[ai + 2 * kCell] = r.fg;
-          P.act1[ai + 3 * kCell] = r.og;
-          P.c1n[(size_t)t * BC + si] = r.c;
-          P.cz1[(size_t)(t + 1) * BC + si] = r.cz;
-          P.hz1[(size_t)(t + 1) * BC + si] = r.hz;
-          P.m1[(size_t)t * BC + si] = r.m;
+          st_stream(P.act1 + ai, r.ig, P.l2_stream);
+          st_stream(P.act1 + ai + kCell, r.jg, P.l2_stream);
+          st_stream(P.act1 + ai + 2 * kCell, r.fg, P.l2_stream);
+          st_stream(P.act1 + ai + 3 * kCell, r.og, P.l2_stream);
+          st_stream(P.c1n + (size_t)t * BC + si, r.c, P.l2_stream);
+          st_stream(P.cz1 + (size_t)(t + 1) * BC + si, r.cz, P.l2_stream);
+          st_stream(P.hz1 + (size_t)(t + 1) * BC + si, r.hz, P.l2_stream);
+          st_stream(P.m1 + (size_t)t * BC + si, r.m, P.l2_stream);
         }
         grid_wait_compute(P.barrier, bar_target, ready_seq, 3u * t + 2);
       }
@@ -1008,6 +1014,12 @@ int dec_fwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   P.b0 = w->cell0_bias; P.b1 = w->cell1_bias; P.Wq = w->query_kernel;
   P.F = F(l.locF); P.fb = F(l.locFb); P.sw = w->score_w;
   P.g0pre = F(l.g0pre); P.keys = F(l.keys); P.values = F(l.values);
+  {
+    const char* e = getenv("MSTTS_LOOP_STREAM");
+    P.l2_stream = e ? atoi(e) : 1;
+    e = getenv("MSTTS_LOOP_L2");
+    P.w_evict_last = e ? atoi(e) : 0;
+  }
   P.text_len = io->text_len; P.zone_mask = io->zone_mask;
   P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n);
   P.cz0 = F(l.cz0); P.hz0 = F(l.hz0); P.cz1 = F(l.cz1); P.hz1 = F(l.hz1);

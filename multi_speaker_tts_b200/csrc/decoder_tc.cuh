@@ -37,6 +37,16 @@ constexpr uint32_t kSlotBytes = kWTileBytes + kXTileBytes;
 constexpr uint32_t kTcLBO = 128, kTcSBO = 1024;
 constexpr int kRecvStride = 40;           // floats per (src, batch) row of the K-split reduction buffer [src][batch][gate*8+unit]
 
+// Saved activations and gate gradients pass through L2 exactly once per loop (written by one loop, read by the other or by the
+// weight-gradient packs, ~1 MB per step each); marked evict-first they do not displace the weight image every step re-reads.
+__device__ __forceinline__ void st_stream(float* p, float v, int on) {
+  if (on)
+    __stcs(p, v);
+  else
+    *p = v;
+}
+__device__ __forceinline__ float ld_stream(const float* p, int on) { return on ? __ldcs(p) : *p; }
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));

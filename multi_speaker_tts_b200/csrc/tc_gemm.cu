@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      const uint64_t l2pol = P.stream_l2 ? ptx::l2_policy_evict_first() : 0ull;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const TcItem w = tc_item(P, item);
         const uint8_t* a = P.A + (size_t)w.b * P.a_bstride + (size_t)w.mt * P.Kb * kGemmAChunk;
@@ -89,8 +90,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const TcGemmPa
           if (round > 0) ptx::mbar_wait(&empty[s], (round - 1) & 1);
           ptx::mbar_arrive_expect_tx(&full[s], kGemmStage);
           uint8_t* dst = ring + (size_t)s * kGemmStage;
-          ptx::bulk_g2s(dst, a + (size_t)kb * kGemmAChunk, kGemmAChunk, &full[s]);
-          ptx::bulk_g2s(dst + kGemmAChunk, b + (size_t)kb * kGemmBChunk, kGemmBChunk, &full[s]);
+          if (P.stream_l2) {
+            ptx::bulk_g2s_hint(dst, a + (size_t)kb * kGemmAChunk, kGemmAChunk, &full[s], l2pol);
+            ptx::bulk_g2s_hint(dst + kGemmAChunk, b + (size_t)kb * kGemmBChunk, kGemmBChunk, &full[s], l2pol);
+          } else {
+            ptx::bulk_g2s(dst, a + (size_t)kb * kGemmAChunk, kGemmAChunk, &full[s]);
+            ptx::bulk_g2s(dst + kGemmAChunk, b + (size_t)kb * kGemmBChunk, kGemmBChunk, &full[s]);
+          }
         }
       }
     }
@@ -311,6 +317,7 @@ __device__ __forceinline__ void tc_gemm_epilogue<3>(const TcGemmParams& P, uint3
   const int ncols = slab ? 256 : min(256, P.N - nt * 256);
   const bool vec = slab || ((P.ldc & 3) == 0 && (P.c_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
   const float beta = slab ? 0.f : P.beta;
+  const bool stream = P.stream_l2 > 1;
 #pragma unroll 1
   for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
     uint32_t v[32];
@@ -323,10 +330,13 @@ __device__ __forceinline__ void tc_gemm_epilogue<3>(const TcGemmParams& P, uint3
       for (int j = 0; j < 32; j += 4) {
         float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         if (beta != 0.f) {
-          const float4 c = *reinterpret_cast<const float4*>(dst + j);
+          const float4 c = stream ? __ldcs(reinterpret_cast<const float4*>(dst + j)) : *reinterpret_cast<const float4*>(dst + j);
           o = make_float4(o.x + beta * c.x, o.y + beta * c.y, o.z + beta * c.z, o.w + beta * c.w);
         }
-        *reinterpret_cast<float4*>(dst + j) = o;
+        if (stream)
+          __stcs(reinterpret_cast<float4*>(dst + j), o);
+        else
+          *reinterpret_cast<float4*>(dst + j) = o;
       }
     } else {
 #pragma unroll
@@ -451,7 +461,7 @@ struct PackSrc {
 template <bool F32>
 __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R, int K, int TR, int Kb, int Kb_total,
                                                          uint8_t* __restrict__ dst, size_t dst_bstride, int batch, int vec,
-                                                         int precise, int b_side) {
+                                                         int precise, int b_side, int stream_l2) {
   const int Rp = (R + TR - 1) / TR * TR, Kp = Kb * 64;
   const long long per = (long long)Rp * Kp / 256, total = per * batch;
   const int lane = threadIdx.x & 31;
@@ -478,7 +488,14 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
       if (!S.trans) {
         const float* p = src + (size_t)r * S.ld + k0;
         if (vec && r < R && k0 + 8 <= K) {
-          const float4 a = *reinterpret_cast<const float4*>(p), c = *reinterpret_cast<const float4*>(p + 4);
+          float4 a, c;
+          if (stream_l2) {
+            a = __ldcs(reinterpret_cast<const float4*>(p));
+            c = __ldcs(reinterpret_cast<const float4*>(p + 4));
+          } else {
+            a = *reinterpret_cast<const float4*>(p);
+            c = *reinterpret_cast<const float4*>(p + 4);
+          }
           x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
         } else {
 #pragma unroll
@@ -486,7 +503,10 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (r < R && k0 + j < K) ? src[(size_t)(k0 + j) * S.ld + r] : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          const float* q = src + (size_t)(k0 + j) * S.ld + r;
+          x[j] = (r < R && k0 + j < K) ? (stream_l2 > 1 ? __ldcs(q) : *q) : 0.f;
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -525,8 +545,13 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
     uint8_t* d = dst + (size_t)b * dst_bstride + ((size_t)(r / TR) * Kb_img + (k0 >> 6)) * 2 * tile_bytes + (size_t)((r % TR) >> 3) * 1024 +
                  (size_t)((k0 & 63) >> 3) * 128 + (size_t)(r & 7) * 16;
     const uint4 h4 = *reinterpret_cast<const uint4*>(hi), m4 = *reinterpret_cast<const uint4*>(lo);
-    *reinterpret_cast<uint4*>(d) = h4;
-    *reinterpret_cast<uint4*>(d + tile_bytes) = m4;
+    if (stream_l2) {
+      __stcs(reinterpret_cast<uint4*>(d), h4);
+      __stcs(reinterpret_cast<uint4*>(d + tile_bytes), m4);
+    } else {
+      *reinterpret_cast<uint4*>(d) = h4;
+      *reinterpret_cast<uint4*>(d + tile_bytes) = m4;
+    }
     if (F32 && precise) {
       // segments 1-3 of the 3-way split (x = h + m + l, 24 mantissa bits), Kb_total k-blocks apart:
       //   seg 0: (h, m) x (h, m) -> hh + mh + hm     seg 1: (m, 0) x (m, 0) -> mm
@@ -545,7 +570,7 @@ __global__ void __launch_bounds__(256) pack_image_kernel(const PackSrc S, int R,
 
 // C_b[m, n] = beta C_b[m, n] + sum_s slab[s][b][m][n]   (fixed summation order: deterministic)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ slabs, int S, int batch, int M, int N, int Mp, int Np,
-                                                            float* __restrict__ C, int ldc, size_t c_bstride, float beta) {
+                                                            float* __restrict__ C, int ldc, size_t c_bstride, float beta, int stream_l2) {
   const size_t total = (size_t)batch * M * N, slab = (size_t)batch * Mp * Np;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(i % N);
@@ -553,9 +578,14 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     const int m = (int)(bm % M), b = (int)(bm / M);
     const float* p = slabs + ((size_t)b * Mp + m) * Np + n;
     double acc = 0.0;  // the slices are short tensor-core accumulation chains; their sum is exact to fp32
-    for (int s = 0; s < S; ++s) acc += (double)p[(size_t)s * slab];
     float* c = C + (size_t)b * c_bstride + (size_t)m * ldc + n;
-    *c = beta != 0.f ? (float)(acc + (double)beta * (double)*c) : (float)acc;
+    if (stream_l2) {
+      for (int s = 0; s < S; ++s) acc += (double)__ldcs(p + (size_t)s * slab);
+      __stcs(c, beta != 0.f ? (float)(acc + (double)beta * (double)__ldcs(c)) : (float)acc);
+    } else {
+      for (int s = 0; s < S; ++s) acc += (double)p[(size_t)s * slab];
+      *c = beta != 0.f ? (float)(acc + (double)beta * (double)*c) : (float)acc;
+    }
   }
 }
 
@@ -565,6 +595,14 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 static thread_local int g_grid_cap = 0;  // 0 = the whole device
 TcGridCap::TcGridCap(int ctas) : prev(g_grid_cap) { g_grid_cap = ctas; }
 TcGridCap::~TcGridCap() { g_grid_cap = prev; }
+// launches under a grid cap run beside a persistent loop: stream their operands through L2 (MSTTS_SIDE_L2=0 switches it off)
+static inline int side_stream_l2() {
+  static const int on = [] {
+    const char* e = getenv("MSTTS_SIDE_L2");
+    return e ? atoi(e) : 2;
+  }();
+  return g_grid_cap > 0 ? on : 0;
+}
 static inline int gemm_ctas() { return g_grid_cap > 0 && g_grid_cap < 148 ? g_grid_cap : 148; }
 
 static int choose_ksplit(int ntiles, int Kb, int kb_max) {
@@ -615,7 +653,7 @@ static int pack_launch(cudaStream_t s, const PackSrc& P, int R, int K, int TR, i
   const int Kb_img = Kb_total * (precise ? 4 : 1);
   uint8_t* base = img + ((size_t)rt0 * Kb_img + kb0) * 2 * (size_t)TR * 128;
   pack_image_kernel<F32><<<(int)g, 256, 0, s>>>(P, R, K, TR, Kb, Kb_total, base, img_bstride, nb, pack_vec_ok(P, F32) ? 1 : 0, precise ? 1 : 0,
-                                                b_side ? 1 : 0);
+                                                b_side ? 1 : 0, side_stream_l2());
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }
@@ -650,7 +688,7 @@ static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, co
   memset(&P, 0, sizeof(P));
   P.A = ai; P.B = bi; P.C = C; P.M = M; P.N = N; P.Mt = Mt; P.Nt = Nt; P.Kb = Kb; P.ldc = ldc;
   P.batch = batch; P.ksplit = ksplit; P.a_bstride = a_bstride; P.b_bstride = b_bstride; P.c_bstride = (size_t)sC; P.beta = beta;
-  P.slabs = slabs; P.n_full = ntiles;
+  P.slabs = slabs; P.n_full = ntiles; P.stream_l2 = side_stream_l2();
   const size_t smem = tc_gemm_smem();
   MSTTS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nitems = (long long)ntiles * ksplit;
@@ -660,7 +698,7 @@ static int launch_images(cudaStream_t s, const uint8_t* ai, size_t a_bstride, co
     size_t g = ((size_t)batch * M * N + 255) / 256;
     const size_t gmax = g_grid_cap > 0 ? (size_t)gemm_ctas() * 6 : 148 * 8;
     if (g > gmax) g = gmax;
-    splitk_reduce_kernel<<<(int)g, 256, 0, s>>>(slabs, ksplit, batch, M, N, Mt * 128, Nt * 256, C, ldc, (size_t)sC, beta);
+    splitk_reduce_kernel<<<(int)g, 256, 0, s>>>(slabs, ksplit, batch, M, N, Mt * 128, Nt * 256, C, ldc, (size_t)sC, beta, side_stream_l2() > 1);
     MSTTS_CUDA(cudaGetLastError());
   }
   return MSTTS_OK;

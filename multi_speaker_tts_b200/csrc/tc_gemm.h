@@ -26,6 +26,8 @@ struct TcGemmParams {
   size_t a_bstride, b_bstride, c_bstride;
   float beta;
   float* slabs;
+  int stream_l2;      // 1: operand images are loaded evict_first (a product running BESIDE a persistent loop must not displace
+                      // the weight image the loop keeps in L2)
 };
 // scratch bytes a caller must provide for the split-K tail (partials + flags)
 constexpr size_t kTcGemmScratchBytes = (size_t)74 * 256 * 128 * 4 + 1024;
