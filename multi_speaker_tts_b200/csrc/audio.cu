@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const StftParams P, size_
 // in 16 distinct 8-byte banks per half-warp.  (Padding i + i/8 fixed the scatter but doubled the wavefronts of every
 // consecutive access: 32 float2 then span 36 slots.)
 __device__ __forceinline__ int padi(int i) { return i ^ ((i >> 4) & 15); }
+// sqrt.approx.f32: max relative error 2^-23 (PTX ISA) -- the magnitudes feed a dB scale compared at 1e-3; the IEEE sqrtf
+// sequence was 9 % of the kernel's instructions
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ void bfly(float2& a, float2& b) {
   const float2 t = a;
@@ -224,42 +231,96 @@ __device__ __forceinline__ void team_sync(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TEAM) : "memory");
 }
 
-// one Stockham stage of radix R over H points: thread j handles inputs j + r H/R, outputs (j/Ns) Ns R + j%Ns + r Ns
-template <int R, int H, int TEAM>
+// padi is linear over GF(2): padi(a + b) = padi(a) ^ padi(b) whenever a and b occupy disjoint bit fields, which every index of
+// the power-of-two schedule does (thread part | unrolled-loop part).  The thread parts are swizzled once per stage, the loop
+// parts are compile-time constants: one XOR per access instead of shift + and + xor + add.
+__host__ __device__ constexpr int padc(int i) { return i ^ ((i >> 4) & 15); }
+template <int V>
+__host__ __device__ constexpr int ilog2c() { return V <= 1 ? 0 : 1 + ilog2c<V / 2>(); }
+
+// one Stockham stage of radix R over H points: butterfly j handles inputs j + r H/R, outputs (j/Ns) Ns R + j%Ns + r Ns
+// (NS = compile-time Ns; NS <= TEAM, so j%Ns and j/Ns split into a thread part and an iteration part)
+template <int R, int H, int TEAM, int NS>
 __device__ __forceinline__ void fft_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ twst,
-                                          const int Ns, const int ltid) {
+                                          const int ltid) {
+  static_assert(NS <= TEAM, "j % Ns must be a function of the thread index alone");
+  constexpr int LR = ilog2c<R>(), LNS = ilog2c<NS>();
+  const int k = ltid & (NS - 1);
+  const int pl = padi(ltid);                                        // loads: index = ltid + (it TEAM + r H/R)
+  const int ps = padi(((ltid >> LNS) << (LNS + LR)) | k);           // stores: index = (ltid/NS) NS R + k + (it TEAM R + r NS)
 #pragma unroll
-  for (int j = ltid; j < H / R; j += TEAM) {
+  for (int it = 0; it < (H / R + TEAM - 1) / TEAM; ++it) {
+    if (H / R < TEAM && ltid >= H / R) break;
     float2 v[R], o[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = src[padi(j + r * (H / R))];
-    const int k = j & (Ns - 1);
-    if (Ns > 1) {
+    for (int r = 0; r < R; ++r) v[r] = src[pl ^ padc(it * TEAM + r * (H / R))];
+    if (NS > 1) {
       // per-stage table twst[(r-1) Ns + k] = exp(-2 pi i k r / (Ns R)): lanes of a warp have consecutive k, so the reads are
       // conflict free (indexing the n_fft-th roots table directly is an 8-way conflict: stride 128 B between lanes)
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], twst[(r - 1) * Ns + k]);
+      for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], twst[(r - 1) * NS + k]);
     }
     dft_regs<R>(v, o);
-    const int base = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[padi(base + r * Ns)] = o[r];
+    for (int r = 0; r < R; ++r) dst[ps ^ padc(it * TEAM * R + r * NS)] = o[r];
+  }
+}
+
+// the FIRST stage (Ns = 1, no twiddles) reads the staged raw segment directly and applies the window from registers: the
+// windowed frame is never written to shared memory.  z[n] = (x[2n] w[2n], x[2n+1] w[2n+1]); wreg holds this thread's H/TEAM
+// window pairs in the order the loop consumes them (the same for every frame).
+template <int R, int H, int TEAM>
+__device__ __forceinline__ void fft_stage_first(const float* __restrict__ rw, const bool even, const float2 (&wreg)[H / TEAM],
+                                                float2* __restrict__ dst, const int ltid) {
+  constexpr int LR = ilog2c<R>();
+  const int ps = padi(ltid << LR);  // stores: index = ltid R + (it TEAM R + r)
+  int idx = 0;
+#pragma unroll
+  for (int it = 0; it < (H / R + TEAM - 1) / TEAM; ++it) {
+    if (H / R < TEAM && ltid >= H / R) break;
+    float2 v[R], o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r, ++idx) {
+      const int n = ltid + it * TEAM + r * (H / R);
+      const float2 x = even ? *reinterpret_cast<const float2*>(rw + 2 * n) : make_float2(rw[2 * n], rw[2 * n + 1]);
+      v[r] = make_float2(x.x * wreg[idx].x, x.y * wreg[idx].y);
+    }
+    dft_regs<R>(v, o);
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[ps ^ padc(it * TEAM * R + r)] = o[r];
+  }
+}
+
+// the radix-8 stages after the first one (Ns = NS, 8 NS, ... < H), ping-ponging src / dst; TWOFF = offset of the stage's twiddles
+template <int H, int TEAM, int NS, int TWOFF>
+__device__ __forceinline__ void fft_rest(float2*& src, float2*& dst, const float2* __restrict__ twst, const int ltid, const int team) {
+  if constexpr (NS < H) {
+    fft_stage<8, H, TEAM, NS>(src, dst, twst + TWOFF, ltid);
+    float2* t = src; src = dst; dst = t;
+    team_sync<TEAM>(team);
+    fft_rest<H, TEAM, NS * 8, TWOFF + 7 * NS>(src, dst, twst, ltid, team);
   }
 }
 
 template <int LOG2H>
-__global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int groups_per_utt, int ngroups) {
-  constexpr int H = 1 << LOG2H, N = 2 * H;
-  constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
-  constexpr int TPC = 256 / TEAM;            // frames per CTA iteration
+struct StftTeamCfg {
+  static constexpr int H = 1 << LOG2H, N = 2 * H;
+  static constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
+  static constexpr int R1 = (LOG2H % 3 == 1) ? 2 : (LOG2H % 3 == 2) ? 4 : 8;  // radix of the first stage
+  static constexpr int kTabFloats = (2 * H + 3 * (H + 1) + 3 * 256 + 1) & ~1;  // tw_s, fbc_s, rng_s (complex arrays 8-byte aligned)
+};
+
+template <int LOG2H, int NT>
+__global__ void __launch_bounds__(NT) stft_team_kernel(const StftParams P, int groups_per_utt, int ngroups) {
+  using Cfg = StftTeamCfg<LOG2H>;
+  constexpr int H = Cfg::H, N = Cfg::N, TEAM = Cfg::TEAM, R1 = Cfg::R1;
+  constexpr int TPC = NT / TEAM;             // frames per CTA iteration
   constexpr int ZP = H;                      // complex array length (XOR swizzle, no padding)
   extern __shared__ __align__(16) float smem_f[];
   float2* tw_s = reinterpret_cast<float2*>(smem_f);              // [H]
-  float* win_s = reinterpret_cast<float*>(tw_s + H);             // [N]
-  float* fbc_s = win_s + N;                                      // [3*(H+1)] compact filter weights
+  float* fbc_s = reinterpret_cast<float*>(tw_s + H);             // [3*(H+1)] compact filter weights
   int* rng_s = reinterpret_cast<int*>(fbc_s + 3 * (H + 1));      // [256][3]
-  constexpr int kTabFloats = (2 * H + N + 3 * (H + 1) + 3 * 256 + 1) & ~1;                 // keep the complex arrays 8-byte aligned
-  float2* z_all = reinterpret_cast<float2*>(smem_f + kTabFloats);
+  float2* z_all = reinterpret_cast<float2*>(smem_f + Cfg::kTabFloats);
   float* mag_all = reinterpret_cast<float*>(z_all + (size_t)TPC * 2 * ZP);  // [TPC][H+4]
   float2* twst_s = reinterpret_cast<float2*>(mag_all + TPC * (H + 4));  // [H] per-stage twiddle tables (radix-8 stages)
   float* raw_s = reinterpret_cast<float*>(twst_s + H);           // [N + (TPC-1)*hop]
@@ -268,23 +329,22 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
   float2* zb = za + ZP;
   float* mag_s = mag_all + team * (H + 4);
 
-  for (int i = tid; i < H; i += 256) tw_s[i] = P.tw[i];
-  for (int i = tid; i < N; i += 256) win_s[i] = P.window[i];
+  for (int i = tid; i < H; i += NT) tw_s[i] = P.tw[i];
   if (P.mel_out) {
     const int nnz = P.fb_off[P.n_mels];
-    for (int i = tid; i < nnz; i += 256) fbc_s[i] = P.fbc[i];
-    for (int m = tid; m < P.n_mels; m += 256) {
+    for (int i = tid; i < nnz; i += NT) fbc_s[i] = P.fbc[i];
+    for (int m = tid; m < P.n_mels; m += NT) {
       rng_s[3 * m] = P.fb_range[2 * m];
       rng_s[3 * m + 1] = P.fb_range[2 * m + 1];
       rng_s[3 * m + 2] = P.fb_off[m];
     }
   }
   {
-    int Ns = (LOG2H % 3 == 1) ? 2 : (LOG2H % 3 == 2) ? 4 : 1, off = 0;
+    int Ns = (R1 == 8) ? 1 : R1, off = 0;
 #pragma unroll
     for (int it = 0; it < LOG2H / 3; ++it) {
       if (Ns > 1) {
-        for (int idx = tid; idx < 7 * Ns; idx += 256) {
+        for (int idx = tid; idx < 7 * Ns; idx += NT) {
           const int r = idx / Ns + 1, k = idx % Ns;
           const int i = r * k * (2 * H / (Ns * 8));  // P.tw[i] = exp(-2 pi i * i / (2H)), i < H; the other half is its negative
           float2 w = P.tw[i & (H - 1)];
@@ -296,76 +356,70 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
       Ns *= 8;
     }
   }
+  // this thread's window pairs, in the order fft_stage_first consumes them
+  float2 wreg[H / TEAM];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int j = ltid; j < H / R1; j += TEAM) {
+#pragma unroll
+      for (int r = 0; r < R1; ++r, ++idx) {
+        const int n = j + r * (H / R1);
+        wreg[idx] = make_float2(P.window[2 * n], P.window[2 * n + 1]);
+      }
+    }
+  }
   __syncthreads();
   const int rawlen = N + (TPC - 1) * P.hop;
+  const float inv_gpu = 1.f / (float)groups_per_utt;
+  const int MG = TEAM / 4;  // mel filters in flight per team: 4 lanes each
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    const int b = g / groups_per_utt, fr0 = (g % groups_per_utt) * TPC;
+    int b = __float2int_rz(((float)g + 0.5f) * inv_gpu);  // floor(g / groups_per_utt) without the integer-division sequence
+    if (b * groups_per_utt > g) --b;                       // (the reciprocal product can be off by one at most)
+    if ((b + 1) * groups_per_utt <= g) ++b;
+    const int fr0 = (g - b * groups_per_utt) * TPC;
     const float* x = P.wav + (size_t)b * P.S;
     // ---- stage the pre-emphasised, reflect-padded segment (librosa pads AFTER Audio.preemphasis ran) ----
-    for (int i = tid; i < rawlen; i += 256) {
-      int j = fr0 * P.hop + i - H;
-      if (j < 0) j = -j;
-      if (j >= P.S) j = 2 * (P.S - 1) - j;
-      j = min(max(j, 0), P.S - 1);
-      const float x0 = __ldg(x + j), x1 = __ldg(x + max(j - 1, 0));
-      raw_s[i] = (j > 0) ? x0 - 0.97f * x1 : x0;
+    const int j0 = fr0 * P.hop - H;
+    if (j0 >= 1 && j0 + rawlen <= P.S) {  // interior group: no reflection, x[j-1] always exists
+      const float* xb = x + j0;
+      for (int i = tid; i < rawlen; i += NT) raw_s[i] = __ldg(xb + i) - 0.97f * __ldg(xb + i - 1);
+    } else {
+      for (int i = tid; i < rawlen; i += NT) {
+        int j = j0 + i;
+        if (j < 0) j = -j;
+        if (j >= P.S) j = 2 * (P.S - 1) - j;
+        j = min(max(j, 0), P.S - 1);
+        const float x0 = __ldg(x + j), x1 = __ldg(x + max(j - 1, 0));
+        raw_s[i] = (j > 0) ? x0 - 0.97f * x1 : x0;
+      }
     }
     __syncthreads();
     const int fr = fr0 + team;
     const bool live = fr < P.frames;
-    if (live) {
-      const float* rw = raw_s + team * P.hop;
-      if (((team * P.hop) & 1) == 0) {  // even offset: the pair (x[2k], x[2k+1]) is one aligned 8-byte load
-#pragma unroll 4
-        for (int k = ltid; k < H; k += TEAM) {
-          const float2 wv = *reinterpret_cast<const float2*>(win_s + 2 * k);
-          const float2 xv = *reinterpret_cast<const float2*>(rw + 2 * k);
-          za[padi(k)] = make_float2(xv.x * wv.x, xv.y * wv.y);
-        }
-      } else {
-#pragma unroll 4
-        for (int k = ltid; k < H; k += TEAM) {
-          const float2 wv = *reinterpret_cast<const float2*>(win_s + 2 * k);
-          za[padi(k)] = make_float2(rw[2 * k] * wv.x, rw[2 * k + 1] * wv.y);
-        }
-      }
+    float2* src = za;
+    float2* dst = zb;
+    if (live) {  // first stage straight from the staged segment (window in registers)
+      fft_stage_first<R1, H, TEAM>(raw_s + team * P.hop, ((team * P.hop) & 1) == 0, wreg, zb, ltid);
     }
     __syncthreads();  // raw_s may be overwritten by the next group from here on; teams run independently below
     if (!live) continue;
-    // ---- complex FFT of size H ----
-    float2* src = za;
-    float2* dst = zb;
-    int Ns = 1;
-    int twoff = 0;
-    if (LOG2H % 3 == 1) {
-      fft_stage<2, H, TEAM>(src, dst, twst_s, 1, ltid);
-      Ns = 2;
-    } else if (LOG2H % 3 == 2) {
-      fft_stage<4, H, TEAM>(src, dst, twst_s, 1, ltid);
-      Ns = 4;
-    }
-    if (Ns > 1) {
-      float2* t = src; src = dst; dst = t;
-      team_sync<TEAM>(team);
-    }
-#pragma unroll
-    for (int it = 0; it < LOG2H / 3; ++it) {
-      fft_stage<8, H, TEAM>(src, dst, twst_s + twoff, Ns, ltid);
-      if (Ns > 1) twoff += 7 * Ns;
-      Ns *= 8;
-      float2* t = src; src = dst; dst = t;
-      team_sync<TEAM>(team);
-    }
-    // ---- split post-pass: X[k] = (Z[k] + conj(Z[H-k]))/2 - i e^{-2 pi i k/N} (Z[k] - conj(Z[H-k]))/2, magnitude ----
-    for (int k = ltid; k <= H; k += TEAM) {
-      const float2 zk = src[padi(k & (H - 1))];
+    // ---- remaining stages of the complex FFT of size H (the first one wrote zb) ----
+    src = zb;
+    dst = za;
+    fft_rest<H, TEAM, R1, 0>(src, dst, twst_s, ltid, team);
+    // ---- split post-pass: X[k] = (Z[k] + conj(Z[H-k]))/2 - i e^{-2 pi i k/N} (Z[k] - conj(Z[H-k]))/2, magnitude.  The pair
+    //      (k, H-k) shares its two loads and its twiddle (w_{H-k} = -conj(w_k)): X[H-k] = (e.x - wo.y, -e.y - wo.x) ----
+    for (int k = ltid; k <= H / 2; k += TEAM) {
+      const float2 zk = src[padi(k)];
       const float2 zc = src[padi((H - k) & (H - 1))];
       const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
       const float2 o = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
-      const float2 w = (k < H) ? tw_s[k] : make_float2(-1.f, 0.f);
-      const float2 wo = cmulf(w, o);
+      const float2 wo = cmulf(tw_s[k], o);
       const float re = e.x + wo.y, im = e.y - wo.x;
-      mag_s[k] = sqrtf(re * re + im * im);
+      const float re2 = e.x - wo.y, im2 = e.y + wo.x;
+      mag_s[k] = sqrt_approx(re * re + im * im);
+      mag_s[H - k] = sqrt_approx(re2 * re2 + im2 * im2);
     }
     team_sync<TEAM>(team);
     const size_t fi = (size_t)b * P.frames + fr;
@@ -373,17 +427,44 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
       for (int k = ltid; k <= H; k += TEAM) P.mag_out[fi * (H + 1) + k] = mag_s[k];
     } else {
       if (P.mel_out) {
+        // 4 lanes per triangular filter (3 .. 45 bins wide): neighbouring filters have similar widths, so a round costs its
+        // widest filter / 4 iterations (thread-per-filter: the widest filter of each warp pass, with every lane on its own bank
+        // pattern); the sums go through shared memory so that dB + clip + store run once per filter, not once per round
+        float* msum = reinterpret_cast<float*>(dst);  // the work array the last FFT stage did not write
+        const int gl = ltid & 3, grp = ltid >> 2;
+        for (int m0 = 0; m0 < P.n_mels; m0 += MG) {
+          const int m = m0 + grp;
+          float sum = 0.f;
+          if (m < P.n_mels) {
+            const int lo = rng_s[3 * m], hi = rng_s[3 * m + 1];
+            const float* wts = fbc_s + rng_s[3 * m + 2] - lo;
+            // pointer pair + 4-deep unroll: 2 LDS + 1 FFMA per element instead of recomputing both addresses
+            const float* wp = wts + lo + gl;
+            const float* mp = mag_s + lo + gl;
+            int n = hi - lo - gl;  // this lane owns offsets 0, 4, 8, ... < n
+#pragma unroll 1
+            for (; n > 12; n -= 16, wp += 16, mp += 16) {
+              sum = fmaf(wp[0], mp[0], sum);
+              sum = fmaf(wp[4], mp[4], sum);
+              sum = fmaf(wp[8], mp[8], sum);
+              sum = fmaf(wp[12], mp[12], sum);
+            }
+            if (n > 0) sum = fmaf(wp[0], mp[0], sum);
+            if (n > 4) sum = fmaf(wp[4], mp[4], sum);
+            if (n > 8) sum = fmaf(wp[8], mp[8], sum);
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          if (gl == 0 && m < P.n_mels) msum[m] = sum;
+        }
+        team_sync<TEAM>(team);
         for (int m = ltid; m < P.n_mels; m += TEAM) {
-          const int lo = rng_s[3 * m], hi = rng_s[3 * m + 1];
-          const float* wts = fbc_s + rng_s[3 * m + 2] - lo;
-          float s = 0.f;
-          for (int k = lo; k < hi; ++k) s = fmaf(wts[k], mag_s[k], s);
-          const float db = amp_to_db(s);
+          const float db = amp_to_db(msum[m]);
           float v;
           if (P.max_abs > 0.f)
-            v = fminf(fmaxf((2.f * P.max_abs) * ((db + 100.f) / 100.f) - P.max_abs, -P.max_abs), P.max_abs);
+            v = fminf(fmaxf((2.f * P.max_abs) * ((db + 100.f) * 0.01f) - P.max_abs, -P.max_abs), P.max_abs);
           else
-            v = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+            v = fminf(fmaxf((db + 100.f) * 0.01f, 0.f), 1.f);
           P.mel_out[fi * P.n_mels + m] = v;
         }
       }
@@ -396,47 +477,62 @@ __global__ void __launch_bounds__(256) stft_team_kernel(const StftParams P, int 
   }
 }
 
-template <int LOG2H>
+template <int LOG2H, int NT>
 static size_t stft_team_smem(int hop) {
-  constexpr int H = 1 << LOG2H, N = 2 * H;
-  constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
-  constexpr int TPC = 256 / TEAM, ZP = H;
-  return (size_t)H * 8 + (size_t)N * 4 + (size_t)3 * (H + 1) * 4 + (size_t)(3 * 256 + 2) * 4 + (size_t)TPC * 2 * ZP * 8 +
-         (size_t)TPC * (H + 4) * 4 + (size_t)H * 8 + (size_t)(N + (TPC - 1) * hop) * 4 + 16;
+  using Cfg = StftTeamCfg<LOG2H>;
+  constexpr int H = Cfg::H, N = Cfg::N, TPC = NT / Cfg::TEAM, ZP = H;
+  return (size_t)Cfg::kTabFloats * 4 + (size_t)TPC * 2 * ZP * 8 + (size_t)TPC * (H + 4) * 4 + (size_t)H * 8 +
+         (size_t)(N + (TPC - 1) * hop) * 4 + 16;
 }
 
 // returns 1 if launched, 0 if this shape is left to the generic kernel, <0 on error
-template <int LOG2H>
+template <int LOG2H, int NT>
 static int stft_team_launch(const StftParams& P, cudaStream_t s) {
-  constexpr int H = 1 << LOG2H;
-  constexpr int TEAM = (H / 8 < 32) ? 32 : (H / 8 > 256 ? 256 : H / 8);
-  constexpr int TPC = 256 / TEAM;
-  const size_t smem = stft_team_smem<LOG2H>(P.hop);
+  constexpr int TPC = NT / StftTeamCfg<LOG2H>::TEAM;
+  const size_t smem = stft_team_smem<LOG2H, NT>(P.hop);
   int dev = 0, max_optin = 0;
   MSTTS_CUDA(cudaGetDevice(&dev));
   MSTTS_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   if (smem > (size_t)max_optin || P.n_mels > 256) return 0;
-  MSTTS_CUDA(cudaFuncSetAttribute(stft_team_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MSTTS_CUDA(cudaFuncSetAttribute(stft_team_kernel<LOG2H, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gpu = (P.frames + TPC - 1) / TPC;
   const long long ngroups = (long long)P.B * gpu;
   int per_sm = 1;
-  MSTTS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_team_kernel<LOG2H>, 256, smem));
+  MSTTS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stft_team_kernel<LOG2H, NT>, NT, smem));
   if (per_sm < 1) per_sm = 1;
   const long long cap = 148LL * per_sm;
-  stft_team_kernel<LOG2H><<<(unsigned)(ngroups < cap ? ngroups : cap), 256, smem, s>>>(P, gpu, (int)ngroups);
+  stft_team_kernel<LOG2H, NT><<<(unsigned)(ngroups < cap ? ngroups : cap), NT, smem, s>>>(P, gpu, (int)ngroups);
   MSTTS_CUDA(cudaGetLastError());
   return 1;
+}
+
+// threads per CTA of the team kernel: 512 (two resident CTAs = 16 frames in flight per SM at n_fft = 1024) unless
+// MSTTS_STFT_NT=256 asks for the smaller CTA (three resident CTAs = 12 frames)
+static int stft_nt() {
+  static const int nt = [] {
+    const char* e = getenv("MSTTS_STFT_NT");
+    return (e && atoi(e) == 256) ? 256 : 512;
+  }();
+  return nt;
+}
+template <int LOG2H>
+static int stft_team_launch_nt(const StftParams& P, cudaStream_t s) {
+  if (stft_nt() == 512) {
+    const int r = stft_team_launch<LOG2H, 512>(P, s);
+    if (r != 0) return r;  // launched or failed; 0 = does not fit: try the smaller CTA
+  }
+  return stft_team_launch<LOG2H, 256>(P, s);
 }
 
 static int stft_launch_main(const StftParams& P, cudaStream_t s, size_t nframes, size_t smem_generic) {
   int done = 0;
   if (P.hop <= P.n_fft) {
     switch (P.log2h) {
-      case 7: done = stft_team_launch<7>(P, s); break;
-      case 8: done = stft_team_launch<8>(P, s); break;
-      case 9: done = stft_team_launch<9>(P, s); break;
-      case 10: done = stft_team_launch<10>(P, s); break;
-      case 11: done = stft_team_launch<11>(P, s); break;
+      case 7: done = stft_team_launch_nt<7>(P, s); break;
+      case 8: done = stft_team_launch_nt<8>(P, s); break;
+      case 9: done = stft_team_launch_nt<9>(P, s); break;
+      case 10: done = stft_team_launch_nt<10>(P, s); break;
+      case 11: done = stft_team_launch_nt<11>(P, s); break;
       default: break;
     }
   }

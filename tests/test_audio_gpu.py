@@ -16,6 +16,8 @@ def _wav(S, seed, B=1):
     (513, 256 / 22050 * 1000, 1024 / 22050 * 1000, 22050, 22050, False),   # BASELINE config 4 parameters
     (1025, 12.5, 50, 16000, 9000, True),            # spectral subtraction (Pattern_Generate.py:52)
     (129, 4, 12.5, 16000, 3000, False),
+    (257, 8, 25, 16000, 5000, False),               # n_fft 512: radix-4 first stage, one frame per warp
+    (2049, 12.5, 50, 16000, 20000, False),          # n_fft 4096: 256-thread teams
 ])
 def test_melspectrogram_parity(cuda_dev, num_freq, shift, length, sr, S, sub):
     from oracle import audio_oracle as A
