@@ -907,32 +907,8 @@ static int launch_bwd_tc(const DecBwdTcParams& P, cudaStream_t stream, size_t sm
   MSTTS_REQUIRE(nclusters * kDecCluster >= kDecGrid, MSTTS_E_DEVICE,
                 "decoder_bwd_tc: device co-schedules only %d clusters of %d (need %d)", nclusters, kDecCluster,
                 kDecGrid / kDecCluster);
-  // MSTTS_L2_PERSIST=1 (experiment): pin the 64 MB weight-stream image in the persisting part of the L2 while the loop runs, so
-  // that the weight-gradient products streaming beside it (decoder_bwd.cu) cannot displace it
-  static const bool persist = [] {
-    const char* e = getenv("MSTTS_L2_PERSIST");
-    return e && e[0] == '1';
-  }();
-  cudaLaunchAttribute attrs[2];
-  if (persist) {
-    static bool limit_set = false;
-    if (!limit_set) {
-      cudaDeviceProp prop;
-      if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0)
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize);
-      limit_set = true;
-    }
-    int n = cfg.numAttrs;
-    for (int i = 0; i < n; ++i) attrs[i] = cfg.attrs[i];
-    attrs[n].id = cudaLaunchAttributeAccessPolicyWindow;
-    attrs[n].val.accessPolicyWindow.base_ptr = (void*)P.wimg;
-    attrs[n].val.accessPolicyWindow.num_bytes = (size_t)kDecGrid * 16 * kWTileBytes;
-    attrs[n].val.accessPolicyWindow.hitRatio = 1.0f;
-    attrs[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attrs[n].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    cfg.attrs = attrs;
-    cfg.numAttrs = n + 1;
-  }
+  // (an access-policy window that pins the weight image in persisting L2 was measured and removed: the carve-out shrinks the
+  //  L2 of everything else and the step got slower; the eviction-priority hints of DecBwdTcParams::l2_stream do the job)
   mstts_timer_start(1, stream);
   MSTTS_CUDA(cudaLaunchKernelEx(&cfg, decoder_bwd_tc_kernel<NS, TE2>, P));
   mstts_timer_stop(1, stream);
