@@ -19,6 +19,18 @@ import numpy as np
 
 from . import Hyper_Parameters as hp
 
+
+def _pinned(a):
+    """The same array in page-locked host memory when a CUDA device is present (plain ndarray otherwise): the collation runs in the
+    feeder's background thread, so the train step's host -> device copies become DMA transfers with no staging copy inside the step."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    except (ImportError, RuntimeError):
+        pass
+    return a
+
 # Token_Index_Dict.json of the reference: <S>, <E>, then the printable characters in ASCII order (42 symbols)
 TOKEN_INDEX_DICT = {t: i for i, t in enumerate(['<S>', '<E>'] + list(' !"\'(),-.:;?ABCDEFGHIJKLMNOPQRSTUVWXYZ[]'))}
 
@@ -110,11 +122,11 @@ class Feeder(object):
         p = self.placeholder_Dict
         return {
             p["Is_Training"]: True,
-            p["Token"]: tok,
-            p["Token_Length"]: np.array([t.shape[0] for t in token_List]).astype(np.int32),
-            p["Mel"]: mel,
-            p["Mel_Length"]: np.array([m.shape[0] for m in mel_List]).astype(np.int32),
-            p["Speaker_Embedding_Mel"]: self.Speaker_Embedding_Mel(mel_List),
+            p["Token"]: _pinned(tok),
+            p["Token_Length"]: _pinned(np.array([t.shape[0] for t in token_List]).astype(np.int32)),
+            p["Mel"]: _pinned(mel),
+            p["Mel_Length"]: _pinned(np.array([m.shape[0] for m in mel_List]).astype(np.int32)),
+            p["Speaker_Embedding_Mel"]: _pinned(self.Speaker_Embedding_Mel(mel_List)),
         }
 
     def Train_Pattern_Generate(self, is_Pre_Train=False):

@@ -217,7 +217,11 @@ class Tacotron2(object):
             a = feed_dict[p[key]]
             t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
             if not t.is_cuda:
-                t = t.pin_memory().to(self.device, non_blocking=True)
+                if key == 'Mel_Length':  # known on the host: the decoder's step count needs no device read-back
+                    out['Mel_Length_Max'] = int(t.max())
+                if not t.is_pinned():  # the Feeder hands out page-locked arrays; anything else is staged here
+                    t = t.pin_memory()
+                t = t.to(self.device, non_blocking=True)
             out[key] = t
         out['Is_Training'] = bool(feed_dict[p['Is_Training']])
         return out
@@ -245,7 +249,8 @@ class Tacotron2(object):
             variables=dv)
         out, state = Modules.Decoder_LSTM(feed['Mel'], feed['Mel_Length'], att, training, variables=dv,
                                           masks=masks.get('decoder'), mode=self.mode,
-                                          seed=self.seed * 1000003 + self.global_Step)
+                                          seed=self.seed * 1000003 + self.global_Step,
+                                          max_length=feed.get('Mel_Length_Max') if training else None)
         post = Modules.Decoder_Conv(out.linear, training, v, masks.get('postnet'))
         post = out.linear + post
         return out, post, state.alignment_history.stack().permute(1, 2, 0)            # Attention_History [B,Te,T]
@@ -277,9 +282,15 @@ class Tacotron2(object):
         """session.run(train_Tensor_Dict, feed_dict): forward, losses, backward, (all-reduce), TF Adam.  The weight
         regularisation enters the update as l2 * p inside the Adam kernel (its gradient), not through autograd."""
         feed = self._to_device(feed_dict)
+        # autograd leaves over the flat parameter buffer: views that share its storage, so they stay current across the in-place
+        # Adam updates and are built once (rebuilt if somebody rebinds an entry of self.variables)
+        lc = getattr(self, '_leaf_cache', None)
+        if lc is None or any(lc[k][0] is not self.variables[k] for k in self.trainable):
+            lc = {k: (self.variables[k], self.variables[k].detach().requires_grad_(True)) for k in self.trainable}
+            self._leaf_cache = lc
         v = dict(self.variables)
         for k in self.trainable:
-            v[k] = self.variables[k].detach().requires_grad_(True)
+            v[k] = lc[k][1]
         out, post, _ = self._forward(v, feed, masks)
         linear_Loss, postnet_Loss, stop_Loss, wr = self._losses(v, out, post, feed)
         leaves = [v[k] for k in self.trainable]

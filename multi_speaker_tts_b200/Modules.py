@@ -98,13 +98,15 @@ def decoder_mode(B, Te, D):
 
 
 def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False, variables=None, masks=None, mode=None,
-                 seed=0):
+                 seed=0, max_length=None):
     """Modules.py:76-119.  inputs = Mel [B, L, 80] and sequence_length = Mel_Length [B] (ignored at inference),
     attention_mechanism = Location_Sensitive_Attention (memory, memory_length and the attention variables),
     variables = the decoder's own variables (prenet_*, cell_*, projection/*; short keys of synthetic.TF_VARIABLE_NAMES).
     masks = (prenet_mask [T,2,B,256] u8, zone_mask [T,2,2,B,1024] u8) or None (drawn on device from ``seed``).
     Returns (Decoder_Output(linear [B,T,80], stop [B,T,1]), state) with state.alignment_history.stack() -> [T,B,Te];
-    T = max(Mel_Length) + 1 in training, the executed steps at inference."""
+    T = max(Mel_Length) + 1 in training, the executed steps at inference.  ``max_length`` = max(Mel_Length) when the caller
+    already knows it on the host (the feed dict arrives as host arrays): saves the device read-back, which would stall the host
+    until the encoder has drained instead of letting it prepare the decoder launch meanwhile."""
     att = attention_mechanism
     if not isinstance(att, Location_Sensitive_Attention):
         raise TypeError("attention_mechanism must be a Location_Sensitive_Attention")
@@ -121,7 +123,10 @@ def Decoder_LSTM(inputs, sequence_length, attention_mechanism, is_training=False
         raise ValueError("Decoder_LSTM: the decoder kernels are built for PreNet.Dropout_Rate = 0.5 and LSTM.Zoneout_Rate = 0.1 "
                          "(got %r / %r); rebuild csrc/common.cuh with the new rates" %
                          (hp.Decoder.PreNet.Dropout_Rate, hp.Decoder.LSTM.Zoneout_Rate))
-    T = int(sequence_length.max().item()) + 1 if training else hp.Decoder.LSTM.Max_Inference_Length + 1
+    if training:
+        T = (int(max_length) if max_length is not None else int(sequence_length.max().item())) + 1
+    else:
+        T = hp.Decoder.LSTM.Max_Inference_Length + 1
     if masks is None:
         pm = torch.empty(T, 2, B, 256, device=dev, dtype=torch.uint8)
         fill_mask(pm, 1.0 - hp.Decoder.PreNet.Dropout_Rate, seed * 4 + 1)
