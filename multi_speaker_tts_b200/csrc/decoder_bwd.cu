@@ -426,7 +426,9 @@ static int launch_bwd(const DecBwdParams& P, cudaStream_t stream) {
   return MSTTS_OK;
 }
 
-int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s);  // decoder_bwd_tc.cu
+int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s,
+                     bool wimg_ready);  // decoder_bwd_tc.cu
+int dec_bwd_tc_prep_weights(const MsttsDecoderWeights* w, const DecLayout& l, char* ws, int D, cudaStream_t s);
 
 static int dec_bwd_persistent(const DecBwdParams& P, cudaStream_t stream) {
   const int B = P.B;
@@ -681,18 +683,26 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   const int K0r = D + kCell, NP = kMel + 1;
   int rc;
 
+  const bool tc = io->mode == MSTTS_MODE_BF16X3;
+  // the reverse loop's weight image depends on the weights only: built on the side stream while this one computes the
+  // projection part of the gradients
+  bool wimg_ready = false;
+  if (tc && T >= 64 && dec_overlap_enabled()) {
+    DecSideStream* sd = nullptr;
+    if ((rc = dec_side_stream(&sd))) return rc;
+    MSTTS_CUDA(cudaEventRecord(sd->fork, s));  // after the previous use of the workspace on this stream
+    MSTTS_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+    if ((rc = dec_bwd_tc_prep_weights(w, l, ws, D, sd->stream))) return rc;
+    MSTTS_CUDA(cudaEventRecord(sd->join, sd->stream));
+    wimg_ready = true;
+  }
   // ---- upstream gradient through the hoisted projection ----
   gather_dproj_kernel<<<ew_grid(TB * NP), 256, 0, s>>>(g->d_linear, g->d_stop, F(l.dproj_tm), B, T);
-  // dWp = [m1 | ctx]^T dproj ; dbp = colsum(dproj)
-  if ((rc = gemm_rowmajor_ex(s, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return rc;
-  if ((rc = gemm_rowmajor_ex(s, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
-                             dw->proj_kernel + (size_t)kCell * NP, NP, 0.f))) return rc;
-  colsum(s, F(l.dproj_tm), dw->proj_bias, TB, NP, F(l.colsum_scratch));
-  // d m1 (projection part) and d ctx (projection part)
+  // d m1 (projection part) and d ctx (projection part): what the loop needs.  The projection's own weight gradient does not
+  // feed the loop and waits until after it (below, beside the second chain).
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kCell, NP, F(l.dproj_tm), NP, w->proj_kernel, NP, F(l.dm1_proj), kCell, 0.f))) return rc;
   if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, D, NP, F(l.dproj_tm), NP, w->proj_kernel + (size_t)kCell * NP, NP,
                              F(l.dctx), D, 0.f))) return rc;
-  const bool tc = io->mode == MSTTS_MODE_BF16X3;
   // ---- transposed recurrent weights (the tcgen05 kernel reads the reference layout directly) ----
   if (!tc) {
     transpose_kernel<<<dim3(kGates / 32, (K0r + 31) / 32), dim3(32, 8), 0, s>>>(F(l.W0r), F(l.W0rT), K0r, kGates);
@@ -755,7 +765,8 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
     MSTTS_CUDA(cudaEventRecord(side->fork, s));           // the barrier counter is zeroed, the saved activations are complete
     MSTTS_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
   }
-  if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s) : dec_bwd_persistent(P, s))) return rc;
+  if (wimg_ready) MSTTS_CUDA(cudaStreamWaitEvent(s, side->join, 0));  // recorded after the weight-image kernel (above)
+  if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s, wimg_ready) : dec_bwd_persistent(P, s))) return rc;
   if (NCH > 1) {
     TcGridCap cap(dec_env_int("MSTTS_OVERLAP_SMS", kDecIdleSMs, 1, kDecIdleSMs));
     ScratchScope ssc(side->stream);
@@ -777,6 +788,16 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
     MSTTS_CUDA(cudaEventRecord(side->join, side->stream));
     MSTTS_CUDA(cudaStreamWaitEvent(s, side->join, 0));
   }
+  // After the loop two chains that share nothing but read-only inputs run side by side: the last time chunk of the cell weight
+  // gradients + the cell bias gradients on the caller's stream, and everything else (query layer, location filter, the prenet
+  // chain, the memory side) on the side stream -- mostly small grids (one-block location kernel, narrow products) that leave
+  // the device half empty when queued one after the other.
+  cudaStream_t st = s;  // the stream of the second chain
+  if (NCH > 1 && dec_env_int("MSTTS_TAIL_STREAMS", 1, 0, 1)) {
+    st = side->stream;
+    MSTTS_CUDA(cudaEventRecord(side->fork, s));  // the loop has finished: dG0 / dq / dF / dctx / dkeys are final
+    MSTTS_CUDA(cudaStreamWaitEvent(st, side->fork, 0));
+  }
   {
     ScratchScope sc(s);
     void *gimg = nullptr, *ximg = nullptr;
@@ -789,28 +810,46 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   copy_rows_kernel<<<ew_grid((size_t)D * kGates), 256, 0, s>>>(dK0_ctx, dK0_ctx + (size_t)D * kGates, (size_t)D * kGates);
   colsum(s, F(l.dG1), dw->cell1_bias, TB, kGates, F(l.colsum_scratch));
   colsum(s, F(l.dG0), dw->cell0_bias, TB, kGates, F(l.colsum_scratch));
-  // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
-  if ((rc = gemm_rowmajor_ex(s, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
-  colsum(s, F(l.dq), F(l.dfb), TB, kAtt, F(l.colsum_scratch));
-  location_grads_kernel<<<1, 1024, 0, s>>>(F(l.dF), F(l.dfb), w->loc_conv_kernel, w->loc_conv_bias, w->loc_dense_kernel,
-                                           dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
-  MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  // prenet: d pre = dG0 @ K0[0:256]^T, then back through the two dense+relu+dropout layers
-  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
-  prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre), F(l.pre), TB * kPrenet);
-  if ((rc = gemm_rowmajor_ex(s, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
-  colsum(s, F(l.dpre), dw->prenet1_bias, TB, kPrenet, F(l.colsum_scratch));
-  if ((rc = gemm_rowmajor_ex(s, false, true, (int)TB, kPrenet, kPrenet, F(l.dpre), kPrenet, w->prenet1_kernel, kPrenet, F(l.dpre_h), kPrenet, 0.f))) return rc;
-  prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, s>>>(F(l.dpre_h), F(l.pre_h), TB * kPrenet);
-  if ((rc = gemm_rowmajor_ex(s, true, false, kMel, kPrenet, (int)TB, F(l.frames), kMel, F(l.dpre_h), kPrenet, dw->prenet0_kernel, kPrenet, 0.f))) return rc;
-  colsum(s, F(l.dpre_h), dw->prenet0_bias, TB, kPrenet, F(l.colsum_scratch));
-  // memory side: dvalues[b] = A_b^T dctx_b (over steps) + dkeys[b] @ Wm^T ; dWm = values^T dkeys
-  if ((rc = gemm_rowmajor_batched(s, true, false, Te, D, T, F(l.align_tm), B * Te, Te, F(l.dctx), B * D, D, F(l.dvalues), D,
-                                  (long long)Te * D, 0.f, B))) return rc;
-  if ((rc = gemm_rowmajor_ex(s, false, true, B * Te, D, kAtt, F(l.dkeys), kAtt, w->memory_kernel, kAtt, F(l.dvalues), D, 1.f))) return rc;
-  if ((rc = gemm_rowmajor_ex(s, true, false, D, kAtt, B * Te, F(l.values), D, F(l.dkeys), kAtt, dw->memory_kernel, kAtt, 0.f))) return rc;
-  if (g->d_memory)
-    mask_dmemory_kernel<<<ew_grid((size_t)B * Te * D), 256, 0, s>>>(F(l.dvalues), io->text_len, g->d_memory, B, Te, D);
+  // projection: dWp = [m1 | ctx]^T dproj ; dbp = colsum(dproj)
+  if ((rc = gemm_rowmajor_ex(s, true, false, kCell, NP, (int)TB, F(l.m1), kCell, F(l.dproj_tm), NP, dw->proj_kernel, NP, 0.f))) return rc;
+  if ((rc = gemm_rowmajor_ex(s, true, false, D, NP, (int)TB, F(l.ctx) + (size_t)B * D, D, F(l.dproj_tm), NP,
+                             dw->proj_kernel + (size_t)kCell * NP, NP, 0.f))) return rc;
+  colsum(s, F(l.dproj_tm), dw->proj_bias, TB, NP, F(l.colsum_scratch));
+  {
+    ScratchScope sc2(st);
+    float* cs = F(l.colsum_scratch);  // the second chain's column sums are at most 256 wide: own partials when it runs concurrently
+    if (st != s) {
+      void* p = nullptr;
+      if ((rc = sc2.get(&p, (size_t)kColsumSlices * 256 * sizeof(float)))) return rc;
+      cs = (float*)p;
+    }
+    // query layer: dWq = m1^T dq ; composed-bias gradient dfb = colsum(dq)
+    if ((rc = gemm_rowmajor_ex(st, true, false, kCell, kAtt, (int)TB, F(l.m1), kCell, F(l.dq), kAtt, dw->query_kernel, kAtt, 0.f))) return rc;
+    colsum(st, F(l.dq), F(l.dfb), TB, kAtt, cs);
+    location_grads_kernel<<<1, 1024, 0, st>>>(F(l.dF), F(l.dfb), w->loc_conv_kernel, w->loc_conv_bias, w->loc_dense_kernel,
+                                              dw->loc_conv_kernel, dw->loc_conv_bias, dw->loc_dense_kernel, dw->score_b);
+    MSTTS_CUDA(cudaMemcpyAsync(dw->score_w, F(l.dsw), kAtt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // prenet: d pre = dG0 @ K0[0:256]^T, then back through the two dense+relu+dropout layers
+    if ((rc = gemm_rowmajor_ex(st, false, true, (int)TB, kPrenet, kGates, F(l.dG0), kGates, w->cell0_kernel, kGates, F(l.dpre), kPrenet, 0.f))) return rc;
+    prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, st>>>(F(l.dpre), F(l.pre), TB * kPrenet);
+    if ((rc = gemm_rowmajor_ex(st, true, false, kPrenet, kPrenet, (int)TB, F(l.pre_h), kPrenet, F(l.dpre), kPrenet, dw->prenet1_kernel, kPrenet, 0.f))) return rc;
+    colsum(st, F(l.dpre), dw->prenet1_bias, TB, kPrenet, cs);
+    if ((rc = gemm_rowmajor_ex(st, false, true, (int)TB, kPrenet, kPrenet, F(l.dpre), kPrenet, w->prenet1_kernel, kPrenet, F(l.dpre_h), kPrenet, 0.f))) return rc;
+    prenet_act_bwd_kernel<<<ew_grid(TB * kPrenet), 256, 0, st>>>(F(l.dpre_h), F(l.pre_h), TB * kPrenet);
+    if ((rc = gemm_rowmajor_ex(st, true, false, kMel, kPrenet, (int)TB, F(l.frames), kMel, F(l.dpre_h), kPrenet, dw->prenet0_kernel, kPrenet, 0.f))) return rc;
+    colsum(st, F(l.dpre_h), dw->prenet0_bias, TB, kPrenet, cs);
+    // memory side: dvalues[b] = A_b^T dctx_b (over steps) + dkeys[b] @ Wm^T ; dWm = values^T dkeys
+    if ((rc = gemm_rowmajor_batched(st, true, false, Te, D, T, F(l.align_tm), B * Te, Te, F(l.dctx), B * D, D, F(l.dvalues), D,
+                                    (long long)Te * D, 0.f, B))) return rc;
+    if ((rc = gemm_rowmajor_ex(st, false, true, B * Te, D, kAtt, F(l.dkeys), kAtt, w->memory_kernel, kAtt, F(l.dvalues), D, 1.f))) return rc;
+    if ((rc = gemm_rowmajor_ex(st, true, false, D, kAtt, B * Te, F(l.values), D, F(l.dkeys), kAtt, dw->memory_kernel, kAtt, 0.f))) return rc;
+    if (g->d_memory)
+      mask_dmemory_kernel<<<ew_grid((size_t)B * Te * D), 256, 0, st>>>(F(l.dvalues), io->text_len, g->d_memory, B, Te, D);
+  }
+  if (st != s) {
+    MSTTS_CUDA(cudaEventRecord(side->join, st));
+    MSTTS_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+  }
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }

@@ -121,17 +121,12 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + L.xs);  // [gate 4][hi/lo][32][8]
   float* cum_s = reinterpret_cast<float*>(smem + L.cum_s);
   float* a_s = reinterpret_cast<float*>(smem + L.a_s);
-  float* da_s = reinterpret_cast<float*>(smem + L.da_s);
-  float* de_s = reinterpret_cast<float*>(smem + L.de_s);
   float* dcum_s = reinterpret_cast<float*>(smem + L.dcum_s);
-  float* e_loc = reinterpret_cast<float*>(smem + L.e_loc);
-  float* g_loc = reinterpret_cast<float*>(smem + L.g_loc);
   float* e_parts1 = reinterpret_cast<float*>(smem + L.e_parts1);
   float* e_parts2 = reinterpret_cast<float*>(smem + L.e_parts2);
   float* dctx_s = reinterpret_cast<float*>(smem + L.dctx_s);
   float* ehalf = reinterpret_cast<float*>(smem + L.ehalf);
   float* qred = reinterpret_cast<float*>(smem + L.qred);
-  float* bred = reinterpret_cast<float*>(smem + L.bred);
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + L.bars);  // [NS]
   uint64_t* empty = wfull + NS;        // [NS]
   uint64_t* xfull = empty + NS;        // [2]
@@ -916,7 +911,15 @@ static int launch_bwd_tc(const DecBwdTcParams& P, cudaStream_t stream, size_t sm
 }
 
 // runs the reverse loop; expects dm1_proj / dctx (projection parts) prepared and dF / dsw zeroed by the caller
-int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s) {
+// hi | lo tile images of the two cell kernels in the reverse loop's streaming order: depends on the weights only
+int dec_bwd_tc_prep_weights(const MsttsDecoderWeights* w, const DecLayout& l, char* ws, int D, cudaStream_t s) {
+  prep_wimg_bwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_b), D);
+  MSTTS_CUDA(cudaGetLastError());
+  return MSTTS_OK;
+}
+
+int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, const DecLayout& l, char* ws, cudaStream_t s,
+                     bool wimg_ready) {
   auto F = [&](size_t off) { return (float*)(ws + off); };
   const int D = io->D, B = io->B;
   MSTTS_REQUIRE(dec_tc_supported(B, io->Te, D), MSTTS_E_UNSUPPORTED, "decoder_bwd bf16x3: unsupported shape B=%d Te=%d D=%d", B,
@@ -942,7 +945,10 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   }
   P.barrier = (unsigned*)(ws + l.barrier);
   P.dbg = (long long*)(ws + l.dbg_b);
-  prep_wimg_bwd_kernel<<<148 * 8, 256, 0, s>>>(w->cell0_kernel, w->cell1_kernel, (uint8_t*)(ws + l.wimg_b), D);
+  if (!wimg_ready) {
+    int rcw = dec_bwd_tc_prep_weights(w, l, ws, D, s);
+    if (rcw) return rcw;
+  }
   MSTTS_CUDA(cudaMemsetAsync(ws + l.ximg_g1, 0, l.ximg_g_end - l.ximg_g1, s));
   bool ok = false;
   int rc;

@@ -137,13 +137,10 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem + L.xs);  // [vec 2][hi/lo][32][8]
   float* m_s = reinterpret_cast<float*>(smem + L.m_s);
   float* qred = reinterpret_cast<float*>(smem + L.qred);
-  float* qf_s = reinterpret_cast<float*>(smem + L.qf_s);
   float* cum_s = reinterpret_cast<float*>(smem + L.cum_s);
-  float* e_loc = reinterpret_cast<float*>(smem + L.e_loc);
   float* e_parts = reinterpret_cast<float*>(smem + L.e_parts);
   float* a_s = reinterpret_cast<float*>(smem + L.a_s);
   float* ctx_s = reinterpret_cast<float*>(smem + L.ctx_s);
-  float* bred = reinterpret_cast<float*>(smem + L.bred);
   uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + L.bars);  // [NS]
   uint64_t* empty = wfull + NS;        // [NS]
   uint64_t* xfull = empty + NS;        // [2]

@@ -401,7 +401,6 @@ __global__ void wn_apply_tiled_kernel(const WnTileJobs J) {
 
 // conditioning [N,T,640] -> the mel K range of the im2col image (written once per call; the layers only rewrite the taps)
 __global__ void mel_tiled_kernel(const float* __restrict__ src, int N, int T, uint8_t* __restrict__ img) {
-  const int Tp = T + 2 * kWgPad;
   const size_t n = (size_t)N * T * (kWnMel / 8);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % (kWnMel / 8)) * 8;
@@ -418,7 +417,7 @@ __global__ void flow_pre_tiled_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ bs, float* __restrict__ y, uint8_t* __restrict__ img, int N, int T, int c,
                                       int apply_w) {
   __shared__ float w_s[64], ws_s[4 * kWnCh], bs_s[kWnCh];
-  const int half = c / 2, Tp = T + 2 * kWgPad;
+  const int half = c / 2;
   for (int i = threadIdx.x; i < c * c; i += blockDim.x) w_s[i] = Wm[i];
   for (int i = threadIdx.x; i < half * kWnCh; i += blockDim.x) ws_s[i] = Ws[i];
   for (int i = threadIdx.x; i < kWnCh; i += blockDim.x) bs_s[i] = bs[i];
@@ -695,7 +694,7 @@ static int waveglow_flows_impl(const MsttsWaveGlowWeights* w, const float* audio
   const int nblk_post = 148 * 2;
   for (int step = 0; step < kWgFlows; ++step) {
     const int f = direction == 0 ? step : kWgFlows - 1 - step;
-    const int c = flow_c(f), half = c / 2;
+    const int c = flow_c(f);
     if (direction == 0 && f % 4 == 0 && f > 0) {
       // early output: first 2 channels leave the chain (Modules.py:334-336)
       copy_channels_kernel<<<ew_grid(rows * 2), 256, 0, s>>>(xcur, c + 2, 0, out, 8, zc0, 2, rows);
