@@ -219,7 +219,7 @@ extern "C" int mstts_adam_tf(float* p, float* m, float* v, const float* g, size_
 // loss2[0] = mean((lin-mel)^2) (+ mean|lin-mel|) over [B,L,80] using linear[:, :L];  loss2[1] = mean BCE over [B,T]
 __global__ void decoder_loss_kernel(const float* __restrict__ linear, const float* __restrict__ stop,
                                     const float* __restrict__ mel, const int* __restrict__ mel_len, int B, int L, int T,
-                                    int use_l1, float* __restrict__ loss2, float* __restrict__ d_linear,
+                                    int use_l1, float* __restrict__ part, float* __restrict__ d_linear,
                                     float* __restrict__ d_stop) {
   const size_t n_lin = (size_t)B * T * kMel;
   const size_t n_stop = (size_t)B * T;
@@ -267,8 +267,23 @@ __global__ void decoder_loss_kernel(const float* __restrict__ linear, const floa
       a += sh[0][w];
       b2 += sh[1][w];
     }
-    atomicAdd(&loss2[0], a);
-    atomicAdd(&loss2[1], b2);
+    part[blockIdx.x] = a;  // per-block partials, added in block order by decoder_loss_final_kernel (atomics would make the
+    part[gridDim.x + blockIdx.x] = b2;  // last bits of the reported loss depend on arrival order)
+  }
+}
+
+__global__ void decoder_loss_final_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ loss2) {
+  const int lane = threadIdx.x;
+  float a = 0.f, b = 0.f;
+  for (int i = lane; i < nblocks; i += 32) {
+    a += part[i];
+    b += part[nblocks + i];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    loss2[0] = a;
+    loss2[1] = b;
   }
 }
 
@@ -279,11 +294,15 @@ extern "C" int mstts_decoder_loss(const float* linear, const float* stop, const 
   MSTTS_REQUIRE(n_steps == L + 1, MSTTS_E_INVALID,
                 "loss: linear[:, :-1] must match mel: n_steps=%d, L=%d (MSTTS_SV.py:138)", n_steps, L);
   cudaStream_t s = (cudaStream_t)stream;
-  MSTTS_CUDA(cudaMemsetAsync(loss2, 0, 2 * sizeof(float), s));
   const size_t n = (size_t)B * n_steps * (kMel + 1);
   size_t g = (n + 255) / 256;
   if (g > 148 * 4) g = 148 * 4;
-  decoder_loss_kernel<<<(int)g, 256, 0, s>>>(linear, stop, mel, mel_len, B, L, n_steps, use_l1, loss2, d_linear, d_stop);
+  ScratchScope scope(s);
+  void* part = nullptr;
+  int rc = scope.get(&part, 2 * g * sizeof(float));
+  if (rc) return rc;
+  decoder_loss_kernel<<<(int)g, 256, 0, s>>>(linear, stop, mel, mel_len, B, L, n_steps, use_l1, (float*)part, d_linear, d_stop);
+  decoder_loss_final_kernel<<<1, 32, 0, s>>>((const float*)part, (int)g, loss2);
   MSTTS_CUDA(cudaGetLastError());
   return MSTTS_OK;
 }

@@ -28,6 +28,7 @@ struct DecBwdParams {
   const float *act0, *act1, *c0n, *c1n, *cz0, *cz1, *qf, *cum, *align_tm;
   const float* dm1_proj;
   float *dctx, *dG0, *dG1, *dq, *dkeys, *dF, *dsw, *dcum;
+  float* dF_part;  // [32 clusters][32][128]
   unsigned* barrier;
 };
 
@@ -367,7 +368,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
     float* dk = P.dkeys + (size_t)cid * Te * kAtt;
     for (int i = tid; i < Te * 32; i += kDecThreads) dk[(size_t)(i >> 5) * kAtt + crank * 32 + (i & 31)] = dkeys_s[i];
   }
-  // cross-warp reduction in shared memory, then one atomic per (tap, unit) per CTA
+  // cross-warp reduction in shared memory, then the cluster's sums go to its own slot of dF_part (added in cluster order by
+  // sum_dF_partials_kernel: deterministic, unlike atomics)
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < kConvK; ++k) scratch[(warp * 32 + k) * 32 + lane] = dF_reg[k];
@@ -378,8 +380,21 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kDecThread
     float v = 0.f;
 #pragma unroll
     for (int w2 = 0; w2 < 8; ++w2) v += scratch[(w2 * 32 + k) * 32 + u];
-    atomicAdd((k < kConvK ? P.dF + k * kAtt : P.dsw) + crank * 32 + u, v);
+    P.dF_part[((size_t)cid * 32 + k) * kAtt + crank * 32 + u] = v;
   }
+}
+
+// d F [31,128] and d score_w [128] = the per-cluster sums added in cluster order
+__global__ void sum_dF_partials_kernel(const float* __restrict__ part, int nclusters, float* __restrict__ dF, float* __restrict__ dsw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (k, j)
+  if (i >= 32 * kAtt) return;
+  const int k = i / kAtt, j = i % kAtt;
+  float v = 0.f;
+  for (int c = 0; c < nclusters; ++c) v += part[((size_t)c * 32 + k) * kAtt + j];
+  if (k < kConvK)
+    dF[k * kAtt + j] = v;
+  else if (k == kConvK)
+    dsw[j] = v;
 }
 
 // ======================================== host side ================================================
@@ -721,7 +736,7 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n); P.cz0 = F(l.cz0); P.cz1 = F(l.cz1);
   P.qf = F(l.qf); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.dm1_proj = F(l.dm1_proj);
   P.dctx = F(l.dctx); P.dG0 = F(l.dG0); P.dG1 = F(l.dG1); P.dq = F(l.dq); P.dkeys = F(l.dkeys);
-  P.dF = F(l.dF); P.dsw = F(l.dsw); P.dcum = F(l.dcum);
+  P.dF = F(l.dF); P.dsw = F(l.dsw); P.dcum = F(l.dcum); P.dF_part = F(l.dF_part);
   P.barrier = (unsigned*)(ws + l.barrier);
   // ---- weight gradients of the two cells: dW[rows, 4096] = X[T*B, rows]^T dG[T*B, 4096] ----
   // ~1 TFLOP at config 2, bf16x3 on the hand-written tcgen05 kernel (every product here is TC_FAST: the higher precision levels
@@ -767,6 +782,7 @@ static int decoder_bwd_one(const MsttsDecoderWeights* w, const MsttsDecoderIO* i
   }
   if (wimg_ready) MSTTS_CUDA(cudaStreamWaitEvent(s, side->join, 0));  // recorded after the weight-image kernel (above)
   if ((rc = tc ? dec_bwd_tc_entry(w, io, l, ws, s, wimg_ready) : dec_bwd_persistent(P, s))) return rc;
+  sum_dF_partials_kernel<<<(32 * kAtt + 255) / 256, 256, 0, s>>>(F(l.dF_part), kDecGrid / kDecCluster, F(l.dF), F(l.dsw));
   if (NCH > 1) {
     TcGridCap cap(dec_env_int("MSTTS_OVERLAP_SMS", kDecIdleSMs, 1, kDecIdleSMs));
     ScratchScope ssc(side->stream);

@@ -36,6 +36,7 @@ struct DecBwdTcParams {
   const float *act0, *act1, *c0n, *c1n, *cz0, *cz1, *qf, *cum, *align_tm;
   const float* dm1_proj;
   float *dctx, *dG0, *dG1, *dq, *dkeys, *dF, *dsw;
+  float* dF_part;  // [32 clusters][32][128]
   unsigned* barrier;
   long long* dbg;
   // texts of 129 .. 256 positions (TE2): two clusters per batch row, each owning 128 positions
@@ -795,7 +796,8 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
         if (x < Te) P.dkeys[((size_t)arow * Teg + x0 + x) * kAtt + crank * 32 + lane] = __uint_as_float(dk[p]);
       }
     }
-    // d F / d w: cross-warp reduction in shared memory (recv is free now), then one atomic per (tap, unit) per CTA
+    // d F / d w: cross-warp reduction in shared memory (recv is free now), then this cluster's sums go to its own slot of
+    // dF_part; a small kernel adds the 32 slots in cluster order (atomics would make the last bits depend on arrival order)
     float* red = recv;  // [8 warps][32 taps][32 units] = 32 KB
 #pragma unroll
     for (int k = 0; k < kConvK; ++k) red[(warp * 32 + k) * 32 + lane] = dF_reg[k];
@@ -806,7 +808,7 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
       float v = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < 8; ++w2) v += red[(w2 * 32 + k) * 32 + u];
-      atomicAdd((k < kConvK ? P.dF + k * kAtt : P.dsw) + crank * 32 + u, v);
+      P.dF_part[((size_t)cid * 32 + k) * kAtt + crank * 32 + u] = v;
     }
   }
 
@@ -935,7 +937,7 @@ int dec_bwd_tc_entry(const MsttsDecoderWeights* w, const MsttsDecoderIO* io, con
   P.act0 = F(l.act0); P.act1 = F(l.act1); P.c0n = F(l.c0n); P.c1n = F(l.c1n); P.cz0 = F(l.cz0); P.cz1 = F(l.cz1);
   P.qf = F(l.qf); P.cum = F(l.cum); P.align_tm = F(l.align_tm); P.dm1_proj = F(l.dm1_proj);
   P.dctx = F(l.dctx); P.dG0 = F(l.dG0); P.dG1 = F(l.dG1); P.dq = F(l.dq); P.dkeys = F(l.dkeys);
-  P.dF = F(l.dF); P.dsw = F(l.dsw);
+  P.dF = F(l.dF); P.dsw = F(l.dsw); P.dF_part = F(l.dF_part);
   P.dctx_in = P.dctx;
   {
     const char* e = getenv("MSTTS_LOOP_L2");

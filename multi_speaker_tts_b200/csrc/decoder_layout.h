@@ -44,6 +44,7 @@ struct DecLayout {
   size_t dvalues;   // [B,Te,D]
   size_t dF;        // [31,128] (+ dfb [128] + dsw [128] right behind, one zeroed block)
   size_t dfb, dsw;
+  size_t dF_part;   // [32 clusters][31 taps + d score_w][128] per-cluster sums of d F / d score_w, added in cluster order after the loop
   size_t dcum;      // [B,Te]
   size_t dpre;      // [T,B,256]
   size_t dpre_h;    // [T,B,256]
@@ -123,6 +124,7 @@ static inline DecLayout dec_layout(int B, int Te, int L, int D, int T, int mode)
   l.dF = take(kConvK * kAtt + 2 * kAtt);
   l.dfb = l.dF + (size_t)kConvK * kAtt * sizeof(float);
   l.dsw = l.dfb + (size_t)kAtt * sizeof(float);
+  l.dF_part = take((size_t)(kDecGrid / kDecCluster) * 32 * kAtt);
   l.dcum = take((size_t)B * Te);
   l.dpre = take(TB * kPrenet);
   l.dpre_h = take(TB * kPrenet);
