@@ -60,6 +60,21 @@ __global__ void __cluster_dims__(kZCluster, 1, 1) __launch_bounds__(kZThreads, 1
   for (int s = 0; s < maxlen; ++s) {
     const float* hcur = h_s + (s & 1) * kZRows * kZH;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // this step's global operands do not depend on the recurrence: issue the loads before the GEMV, use them after it
+    float xin[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (s < len_r[r]) {
+        const int t = P.reverse ? len_r[r] - 1 - s : s;
+        xin[r] = __ldg(P.xk + ((size_t)(row0 + rh * 4 + r) * P.T + t) * 4 * kZH + (gc >> 5) * kZH + crank * kZUnits + (gc & 31));
+      }
+    }
+    float mk_c = 1.f, mk_h = 1.f;
+    if (P.masks && s < len_own) {
+      const size_t mi = (((size_t)s * 2) * P.B + brow) * kZH + crank * kZUnits + u;
+      mk_c = (float)P.masks[mi];
+      mk_h = (float)P.masks[mi + (size_t)P.B * kZH];
+    }
 #pragma unroll 4
     for (int k = 0; k < kZH; k += 4) {
       const float w0 = W_s[(k + 0) * 128 + gc], w1 = W_s[(k + 1) * 128 + gc], w2 = W_s[(k + 2) * 128 + gc], w3 = W_s[(k + 3) * 128 + gc];
@@ -74,13 +89,8 @@ __global__ void __cluster_dims__(kZCluster, 1, 1) __launch_bounds__(kZThreads, 1
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int rr = rh * 4 + r, b = row0 + rr;
-      float v = acc[r];
-      if (s < len_r[r]) {
-        const int t = P.reverse ? len_r[r] - 1 - s : s;
-        v += P.xk[((size_t)b * P.T + t) * 4 * kZH + (gc >> 5) * kZH + crank * kZUnits + (gc & 31)];
-      }
-      g_s[rr * 128 + gc] = v;
+      const int rr = rh * 4 + r;
+      g_s[rr * 128 + gc] = acc[r] + xin[r];
     }
     __syncthreads();
     float h_pub = h_state;
@@ -93,12 +103,7 @@ __global__ void __cluster_dims__(kZCluster, 1, 1) __launch_bounds__(kZThreads, 1
       const float og = sigmoidf_precise(g_s[r8 * 128 + 96 + u]);
       const float cn = fg * c_state + ig * jg;
       const float m = og * tanhf(cn);
-      float dc = cn - c_state, dm = m - h_state;
-      if (P.masks) {
-        const size_t mi = (((size_t)s * 2) * P.B + brow) * kZH + unit;
-        dc *= (float)P.masks[mi];
-        dm *= (float)P.masks[mi + (size_t)P.B * kZH];
-      }
+      const float dc = (cn - c_state) * mk_c, dm = (m - h_state) * mk_h;
       const size_t oi = ((size_t)brow * P.T + t) * kZH + unit;
       if (P.acts) {
         const size_t ai = ((size_t)brow * P.T + t) * 4 * kZH + unit;
@@ -114,10 +119,18 @@ __global__ void __cluster_dims__(kZCluster, 1, 1) __launch_bounds__(kZThreads, 1
       h_state = P.keep * dm + h_state;
       h_pub = h_state;
     }
-    // publish this CTA's slice of the next h to every CTA of the cluster
-    float* hnext = h_s + ((s + 1) & 1) * kZRows * kZH + r8 * kZH + crank * kZUnits + u;
+    // publish this CTA's slice of the next h to every CTA of the cluster: four neighbouring units per 16-byte remote store
+    // (scalar remote stores, 8 per thread, were the largest part of the step)
+    {
+      const float h1 = __shfl_down_sync(0xffffffffu, h_pub, 1), h2 = __shfl_down_sync(0xffffffffu, h_pub, 2),
+                  h3 = __shfl_down_sync(0xffffffffu, h_pub, 3);
+      if ((u & 3) == 0) {
+        float* hnext = h_s + ((s + 1) & 1) * kZRows * kZH + r8 * kZH + crank * kZUnits + u;
+        const float4 v4 = make_float4(h_pub, h1, h2, h3);
 #pragma unroll
-    for (int dst = 0; dst < kZCluster; ++dst) *cluster.map_shared_rank(hnext, dst) = h_pub;
+        for (int dst = 0; dst < kZCluster; ++dst) *reinterpret_cast<float4*>(cluster.map_shared_rank(hnext, dst)) = v4;
+      }
+    }
     cluster.sync();
   }
 }
@@ -156,25 +169,37 @@ __global__ void __cluster_dims__(kZCluster, 1, 1) __launch_bounds__(kZThreads, 1
   const int unit = crank * kZUnits + u;
   float dcz = 0.f, dhz = 0.f;  // gradients w.r.t. the zoned state leaving the current step
   const int cq = tid >> 5;     // GEMV: this warp handles columns [128 cq, +128), lane = unit
+  // saved operands of a step do not depend on the recurrence: those of step s - 1 are fetched while step s runs its GEMV
+  float pf_act[4] = {0.f, 0.f, 0.f, 0.f}, pf_cp = 0.f, pf_dout = 0.f, pf_mc = 1.f, pf_mh = 1.f;
+  auto prefetch = [&](int s) {
+    if (s < 0 || s >= len_own) return;
+    const int t = P.reverse ? len_own - 1 - s : s;
+    const size_t oi = ((size_t)brow * P.T + t) * kZH + unit, ai = ((size_t)brow * P.T + t) * 4 * kZH + unit;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pf_act[g] = __ldg(P.acts + ai + g * kZH);
+    pf_cp = __ldg(P.c_prev + oi);
+    pf_dout = __ldg(P.dout + oi);
+    if (P.masks) {
+      const size_t mi = (((size_t)s * 2) * P.B + brow) * kZH + unit;
+      pf_mc = (float)P.masks[mi];
+      pf_mh = (float)P.masks[mi + (size_t)P.B * kZH];
+    }
+  };
+  prefetch(maxlen - 1);
   cluster.sync();
   for (int s = maxlen - 1; s >= 0; --s) {
     float dgv[4] = {0.f, 0.f, 0.f, 0.f};
     float dh_direct = dhz, dc_direct = dcz;
     const bool live = s < len_own;
+    int t = 0;
     if (live) {
-      const int t = P.reverse ? len_own - 1 - s : s;
-      const size_t oi = ((size_t)brow * P.T + t) * kZH + unit, ai = ((size_t)brow * P.T + t) * 4 * kZH + unit;
-      const float ig = P.acts[ai], jg = P.acts[ai + kZH], fg = P.acts[ai + 2 * kZH], og = P.acts[ai + 3 * kZH];
-      const float cp = P.c_prev[oi];
-      float kc = P.keep, kh = P.keep;
-      if (P.masks) {
-        const size_t mi = (((size_t)s * 2) * P.B + brow) * kZH + unit;
-        kc *= (float)P.masks[mi];
-        kh *= (float)P.masks[mi + (size_t)P.B * kZH];
-      }
+      t = P.reverse ? len_own - 1 - s : s;
+      const float ig = pf_act[0], jg = pf_act[1], fg = pf_act[2], og = pf_act[3];
+      const float cp = pf_cp;
+      const float kc = P.keep * pf_mc, kh = P.keep * pf_mh;
       const float cn = fg * cp + ig * jg;
       const float tc = tanhf(cn);
-      const float dm = P.dout[oi] + dhz * kh;
+      const float dm = pf_dout + dhz * kh;
       dh_direct = dhz * (1.f - kh);
       const float dcn = dm * og * (1.f - tc * tc) + dcz * kc;
       dc_direct = dcz * (1.f - kc) + dcn * fg;
@@ -188,14 +213,21 @@ __global__ void __cluster_dims__(kZCluster, 1, 1) __launch_bounds__(kZThreads, 1
       dx[2 * kZH] = dgv[2];
       dx[3 * kZH] = dgv[3];
     }
-    // all-gather the d gates of this step into every CTA: dg_s[buf][col][row]
+    // all-gather the d gates of this step into every CTA: dg_s[buf][col][row].  The CTA's 128 columns x 8 rows are first laid
+    // out [col][row] in local shared memory (red_s is idle here), then pushed as 16-byte vectors: 8 remote stores per thread
+    // instead of 32 scalar ones
     float* dgb = dg_s + (s & 1) * 4 * kZH * kZRows;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float* p = dgb + (size_t)(g * kZH + unit) * kZRows + r8;
+    for (int g = 0; g < 4; ++g) red_s[(g * kZUnits + u) * kZRows + r8] = dgv[g];
+    __syncthreads();
+    {
+      const int lc = tid >> 1, hf = tid & 1;  // local column (gate * 32 + unit), row half
+      const float4 v4 = *reinterpret_cast<const float4*>(red_s + lc * kZRows + 4 * hf);
+      float* p = dgb + (size_t)((lc >> 5) * kZH + crank * kZUnits + (lc & 31)) * kZRows + 4 * hf;
 #pragma unroll
-      for (int dst = 0; dst < kZCluster; ++dst) *cluster.map_shared_rank(p, dst) = dgv[g];
+      for (int dst = 0; dst < kZCluster; ++dst) *reinterpret_cast<float4*>(cluster.map_shared_rank(p, dst)) = v4;
     }
+    prefetch(s - 1);
     cluster.sync();
     // d h_prev[row][unit] = sum_col dG[row][col] Kh[unit][col]: warp cq sums its 128 columns for all 8 rows, lane = unit
     float acc[kZRows];
