@@ -495,14 +495,16 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
           if (x < TeP) ehalf[half * TeP + x] = s;
         }
         ptx::bar_sync(1, kTcCompute);
-        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
+        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * ((tl + 3) & ~3) * 4));  // whole groups of four
         {
           const uint32_t ep = ptx::smem_u32(e_parts1) + (uint32_t)(crank * TeP * 4);
           const uint32_t eb = ptx::smem_u32(e_bar);
-          for (int x = tid; x < tl; x += kTcCompute) {
-            const float v = ehalf[x] + ehalf[TeP + x];
+          for (int x = tid * 4; x < tl; x += kTcCompute * 4) {  // 16-byte remote stores (scalar ones are disproportionately expensive)
+            const float4 a = *reinterpret_cast<const float4*>(ehalf + x), b = *reinterpret_cast<const float4*>(ehalf + TeP + x);
 #pragma unroll
-            for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst) + x * 4, v, ptx::mapa(eb, dst));
+            for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst)
+              ptx::st_async_v4(ptx::mapa(ep, dst) + x * 4, __float_as_uint(a.x + b.x), __float_as_uint(a.y + b.y), __float_as_uint(a.z + b.z),
+                               __float_as_uint(a.w + b.w), ptx::mapa(eb, dst));
           }
         }
         mbar_wait_warp(e_bar, e_parity);
@@ -647,17 +649,22 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
               }
             }
             const float tot = warp_sum16(G, lane);
-            if ((lane & 1) == 0) {
+            // lanes L, L+2, L+4, L+6 (L % 8 == 0) hold four consecutive positions: one 16-byte remote store
+            const float a1 = __shfl_down_sync(0xffffffffu, tot, 2), a2 = __shfl_down_sync(0xffffffffu, tot, 4),
+                        a3 = __shfl_down_sync(0xffffffffu, tot, 6);
+            if ((lane & 7) == 0) {
               const int x = t0 + warp_sum16_index(lane);
               if (x < tl) {
                 const uint32_t ep = ptx::smem_u32(e_parts2) + (uint32_t)((crank * TeP + x) * 4);
                 const uint32_t eb = ptx::smem_u32(e_bar);
 #pragma unroll
-                for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), tot, ptx::mapa(eb, dst));
+                for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst)
+                  ptx::st_async_v4(ptx::mapa(ep, dst), __float_as_uint(tot), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3),
+                                   ptx::mapa(eb, dst));
               }
             }
           }
-          if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));  // collected in the wait of barrier 3
+          if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * ((tl + 3) & ~3) * 4));  // collected in the wait of barrier 3
           if (halo && warp == 7) {
             // the same transpose for the 15 border positions of the OTHER half (|x - x'| <= 15 reaches across): partial over
             // this CTA's 32 units; the peer cluster adds the four CTA parts to its d cum before its next phase C'

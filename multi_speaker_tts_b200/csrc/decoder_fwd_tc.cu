@@ -662,18 +662,24 @@ __global__ void __cluster_dims__(kDecCluster, 1, 1) __launch_bounds__(kTcThreads
             v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
             // lane L now holds position ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1) of the block:
             // push it straight to the four CTAs of the cluster (st.async counts the bytes on their e_bar)
-            if ((lane & 1) == 0) {
-              const int x = t0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            // lanes L, L+2, L+4, L+6 (L % 8 == 0) hold four consecutive positions: gathered into one 16-byte remote store
+            // (scalar remote stores are disproportionately expensive: zlstm.cu measured it)
+            const float a1 = __shfl_down_sync(0xffffffffu, v[0], 2), a2 = __shfl_down_sync(0xffffffffu, v[0], 4),
+                        a3 = __shfl_down_sync(0xffffffffu, v[0], 6);
+            if ((lane & 7) == 0) {
+              const int x = t0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4;
               if (x < tl) {
                 const uint32_t ep = ptx::smem_u32(e_parts) + (uint32_t)((crank * TeP + x) * 4);
                 const uint32_t eb = ptx::smem_u32(e_bar);
 #pragma unroll
-                for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst) ptx::st_async_f32(ptx::mapa(ep, dst), v[0], ptx::mapa(eb, dst));
+                for (uint32_t dst = 0; dst < (uint32_t)kDecCluster; ++dst)
+                  ptx::st_async_v4(ptx::mapa(ep, dst), __float_as_uint(v[0]), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3),
+                                   ptx::mapa(eb, dst));
               }
             }
           }
         }
-        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * tl * 4));
+        if (tid == 0) ptx::mbar_arrive_expect_tx(e_bar, (uint32_t)(kDecCluster * ((tl + 3) & ~3) * 4));  // whole groups of four
         STAMP(11);
         mbar_wait_warp(e_bar, e_parity);
         e_parity ^= 1u;
