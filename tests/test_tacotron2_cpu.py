@@ -170,3 +170,46 @@ def test_feeder_reads_the_reference_pickle_dataset(tmp_path):
         assert (mel[b, ml[b]:] == 0).all()
     assert list(ml) == sorted(ml)                                                            # Pattern_Sorting_by_Mel_Length
     assert d[p['Speaker_Embedding_Mel']].shape == (tok.shape[0] * 5, 64, 80)
+
+
+def test_stream_and_dense_helpers_are_transparent_on_the_cpu():
+    """Modules.side_stream / Modules.dense / Feeder._pinned only change WHERE work runs on a CUDA device; on CPU tensors they must be
+    the plain expressions (the CPU graph tests above go through them)"""
+    from multi_speaker_tts_b200 import Modules
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 7, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(7, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(4, generator=g, dtype=torch.float64)
+    y = Modules.dense(x, w, b)
+    assert torch.equal(y, x @ w + b)
+    assert torch.equal(Modules.dense(x, w), x @ w)
+    y.sum().backward()
+    assert x.grad is not None and w.grad is not None
+    branch = Modules.side_stream(x.device, 'anything')
+    with branch:
+        z = x * 2
+    assert branch.join(z) is z
+    a, c = branch.join(z, y)
+    assert a is z and c is y
+    arr = np.arange(12, dtype=np.float32).reshape(3, 4)
+    out = Feeder._pinned(arr)
+    assert isinstance(out, np.ndarray) and out.dtype == arr.dtype and np.array_equal(out, arr)
+
+
+def test_weight_regularisation_loss_is_one_reduction_over_the_flat_buffer():
+    """MSTTS_SV.py:145-159: 0.5 * rate * sum over the regularised variables of sum(v ** 2).  The flat parameter buffer holds exactly
+    those variables in its first n_l2 floats (padding zero), which the train step reduces in one call"""
+    from multi_speaker_tts_b200 import MSTTS_SV as M
+    shapes = M.variable_shapes()
+    train = [k for k, (s, kind) in shapes.items() if M.is_trainable(k, kind)]
+    reg = [k for k in train if M.in_weight_regularization(k)]
+    gen = torch.Generator().manual_seed(1)
+    vals = {k: torch.randn(shapes[k][0], generator=gen, dtype=torch.float64) for k in reg[:6]}
+    flat = torch.zeros(sum((v.numel() + 3) // 4 * 4 for v in vals.values()), dtype=torch.float64)
+    off = 0
+    for v in vals.values():
+        flat[off:off + v.numel()] = v.reshape(-1)
+        off += (v.numel() + 3) // 4 * 4
+    ref = sum(0.5 * (v ** 2).sum() for v in vals.values())
+    got = 0.5 * torch.linalg.vector_norm(flat) ** 2
+    assert abs(float(got) - float(ref)) <= 1e-12 * float(ref)
