@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of environment switches on the decoder train step: tools/ab_env.sh "A=1 B=2" "A=0" ...  -> one kernel_share line per setting
-for cfg in "$@"; do
+for cfg in "$@"; do  # an empty string = the defaults
   out=$(env $cfg timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary 2>/dev/null | tail -1)
   python - "$cfg" "$out" <<'PY'
 import json, sys
