@@ -190,9 +190,9 @@ class _Conv1dFunction(torch.autograd.Function):
         x, kernel, bias = x.contiguous(), kernel.contiguous(), bias.contiguous()
         y = torch.empty(B, T, Cout, device=x.device)
         ws = _Conv1dFunction._ws(x, B, T, Cin, Cout, k)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             rc = _lib.lib().mstts_conv1d_fwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(bias), B, T, Cin, Cout, k, _lib.ptr(y),
-                                             C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+                                             C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr(x.device))
         _lib.check(rc, "mstts_conv1d_fwd")
         ctx.save_for_backward(x, kernel)
         return y
@@ -207,9 +207,9 @@ class _Conv1dFunction(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dk = torch.empty_like(kernel)
         ws = _Conv1dFunction._ws(x, B, T, Cin, Cout, k)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             rc = _lib.lib().mstts_conv1d_bwd(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(dy), B, T, Cin, Cout, k, _lib.ptr(dx), _lib.ptr(dk),
-                                             C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+                                             C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr(x.device))
         _lib.check(rc, "mstts_conv1d_bwd")
         return dx, dk, dy.sum(dim=(0, 1))
 
@@ -228,11 +228,11 @@ class _ActBnDropoutFunction(torch.autograd.Function):
         a_saved = torch.empty_like(x) if training else None
         ws = torch.empty(lib.mstts_act_bn_dropout_workspace_bytes(Cc), device=x.device, dtype=torch.uint8)
         keep = 1.0 - rate
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             rc = lib.mstts_act_bn_dropout_fwd(_lib.ptr(x), _lib.ptr(gamma.contiguous()), _lib.ptr(beta.contiguous()), _lib.ptr(moving_mean),
                                               _lib.ptr(moving_var), _lib.ptr(mask), B * T, Cc, act, int(training), keep, 0.99, 1e-3,
                                               _lib.ptr(y), _lib.ptr(a_saved), _lib.ptr(stats), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                              C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+                                              _lib.stream_ptr(x.device))
         _lib.check(rc, "mstts_act_bn_dropout_fwd")
         if training:
             ctx.save_for_backward(a_saved, stats, gamma, mask)
@@ -250,10 +250,10 @@ class _ActBnDropoutFunction(torch.autograd.Function):
         dgamma = torch.empty(Cc, device=dy.device)
         dbeta = torch.empty(Cc, device=dy.device)
         ws = torch.empty(lib.mstts_act_bn_dropout_workspace_bytes(Cc), device=dy.device, dtype=torch.uint8)
-        with torch.cuda.device(dy.device):
+        with _lib.on_device(dy.device):
             rc = lib.mstts_act_bn_dropout_bwd(_lib.ptr(dy), _lib.ptr(a_saved), _lib.ptr(stats), _lib.ptr(gamma.contiguous()), _lib.ptr(mask),
                                               B * T, Cc, act, keep, _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta),
-                                              C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(torch.cuda.current_stream(dy.device).cuda_stream))
+                                              C.c_void_p(ws.data_ptr()), ws.numel(), _lib.stream_ptr(dy.device))
         _lib.check(rc, "mstts_act_bn_dropout_bwd")
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
@@ -307,9 +307,9 @@ def Encoder_Conv(inputs, is_training=False, variables=None, masks=None):
 def _gemm(tA, tB, M, N, K, A, lda, Bm, ldb, Cm, ldc, beta=0.0, precise=0):
     """C[M,N] = op(A) op(B) + beta C on the hand-written tcgen05 kernel (mstts_gemm_f32: bf16x3, fp32 accumulation)"""
     import ctypes as C
-    with torch.cuda.device(A.device):
+    with _lib.on_device(A.device):
         rc = _lib.lib().mstts_gemm_f32(int(tA), int(tB), M, N, K, _lib.ptr(A), lda, 0, _lib.ptr(Bm), ldb, 0, _lib.ptr(Cm), ldc, 0,
-                                       float(beta), 1, int(precise), C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream))
+                                       float(beta), 1, int(precise), _lib.stream_ptr(A.device))
     _lib.check(rc, "mstts_gemm_f32")
 
 
@@ -426,10 +426,10 @@ class _ZlstmFunction(torch.autograd.Function):
         cp = torch.zeros(B, T, H, device=xk.device) if need else None
         hp_ = torch.zeros(B, T, H, device=xk.device) if need else None
         xr = x_res.contiguous() if x_res is not None else None
-        with torch.cuda.device(xk.device):
+        with _lib.on_device(xk.device):
             rc = lib.mstts_zlstm_fwd(_lib.ptr(xk), _lib.ptr(kh), _lib.ptr(lengths), _lib.ptr(masks), _lib.ptr(xr), B, T, H, int(reverse),
                                      float(keep), _lib.ptr(out), _lib.ptr(acts), _lib.ptr(cp), _lib.ptr(hp_),
-                                     C.c_void_p(torch.cuda.current_stream(xk.device).cuda_stream))
+                                     _lib.stream_ptr(xk.device))
         _lib.check(rc, "mstts_zlstm_fwd")
         ctx.save_for_backward(kh, lengths, masks, acts, cp, hp_)
         ctx.meta = (B, T, H, int(reverse), float(keep), x_res is not None)
@@ -442,10 +442,10 @@ class _ZlstmFunction(torch.autograd.Function):
         B, T, H, reverse, keep, has_res = ctx.meta
         dout = dout.contiguous()
         dxk = torch.empty(B, T, 4 * H, device=dout.device)
-        with torch.cuda.device(dout.device):
+        with _lib.on_device(dout.device):
             rc = _lib.lib().mstts_zlstm_bwd(_lib.ptr(dout), _lib.ptr(kh), _lib.ptr(lengths), _lib.ptr(masks), _lib.ptr(acts), _lib.ptr(cp),
                                             B, T, H, reverse, keep, _lib.ptr(dxk),
-                                            C.c_void_p(torch.cuda.current_stream(dout.device).cuda_stream))
+                                            _lib.stream_ptr(dout.device))
         _lib.check(rc, "mstts_zlstm_bwd")
         dkh = torch.empty(H, 4 * H, device=dout.device)
         _gemm(1, 0, H, 4 * H, B * T, hp_, H, dxk, 4 * H, dkh, 4 * H)  # h_prev^T d xk

@@ -138,6 +138,34 @@ def check(rc, what=""):
         raise MsttsError("%s failed (%d): %s" % (what or "libmstts_b200 call", rc, msg.decode() if msg else ""))
 
 
+def stream_ptr(device):
+    """raw handle of the current CUDA stream on ``device``.  Every library call needs it; building a torch Stream object for it
+    (torch.cuda.current_stream) cost more host time than the launch itself."""
+    import torch
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+
+
+class on_device(object):
+    """``with on_device(dev):`` -- torch.cuda.device(dev) that costs nothing when ``dev`` is already the current device"""
+    __slots__ = ('ctx',)
+
+    def __init__(self, device):
+        import torch
+        idx = device.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
+
+
 def ptr(t):
     """device pointer of a contiguous tensor (None -> NULL)"""
     if t is None:

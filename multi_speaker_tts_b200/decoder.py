@@ -86,10 +86,10 @@ def decoder_forward(weights, memory, text_len, mel, mel_len, prenet_mask, zone_m
         mel_len=mel_len.data_ptr() if mel_len is not None else None,
         prenet_mask=prenet_mask.data_ptr(), zone_mask=zone_mask.data_ptr() if zone_mask is not None else None,
         linear=linear.data_ptr(), stop=stop.data_ptr(), align=align.data_ptr(), steps_done=steps_done.data_ptr())
-    s = stream if stream is not None else torch.cuda.current_stream(dev)
-    with torch.cuda.device(dev):
+    s = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(dev)
+    with _lib.on_device(dev):
         rc = lib.mstts_decoder_fwd(C.byref(wstruct), C.byref(io), C.c_void_p(workspace.data_ptr()), workspace.numel(),
-                                   C.c_void_p(s.cuda_stream))
+                                   s)
     _lib.check(rc, "mstts_decoder_fwd")
     st = DecoderState()
     st.io, st.ws, st.wstruct = io, workspace, wstruct
@@ -118,10 +118,10 @@ def decoder_backward(state, weights, d_linear, d_stop, stream=None, want_d_memor
     d_memory = torch.empty(B, Te, D, device=dev, dtype=torch.float32) if want_d_memory else None
     g = _lib.MsttsDecoderGrads(d_linear=d_linear.data_ptr(), d_stop=d_stop.data_ptr(),
                                d_memory=d_memory.data_ptr() if d_memory is not None else None)
-    s = stream if stream is not None else torch.cuda.current_stream(dev)
-    with torch.cuda.device(dev):
+    s = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(dev)
+    with _lib.on_device(dev):
         rc = lib.mstts_decoder_bwd(C.byref(state.wstruct), C.byref(state.io), C.byref(g), C.byref(gstruct),
-                                   C.c_void_p(state.ws.data_ptr()), state.ws.numel(), C.c_void_p(s.cuda_stream))
+                                   C.c_void_p(state.ws.data_ptr()), state.ws.numel(), s)
     _lib.check(rc, "mstts_decoder_bwd")
     return grads, d_memory
 
@@ -138,11 +138,11 @@ def decoder_loss(linear, stop, mel, mel_len, use_l1=True, stream=None):
     d_stop = torch.empty_like(stop)
     mel = mel.contiguous().float()
     mel_len = mel_len.contiguous().to(torch.int32)
-    s = stream if stream is not None else torch.cuda.current_stream(dev)
-    with torch.cuda.device(dev):
+    s = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(dev)
+    with _lib.on_device(dev):
         rc = lib.mstts_decoder_loss(_lib.ptr(linear), _lib.ptr(stop), _lib.ptr(mel), _lib.ptr(mel_len), B, L, T,
                                     int(bool(use_l1)), _lib.ptr(loss2), _lib.ptr(d_linear), _lib.ptr(d_stop),
-                                    C.c_void_p(s.cuda_stream))
+                                    s)
     _lib.check(rc, "mstts_decoder_loss")
     return loss2, d_linear, d_stop
 
@@ -151,10 +151,10 @@ def fill_mask(out, keep_prob, seed, stream=None):
     """out (uint8 CUDA tensor) <- Bernoulli(keep_prob) bits from the counter-based generator."""
     lib = _lib.lib()
     assert out.dtype == torch.uint8 and out.is_cuda and out.is_contiguous()
-    s = stream if stream is not None else torch.cuda.current_stream(out.device)
-    with torch.cuda.device(out.device):
+    s = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(out.device)
+    with _lib.on_device(out.device):
         rc = lib.mstts_fill_mask(_lib.ptr(out), out.numel(), float(keep_prob), int(seed) & (2 ** 64 - 1),
-                                 C.c_void_p(s.cuda_stream))
+                                 s)
     _lib.check(rc, "mstts_fill_mask")
     return out
 
@@ -164,10 +164,10 @@ def adam_tf(p, m, v, g, lr_t, b1=0.9, b2=0.999, eps=1e-6, grad_scale=1.0, l2=0.0
     lib = _lib.lib()
     for t in (p, m, v, g):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
-    s = stream if stream is not None else torch.cuda.current_stream(p.device)
-    with torch.cuda.device(p.device):
+    s = C.c_void_p(stream.cuda_stream) if stream is not None else _lib.stream_ptr(p.device)
+    with _lib.on_device(p.device):
         rc = lib.mstts_adam_tf(_lib.ptr(p), _lib.ptr(m), _lib.ptr(v), _lib.ptr(g), p.numel(), float(lr_t), float(b1),
-                               float(b2), float(eps), float(grad_scale), float(l2), C.c_void_p(s.cuda_stream))
+                               float(b2), float(eps), float(grad_scale), float(l2), s)
     _lib.check(rc, "mstts_adam_tf")
 
 
