@@ -97,6 +97,25 @@ def _init(shape, kind, gen):
     return ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim).float()
 
 
+class _FusedLosses(torch.autograd.Function):
+    """linear / postnet / stop losses of MSTTS_SV.py:127-144 with their gradients from mstts_decoder_loss (csrc/capi.cu): the
+    kernel computes mean((x - mel)^2) (+ mean|x - mel|) over [B, L, 80] and the stop-token BCE over [B, T] together with d x and
+    d stop; it runs once on the linear output (+ stop) and once on the postnet output"""
+
+    @staticmethod
+    def forward(ctx, linear, stop, post, mel, mel_len, use_l1):
+        from .decoder import decoder_loss
+        l_a, d_lin, d_stop = decoder_loss(linear.contiguous(), stop.contiguous(), mel, mel_len, use_l1)
+        l_b, d_post, _ = decoder_loss(post.contiguous(), stop.contiguous(), mel, mel_len, use_l1)
+        ctx.save_for_backward(d_lin, d_stop, d_post)
+        return l_a[0].clone(), l_b[0].clone(), l_a[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_lin, g_post, g_stop):
+        d_lin, d_stop, d_post = ctx.saved_tensors
+        return d_lin * g_lin, d_stop * g_stop, d_post * g_post, None, None, None
+
+
 class Tacotron2(object):
     def __init__(self, is_Training=False, device=None, seed=0, process_group=None, feeder=None, mode=None):
         if not torch.cuda.is_available():
@@ -259,6 +278,13 @@ class Tacotron2(object):
         """MSTTS_SV.py:127-161"""
         mel, mel_len = feed['Mel'], feed['Mel_Length']
         T = out.linear.shape[1]
+        if out.linear.is_cuda and out.linear.dtype == torch.float32 and mel.shape[1] == T - 1:
+            # the three loss terms and their gradients in two launches of the library's loss kernel (the op-by-op form below
+            # is ~100 tiny launches forward + backward); same unmasked means
+            linear_Loss, postnet_Loss, stop_Loss = _FusedLosses.apply(out.linear, out.stop.squeeze(2), post, mel, mel_len,
+                                                                      bool(hp.Train.Use_L1_Loss))
+            wr = (0.5 * hp.Train.Weight_Regularization_Rate) * torch.linalg.vector_norm(self.flat_p[:self.n_l2]) ** 2
+            return linear_Loss, postnet_Loss, stop_Loss, wr
         stop_target = (torch.arange(T, device=mel.device)[None, :] >= mel_len[:, None]).float()
         lin, pst = out.linear[:, :-1], post[:, :-1]
         linear_Loss = torch.mean((lin - mel) ** 2)
