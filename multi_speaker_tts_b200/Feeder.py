@@ -20,6 +20,14 @@ import numpy as np
 from . import Hyper_Parameters as hp
 
 
+def _current_cuda_device():
+    try:
+        import torch
+        return torch.cuda.current_device() if torch.cuda.is_available() else None
+    except (ImportError, RuntimeError):
+        return None
+
+
 def _pinned(a):
     """The same array in page-locked host memory when a CUDA device is present (plain ndarray otherwise): the collation runs in the
     feeder's background thread, so the train step's host -> device copies become DMA transfers with no staging copy inside the step."""
@@ -51,6 +59,7 @@ class Feeder(object):
         self.Placeholder_Generate()
         self._rng = np.random.default_rng(seed + rank)
         self._synthetic_shape = synthetic_shape  # (B, Te, L) or None: hp.Train.Batch_Size and ragged lengths
+        self._cuda_device = _current_cuda_device()  # the generator thread pins its arrays in this device's context
         self._pattern_path = hp.Train.Pattern_Path  # captured: the generator thread outlives later changes of hp
         self._batch_size = hp.Train.Batch_Size
         meta = os.path.join(self._pattern_path, hp.Train.Metadata_File.upper()).replace("\\", "/")
@@ -131,6 +140,9 @@ class Feeder(object):
 
     def Train_Pattern_Generate(self, is_Pre_Train=False):
         """Feeder.py:89-174 (background thread over the pickled dataset)"""
+        if self._cuda_device is not None:  # a new thread starts on device 0: page-locking there would open a context on GPU 0
+            import torch                   # from every rank of a data-parallel job
+            torch.cuda.set_device(self._cuda_device)
         md = self.metadata_Dict
         wanted = hp.Train.Pre_Train_Dataset_List if is_Pre_Train else hp.Train.Main_Train_Dataset_List
         queue = self.pre_Pattern_Queue if is_Pre_Train else self.pattern_Queue
